@@ -1,0 +1,212 @@
+// VNA chirp / swipe path for sm_100a.
+//
+// RX: replaces chirp_demodulator (cpp/kernels.cu:389-427) + cublas_decim (cpp/kernels.cu:852-872,
+// a cublasCgemv against the flat lock-in profile) + move_buffer with ONE fused pass:
+//     S[j] = sum_{i<ppt} in[j*ppt+i] * conj(chirp(pos0 + j*ppt + i)) * profile[i]
+// so the 8 B/sample demodulated intermediate is never written.  The chirp phase is an integer
+// accumulator: within a frequency step the int32 phase index advances by a constant, so the
+// per-sample cost is one integer add plus an exact-range-reduced float32 sincos.
+// TX: chirp_gen (cpp/kernels.cu:335-372) is the same phase walk with a store instead of a load.
+#include "devmath.cuh"
+
+namespace gsdr {
+namespace {
+
+constexpr int SEG = 8192;  // samples per partial sum when ppt is large
+
+// One warp per (output j, segment): lanes stride the samples, xor-shuffle reduction.
+__global__ void __launch_bounds__(256)
+chirp_lockin_warp_kernel(const Window w, unsigned long long pos0, const ChirpDev cp, const float* __restrict__ profile,
+                         int ppt, long long n_out, int n_seg, float2* __restrict__ dst /* out or partial */) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long units = n_out * n_seg;
+    for (long long unit = warp0; unit < units; unit += n_warps) {
+        const long long j = unit / n_seg;
+        const int sg = (int)(unit - j * n_seg);
+        const int i0 = sg * SEG;
+        const int i1 = min(ppt, i0 + SEG);
+        float2 acc = make_float2(0.f, 0.f);
+        if (i0 + lane < i1) {
+            const long long s0 = j * (long long)ppt + i0 + lane;
+            ChirpWalker cw;
+            cw.seek(pos0 + (unsigned long long)s0, cp);
+            for (int i = i0 + lane; i < i1; i += 32) {
+                const float2 x = dev_win_at(w, j * (long long)ppt + i);
+                const float2 ch = chirp_phasor(cw.idx);
+                const float pw = __ldg(&profile[i]);
+                // out = in * conj(chirp): (cx*ix + cy*iy, cx*iy - cy*ix), cpp/kernels.cu:424-425
+                acc.x = fmaf(fmaf(ch.x, x.x, ch.y * x.y), pw, acc.x);
+                acc.y = fmaf(fmaf(ch.x, x.y, -ch.y * x.x), pw, acc.y);
+                cw.advance(32u, cp);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+            acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        }
+        if (lane == 0) dst[unit] = acc;
+    }
+}
+
+// Short integration windows (ppt < 32): one thread per output.
+__global__ void __launch_bounds__(256)
+chirp_lockin_thread_kernel(const Window w, unsigned long long pos0, const ChirpDev cp, const float* __restrict__ profile,
+                           int ppt, long long n_out, float2* __restrict__ out) {
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n_out; j += (long long)gridDim.x * blockDim.x) {
+        ChirpWalker cw;
+        cw.seek(pos0 + (unsigned long long)(j * ppt), cp);
+        float2 acc = make_float2(0.f, 0.f);
+        for (int i = 0; i < ppt; ++i) {
+            const float2 x = dev_win_at(w, j * (long long)ppt + i);
+            const float2 ch = chirp_phasor(cw.idx);
+            const float pw = __ldg(&profile[i]);
+            acc.x = fmaf(fmaf(ch.x, x.x, ch.y * x.y), pw, acc.x);
+            acc.y = fmaf(fmaf(ch.x, x.y, -ch.y * x.x), pw, acc.y);
+            cw.advance(1u, cp);
+        }
+        out[j] = acc;
+    }
+}
+
+__global__ void chirp_lockin_finalize_kernel(const float2* __restrict__ partial, int n_seg, long long n_out, float2* __restrict__ out) {
+    for (long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x; j < n_out; j += (long long)gridDim.x * blockDim.x) {
+        float2 acc = make_float2(0.f, 0.f);
+        for (int s = 0; s < n_seg; ++s) {
+            const float2 p = partial[j * n_seg + s];
+            acc.x += p.x;
+            acc.y += p.y;
+        }
+        out[j] = acc;
+    }
+}
+
+// decim == 0: plain demodulation, one output per input (cpp/USRP_demodulator.cpp:384-391).
+// Each thread owns RUN consecutive samples so the phase walk is incremental.
+constexpr int RUN = 8;
+__global__ void __launch_bounds__(256)
+chirp_demod_full_kernel(const float2* __restrict__ in, long long n, unsigned long long pos0, const ChirpDev cp,
+                        float2* __restrict__ out) {
+    const long long n_runs = (n + RUN - 1) / RUN;
+    for (long long rn = blockIdx.x * (long long)blockDim.x + threadIdx.x; rn < n_runs; rn += (long long)gridDim.x * blockDim.x) {
+        const long long s0 = rn * RUN;
+        ChirpWalker cw;
+        cw.seek(pos0 + (unsigned long long)s0, cp);
+#pragma unroll
+        for (int i = 0; i < RUN; ++i) {
+            if (s0 + i < n) {
+                const float2 x = in[s0 + i];
+                const float2 ch = chirp_phasor(cw.idx);
+                out[s0 + i] = make_float2(fmaf(ch.x, x.x, ch.y * x.y), fmaf(ch.x, x.y, -ch.y * x.x));
+                cw.advance(1u, cp);
+            }
+        }
+    }
+}
+
+// TX: out = scale * (sin(pi theta), -cos(pi theta)), cpp/kernels.cu:367-368.
+__global__ void __launch_bounds__(256)
+chirp_gen_kernel(float2* __restrict__ out, long long n, unsigned long long pos0, const ChirpDev cp, float scale) {
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    constexpr int TILE = 32 * 16;  // samples per warp tile
+    const long long tiles = (n + TILE - 1) / TILE;
+    for (long long tile = warp0; tile < tiles; tile += n_warps) {
+        const long long s0 = tile * TILE + lane;
+        if (s0 >= n) continue;
+        ChirpWalker cw;
+        cw.seek(pos0 + (unsigned long long)s0, cp);
+#pragma unroll 4
+        for (int i = 0; i < 16; ++i) {
+            const long long s = s0 + 32 * i;
+            if (s < n) {
+                const float2 ch = chirp_phasor(cw.idx);
+                out[s] = make_float2(ch.x * scale, ch.y * scale);
+                cw.advance(32u, cp);
+            }
+        }
+    }
+}
+
+__global__ void chirp_index_probe_kernel(int* __restrict__ out, unsigned int n, unsigned long long pos0, const ChirpDev cp) {
+    // two ways on purpose: a fresh seek per element and an incremental walk must agree
+    const unsigned int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned int stride = gridDim.x * blockDim.x;
+    if (t >= n) return;
+    ChirpWalker cw;
+    cw.seek(pos0 + t, cp);
+    for (unsigned int i = t; i < n; i += stride) {
+        out[i] = (int)cw.idx;
+        cw.advance(stride, cp);
+    }
+}
+
+}  // namespace
+
+size_t chirp_partial_count(int ppt, long long n_out, int) {
+    const int n_seg = (ppt + SEG - 1) / SEG;
+    return n_seg > 1 ? (size_t)n_out * n_seg : 0;
+}
+
+int chirp_demod_launch(const Window& w, unsigned long long pos0, const ChirpDev& cp, const float* profile, int ppt,
+                       long long n_out, float2* out, float2* partial, int sm_count, cudaStream_t stream) {
+    if (n_out <= 0) return 0;
+    int launches = 0;
+    if (ppt < 32) {
+        int blocks = (int)((n_out + 255) / 256);
+        if (blocks > sm_count * 8) blocks = sm_count * 8;
+        chirp_lockin_thread_kernel<<<blocks, 256, 0, stream>>>(w, pos0, cp, profile, ppt, n_out, out);
+        launches = 1;
+    } else {
+        const int n_seg = (ppt + SEG - 1) / SEG;
+        const long long units = n_out * n_seg;
+        long long blocks = (units + 7) / 8;  // 8 warps per block
+        if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
+        if (n_seg > 1 && !partial) {
+            set_error("chirp_demod_launch: partial buffer missing");
+            return -1;
+        }
+        chirp_lockin_warp_kernel<<<(int)blocks, 256, 0, stream>>>(w, pos0, cp, profile, ppt, n_out, n_seg,
+                                                                   n_seg > 1 ? partial : out);
+        launches = 1;
+        if (n_seg > 1) {
+            int fb = (int)((n_out + 255) / 256);
+            if (fb > 1024) fb = 1024;
+            chirp_lockin_finalize_kernel<<<fb, 256, 0, stream>>>(partial, n_seg, n_out, out);
+            launches = 2;
+        }
+    }
+    GSDR_CUDA_OK(cudaGetLastError());
+    return launches;
+}
+
+int chirp_demod_full_launch(const float2* in, long long n, unsigned long long pos0, const ChirpDev& cp, float2* out,
+                            cudaStream_t stream) {
+    if (n <= 0) return 0;
+    long long blocks = ((n + RUN - 1) / RUN + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    chirp_demod_full_kernel<<<(int)blocks, 256, 0, stream>>>(in, n, pos0, cp, out);
+    GSDR_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
+int chirp_gen_launch(float2* out, long long n, unsigned long long pos0, const ChirpDev& cp, float scale, cudaStream_t stream) {
+    if (n <= 0) return 0;
+    long long blocks = ((n + 511) / 512 + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    chirp_gen_kernel<<<(int)blocks, 256, 0, stream>>>(out, n, pos0, cp, scale);
+    GSDR_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
+int chirp_index_probe_launch(int* out, unsigned int n, unsigned long long pos0, const ChirpDev& cp, cudaStream_t stream) {
+    if (n == 0) return 0;
+    chirp_index_probe_kernel<<<64, 128, 0, stream>>>(out, n, pos0, cp);
+    GSDR_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
+}  // namespace gsdr

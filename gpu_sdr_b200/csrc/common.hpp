@@ -1,0 +1,110 @@
+// Shared declarations for libgsdr (B200 / sm_100a readout DSP path).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/gsdr.h"
+
+namespace gsdr {
+
+// thread-local error string behind gsdr_last_error()
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define GSDR_CUDA_OK(expr)                                                                 \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            ::gsdr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                              __FILE__, __LINE__);                                         \
+            return -1;                                                                     \
+        }                                                                                  \
+    } while (0)
+
+#define GSDR_CUDA_OK_NULL(expr)                                                            \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            ::gsdr::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                              __FILE__, __LINE__);                                         \
+            return nullptr;                                                                \
+        }                                                                                  \
+    } while (0)
+
+// ---- host logic that defines results (hostlogic.cpp) ----------------------------------------
+void make_sinc_window(int length, float fc, float* out);
+void make_flat_window(int length, int side, float* out);
+int pfb_batching(int buffer_len, int fft_tones, int pf_average);
+void tone_bins(int rate, int fft_tones, const int32_t* freq, int n, int32_t* bins);
+void buffer_helper_init(gsdr_buffer_helper* h, int n_tones, int buffer_len, int average, int n_eff_tones);
+void buffer_helper_update(gsdr_buffer_helper* h);
+void vna_helper_init(gsdr_vna_helper* h, int ppt, int buffer_len);
+void vna_helper_update(gsdr_vna_helper* h);
+void chirp_params(int rate, int freq0, int chirp_f0, int swipe_s0, float chirp_t0, bool tx, gsdr_chirp_param* out);
+
+// A view of a stream window that is the concatenation of the carried-over samples of the
+// previous call (`hist`, n_hist float2) and the new samples (`in`, n_in float2).  This is what
+// replaces the reference's move_buffer + upload-at-new_0 (cpp/USRP_demodulator.cpp:491-509).
+struct Window {
+    const float2* hist;
+    const float2* in;
+    long long n_hist;
+    long long n_in;
+};
+
+// ---- PFB (TONES / NOISE) launches (pfb_kernels.cu) -------------------------------------------
+struct PfbJob {          // one stream's share of a launch
+    Window win;
+    const float* taps;   // [P*N] real taps (device)
+    const int* bins;     // [T] selected FFT bins (device); nullptr => all bins in order (T == N)
+    float2* out;         // [n_frames*T] sample-major
+    int first_frame;     // frame index within the window (0 = window start)
+    int n_frames;
+    int N, P, T;
+};
+// Returns the number of kernel launches issued (>0) or -1.  `workspace` is device scratch of at
+// least pfb_workspace_bytes() for the generic path (may be null for the fused path).
+bool pfb_fused_supported(int N, int P, int T, const Window& w);
+const char* pfb_kernel_name(int N, int P, int T);
+size_t pfb_workspace_bytes(int N, int P, int max_frames);
+int pfb_launch(const PfbJob* jobs_host, int n_jobs, void* jobs_dev_scratch, void* workspace, const float2* twiddle_dev,
+               int sm_count, cudaStream_t stream);
+// Copies the last n_tail samples of the window into dst (device), double-buffer safe.
+int window_tail_copy(const Window& w, long long n_tail, float2* dst, cudaStream_t stream);
+
+// ---- CHIRP launches (chirp_kernels.cu) --------------------------------------------------------
+struct ChirpDev {   // kernel-side copy of gsdr_chirp_param plus derived 32-bit constants
+    unsigned long long period;   // num_steps*length
+    unsigned long long length;
+    unsigned int chirpness;
+    int f0;
+};
+int chirp_demod_launch(const Window& w, unsigned long long pos0 /* chirp position of window sample 0 */,
+                       const ChirpDev& cp, const float* profile, int ppt, long long n_out, float2* out,
+                       float2* partial, int sm_count, cudaStream_t stream);
+int chirp_demod_full_launch(const float2* in, long long n, unsigned long long pos0, const ChirpDev& cp, float2* out,
+                            cudaStream_t stream);
+int chirp_gen_launch(float2* out, long long n, unsigned long long pos0, const ChirpDev& cp, float scale, cudaStream_t stream);
+int chirp_index_probe_launch(int* out, unsigned int n, unsigned long long pos0, const ChirpDev& cp, cudaStream_t stream);
+size_t chirp_partial_count(int ppt, long long n_out, int sm_count);
+
+// ---- DIRECT launches (direct_kernels.cu) ------------------------------------------------------
+int direct_fir_launch(const Window& w, const float2* g /* [T][ntaps] */, const int* freq_dev, int T, int M, int ntaps,
+                      int rate, long long pos0 /* stream position (mod rate) of window sample 0 */, long long n_out,
+                      float2* out, cudaStream_t stream);
+int direct_mix_launch(const float2* in, long long n, const int* freq_dev, int T, int rate, long long pos0, float2* out,
+                      cudaStream_t stream);
+int direct_phase_probe_launch(long long* out, unsigned int n, int tone_freq, int rate, unsigned long long index_counter,
+                              unsigned long long n0, cudaStream_t stream);
+
+// ---- TX tones synthesis (tones_kernels.cu) ----------------------------------------------------
+int tones_synth_launch(float2* out, long long n0, long long n, const int* bins_dev, const float* ampl_dev, int T, int rate,
+                       cudaStream_t stream);
+
+}  // namespace gsdr

@@ -1,0 +1,96 @@
+// Device-side helpers shared by the DSP kernels: window access, complex arithmetic, and a
+// float32 sincos driven by an INTEGER phase so that range reduction is exact.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "common.hpp"
+
+namespace gsdr {
+
+__device__ __forceinline__ float2 dev_win_at(const Window& w, long long s) {
+    if (s < w.n_hist) return w.hist[s];
+    s -= w.n_hist;
+    if (s < w.n_in) return w.in[s];
+    return make_float2(0.f, 0.f);
+}
+
+__device__ __forceinline__ float2 dev_cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// sin and cos of 2*pi*phase/2^32 for a 32-bit phase word.
+// Quadrant (top two bits, rounded) is peeled off in integers, so the polynomial only ever sees
+// |x| <= pi/4 and the int->float conversion error is <= 2^-24 * pi/4 ~ 4.7e-8 rad.  Polynomials
+// are the classic single-precision minimax kernels (error ~1 ulp on the reduced range).
+__device__ __forceinline__ void sincos_phase32(unsigned int phase, float& s, float& c) {
+    const unsigned int u = phase + 0x20000000u;
+    const unsigned int q = u >> 30;
+    const int rem = (int)(u & 0x3FFFFFFFu) - 0x20000000;       // [-2^29, 2^29)
+    const float x = (float)rem * 1.4629180792671596e-9f;       // 2*pi / 2^32
+    const float z = x * x;
+    float sp = fmaf(-1.9515295891e-4f, z, 8.3321608736e-3f);
+    sp = fmaf(sp, z, -1.6666654611e-1f);
+    const float sn = fmaf(x * z, sp, x);
+    float cp = fmaf(2.443315711809948e-5f, z, -1.388731625493765e-3f);
+    cp = fmaf(cp, z, 4.166664568298827e-2f);
+    const float cs = fmaf(z * z, cp, fmaf(-0.5f, z, 1.0f));
+    // rotate by q quarter turns
+    const float s1 = (q & 1u) ? cs : sn;
+    const float c1 = (q & 1u) ? sn : cs;
+    s = (q & 2u) ? -s1 : s1;
+    c = ((q + 1u) & 2u) ? -c1 : c1;
+}
+
+// ---- chirp integer phase (cpp/kernels.cu:401-419 == :348-365) ---------------------------------
+// index = eff*(f0 + k*chirpness) - chirpness*(length*T(k)), T(k) = k(k+1)/2, evaluated by the
+// reference in unsigned 64-bit and truncated to int32.  Truncation commutes with + - *, so the
+// same bits come out of 32-bit arithmetic as long as T(k) itself is formed exactly (64-bit).
+__device__ __forceinline__ unsigned int chirp_index_word(unsigned long long eff, unsigned long long k, const ChirpDev& cp) {
+    const unsigned long long tri = (k & 1ull) ? ((k + 1ull) >> 1) * k : (k >> 1) * (k + 1ull);  // exact for k < 2^32
+    const unsigned int step = (unsigned int)cp.f0 + (unsigned int)k * cp.chirpness;
+    const unsigned int corr = cp.chirpness * ((unsigned int)cp.length * (unsigned int)tri);
+    return (unsigned int)eff * step - corr;
+}
+
+// The reference feeds (double)index / 2147483647.5 to sinpi/cospi: one turn is 2^32-1 counts, not
+// 2^32.  Treating the int32 index as a 2^32-per-turn phase word is off by |index| * 2.3e-10
+// relative, at most 1.5e-9 rad -- forty times below float32 resolution of the result.
+// Returns chirp = (sin(pi*theta), -cos(pi*theta)).
+__device__ __forceinline__ float2 chirp_phasor(unsigned int index_word) {
+    float s, c;
+    sincos_phase32(index_word, s, c);
+    return make_float2(s, -c);
+}
+
+// Walks chirp positions pos, pos+stride, pos+2*stride ... without a 64-bit division per sample.
+struct ChirpWalker {
+    unsigned long long eff, k;
+    unsigned long long r;  // eff - k*length
+    unsigned int idx, step;
+    __device__ __forceinline__ void seek(unsigned long long pos, const ChirpDev& cp) {
+        eff = pos % cp.period;
+        k = eff / cp.length;
+        r = eff - k * cp.length;
+        refresh(cp);
+    }
+    __device__ __forceinline__ void refresh(const ChirpDev& cp) {
+        idx = chirp_index_word(eff, k, cp);
+        step = (unsigned int)cp.f0 + (unsigned int)k * cp.chirpness;
+    }
+    __device__ __forceinline__ void advance(unsigned int stride, const ChirpDev& cp) {
+        eff += stride;
+        r += stride;
+        if (eff >= cp.period) {
+            seek(eff, cp);
+        } else if (r >= cp.length) {
+            const unsigned long long dk = r / cp.length;
+            k += dk;
+            r -= dk * cp.length;
+            refresh(cp);
+        } else {
+            idx += stride * step;
+        }
+    }
+};
+
+}  // namespace gsdr

@@ -1,0 +1,190 @@
+// DIRECT-mode demodulator (multi-tone DDC + windowed-sinc FIR + decimation) for sm_100a.
+//
+// Replaces, per buffer, direct_demodulator_integer (cpp/kernels.cu:45-86: an fp64 sincospi and two
+// 64-bit remainders per tone-sample, writing a T x L tone-major intermediate), T x FIR::run_fir
+// (cpp/fir.cu:44-88: cublasCgemm + f x cublasCaxpy + 2 memcpy + memset per tone) and the
+// cublasCgeam transpose (cpp/USRP_demodulator.cpp:422-433) with ONE kernel.
+//
+// The LO phase is an integer: phase(n) = (tf * n) mod R turns/R.  Because it is exactly additive,
+//     y[p,ch] = sum_m h[m] x[n0+m] e^{-j theta_ch (n0+m)}
+//             = e^{-j theta_ch n0} * sum_m ( h[m] e^{-j theta_ch m} ) x[n0+m],   n0 = (p-f+1) M
+// i.e. a bank of per-tone complex FIRs g_ch[m] (built once, in double, from the same integer
+// phases) followed by one rotation per OUTPUT sample.  No trig and no 64-bit remainder per input
+// sample remain, and nothing but the decimated, sample-major result is written.
+#include "devmath.cuh"
+
+namespace gsdr {
+namespace {
+
+constexpr int TP = 4;   // outputs per warp tile
+constexpr int TC = 4;   // tones per warp tile
+constexpr int WARPS = 8;
+
+// signed LO phase exactly as the reference forms it (C remainder keeps the dividend's sign)
+__device__ __forceinline__ long long direct_phase_signed(long long tf, unsigned long long stream_index, long long R) {
+    const long long ii = (long long)(stream_index % (unsigned long long)R);
+    return (tf * ii) % R;
+}
+
+// e^{-2 pi j ph / R} for ph in [0, R): double divide, 32-bit phase word, exact-reduction sincos
+__device__ __forceinline__ float2 lo_phasor(long long ph, double inv_R) {
+    const double turns = (double)ph * inv_R;                       // [0,1)
+    const unsigned int word = (unsigned int)(long long)(turns * 4294967296.0);
+    float s, c;
+    sincos_phase32(word, s, c);
+    return make_float2(c, -s);
+}
+
+__global__ void __launch_bounds__(WARPS * 32)
+direct_fir_kernel(const Window w, const float2* __restrict__ g, const int* __restrict__ freq, int T, int M, int ntaps,
+                  int rate, long long pos0, long long n_out, int PB, float2* __restrict__ out) {
+    extern __shared__ __align__(16) float2 xs[];  // (PB-1)*M + ntaps samples
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long p0 = (long long)blockIdx.x * PB;
+    const int span = (PB - 1) * M + ntaps;
+    for (int i = threadIdx.x; i < span; i += blockDim.x) xs[i] = dev_win_at(w, p0 * M + i);
+    __syncthreads();
+
+    const int tone_groups = (T + TC - 1) / TC;
+    const int out_groups = PB / TP;
+    const double inv_R = 1.0 / (double)rate;
+    for (int unit = warp + WARPS * blockIdx.y; unit < out_groups * tone_groups; unit += WARPS * gridDim.y) {
+        const int og = unit % out_groups, tg = unit / out_groups;
+        float2 acc[TP][TC];
+#pragma unroll
+        for (int a = 0; a < TP; ++a)
+#pragma unroll
+            for (int b = 0; b < TC; ++b) acc[a][b] = make_float2(0.f, 0.f);
+        const float2* gbase[TC];
+#pragma unroll
+        for (int b = 0; b < TC; ++b) gbase[b] = g + (long long)min(tg * TC + b, T - 1) * ntaps;
+        const float2* xbase = xs + (og * TP) * M;
+        for (int m = lane; m < ntaps; m += 32) {
+            float2 xv[TP], gv[TC];
+#pragma unroll
+            for (int a = 0; a < TP; ++a) xv[a] = xbase[a * M + m];
+#pragma unroll
+            for (int b = 0; b < TC; ++b) gv[b] = __ldg(gbase[b] + m);
+#pragma unroll
+            for (int a = 0; a < TP; ++a)
+#pragma unroll
+                for (int b = 0; b < TC; ++b) {
+                    acc[a][b].x = fmaf(gv[b].x, xv[a].x, fmaf(-gv[b].y, xv[a].y, acc[a][b].x));
+                    acc[a][b].y = fmaf(gv[b].x, xv[a].y, fmaf(gv[b].y, xv[a].x, acc[a][b].y));
+                }
+        }
+        // warp-shuffle accumulation of the 16 partial sums
+#pragma unroll
+        for (int a = 0; a < TP; ++a)
+#pragma unroll
+            for (int b = 0; b < TC; ++b)
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    acc[a][b].x += __shfl_xor_sync(0xffffffffu, acc[a][b].x, o);
+                    acc[a][b].y += __shfl_xor_sync(0xffffffffu, acc[a][b].y, o);
+                }
+        // lanes 0..15 each finish one (output, tone): rotate by the block-start LO phase and store
+        float2 mine = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int a = 0; a < TP; ++a)
+#pragma unroll
+            for (int b = 0; b < TC; ++b)
+                if (lane == a * TC + b) mine = acc[a][b];
+        if (lane < TP * TC) {
+            const int a = lane / TC, b = lane % TC;
+            const long long p = p0 + og * TP + a;
+            const int ch = tg * TC + b;
+            if (p < n_out && ch < T) {
+                // stream position of the first tap of output p: pos0 + p*M (pos0 already includes -(f-1)M)
+                long long n0 = (pos0 + p * (long long)M) % rate;
+                if (n0 < 0) n0 += rate;
+                long long ph = direct_phase_signed(freq[ch], (unsigned long long)n0, rate);
+                if (ph < 0) ph += rate;  // same residue class; the reference keeps the sign
+                out[p * T + ch] = dev_cmul(mine, lo_phasor(ph, inv_R));
+            }
+        }
+    }
+}
+
+// decim == 0: pure mixing, out[n*T + ch] = x[n] e^{-j theta_ch n} (cpp/USRP_demodulator.cpp:442-457).
+constexpr int MIX_S = 32;  // samples per block
+__global__ void __launch_bounds__(256)
+direct_mix_kernel(const float2* __restrict__ in, long long n, const int* __restrict__ freq, int T, int rate, long long pos0,
+                  float2* __restrict__ out) {
+    __shared__ float2 xs[MIX_S];
+    __shared__ long long base_ph[256];
+    const long long s0 = (long long)blockIdx.x * MIX_S;
+    if (threadIdx.x < MIX_S) xs[threadIdx.x] = (s0 + threadIdx.x < n) ? in[s0 + threadIdx.x] : make_float2(0.f, 0.f);
+    const double inv_R = 1.0 / (double)rate;
+    const long long nb = (pos0 + s0) % rate;
+    for (int c0 = 0; c0 < T; c0 += 256) {
+        __syncthreads();
+        const int ch = c0 + threadIdx.x;
+        if (ch < T) {
+            long long ph = direct_phase_signed(freq[ch], (unsigned long long)nb, rate);
+            if (ph < 0) ph += rate;
+            base_ph[threadIdx.x] = ph;
+        }
+        __syncthreads();
+        const int tones_here = min(256, T - c0);
+        for (int e = threadIdx.x; e < tones_here * MIX_S; e += 256) {
+            const int i = e / tones_here, cl = e - i * tones_here;  // tone fastest: coalesced stores
+            if (s0 + i >= n) continue;
+            long long tf = freq[c0 + cl] % rate;
+            if (tf < 0) tf += rate;
+            const long long ph = (base_ph[cl] + tf * i) % rate;
+            out[(s0 + i) * T + c0 + cl] = dev_cmul(xs[i], lo_phasor(ph, inv_R));
+        }
+    }
+}
+
+__global__ void direct_phase_probe_kernel(long long* __restrict__ out, unsigned int n, int tf, int rate,
+                                          unsigned long long index_counter, unsigned long long n0) {
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        out[i] = direct_phase_signed(tf, n0 + i + index_counter, rate);
+}
+
+}  // namespace
+
+int direct_fir_launch(const Window& w, const float2* g, const int* freq_dev, int T, int M, int ntaps, int rate,
+                      long long pos0, long long n_out, float2* out, cudaStream_t stream) {
+    if (n_out <= 0) return 0;
+    // outputs per block: as many as fit 96 KB of staged input, multiple of TP, at most 64
+    int PB = 64;
+    while (PB > TP && ((size_t)(PB - 1) * M + ntaps) * sizeof(float2) > 96 * 1024) PB -= TP;
+    const size_t smem = ((size_t)(PB - 1) * M + ntaps) * sizeof(float2);
+    if (smem > 200 * 1024) {
+        set_error("direct_fir_launch: decimation %d x %d taps needs %zu B of shared memory", M, ntaps, smem);
+        return -1;
+    }
+    static size_t configured = 0;
+    if (smem > configured) {
+        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int units = (PB / TP) * ((T + TC - 1) / TC);
+    int gy = (units + WARPS - 1) / WARPS;
+    if (gy > 8) gy = 8;
+    dim3 grid((unsigned)((n_out + PB - 1) / PB), gy);
+    direct_fir_kernel<<<grid, WARPS * 32, smem, stream>>>(w, g, freq_dev, T, M, ntaps, rate, pos0, n_out, PB, out);
+    GSDR_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
+int direct_mix_launch(const float2* in, long long n, const int* freq_dev, int T, int rate, long long pos0, float2* out,
+                      cudaStream_t stream) {
+    if (n <= 0) return 0;
+    direct_mix_kernel<<<(unsigned)((n + MIX_S - 1) / MIX_S), 256, 0, stream>>>(in, n, freq_dev, T, rate, pos0, out);
+    GSDR_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
+int direct_phase_probe_launch(long long* out, unsigned int n, int tone_freq, int rate, unsigned long long index_counter,
+                              unsigned long long n0, cudaStream_t stream) {
+    if (n == 0) return 0;
+    direct_phase_probe_kernel<<<64, 128, 0, stream>>>(out, n, tone_freq, rate, index_counter, n0);
+    GSDR_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
+}  // namespace gsdr

@@ -1,0 +1,372 @@
+// Host-side runtime pieces of the path: the pinned buffer pool (preallocator<float2> contract),
+// the hardware-free replay source, and the small C-ABI utilities (errors, memory, probes).
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <random>
+#include <thread>
+
+#include "common.hpp"
+
+using namespace gsdr;
+
+// ------------------------------------------------------------------------------------------------
+// Pinned pool.  Reference: template preallocator<T>, headers/USRP_server_memory_management.hpp:
+// 103-273 -- cudaMallocHost buffers behind two lock-free queues, a filler thread that pre-fills
+// pipe_size-1 buffers and grows the pool when fewer than 10 % are free, a recycler thread, and
+// get()/trash()/close().  Same contract; one mutex-protected free list, one grower thread (so the
+// real-time get() never pays a cudaMallocHost unless the pool is completely dry), and trash()
+// recycles immediately instead of after the reference's 3 ms sleep per buffer.
+// ------------------------------------------------------------------------------------------------
+struct gsdr_pool {
+    size_t vector_size = 0;
+    int pipe_size = 0;
+    bool grow = true;
+    std::mutex m;
+    std::condition_variable cv_free, cv_grow;
+    std::deque<gsdr_float2*> free_list;
+    std::vector<gsdr_float2*> all;
+    std::thread grower;
+    bool closing = false;
+
+    gsdr_float2* alloc_one() {
+        void* p = nullptr;
+        if (cudaMallocHost(&p, vector_size * sizeof(gsdr_float2)) != cudaSuccess) return nullptr;
+        return static_cast<gsdr_float2*>(p);
+    }
+    void grow_loop() {
+        std::unique_lock<std::mutex> lk(m);
+        while (!closing) {
+            cv_grow.wait(lk, [&] { return closing || (grow && (double)free_list.size() < pipe_size / 10.); });
+            if (closing) break;
+            lk.unlock();
+            gsdr_float2* b = alloc_one();
+            lk.lock();
+            if (!b) break;
+            all.push_back(b);
+            free_list.push_back(b);
+            ++pipe_size;
+            cv_free.notify_one();
+        }
+    }
+};
+
+extern "C" {
+
+gsdr_pool* gsdr_pool_create(size_t vector_size, int pipe_size, int prefill) {
+    if (vector_size == 0 || pipe_size < 2) {
+        set_error("gsdr_pool_create: vector_size=%zu pipe_size=%d", vector_size, pipe_size);
+        return nullptr;
+    }
+    std::unique_ptr<gsdr_pool> pool(new gsdr_pool());
+    pool->vector_size = vector_size;
+    pool->pipe_size = pipe_size;
+    pool->grow = prefill != 0;
+    for (int i = 0; i < pipe_size - 1; ++i) {  // reference pre-fills pipe_size-1 buffers (:211-227)
+        gsdr_float2* b = pool->alloc_one();
+        if (!b) {
+            set_error("Memory manager cannot allocate pinned host memory!");
+            for (auto* q : pool->all) cudaFreeHost(q);
+            return nullptr;
+        }
+        pool->all.push_back(b);
+        pool->free_list.push_back(b);
+    }
+    gsdr_pool* raw = pool.release();
+    raw->grower = std::thread([raw] { raw->grow_loop(); });
+    return raw;
+}
+
+gsdr_float2* gsdr_pool_get(gsdr_pool* pool) {
+    if (!pool) return nullptr;
+    std::unique_lock<std::mutex> lk(pool->m);
+    if ((double)pool->free_list.size() - 1 < pool->pipe_size / 10.) pool->cv_grow.notify_one();
+    pool->cv_free.wait(lk, [&] { return pool->closing || !pool->free_list.empty(); });
+    if (pool->free_list.empty()) return nullptr;
+    gsdr_float2* b = pool->free_list.front();
+    pool->free_list.pop_front();
+    return b;
+}
+
+void gsdr_pool_trash(gsdr_pool* pool, gsdr_float2* buf) {
+    if (!pool || !buf) return;
+    {
+        std::lock_guard<std::mutex> lk(pool->m);
+        pool->free_list.push_back(buf);
+    }
+    pool->cv_free.notify_one();
+}
+
+void gsdr_pool_close(gsdr_pool* pool) {
+    if (!pool) return;
+    {
+        std::lock_guard<std::mutex> lk(pool->m);
+        pool->closing = true;
+    }
+    pool->cv_grow.notify_all();
+    pool->cv_free.notify_all();
+    if (pool->grower.joinable()) pool->grower.join();
+    for (auto* b : pool->all) cudaFreeHost(b);
+    delete pool;
+}
+
+int gsdr_pool_available(const gsdr_pool* pool) {
+    if (!pool) return 0;
+    std::lock_guard<std::mutex> lk(const_cast<gsdr_pool*>(pool)->m);
+    return (int)pool->free_list.size();
+}
+int gsdr_pool_size(const gsdr_pool* pool) {
+    if (!pool) return 0;
+    std::lock_guard<std::mutex> lk(const_cast<gsdr_pool*>(pool)->m);
+    return (int)pool->all.size();
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Replay source.  Model: hardware_manager::software_rx_thread (cpp/USRP_hardware_manager.cpp:
+// 1331-1395): take a buffer from the RX pool, fill it, wrap it in an RX_wrapper with a running
+// packet_number, errors = 0 and the software front-end code ('B'/'D').  The samples come from a
+// gsdr_tx of the same parameters (the --sw_loop identity: RX sees exactly the TX waveform),
+// optionally plus deterministic complex Gaussian noise.
+// ------------------------------------------------------------------------------------------------
+struct gsdr_replay {
+    gsdr_tx* tx = nullptr;
+    gsdr_pool* pool = nullptr;
+    long long L = 0;
+    int channels = 0;
+    char code = 'B';
+    float sigma = 0.f;
+    std::vector<gsdr_float2> noise;  // bank of L + kBankExtra samples
+    uint64_t packets = 0;
+    double rate_limit = 0.0;  // samples per second, 0 = unlimited
+    std::chrono::steady_clock::time_point start;
+    std::vector<gsdr_float2> chirp_tmp;
+    static constexpr size_t kBankExtra = 65536;
+};
+
+extern "C" {
+
+gsdr_replay* gsdr_replay_create(const gsdr_param* p, int kind, float noise_sigma, uint64_t seed, gsdr_pool* pool,
+                                char front_end_code, double rate_limit_msps, int device) {
+    if (!p || !pool) {
+        set_error("gsdr_replay_create: null argument");
+        return nullptr;
+    }
+    if (pool->vector_size < p->buffer_len) {
+        set_error("gsdr_replay_create: pool buffers (%zu) shorter than buffer_len (%llu)", pool->vector_size,
+                  (unsigned long long)p->buffer_len);
+        return nullptr;
+    }
+    // the source waveform: TONES for every multi-tone RX mode, CHIRP for chirp
+    gsdr_param q = *p;
+    std::vector<int32_t> wt(p->n_wave_type ? p->n_wave_type : 1,
+                            (p->n_wave_type && p->wave_type[0] == GSDR_CHIRP) ? GSDR_CHIRP : GSDR_TONES);
+    std::vector<float> ampl;
+    q.wave_type = wt.data();
+    q.n_wave_type = wt.size();
+    if (p->n_ampl < wt.size()) {  // RX parameter blocks often carry no amplitudes: use 1/T each
+        ampl.assign(wt.size(), 1.0f / (float)wt.size());
+        q.ampl = ampl.data();
+        q.n_ampl = ampl.size();
+    }
+    std::unique_ptr<gsdr_replay> r(new gsdr_replay());
+    r->tx = gsdr_tx_create(&q, device);
+    if (!r->tx) return nullptr;
+    r->pool = pool;
+    r->L = (long long)p->buffer_len;
+    r->channels = (int)p->n_wave_type;
+    r->code = front_end_code;
+    r->sigma = (kind == GSDR_REPLAY_TX_LOOP) ? 0.f : noise_sigma;
+    r->rate_limit = rate_limit_msps > 0 ? rate_limit_msps * 1e6 : 0.0;
+    if (r->sigma > 0.f) {
+        std::mt19937_64 gen(seed);
+        std::normal_distribution<float> nd(0.f, r->sigma);
+        r->noise.resize((size_t)r->L + gsdr_replay::kBankExtra);
+        for (auto& v : r->noise) {
+            v.x = nd(gen);
+            v.y = nd(gen);
+        }
+    }
+    r->start = std::chrono::steady_clock::now();
+    return r.release();
+}
+
+int gsdr_replay_next(gsdr_replay* r, gsdr_rx_packet* pkt) {
+    if (!r || !pkt) return -1;
+    if (r->rate_limit > 0) {  // pace like a radio delivering rate_limit samples per second
+        const double due = (double)((r->packets + 1) * (uint64_t)r->L) / r->rate_limit;
+        std::this_thread::sleep_until(r->start + std::chrono::duration_cast<std::chrono::steady_clock::duration>(
+                                                      std::chrono::duration<double>(due)));
+    }
+    gsdr_float2* buf = gsdr_pool_get(r->pool);
+    if (!buf) {
+        set_error("gsdr_replay_next: pool closed");
+        return -1;
+    }
+    gsdr_float2* src = buf;
+    if (gsdr_tx_get(r->tx, &src)) return -1;  // TONES re-points src; CHIRP fills buf
+    if (src != buf) std::memcpy(buf, src, sizeof(gsdr_float2) * r->L);
+    if (r->sigma > 0.f) {
+        const gsdr_float2* nz = r->noise.data() + (r->packets * 7919ull) % gsdr_replay::kBankExtra;
+        for (long long i = 0; i < r->L; ++i) {
+            buf[i].x += nz[i].x;
+            buf[i].y += nz[i].y;
+        }
+    }
+    ++r->packets;
+    pkt->buffer = buf;
+    pkt->usrp_number = 0;
+    pkt->front_end_code = r->code;
+    pkt->packet_number = (int32_t)r->packets;
+    pkt->length = (int32_t)r->L;
+    pkt->errors = 0;
+    pkt->channels = r->channels;
+    return 0;
+}
+
+void gsdr_replay_destroy(gsdr_replay* r) {
+    if (!r) return;
+    gsdr_tx_destroy(r->tx);
+    delete r;
+}
+uint64_t gsdr_replay_packets(const gsdr_replay* r) { return r ? r->packets : 0; }
+
+// ------------------------------------------------------------------------------------------------
+// misc C-ABI
+// ------------------------------------------------------------------------------------------------
+const char* gsdr_last_error(void) { return get_error(); }
+const char* gsdr_version(void) { return "gsdr-b200 0.1 (sm_100a)"; }
+int gsdr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int gsdr_sm_count(int device) {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1;
+    return prop.multiProcessorCount;
+}
+
+int gsdr_make_sinc_window(int length, float fc, float* out) {
+    if (length < 1 || !out) return -1;
+    make_sinc_window(length, fc, out);
+    return length;
+}
+int gsdr_make_flat_window(int length, int side, float* out) {
+    if (length < 1 || side < 0 || side > length || !out) return -1;
+    make_flat_window(length, side, out);
+    return length;
+}
+int gsdr_pfb_batching(int buffer_len, int fft_tones, int pf_average) { return pfb_batching(buffer_len, fft_tones, pf_average); }
+int gsdr_tone_bins(int rate, int fft_tones, const int32_t* freq, int n, int32_t* bins) {
+    if (fft_tones < 1 || n < 0 || !freq || !bins) return -1;
+    tone_bins(rate, fft_tones, freq, n, bins);
+    return n;
+}
+void gsdr_buffer_helper_init(gsdr_buffer_helper* h, int n_tones, int buffer_len, int average, int n_eff) {
+    buffer_helper_init(h, n_tones, buffer_len, average, n_eff);
+}
+void gsdr_buffer_helper_update(gsdr_buffer_helper* h) { buffer_helper_update(h); }
+void gsdr_vna_helper_init(gsdr_vna_helper* h, int ppt, int buffer_len) { vna_helper_init(h, ppt, buffer_len); }
+void gsdr_vna_helper_update(gsdr_vna_helper* h) { vna_helper_update(h); }
+int gsdr_chirp_params(int rate, int freq0, int chirp_f0, int swipe_s0, float chirp_t0, int tx, gsdr_chirp_param* out) {
+    if (!out) return -1;
+    chirp_params(rate, freq0, chirp_f0, swipe_s0, chirp_t0, tx != 0, out);
+    return 0;
+}
+
+int gsdr_probe_chirp_index(int device, const gsdr_chirp_param* p, uint64_t last_index, uint32_t n, int32_t* out_host) {
+    if (!p || !out_host || p->num_steps * p->length == 0) {
+        set_error("gsdr_probe_chirp_index: bad argument");
+        return -1;
+    }
+    GSDR_CUDA_OK(cudaSetDevice(device));
+    ChirpDev cd{p->num_steps * p->length, p->length, p->chirpness, p->f0};
+    int* d = nullptr;
+    GSDR_CUDA_OK(cudaMalloc(&d, sizeof(int) * (n ? n : 1)));
+    const int rc = chirp_index_probe_launch(d, n, last_index, cd, 0);
+    if (rc >= 0) {
+        if (cudaMemcpy(out_host, d, sizeof(int) * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error("gsdr_probe_chirp_index: %s", cudaGetErrorString(cudaGetLastError()));
+            cudaFree(d);
+            return -1;
+        }
+    }
+    cudaFree(d);
+    return rc < 0 ? -1 : 0;
+}
+
+int gsdr_probe_direct_phase(int device, int tone_freq, int rate, uint64_t index_counter, uint64_t n0, uint32_t n,
+                            int64_t* out_host) {
+    if (!out_host || rate <= 0) {
+        set_error("gsdr_probe_direct_phase: bad argument");
+        return -1;
+    }
+    GSDR_CUDA_OK(cudaSetDevice(device));
+    long long* d = nullptr;
+    GSDR_CUDA_OK(cudaMalloc(&d, sizeof(long long) * (n ? n : 1)));
+    const int rc = direct_phase_probe_launch(d, n, tone_freq, rate, index_counter, n0, 0);
+    if (rc >= 0) {
+        if (cudaMemcpy(out_host, d, sizeof(long long) * n, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            set_error("gsdr_probe_direct_phase: %s", cudaGetErrorString(cudaGetLastError()));
+            cudaFree(d);
+            return -1;
+        }
+    }
+    cudaFree(d);
+    return rc < 0 ? -1 : 0;
+}
+
+void* gsdr_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+        set_error("cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+void gsdr_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+void* gsdr_dev_alloc(int device, size_t bytes) {
+    void* p = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMalloc(&p, bytes ? bytes : 1) != cudaSuccess) {
+        set_error("cudaMalloc(%zu) on device %d: %s", bytes, device, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return p;
+}
+void gsdr_dev_free(int device, void* p) {
+    if (!p) return;
+    cudaSetDevice(device);
+    cudaFree(p);
+}
+int gsdr_memcpy_h2d(int device, void* dst, const void* src, size_t bytes) {
+    GSDR_CUDA_OK(cudaSetDevice(device));
+    GSDR_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice));
+    return 0;
+}
+int gsdr_memcpy_d2h(int device, void* dst, const void* src, size_t bytes) {
+    GSDR_CUDA_OK(cudaSetDevice(device));
+    GSDR_CUDA_OK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return 0;
+}
+int gsdr_dev_memset(int device, void* dst, int value, size_t bytes) {
+    GSDR_CUDA_OK(cudaSetDevice(device));
+    GSDR_CUDA_OK(cudaMemset(dst, value, bytes));
+    return 0;
+}
+int gsdr_device_synchronize(int device) {
+    GSDR_CUDA_OK(cudaSetDevice(device));
+    GSDR_CUDA_OK(cudaDeviceSynchronize());
+    return 0;
+}
+
+}  // extern "C"

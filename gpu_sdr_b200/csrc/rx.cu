@@ -1,0 +1,801 @@
+// gsdr_rx: host side of the RX demodulator (the RX_buffer_demodulator replacement).
+//
+// Reference call structure being replaced (cpp/USRP_demodulator.cpp):
+//   ctor :7-327 (mode dispatch, taps, plans, helpers)   process_* :335-649   close_* :466-698
+// One instance == one IQ stream.  Differences in *how*, not *what*:
+//   - three streams per instance (copy-in | compute | copy-out) and a ring of pipeline slots, so
+//     H2D of buffer k+1 overlaps the kernels of buffer k and the D2H of buffer k-1; the blocking
+//     process() is submit()+wait();
+//   - the carry-over between buffers (PFB spare samples, FIR history, chirp remainder) lives in a
+//     small ping-pong device buffer and the kernels read "history ++ new samples" directly: there
+//     is no move_buffer and no upload-at-offset;
+//   - valid lengths come from the same integer helpers as the reference, evaluated on the host
+//     before the GPU runs, and only the valid part is copied back.
+#include <cmath>
+#include <memory>
+#include <mutex>
+
+#include "common.hpp"
+
+using namespace gsdr;
+
+namespace {
+
+struct Slot {
+    float2* d_in = nullptr;
+    float2* d_out = nullptr;
+    cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
+    bool used = false;
+};
+
+}  // namespace
+
+struct gsdr_rx {
+    int device = 0, sm_count = 148;
+    int mode = GSDR_NODSP;
+    bool diagnostic = false;
+    // parameters (copied)
+    int rate = 0, N = 0;
+    long long L = 0, decim = 0, P = 0;
+    std::vector<int32_t> freq;
+    int T = 0;  // channels == wave_type.size()
+    float fcut = 0.f;
+
+    cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    std::vector<Slot> slots;
+    uint64_t tickets = 0;
+    uint64_t launches = 0;
+    size_t max_out = 0;
+    const char* kernel_name = "none";
+
+    // carry-over (ping-pong)
+    float2* hist[2] = {nullptr, nullptr};
+    int hist_cur = 0;
+    long long n_hist = 0, hist_cap = 0;
+
+    // TONES / NOISE
+    std::vector<float> taps_host;
+    std::vector<int32_t> bins_host;
+    float* d_taps = nullptr;
+    int* d_bins = nullptr;
+    float2* d_tw = nullptr;
+    void* d_work = nullptr;
+    size_t work_bytes = 0;
+    int batching = 0, T_sel = 0;
+    bool fused = false;
+    gsdr_buffer_helper bh{};
+
+    // CHIRP
+    gsdr_chirp_param cpar{};
+    ChirpDev cdev{};
+    unsigned long long last_index = 0;
+    int ppt = 0;
+    gsdr_vna_helper vh{};
+    float* d_profile = nullptr;
+    float2* d_partial = nullptr;
+    size_t partial_cap = 0;
+
+    // DIRECT
+    float2* d_g = nullptr;
+    int* d_freq = nullptr;
+    int ntaps = 0;
+    long long index_counter = 0;
+};
+
+namespace {
+
+int set_dev(const gsdr_rx* rx) {
+    GSDR_CUDA_OK(cudaSetDevice(rx->device));
+    return 0;
+}
+
+template <class Tp>
+int dev_upload(Tp** dst, const Tp* src, size_t n) {
+    GSDR_CUDA_OK(cudaMalloc(dst, sizeof(Tp) * (n ? n : 1)));
+    if (n) GSDR_CUDA_OK(cudaMemcpy(*dst, src, sizeof(Tp) * n, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// twiddle tables of the fused 2048-point kernel: [16][128] W_2048^(l k1) then [8][16] W_128^(n3 k2)
+std::vector<float2> fused_twiddles() {
+    std::vector<float2> tw(16 * 128 + 8 * 16);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int k1 = 0; k1 < 16; ++k1)
+        for (int l = 0; l < 128; ++l) {
+            const double a = -two_pi * (double)((l * k1) % 2048) / 2048.0;
+            tw[k1 * 128 + l] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+    for (int n3 = 0; n3 < 8; ++n3)
+        for (int k2 = 0; k2 < 16; ++k2) {
+            const double a = -two_pi * (double)((n3 * k2) % 128) / 128.0;
+            tw[16 * 128 + n3 * 16 + k2] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+    return tw;
+}
+
+std::vector<float2> generic_twiddles(int N) {
+    std::vector<float2> tw(N);
+    const double two_pi = 6.283185307179586476925286766559;
+    for (int i = 0; i < N; ++i) {
+        const double a = -two_pi * (double)i / (double)N;
+        tw[i] = make_float2((float)std::cos(a), (float)std::sin(a));
+    }
+    return tw;
+}
+
+int init_pfb(gsdr_rx* rx, bool all_bins) {
+    const int N = rx->N, P = (int)rx->P;
+    if (N < 2 || P < 1) {
+        set_error("TONES/NOISE: fft_tones=%d pf_average=%d is not a valid filter bank", N, P);
+        return -1;
+    }
+    rx->fcut = (float)(1. / (2 * N));  // cpp/USRP_demodulator.cpp:131
+    rx->taps_host.resize((size_t)N * P);
+    make_sinc_window(N * P, rx->fcut, rx->taps_host.data());
+    rx->batching = pfb_batching((int)rx->L, N, P);
+    if (all_bins) {
+        rx->T_sel = N;  // full spectrum, bins in natural order (cpp/USRP_demodulator.cpp:301)
+    } else {
+        rx->T_sel = rx->T;
+        rx->bins_host.resize(rx->T);
+        tone_bins(rx->rate, N, rx->freq.data(), rx->T, rx->bins_host.data());
+        for (auto& b : rx->bins_host)
+            if (b < 0) b = 0;  // the reference leaves unmatched tones uninitialised; pin them to DC
+        if (dev_upload(&rx->d_bins, rx->bins_host.data(), rx->bins_host.size())) return -1;
+    }
+    if (dev_upload(&rx->d_taps, rx->taps_host.data(), rx->taps_host.size())) return -1;
+    buffer_helper_init(&rx->bh, N, (int)rx->L, P, rx->T_sel);
+    Window probe{};
+    rx->fused = pfb_fused_supported(N, P, rx->T_sel, probe);
+    rx->kernel_name = pfb_kernel_name(N, P, rx->T_sel);
+    if (rx->fused) {
+        auto tw = fused_twiddles();
+        if (dev_upload(&rx->d_tw, tw.data(), tw.size())) return -1;
+    } else {
+        auto tw = generic_twiddles(N);
+        if (dev_upload(&rx->d_tw, tw.data(), tw.size())) return -1;
+    }
+    rx->hist_cap = (long long)N * P + 16;
+    rx->max_out = (size_t)rx->T_sel * rx->batching;
+    return 0;
+}
+
+int init_chirp(gsdr_rx* rx, const gsdr_param* p) {
+    if (p->n_chirp_t < 1 || p->n_chirp_f < 1 || p->n_swipe_s < 1 || p->n_freq < 1) {
+        set_error("CHIRP: chirp_t/chirp_f/swipe_s/freq must each hold one value");
+        return -1;
+    }
+    chirp_params(rx->rate, p->freq[0], p->chirp_f[0], p->swipe_s[0], p->chirp_t[0], false, &rx->cpar);
+    if (rx->cpar.num_steps * rx->cpar.length == 0) {
+        set_error("CHIRP: empty sweep (num_steps*length == 0)");
+        return -1;
+    }
+    rx->cdev.period = rx->cpar.num_steps * rx->cpar.length;
+    rx->cdev.length = rx->cpar.length;
+    rx->cdev.chirpness = rx->cpar.chirpness;
+    rx->cdev.f0 = rx->cpar.f0;
+    rx->last_index = 0;
+    rx->kernel_name = "chirp_demod_full_kernel";
+    rx->max_out = (size_t)rx->L;
+    if (rx->decim > 0) {
+        const long long ppt = (long long)rx->cpar.length * rx->decim;  // cpp/USRP_demodulator.cpp:231
+        if (ppt <= 0 || ppt > 0x7fffffffLL) {
+            set_error("CHIRP: points per tone %lld out of range", ppt);
+            return -1;
+        }
+        rx->ppt = (int)ppt;
+        vna_helper_init(&rx->vh, rx->ppt, (int)rx->L);
+        std::vector<float> prof(rx->ppt);
+        make_flat_window(rx->ppt, rx->ppt / 10, prof.data());  // :246
+        if (dev_upload(&rx->d_profile, prof.data(), prof.size())) return -1;
+        rx->taps_host = prof;
+        rx->hist_cap = rx->ppt + 16;
+        rx->max_out = (size_t)(rx->L / rx->ppt + 2);
+        rx->kernel_name = rx->ppt < 32 ? "chirp_lockin_thread_kernel" : "chirp_lockin_warp_kernel";
+    }
+    return 0;
+}
+
+int init_direct(gsdr_rx* rx) {
+    const int T = rx->T;
+    if ((int)rx->freq.size() < T) {
+        set_error("DIRECT: %d wave types but only %zu frequencies", T, rx->freq.size());
+        return -1;
+    }
+    if (dev_upload(&rx->d_freq, rx->freq.data(), (size_t)T)) return -1;
+    rx->index_counter = 0;
+    rx->kernel_name = "direct_mix_kernel";
+    rx->max_out = (size_t)rx->L * T;
+    if (rx->decim > 0) {
+        const long long M = rx->decim, f = rx->P;
+        if (rx->L % M != 0) {  // cpp/fir.cu:20 assert(nt % M == 0)
+            set_error("DIRECT: buffer_len %lld is not a multiple of decim %lld", rx->L, M);
+            return -1;
+        }
+        if (f < 1) {
+            set_error("DIRECT: pf_average must be >= 1");
+            return -1;
+        }
+        rx->ntaps = (int)(M * f);
+        rx->taps_host.resize(rx->ntaps);
+        make_sinc_window(rx->ntaps, (float)(0.75 / (M * 2)), rx->taps_host.data());  // cpp/USRP_demodulator.cpp:99
+        // g[ch][m] = h[m] * exp(-2 pi j ((tf*m) mod R)/R): per-tone complex FIR, built in double
+        std::vector<float2> g((size_t)T * rx->ntaps);
+        const double two_pi = 6.283185307179586476925286766559;
+        for (int ch = 0; ch < T; ++ch)
+            for (int m = 0; m < rx->ntaps; ++m) {
+                long long ph = ((long long)rx->freq[ch] * (long long)(m % rx->rate)) % rx->rate;
+                const double a = -two_pi * (double)ph / (double)rx->rate;
+                const double h = rx->taps_host[m];
+                g[(size_t)ch * rx->ntaps + m] = make_float2((float)(h * std::cos(a)), (float)(h * std::sin(a)));
+            }
+        if (dev_upload(&rx->d_g, g.data(), g.size())) return -1;
+        rx->hist_cap = (f - 1) * M + 16;
+        rx->n_hist = (f - 1) * M;  // FIR history starts as zeros (cpp/fir.cu:23-26)
+        rx->max_out = (size_t)(rx->L / M) * T;
+        rx->kernel_name = "direct_fir_kernel";
+    }
+    return 0;
+}
+
+// Enqueue the compute for n_buf consecutive buffers at d_in on s_comp.  Fills lens (per buffer) and
+// returns the total valid float2 count.
+long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_out, int* lens) {
+    cudaStream_t st = rx->s_comp;
+    const long long L = rx->L;
+    Window w{rx->hist[rx->hist_cur], d_in, rx->n_hist, L * n_buf};
+    long long total = 0;
+    switch (rx->mode) {
+        case GSDR_TONES:
+        case GSDR_NOISE: {
+            long long frames = 0;
+            for (int b = 0; b < n_buf; ++b) {
+                const int v = rx->T_sel * rx->bh.current_batch;
+                if (lens) lens[b] = v;
+                frames += rx->bh.current_batch;
+                total += v;
+                buffer_helper_update(&rx->bh);
+            }
+            const long long tail = rx->bh.new_0;  // spare samples to carry into the next call
+            if (w.n_hist + w.n_in - frames * rx->N != tail) {
+                set_error("internal: PFB carry-over mismatch (%lld vs %lld)", w.n_hist + w.n_in - frames * rx->N, tail);
+                return -1;
+            }
+            PfbJob job{w, rx->d_taps, rx->d_bins, d_out, 0, (int)frames, rx->N, (int)rx->P, rx->T_sel};
+            if (!rx->fused) {
+                const size_t need = pfb_workspace_bytes(rx->N, (int)rx->P, (int)frames);
+                if (need > rx->work_bytes) {
+                    if (rx->d_work) cudaFree(rx->d_work);
+                    rx->d_work = nullptr;
+                    if (cudaMalloc(&rx->d_work, need) != cudaSuccess) {
+                        set_error("cudaMalloc(%zu) for the PFB workspace failed", need);
+                        return -1;
+                    }
+                    rx->work_bytes = need;
+                }
+            }
+            const int nl = pfb_launch(&job, 1, nullptr, rx->d_work, rx->d_tw, rx->sm_count, st);
+            if (nl < 0) return -1;
+            rx->launches += nl;
+            const int tl = window_tail_copy(w, tail, rx->hist[rx->hist_cur ^ 1], st);
+            if (tl < 0) return -1;
+            rx->launches += tl;
+            rx->hist_cur ^= 1;
+            rx->n_hist = tail;
+            break;
+        }
+        case GSDR_CHIRP: {
+            if (rx->decim <= 0) {
+                const int nl = chirp_demod_full_launch(d_in, L * n_buf, rx->last_index, rx->cdev, d_out, st);
+                if (nl < 0) return -1;
+                rx->launches += nl;
+                for (int b = 0; b < n_buf; ++b)
+                    if (lens) lens[b] = (int)L;
+                total = L * n_buf;
+            } else {
+                long long n_out = 0;
+                for (int b = 0; b < n_buf; ++b) {
+                    if (lens) lens[b] = rx->vh.valid_size;
+                    n_out += rx->vh.valid_size;
+                    vna_helper_update(&rx->vh);
+                }
+                const long long tail = rx->vh.new0;
+                if (w.n_hist + w.n_in - n_out * rx->ppt != tail) {
+                    set_error("internal: chirp carry-over mismatch");
+                    return -1;
+                }
+                const size_t pc = chirp_partial_count(rx->ppt, n_out, rx->sm_count);
+                if (pc > rx->partial_cap) {
+                    if (rx->d_partial) cudaFree(rx->d_partial);
+                    rx->d_partial = nullptr;
+                    if (cudaMalloc(&rx->d_partial, pc * sizeof(float2)) != cudaSuccess) {
+                        set_error("cudaMalloc for chirp partial sums failed");
+                        return -1;
+                    }
+                    rx->partial_cap = pc;
+                }
+                // chirp position of window sample 0 = position of the first new sample minus the carry
+                const unsigned long long per = rx->cdev.period;
+                const unsigned long long pos0 = (rx->last_index + per - ((unsigned long long)w.n_hist % per)) % per;
+                const int nl = chirp_demod_launch(w, pos0, rx->cdev, rx->d_profile, rx->ppt, n_out, d_out, rx->d_partial,
+                                                  rx->sm_count, st);
+                if (nl < 0) return -1;
+                rx->launches += nl;
+                const int tl = window_tail_copy(w, tail, rx->hist[rx->hist_cur ^ 1], st);
+                if (tl < 0) return -1;
+                rx->launches += tl;
+                rx->hist_cur ^= 1;
+                rx->n_hist = tail;
+                total = n_out;
+            }
+            rx->last_index = (rx->last_index + (unsigned long long)(L * n_buf)) % rx->cdev.period;
+            break;
+        }
+        case GSDR_DIRECT: {
+            if (rx->decim <= 0) {
+                const int nl = direct_mix_launch(d_in, L * n_buf, rx->d_freq, rx->T, rx->rate, rx->index_counter, d_out, st);
+                if (nl < 0) return -1;
+                rx->launches += nl;
+                for (int b = 0; b < n_buf; ++b)
+                    if (lens) lens[b] = (int)(L * rx->T);
+                total = L * n_buf * rx->T;
+            } else {
+                const long long M = rx->decim;
+                const long long n_out = (L / M) * n_buf;
+                long long pos0 = (rx->index_counter - w.n_hist) % rx->rate;
+                if (pos0 < 0) pos0 += rx->rate;
+                const int nl = direct_fir_launch(w, rx->d_g, rx->d_freq, rx->T, (int)M, rx->ntaps, rx->rate, pos0, n_out,
+                                                 d_out, st);
+                if (nl < 0) return -1;
+                rx->launches += nl;
+                const long long tail = w.n_hist;  // (f-1)*M samples, constant
+                const int tl = window_tail_copy(w, tail, rx->hist[rx->hist_cur ^ 1], st);
+                if (tl < 0) return -1;
+                rx->launches += tl;
+                rx->hist_cur ^= 1;
+                for (int b = 0; b < n_buf; ++b)
+                    if (lens) lens[b] = (int)((L / M) * rx->T);
+                total = n_out * rx->T;
+            }
+            rx->index_counter = (rx->index_counter + L * n_buf) % rx->rate;  // cpp/USRP_demodulator.cpp:437-440
+            break;
+        }
+        default:
+            set_error("mode %d has no device compute", rx->mode);
+            return -1;
+    }
+    return total;
+}
+
+void free_all(gsdr_rx* rx) {
+    cudaSetDevice(rx->device);
+    for (auto& s : rx->slots) {
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.in_done) cudaEventDestroy(s.in_done);
+        if (s.comp_done) cudaEventDestroy(s.comp_done);
+        if (s.out_done) cudaEventDestroy(s.out_done);
+    }
+    for (int i = 0; i < 2; ++i)
+        if (rx->hist[i]) cudaFree(rx->hist[i]);
+    if (rx->d_taps) cudaFree(rx->d_taps);
+    if (rx->d_bins) cudaFree(rx->d_bins);
+    if (rx->d_tw) cudaFree(rx->d_tw);
+    if (rx->d_work) cudaFree(rx->d_work);
+    if (rx->d_profile) cudaFree(rx->d_profile);
+    if (rx->d_partial) cudaFree(rx->d_partial);
+    if (rx->d_g) cudaFree(rx->d_g);
+    if (rx->d_freq) cudaFree(rx->d_freq);
+    if (rx->t0) cudaEventDestroy(rx->t0);
+    if (rx->t1) cudaEventDestroy(rx->t1);
+    if (rx->s_in) cudaStreamDestroy(rx->s_in);
+    if (rx->s_comp) cudaStreamDestroy(rx->s_comp);
+    if (rx->s_out) cudaStreamDestroy(rx->s_out);
+}
+
+constexpr int kDepth = 3;
+
+}  // namespace
+
+extern "C" {
+
+gsdr_rx* gsdr_rx_create(const gsdr_param* p, int device, int diagnostic) {
+    if (!p) {
+        set_error("gsdr_rx_create: null parameters");
+        return nullptr;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        set_error("gsdr_rx_create: no CUDA device available (this library has no CPU path)");
+        return nullptr;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("gsdr_rx_create: device %d out of range (0..%d)", device, ndev - 1);
+        return nullptr;
+    }
+    // mode dispatch: cpp/USRP_demodulator.cpp:15-39
+    int mode = GSDR_NODSP;
+    if (p->n_wave_type > 0) mode = p->wave_type[0];
+    int chirps = 0;
+    for (uint64_t i = 0; i < p->n_wave_type; ++i) {
+        if (p->wave_type[i] != mode) {
+            set_error("Mixed RX buffer demodulation has been requested. This feature is not implemented yet.");
+            return nullptr;
+        }
+        if (p->wave_type[i] == GSDR_CHIRP) ++chirps;
+    }
+    if (chirps > 1) {
+        set_error("Multiple chirp RX buffer demodulation has been requested. This feature is not implemented yet.");
+        return nullptr;
+    }
+    if (p->buffer_len == 0 || p->buffer_len > 0x7fffffffULL) {
+        set_error("gsdr_rx_create: buffer_len %llu out of range", (unsigned long long)p->buffer_len);
+        return nullptr;
+    }
+    std::unique_ptr<gsdr_rx> rx(new gsdr_rx());
+    rx->device = device;
+    rx->mode = mode;
+    rx->diagnostic = diagnostic != 0;
+    rx->rate = p->rate;
+    rx->N = p->fft_tones;
+    rx->L = (long long)p->buffer_len;
+    rx->decim = (long long)p->decim;
+    rx->P = (long long)p->pf_average;
+    rx->T = (int)p->n_wave_type;
+    rx->freq.assign(p->freq, p->freq + p->n_freq);
+    if (cudaSetDevice(device) != cudaSuccess) {
+        set_error("cudaSetDevice(%d) failed", device);
+        return nullptr;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) rx->sm_count = prop.multiProcessorCount;
+
+    int rc = 0;
+    switch (mode) {
+        case GSDR_TONES:
+            if ((int)rx->freq.size() < rx->T) {
+                set_error("TONES: %d wave types but only %zu frequencies", rx->T, rx->freq.size());
+                return nullptr;
+            }
+            if (rx->decim > 1 && rx->diagnostic)
+                fprintf(stderr, "gsdr: TONES post-PFB decimation is not applied (broken in the reference; see DESIGN.md)\n");
+            rc = init_pfb(rx.get(), false);
+            break;
+        case GSDR_NOISE:
+            if (rx->decim > 0) {
+                set_error("NOISE (full spectrum) with decim>0 is not implemented (SURVEY 8f)");
+                return nullptr;
+            }
+            rc = init_pfb(rx.get(), true);
+            break;
+        case GSDR_CHIRP:
+            rc = init_chirp(rx.get(), p);
+            break;
+        case GSDR_DIRECT:
+            if (rx->rate <= 0) {
+                set_error("DIRECT: rate must be positive");
+                return nullptr;
+            }
+            rc = init_direct(rx.get());
+            break;
+        case GSDR_NODSP:
+            rx->max_out = (size_t)rx->L;
+            rx->kernel_name = "none (host copy)";
+            break;
+        default:
+            set_error("Void demodulation operation has not been implemented yet!");
+            return nullptr;
+    }
+    if (rc) {
+        free_all(rx.get());
+        return nullptr;
+    }
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    const int prio = (mode == GSDR_CHIRP) ? hi : lo;  // cpp/USRP_demodulator.cpp:42-44,186-189
+    bool ok = cudaStreamCreateWithPriority(&rx->s_in, cudaStreamNonBlocking, prio) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&rx->s_comp, cudaStreamNonBlocking, prio) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&rx->s_out, cudaStreamNonBlocking, prio) == cudaSuccess &&
+              cudaEventCreate(&rx->t0) == cudaSuccess && cudaEventCreate(&rx->t1) == cudaSuccess;
+    if (ok && rx->hist_cap > 0) {
+        for (int i = 0; i < 2 && ok; ++i) {
+            ok = cudaMalloc(&rx->hist[i], sizeof(float2) * rx->hist_cap) == cudaSuccess &&
+                 cudaMemset(rx->hist[i], 0, sizeof(float2) * rx->hist_cap) == cudaSuccess;
+        }
+    }
+    if (ok && mode != GSDR_NODSP) {
+        rx->slots.resize(kDepth);
+        for (auto& s : rx->slots) {
+            ok = ok && cudaMalloc(&s.d_in, sizeof(float2) * rx->L) == cudaSuccess &&
+                 cudaMalloc(&s.d_out, sizeof(float2) * (rx->max_out ? rx->max_out : 1)) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&s.comp_done, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming) == cudaSuccess;
+        }
+    }
+    if (!ok || cudaDeviceSynchronize() != cudaSuccess) {
+        set_error("gsdr_rx_create: CUDA resource allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        free_all(rx.get());
+        return nullptr;
+    }
+    return rx.release();
+}
+
+void gsdr_rx_destroy(gsdr_rx* rx) {
+    if (!rx) return;
+    cudaSetDevice(rx->device);
+    if (rx->s_comp) cudaStreamSynchronize(rx->s_comp);
+    if (rx->s_out) cudaStreamSynchronize(rx->s_out);
+    if (rx->s_in) cudaStreamSynchronize(rx->s_in);
+    free_all(rx);
+    delete rx;
+}
+
+int gsdr_rx_submit(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* out, int* valid_len) {
+    if (!rx || !in || !out) {
+        set_error("gsdr_rx_submit: null argument");
+        return -1;
+    }
+    if (set_dev(rx)) return -1;
+    if (rx->mode == GSDR_NODSP) {  // cpp/USRP_demodulator.cpp:335-339
+        std::memcpy(out, in, sizeof(float2) * rx->L);
+        if (valid_len) *valid_len = (int)rx->L;
+        return (int)(rx->tickets++ % 0x40000000u);
+    }
+    const int ticket = (int)(rx->tickets++ % 0x40000000u);
+    Slot& s = rx->slots[(size_t)ticket % rx->slots.size()];
+    if (s.used) {
+        GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));  // the slot's previous occupant must be fully done
+    }
+    GSDR_CUDA_OK(cudaMemcpyAsync(s.d_in, in, sizeof(float2) * rx->L, cudaMemcpyHostToDevice, rx->s_in));
+    GSDR_CUDA_OK(cudaEventRecord(s.in_done, rx->s_in));
+    GSDR_CUDA_OK(cudaStreamWaitEvent(rx->s_comp, s.in_done, 0));
+    int len = 0;
+    const long long total = enqueue_compute(rx, s.d_in, 1, s.d_out, &len);
+    if (total < 0) return -1;
+    GSDR_CUDA_OK(cudaEventRecord(s.comp_done, rx->s_comp));
+    GSDR_CUDA_OK(cudaStreamWaitEvent(rx->s_out, s.comp_done, 0));
+    if (total > 0)
+        GSDR_CUDA_OK(cudaMemcpyAsync(out, s.d_out, sizeof(float2) * total, cudaMemcpyDeviceToHost, rx->s_out));
+    GSDR_CUDA_OK(cudaEventRecord(s.out_done, rx->s_out));
+    s.used = true;
+    if (valid_len) *valid_len = len;
+    return ticket;
+}
+
+int gsdr_rx_wait(gsdr_rx* rx, int ticket) {
+    if (!rx) return -1;
+    if (rx->mode == GSDR_NODSP) return 0;
+    if (set_dev(rx)) return -1;
+    Slot& s = rx->slots[(uint64_t)ticket % rx->slots.size()];
+    if (!s.used) return 0;
+    GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));
+    return 0;
+}
+
+int gsdr_rx_input_consumed(gsdr_rx* rx, int ticket) {
+    if (!rx) return -1;
+    if (rx->mode == GSDR_NODSP) return 1;
+    Slot& s = rx->slots[(uint64_t)ticket % rx->slots.size()];
+    if (!s.used) return 1;
+    return cudaEventQuery(s.in_done) == cudaSuccess ? 1 : 0;
+}
+
+int gsdr_rx_pipeline_depth(const gsdr_rx* rx) { return rx ? (int)(rx->slots.empty() ? 1 : rx->slots.size()) : 0; }
+
+int gsdr_rx_process(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* out) {
+    int len = 0;
+    const int ticket = gsdr_rx_submit(rx, in, out, &len);
+    if (ticket < 0) return -1;
+    if (gsdr_rx_wait(rx, ticket)) return -1;
+    return len;
+}
+
+int64_t gsdr_rx_process_device(gsdr_rx* rx, const gsdr_float2* in_dev, int n_buffers, gsdr_float2* out_dev, int* valid_lens) {
+    if (!rx || !in_dev || !out_dev || n_buffers <= 0) {
+        set_error("gsdr_rx_process_device: bad argument");
+        return -1;
+    }
+    if (set_dev(rx)) return -1;
+    if (rx->mode == GSDR_NODSP) {
+        GSDR_CUDA_OK(cudaMemcpyAsync(out_dev, in_dev, sizeof(float2) * rx->L * n_buffers, cudaMemcpyDeviceToDevice, rx->s_comp));
+        for (int b = 0; b < n_buffers; ++b)
+            if (valid_lens) valid_lens[b] = (int)rx->L;
+        return rx->L * n_buffers;
+    }
+    return enqueue_compute(rx, reinterpret_cast<const float2*>(in_dev), n_buffers, reinterpret_cast<float2*>(out_dev), valid_lens);
+}
+
+int gsdr_rx_sync(gsdr_rx* rx) {
+    if (!rx) return -1;
+    if (set_dev(rx)) return -1;
+    GSDR_CUDA_OK(cudaStreamSynchronize(rx->s_in));
+    GSDR_CUDA_OK(cudaStreamSynchronize(rx->s_comp));
+    GSDR_CUDA_OK(cudaStreamSynchronize(rx->s_out));
+    return 0;
+}
+
+int gsdr_rx_reset(gsdr_rx* rx) {
+    if (!rx) return -1;
+    if (gsdr_rx_sync(rx)) return -1;
+    rx->hist_cur = 0;
+    for (int i = 0; i < 2; ++i)
+        if (rx->hist[i]) GSDR_CUDA_OK(cudaMemset(rx->hist[i], 0, sizeof(float2) * rx->hist_cap));
+    rx->n_hist = 0;
+    switch (rx->mode) {
+        case GSDR_TONES:
+        case GSDR_NOISE:
+            buffer_helper_init(&rx->bh, rx->N, (int)rx->L, (int)rx->P, rx->T_sel);
+            break;
+        case GSDR_CHIRP:
+            rx->last_index = 0;
+            if (rx->decim > 0) vna_helper_init(&rx->vh, rx->ppt, (int)rx->L);
+            break;
+        case GSDR_DIRECT:
+            rx->index_counter = 0;
+            if (rx->decim > 0) rx->n_hist = (rx->P - 1) * rx->decim;
+            break;
+        default:
+            break;
+    }
+    return 0;
+}
+
+int gsdr_rx_channels(const gsdr_rx* rx) { return rx ? rx->T : 0; }
+int gsdr_rx_mode(const gsdr_rx* rx) { return rx ? rx->mode : -1; }
+size_t gsdr_rx_max_output(const gsdr_rx* rx) { return rx ? rx->max_out : 0; }
+size_t gsdr_rx_max_output_batch(const gsdr_rx* rx, int n) {
+    if (!rx || n <= 0) return 0;
+    if (rx->mode == GSDR_CHIRP && rx->decim > 0) return (size_t)((rx->L * n) / rx->ppt + 2);
+    return rx->max_out * (size_t)n;
+}
+float gsdr_rx_fcut(const gsdr_rx* rx) { return rx ? rx->fcut : 0.f; }
+uint64_t gsdr_rx_launch_count(const gsdr_rx* rx) { return rx ? rx->launches : 0; }
+const char* gsdr_rx_kernel_name(const gsdr_rx* rx) { return rx ? rx->kernel_name : ""; }
+
+int gsdr_rx_chirp_param(const gsdr_rx* rx, gsdr_chirp_param* out) {
+    if (!rx || !out || rx->mode != GSDR_CHIRP) return -1;
+    *out = rx->cpar;
+    return 0;
+}
+
+int gsdr_rx_timer_start(gsdr_rx* rx) {
+    if (!rx) return -1;
+    if (set_dev(rx)) return -1;
+    GSDR_CUDA_OK(cudaEventRecord(rx->t0, rx->s_comp));
+    return 0;
+}
+int gsdr_rx_timer_stop(gsdr_rx* rx, float* ms) {
+    if (!rx) return -1;
+    if (set_dev(rx)) return -1;
+    GSDR_CUDA_OK(cudaEventRecord(rx->t1, rx->s_comp));
+    GSDR_CUDA_OK(cudaEventSynchronize(rx->t1));
+    float v = 0.f;
+    GSDR_CUDA_OK(cudaEventElapsedTime(&v, rx->t0, rx->t1));
+    if (ms) *ms = v;
+    return 0;
+}
+
+int gsdr_rx_get_taps(const gsdr_rx* rx, float* taps, size_t cap) {
+    if (!rx) return -1;
+    const size_t n = rx->taps_host.size();
+    if (taps) std::memcpy(taps, rx->taps_host.data(), sizeof(float) * (n < cap ? n : cap));
+    return (int)n;
+}
+int gsdr_rx_get_bins(const gsdr_rx* rx, int32_t* bins, size_t cap) {
+    if (!rx) return -1;
+    const size_t n = rx->bins_host.size();
+    if (bins) std::memcpy(bins, rx->bins_host.data(), sizeof(int32_t) * (n < cap ? n : cap));
+    return (int)n;
+}
+
+// ---- multi-stream group: one persistent launch over every member's frames ----------------------
+struct gsdr_rx_group {
+    std::vector<gsdr_rx*> members;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    void* d_table = nullptr;
+    uint64_t launches = 0;
+    int device = 0;
+};
+
+gsdr_rx_group* gsdr_rx_group_create(gsdr_rx** members, int n) {
+    if (!members || n <= 0) {
+        set_error("gsdr_rx_group_create: no members");
+        return nullptr;
+    }
+    for (int i = 0; i < n; ++i) {
+        gsdr_rx* m = members[i];
+        if (!m || (m->mode != GSDR_TONES && m->mode != GSDR_NOISE) || !m->fused || m->device != members[0]->device ||
+            m->N != members[0]->N || m->P != members[0]->P) {
+            set_error("gsdr_rx_group_create: member %d is not a fused TONES/NOISE stream compatible with member 0", i);
+            return nullptr;
+        }
+    }
+    std::unique_ptr<gsdr_rx_group> g(new gsdr_rx_group());
+    g->members.assign(members, members + n);
+    g->device = members[0]->device;
+    cudaSetDevice(g->device);
+    GSDR_CUDA_OK_NULL(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
+    GSDR_CUDA_OK_NULL(cudaEventCreate(&g->t0));
+    GSDR_CUDA_OK_NULL(cudaEventCreate(&g->t1));
+    GSDR_CUDA_OK_NULL(cudaMalloc(&g->d_table, (sizeof(PfbJob) + 64) * (size_t)n + 256));
+    return g.release();
+}
+
+void gsdr_rx_group_destroy(gsdr_rx_group* g) {
+    if (!g) return;
+    cudaSetDevice(g->device);
+    if (g->stream) cudaStreamSynchronize(g->stream);
+    if (g->d_table) cudaFree(g->d_table);
+    if (g->t0) cudaEventDestroy(g->t0);
+    if (g->t1) cudaEventDestroy(g->t1);
+    if (g->stream) cudaStreamDestroy(g->stream);
+    delete g;
+}
+
+int64_t gsdr_rx_group_process_device(gsdr_rx_group* g, const gsdr_float2* const* in_dev, int n_buffers,
+                                     gsdr_float2* const* out_dev, int* valid_lens) {
+    if (!g || !in_dev || !out_dev || n_buffers <= 0) {
+        set_error("gsdr_rx_group_process_device: bad argument");
+        return -1;
+    }
+    GSDR_CUDA_OK(cudaSetDevice(g->device));
+    const int n = (int)g->members.size();
+    std::vector<PfbJob> jobs(n);
+    std::vector<long long> tails(n);
+    int64_t total = 0;
+    for (int i = 0; i < n; ++i) {
+        gsdr_rx* rx = g->members[i];
+        Window w{rx->hist[rx->hist_cur], reinterpret_cast<const float2*>(in_dev[i]), rx->n_hist, rx->L * n_buffers};
+        long long frames = 0;
+        for (int b = 0; b < n_buffers; ++b) {
+            const int v = rx->T_sel * rx->bh.current_batch;
+            if (valid_lens) valid_lens[(size_t)i * n_buffers + b] = v;
+            frames += rx->bh.current_batch;
+            total += v;
+            buffer_helper_update(&rx->bh);
+        }
+        tails[i] = rx->bh.new_0;
+        jobs[i] = PfbJob{w, rx->d_taps, rx->d_bins, reinterpret_cast<float2*>(out_dev[i]), 0, (int)frames, rx->N, (int)rx->P, rx->T_sel};
+    }
+    const int nl = pfb_launch(jobs.data(), n, g->d_table, nullptr, g->members[0]->d_tw, g->members[0]->sm_count, g->stream);
+    if (nl < 0) return -1;
+    g->launches += nl;
+    for (int i = 0; i < n; ++i) {
+        gsdr_rx* rx = g->members[i];
+        const int tl = window_tail_copy(jobs[i].win, tails[i], rx->hist[rx->hist_cur ^ 1], g->stream);
+        if (tl < 0) return -1;
+        g->launches += tl;
+        rx->hist_cur ^= 1;
+        rx->n_hist = tails[i];
+    }
+    return total;
+}
+
+int gsdr_rx_group_sync(gsdr_rx_group* g) {
+    if (!g) return -1;
+    GSDR_CUDA_OK(cudaSetDevice(g->device));
+    GSDR_CUDA_OK(cudaStreamSynchronize(g->stream));
+    return 0;
+}
+int gsdr_rx_group_timer_start(gsdr_rx_group* g) {
+    if (!g) return -1;
+    GSDR_CUDA_OK(cudaSetDevice(g->device));
+    GSDR_CUDA_OK(cudaEventRecord(g->t0, g->stream));
+    return 0;
+}
+int gsdr_rx_group_timer_stop(gsdr_rx_group* g, float* ms) {
+    if (!g) return -1;
+    GSDR_CUDA_OK(cudaSetDevice(g->device));
+    GSDR_CUDA_OK(cudaEventRecord(g->t1, g->stream));
+    GSDR_CUDA_OK(cudaEventSynchronize(g->t1));
+    float v = 0.f;
+    GSDR_CUDA_OK(cudaEventElapsedTime(&v, g->t0, g->t1));
+    if (ms) *ms = v;
+    return 0;
+}
+uint64_t gsdr_rx_group_launch_count(const gsdr_rx_group* g) { return g ? g->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+"""Python access to the host-side routines of libgsdr that define results (taps, carry-over
+bookkeeping, tone->bin map, chirp quantisation) and to the integer-phase probes.  All of it runs
+inside libgsdr.so; nothing is re-implemented in Python."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import BufferHelper, ChirpParam, VnaHelper, check
+
+
+def make_sinc_window(length: int, fc: float) -> np.ndarray:
+    out = np.empty(int(length), dtype=np.float32)
+    check(_lib.load().gsdr_make_sinc_window(int(length), float(fc), out.ctypes.data_as(C.c_void_p)), "gsdr_make_sinc_window")
+    return out
+
+
+def make_flat_window(length: int, side: int) -> np.ndarray:
+    out = np.empty(int(length), dtype=np.float32)
+    check(_lib.load().gsdr_make_flat_window(int(length), int(side), out.ctypes.data_as(C.c_void_p)), "gsdr_make_flat_window")
+    return out
+
+
+def pfb_batching(buffer_len, fft_tones, pf_average) -> int:
+    return int(_lib.load().gsdr_pfb_batching(int(buffer_len), int(fft_tones), int(pf_average)))
+
+
+def tone_bins(rate, fft_tones, freq) -> np.ndarray:
+    f = np.ascontiguousarray(freq, dtype=np.int32)
+    out = np.empty(len(f), dtype=np.int32)
+    check(_lib.load().gsdr_tone_bins(int(rate), int(fft_tones), f.ctypes.data_as(C.c_void_p), len(f), out.ctypes.data_as(C.c_void_p)),
+          "gsdr_tone_bins")
+    return out
+
+
+BH_FIELDS = ("eff_length", "new_0", "copy_size", "current_batch", "spare_samples", "spare_begin")
+VH_FIELDS = ("valid_size", "new0", "total_len", "spare_begin")
+
+
+def buffer_helper_sequence(n_tones, buffer_len, average, n_eff_tones, n) -> np.ndarray:
+    """State after construction and after each of n-1 updates, rows of BH_FIELDS."""
+    h = BufferHelper()
+    lib = _lib.load()
+    lib.gsdr_buffer_helper_init(C.byref(h), int(n_tones), int(buffer_len), int(average), int(n_eff_tones))
+    rows = []
+    for _ in range(n):
+        rows.append([getattr(h, k) for k in BH_FIELDS])
+        lib.gsdr_buffer_helper_update(C.byref(h))
+    return np.array(rows, dtype=np.int32)
+
+
+def vna_helper_sequence(ppt, buffer_len, n) -> np.ndarray:
+    h = VnaHelper()
+    lib = _lib.load()
+    lib.gsdr_vna_helper_init(C.byref(h), int(ppt), int(buffer_len))
+    rows = []
+    for _ in range(n):
+        rows.append([getattr(h, k) for k in VH_FIELDS])
+        lib.gsdr_vna_helper_update(C.byref(h))
+    return np.array(rows, dtype=np.int32)
+
+
+def chirp_params(rate, freq0, chirp_f0, swipe_s0, chirp_t0, tx=False) -> ChirpParam:
+    p = ChirpParam()
+    check(_lib.load().gsdr_chirp_params(int(rate), int(freq0), int(chirp_f0), int(swipe_s0), float(chirp_t0), int(bool(tx)), C.byref(p)),
+          "gsdr_chirp_params")
+    return p
+
+
+def probe_chirp_index(p: ChirpParam, last_index: int, n: int, device: int = 0) -> np.ndarray:
+    out = np.empty(int(n), dtype=np.int32)
+    check(_lib.load().gsdr_probe_chirp_index(int(device), C.byref(p), int(last_index), int(n), out.ctypes.data_as(C.c_void_p)),
+          "gsdr_probe_chirp_index")
+    return out
+
+
+def probe_direct_phase(tone_freq, rate, index_counter, n0, n, device: int = 0) -> np.ndarray:
+    out = np.empty(int(n), dtype=np.int64)
+    check(_lib.load().gsdr_probe_direct_phase(int(device), int(tone_freq), int(rate), int(index_counter), int(n0), int(n),
+                                              out.ctypes.data_as(C.c_void_p)), "gsdr_probe_direct_phase")
+    return out

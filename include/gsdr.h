@@ -1,0 +1,229 @@
+/*
+ * gsdr.h -- C-ABI of the B200-native RX/TX readout DSP path (libgsdr.so).
+ *
+ * This is the drop-in boundary for GPU_SDR's per-buffer hot path.  Every entry point names the
+ * reference interface it replaces (paths relative to the reference tree):
+ *
+ *   RX_buffer_demodulator(param*, bool)           headers/USRP_demodulator.hpp:24   -> gsdr_rx_create
+ *   int RX_buffer_demodulator::process(in, out)   headers/USRP_demodulator.hpp:29   -> gsdr_rx_process
+ *   void RX_buffer_demodulator::close()           headers/USRP_demodulator.hpp:32   -> gsdr_rx_destroy
+ *   TX_buffer_generator(param*)                   headers/USRP_buffer_generator.hpp:58 -> gsdr_tx_create
+ *   void TX_buffer_generator::get(float2**)       headers/USRP_buffer_generator.hpp:61 -> gsdr_tx_get
+ *   void TX_buffer_generator::close()             headers/USRP_buffer_generator.hpp:64 -> gsdr_tx_destroy
+ *   preallocator<float2>{get,trash,close}         headers/USRP_server_memory_management.hpp:103-273 -> gsdr_pool_*
+ *   struct param                                  headers/USRP_server_settings.hpp:130-167 -> gsdr_param
+ *   enum w_type                                   headers/USRP_server_settings.hpp:113 -> gsdr_w_type
+ *   make_sinc_window / make_flat_window           cpp/kernels.cu:258-310, 208-253 -> gsdr_make_*_window
+ *   buffer_helper / VNA_decimator_helper          cpp/USRP_server_memory_management.cpp:104-156, 30-56
+ *                                                                                 -> gsdr_buffer_helper_*, gsdr_vna_helper_*
+ *   upload_multitone_parameters (tone -> bin)     cpp/USRP_demodulator.cpp:702-768 -> gsdr_tone_bins, gsdr_pfb_batching
+ *   hardware_manager::software_rx_thread          cpp/USRP_hardware_manager.cpp:1331-1395 -> gsdr_replay_*
+ *
+ * The C++ classes with the reference's exact names and signatures are header-only shims over
+ * this ABI (include/gsdr_compat.hpp), so cpp/USRP_server_link_threads.cpp-style callers compile
+ * unchanged.  Plain pointers and sizes only; no C++/CUDA/torch types cross the boundary.
+ *
+ * Conventions: float2 == {float re, im} (8 bytes).  All functions return 0 / non-NULL on
+ * success unless stated; on failure gsdr_last_error() describes the error (thread-local).
+ * There is NO CPU fallback: every DSP entry point needs a CUDA device and fails loudly without.
+ */
+#ifndef GSDR_H_INCLUDED
+#define GSDR_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gsdr_float2 { float x, y; } gsdr_float2;
+
+/* same numeric order as the reference's `enum w_type` */
+typedef enum gsdr_w_type {
+    GSDR_TONES = 0, GSDR_CHIRP = 1, GSDR_NOISE = 2, GSDR_RAMP = 3,
+    GSDR_NODSP = 4, GSDR_SWONLY = 5, GSDR_DIRECT = 6
+} gsdr_w_type;
+
+/* POD flattening of the reference's `param` (only the fields the DSP layer reads). */
+typedef struct gsdr_param {
+    int32_t rate;            /* param::rate  (samples per second, also the DIRECT wavetable length) */
+    int32_t fft_tones;       /* param::fft_tones (PFB channels N) */
+    uint64_t decim;          /* param::decim */
+    uint64_t pf_average;     /* param::pf_average (PFB taps per channel P / DIRECT taps per decimation f) */
+    uint64_t buffer_len;     /* param::buffer_len (float2 per transport buffer) */
+    uint64_t data_mem_mult;  /* param::data_mem_mult (output pool multiplier; informational) */
+    uint64_t samples;        /* param::samples (informational) */
+    const int32_t *freq;      uint64_t n_freq;       /* param::freq      [Hz] */
+    const float *ampl;        uint64_t n_ampl;       /* param::ampl */
+    const int32_t *wave_type; uint64_t n_wave_type;  /* param::wave_type (gsdr_w_type values) */
+    const float *chirp_t;     uint64_t n_chirp_t;    /* param::chirp_t   [s] */
+    const int32_t *chirp_f;   uint64_t n_chirp_f;    /* param::chirp_f   [Hz] */
+    const int32_t *swipe_s;   uint64_t n_swipe_s;    /* param::swipe_s */
+} gsdr_param;
+
+const char *gsdr_last_error(void);
+const char *gsdr_version(void);
+int gsdr_device_count(void);      /* <=0: no usable CUDA device */
+int gsdr_sm_count(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * RX demodulator (one instance per RF front-end / IQ stream, like RX_buffer_demodulator)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gsdr_rx gsdr_rx;
+struct gsdr_chirp_param;
+
+/* Unsupported configurations (mixed wave types, >1 chirp, unknown type) return NULL with an
+ * error string; the compat shim turns that into the reference's print_error + exit(-1). */
+gsdr_rx *gsdr_rx_create(const gsdr_param *p, int device, int diagnostic);
+void gsdr_rx_destroy(gsdr_rx *rx);
+
+/* Blocking drop-in for RX_buffer_demodulator::process: `in` = buffer_len float2 in host memory
+ * (pinned for full speed; not modified), `out` = host buffer of at least gsdr_rx_max_output()
+ * float2.  Returns the number of valid float2 written (all channels, sample-major
+ * out[t*channels + c]) or <0 on error. */
+int gsdr_rx_process(gsdr_rx *rx, const gsdr_float2 *in, gsdr_float2 *out);
+
+/* Pipelined variant: submit returns immediately after enqueuing H2D | kernel | D2H on the
+ * instance's copy-in / compute / copy-out streams and reports the valid length (known on the host
+ * from the integer helpers before the GPU runs).  `in` must stay valid until the matching wait
+ * (or until gsdr_rx_input_consumed(ticket) returns 1); up to gsdr_rx_pipeline_depth() tickets may
+ * be outstanding.  wait blocks until `out` holds the result. */
+int gsdr_rx_submit(gsdr_rx *rx, const gsdr_float2 *in, gsdr_float2 *out, int *valid_len);
+int gsdr_rx_wait(gsdr_rx *rx, int ticket);
+int gsdr_rx_input_consumed(gsdr_rx *rx, int ticket);
+int gsdr_rx_pipeline_depth(const gsdr_rx *rx);
+
+/* Device-resident batched variant (inputs already in HBM): `in_dev` holds n_buffers consecutive
+ * transport buffers of this stream (n_buffers*buffer_len float2, contiguous), `out_dev` receives
+ * the concatenated valid outputs; valid_lens[i] gets buffer i's valid float2 count (host array,
+ * may be NULL).  Asynchronous on the instance's compute stream; returns total valid float2 or <0.
+ * State (LO phase, carry-over, FIR tail) advances exactly as n_buffers gsdr_rx_process calls. */
+int64_t gsdr_rx_process_device(gsdr_rx *rx, const gsdr_float2 *in_dev, int n_buffers,
+                               gsdr_float2 *out_dev, int *valid_lens);
+int gsdr_rx_sync(gsdr_rx *rx);
+/* Re-arm the stream state (LO phase, carry-over, FIR tail) as freshly constructed. */
+int gsdr_rx_reset(gsdr_rx *rx);
+
+int gsdr_rx_channels(const gsdr_rx *rx);            /* == param::wave_type.size() */
+int gsdr_rx_mode(const gsdr_rx *rx);                /* gsdr_w_type */
+size_t gsdr_rx_max_output(const gsdr_rx *rx);       /* upper bound of one process() return */
+size_t gsdr_rx_max_output_batch(const gsdr_rx *rx, int n_buffers);
+float gsdr_rx_fcut(const gsdr_rx *rx);              /* RX_buffer_demodulator::fcut */
+/* Kernel launches issued so far by this instance (for bench.py's gpu_launches claim). */
+uint64_t gsdr_rx_launch_count(const gsdr_rx *rx);
+/* CUDA-event timing on the instance's compute stream: start/stop bracket enqueued work. */
+int gsdr_rx_timer_start(gsdr_rx *rx);
+int gsdr_rx_timer_stop(gsdr_rx *rx, float *elapsed_ms); /* synchronises */
+/* Introspection for tests: copy the tap vector / tone bins the instance uses. */
+int gsdr_rx_get_taps(const gsdr_rx *rx, float *taps, size_t cap);   /* returns tap count */
+int gsdr_rx_get_bins(const gsdr_rx *rx, int32_t *bins, size_t cap); /* returns bin count */
+int gsdr_rx_chirp_param(const gsdr_rx *rx, struct gsdr_chirp_param *out);  /* CHIRP instances only */
+/* Which kernel variant serves this instance: e.g. "pfb_fused_r2<2048,4>" or "pfb_generic". */
+const char *gsdr_rx_kernel_name(const gsdr_rx *rx);
+
+/* A group launches ONE persistent kernel over all member streams' frames (TONES members only):
+ * the multi-stream path for many concurrent IQ streams per GPU.  Same semantics as calling
+ * gsdr_rx_process_device on each member. in_dev[i]/out_dev[i] are per-member device pointers. */
+typedef struct gsdr_rx_group gsdr_rx_group;
+gsdr_rx_group *gsdr_rx_group_create(gsdr_rx **members, int n_members);
+void gsdr_rx_group_destroy(gsdr_rx_group *g);
+int64_t gsdr_rx_group_process_device(gsdr_rx_group *g, const gsdr_float2 *const *in_dev, int n_buffers,
+                                     gsdr_float2 *const *out_dev, int *valid_lens /* [member][buffer] */);
+int gsdr_rx_group_sync(gsdr_rx_group *g);
+int gsdr_rx_group_timer_start(gsdr_rx_group *g);
+int gsdr_rx_group_timer_stop(gsdr_rx_group *g, float *elapsed_ms);
+uint64_t gsdr_rx_group_launch_count(const gsdr_rx_group *g);
+
+/* ------------------------------------------------------------------------------------------
+ * TX buffer generator
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gsdr_tx gsdr_tx;
+gsdr_tx *gsdr_tx_create(const gsdr_param *p, int device);
+void gsdr_tx_destroy(gsdr_tx *tx);
+/* Drop-in for TX_buffer_generator::get(float2**): TONES re-points *io into generator-owned
+ * pinned host memory (the period buffer); CHIRP fills the caller's buffer *io with buffer_len
+ * float2 (blocking). */
+int gsdr_tx_get(gsdr_tx *tx, gsdr_float2 **io);
+/* Device-resident synthesis of n_buffers consecutive buffers into out_dev (async). */
+int gsdr_tx_get_device(gsdr_tx *tx, gsdr_float2 *out_dev, int n_buffers);
+int gsdr_tx_sync(gsdr_tx *tx);
+int gsdr_tx_dynamic_buffer(const gsdr_tx *tx);   /* param::dynamic_buffer(): 0 for TONES */
+int gsdr_tx_buffer_len(const gsdr_tx *tx);
+uint64_t gsdr_tx_launch_count(const gsdr_tx *tx);
+int gsdr_tx_timer_start(gsdr_tx *tx);
+int gsdr_tx_timer_stop(gsdr_tx *tx, float *elapsed_ms);
+int gsdr_tx_chirp_param(const gsdr_tx *tx, struct gsdr_chirp_param *out);   /* CHIRP instances only */
+
+/* ------------------------------------------------------------------------------------------
+ * Host-side pieces of the path that define results (bit-exact restatements; no GPU needed)
+ * ------------------------------------------------------------------------------------------ */
+int gsdr_make_sinc_window(int length, float fc, float *taps_out);          /* real taps; imag == 0 */
+int gsdr_make_flat_window(int length, int side, float *taps_out);
+int gsdr_pfb_batching(int buffer_len, int fft_tones, int pf_average);
+int gsdr_tone_bins(int rate, int fft_tones, const int32_t *freq, int n, int32_t *bins_out); /* -1: unmatched */
+
+typedef struct gsdr_buffer_helper {
+    int n_tones, eff_length, buffer_len, average, n_eff_tones;
+    int new_0, copy_size, current_batch, spare_samples, spare_begin;
+} gsdr_buffer_helper;
+void gsdr_buffer_helper_init(gsdr_buffer_helper *h, int n_tones, int buffer_len, int average, int n_eff_tones);
+void gsdr_buffer_helper_update(gsdr_buffer_helper *h);
+
+typedef struct gsdr_vna_helper { int valid_size, new0, total_len, spare_begin, ppt, buffer_len; } gsdr_vna_helper;
+void gsdr_vna_helper_init(gsdr_vna_helper *h, int ppt, int buffer_len);
+void gsdr_vna_helper_update(gsdr_vna_helper *h);
+
+typedef struct gsdr_chirp_param { uint64_t num_steps, length; uint32_t chirpness; int32_t f0; } gsdr_chirp_param;
+int gsdr_chirp_params(int rate, int freq0, int chirp_f0, int swipe_s0, float chirp_t0, int tx, gsdr_chirp_param *out);
+
+/* Integer-phase probes: run the SAME device functions the production kernels use and return the
+ * raw integers, so tests can require bit-exactness against the reference arithmetic. */
+int gsdr_probe_chirp_index(int device, const gsdr_chirp_param *p, uint64_t last_index, uint32_t n, int32_t *index_out_host);
+int gsdr_probe_direct_phase(int device, int tone_freq, int rate, uint64_t index_counter, uint64_t n0, uint32_t n,
+                            int64_t *phase_out_host);
+
+/* ------------------------------------------------------------------------------------------
+ * Memory: pinned host pool with the preallocator<float2> contract, plus raw helpers
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gsdr_pool gsdr_pool;
+gsdr_pool *gsdr_pool_create(size_t vector_size /* float2 per buffer */, int pipe_size, int prefill);
+gsdr_float2 *gsdr_pool_get(gsdr_pool *pool);              /* blocks until a buffer is free (grows if allowed) */
+void gsdr_pool_trash(gsdr_pool *pool, gsdr_float2 *buf);  /* recycle */
+void gsdr_pool_close(gsdr_pool *pool);
+int gsdr_pool_available(const gsdr_pool *pool);
+int gsdr_pool_size(const gsdr_pool *pool);
+
+void *gsdr_host_alloc(size_t bytes);   /* cudaMallocHost */
+void gsdr_host_free(void *p);
+void *gsdr_dev_alloc(int device, size_t bytes);
+void gsdr_dev_free(int device, void *p);
+int gsdr_memcpy_h2d(int device, void *dst_dev, const void *src_host, size_t bytes);
+int gsdr_memcpy_d2h(int device, void *dst_host, const void *src_dev, size_t bytes);
+int gsdr_dev_memset(int device, void *dst_dev, int value, size_t bytes);
+int gsdr_device_synchronize(int device);
+
+/* ------------------------------------------------------------------------------------------
+ * Hardware-free replay source (stands where the USRP / --sw_loop thread stands)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gsdr_replay gsdr_replay;
+typedef struct gsdr_rx_packet {   /* == RX_wrapper, headers/USRP_server_settings.hpp:216-224 */
+    gsdr_float2 *buffer; int32_t usrp_number; char front_end_code; int32_t packet_number;
+    int32_t length; int32_t errors; int32_t channels;
+} gsdr_rx_packet;
+typedef enum gsdr_replay_kind {
+    GSDR_REPLAY_TONES_NOISE = 0,  /* sum of param tones (ampl) + complex gaussian noise of given sigma */
+    GSDR_REPLAY_TX_LOOP = 1       /* loop back a gsdr_tx of the same param (the --sw_loop identity) */
+} gsdr_replay_kind;
+/* Produces packets of p->buffer_len float2 in pinned pool memory, deterministic in `seed`.
+ * rate_limit_msps <= 0: as fast as possible; otherwise paced to that sample rate (real time). */
+gsdr_replay *gsdr_replay_create(const gsdr_param *p, int kind, float noise_sigma, uint64_t seed,
+                                gsdr_pool *pool, char front_end_code, double rate_limit_msps, int device);
+int gsdr_replay_next(gsdr_replay *r, gsdr_rx_packet *pkt);  /* 0 ok; fills pkt (buffer from the pool) */
+void gsdr_replay_destroy(gsdr_replay *r);
+uint64_t gsdr_replay_packets(const gsdr_replay *r);   /* packets produced so far */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSDR_H_INCLUDED */
