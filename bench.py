@@ -1,0 +1,416 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the RX hot path (TONES-mode polyphase channelizer) on B200.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`, one rank per
+GPU under torchrun for N>1, ONE JSON line on rank 0.
+
+Workload = BASELINE.json configs[1]: 2048-channel, 4-tap PFB, 1000 selected tones, pf_average=4,
+one 200 MS/s IQ stream per GPU, transport buffers of 1e6 complex samples.  A "step" is one pass of
+the hot path over one batch of BUFFERS consecutive transport buffers of that stream:
+
+  value    inputs already resident in HBM (two alternating 512 MB batches, i.e. larger than the
+           126 MB L2, so no step can be served from cache); CUDA events on the launching stream.
+  e2e      the same batch through the reference-facing call (pinned HOST buffers in, pinned host
+           buffers out; H2D and D2H inside the timed region), pipelined submit/wait.
+  roofline algorithmic bytes (8 + 8*T/N per input sample) / event-timed launch duration vs the
+           measured HBM copy peak in MEASURED_PEAKS.json.
+  cpu_baseline  the NumPy/SciPy port of the same chain (oracle/cpu_port.py) on the host cores, on a
+           bounded sample, rank 0 at N=1 only.
+
+`--impl reference` times the reference's own RX_buffer_demodulator::process (unmodified sources
+compiled for sm_100a into oracle/_ref/libgsdr_ref.so) on the same workload through host buffers;
+the reference has no CPU DSP implementation, so its arm runs on the GPU as it does in production.
+Multi-GPU: streams are independent (one demodulator instance each), so ranks shard by stream with
+no data-path collective ("weak" scaling); torch.distributed is used for the barrier and the
+max-over-ranks time only.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RATE, NFFT, PTAPS, NTONES, BUFLEN = 200_000_000, 2048, 4, 1000, 1_000_000
+BYTES_PER_SAMPLE = 8.0 + 8.0 * NTONES / NFFT  # 11.90625 B per input sample
+SEED = 1337
+
+
+def workload_param():
+    import gpu_sdr_b200 as g
+    rng = np.random.default_rng(SEED)
+    ks = rng.choice(np.arange(-NFFT // 2 + 1, NFFT // 2), size=NTONES, replace=False)
+    freq = [int(k * (RATE / NFFT)) for k in ks]
+    return g.param(mode="RX", rate=RATE, fft_tones=NFFT, pf_average=PTAPS, buffer_len=BUFLEN, decim=0, freq=freq,
+                   wave_type=[g.TONES] * NTONES, ampl=[1.0 / NTONES] * NTONES)
+
+
+def synth_buffers(p, n_distinct, seed):
+    """n_distinct transport buffers of tones + noise on the sc16 grid (float32 exact)."""
+    rng = np.random.default_rng(seed)
+    f = np.array(p.freq[:32], dtype=np.int64)  # 32 of the tones carry power; the rest see noise
+    out = []
+    for b in range(n_distinct):
+        n = np.arange(b * BUFLEN, (b + 1) * BUFLEN, dtype=np.int64)
+        x = np.zeros(BUFLEN, dtype=np.complex64)
+        for fi in f:
+            ph = ((fi * n) % RATE).astype(np.float32) * np.float32(2 * np.pi / RATE)
+            x += (np.cos(ph) + 1j * np.sin(ph)).astype(np.complex64) * np.float32(1.0 / 64)
+        x += (rng.standard_normal(BUFLEN, dtype=np.float32) + 1j * rng.standard_normal(BUFLEN, dtype=np.float32)) * np.float32(1e-3)
+        x = (np.round(x.real * 32768) + 1j * np.round(x.imag * 32768)).astype(np.complex64) / np.float32(32768)
+        out.append(x.astype(np.complex64))
+    return out
+
+
+# ---- distributed plumbing ------------------------------------------------------------------------
+class Dist:
+    def __init__(self, n_gpus):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.torch = None
+        self.dist = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            self.torch, self.dist = torch, dist
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+            if backend == "nccl":
+                torch.cuda.set_device(self.local_rank)
+            dist.init_process_group(backend)
+            self.dev = torch.device("cuda", self.local_rank) if backend == "nccl" else torch.device("cpu")
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+
+    def max(self, v: float) -> float:
+        if not self.dist:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum(self, v: float) -> float:
+        if not self.dist:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
+def shard_streams(n_streams: int, rank: int, world: int):
+    """stream s -> rank s mod world."""
+    return [s for s in range(n_streams) if s % world == rank]
+
+
+# ---- clocks --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8 or not (t_begin - 0.05 <= ts <= t_end + 0.15):
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the fused kernel from the committed ncu summary, if any."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "pfb_traffic.json")))
+        return d
+    except Exception:
+        return None
+
+
+# ---- CPU baseline --------------------------------------------------------------------------------
+def cpu_baseline(p, budget_s=12.0):
+    from oracle import cpu_port
+    port = cpu_port.PFBPort(p.rate, p.fft_tones, p.pf_average, p.buffer_len, p.freq)
+    bufs = synth_buffers(p, 2, SEED + 7)
+    port.process(bufs[0])  # warm-up (FFT plan, page faults)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        port.process(bufs[n % 2])
+        n += 1
+        el = time.perf_counter() - t0
+        if (el >= budget_s and n >= 8) or n >= 4000:
+            break
+    return {"value": n * BUFLEN / el / 1e6, "unit": "MS/s", "cores": cpu_port.cores(), "kind": "port",
+            "sample": f"{n} transport buffers of 1e6 samples ({el:.1f} s) through oracle/cpu_port.PFBPort "
+                      f"(complex64 NumPy + scipy.fft workers={cpu_port.cores()})"}
+
+
+# ---- our arm -------------------------------------------------------------------------------------
+def run_ours(args, dd: Dist):
+    import gpu_sdr_b200 as g
+    lib = g.load()
+    ndev = lib.gsdr_device_count()
+    if ndev <= 0:
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (" + g._lib.last_error() + ")")
+    dev = dd.local_rank % ndev
+    p = workload_param()
+    B = args.buffers
+    n_streams_total = args.streams * dd.world
+    my_streams = shard_streams(n_streams_total, dd.rank, dd.world)
+    S = len(my_streams)
+
+    rxs = [g.RX_buffer_demodulator(p, device=dev) for _ in my_streams]
+    kernel_name = rxs[0].kernel_name()
+    # device-resident input: two alternating batches per stream built from 4 distinct buffers
+    distinct = synth_buffers(p, 4, SEED)
+    ins = []
+    for s in range(S):
+        pair = []
+        for half in range(2):
+            d = g.DeviceBuffer(B * BUFLEN, device=dev)
+            for b in range(B):
+                d.upload(distinct[(b + half + s) % 4], offset=b * BUFLEN)
+            pair.append(d)
+        ins.append(pair)
+    outs = [g.DeviceBuffer(rxs[0].max_output_batch(B), device=dev) for _ in range(S)]
+    group = g.RxGroup(rxs) if S > 1 else None
+
+    def step(i):
+        if group:
+            group.process_device([ins[s][i & 1].ptr for s in range(S)], B, [o.ptr for o in outs])
+        else:
+            rxs[0].process_device(ins[0][i & 1].ptr, B, outs[0].ptr)
+
+    timer = group if group else rxs[0]
+
+    def launches():
+        return (group.launch_count() if group else 0) + sum(r.launch_count() for r in rxs)
+
+    for i in range(args.warmup):
+        step(i)
+    timer.sync()
+    sampler = ClockSampler(dev)
+    time.sleep(0.25)
+    dd.barrier()
+    timer.sync()
+    l0 = launches()
+    t_begin = time.time()
+    timer.timer_start()
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ms_total = timer.timer_stop()
+    dd.barrier()
+    timer.sync()
+    t_end = time.time()
+    l1 = launches()
+    # keep the same load running until the clock sampler has seen it for ~1.2 s (100 ms period)
+    extra_i = 0
+    while time.time() - t_begin < 1.2:
+        step(extra_i)
+        extra_i += 1
+        if extra_i % 16 == 0:
+            timer.sync()
+    timer.sync()
+    clocks = sampler.stop(t_begin, time.time())
+    clocks["window"] = "timed region + same load continued to 1.2 s"
+
+    ms_step = dd.max(ms_total / args.steps)
+    samples_step = dd.sum(float(S * B * BUFLEN))
+    value = samples_step / (ms_step * 1e-3) / 1e6
+    peak, peak_src = measured_peak()
+    achieved = (S * B * BUFLEN * BYTES_PER_SAMPLE) / ((ms_total / args.steps) * 1e-3) / 1e9  # this rank's GB/s
+    traffic = ncu_traffic()
+
+    # ---- e2e: host buffers through the public pipelined call, same batch size ----------------------
+    rx = rxs[0]
+    rx.reset()
+    depth = 4
+    hin = [g.pinned_empty(BUFLEN) for _ in range(depth)]
+    hout = [g.pinned_empty(rx.max_output()) for _ in range(depth)]
+    for k in range(depth):
+        hin[k][:] = distinct[k % 4]
+    e2e_steps = max(2, min(args.steps, 10))
+
+    def e2e_pass(n_buf):
+        tickets, d2h = [], 0
+        for b in range(n_buf):
+            k = b % depth
+            if len(tickets) >= depth - 1:
+                rx.wait(tickets.pop(0))
+            t, n = rx.submit(hin[k], hout[k])
+            d2h += n * 8
+            tickets.append(t)
+        for t in tickets:
+            rx.wait(t)
+        return d2h
+
+    e2e_pass(B)  # warm-up
+    dd.barrier()
+    t0 = time.perf_counter()
+    d2h_bytes = 0
+    for _ in range(e2e_steps):
+        d2h_bytes = e2e_pass(B)
+    e2e_s = dd.max((time.perf_counter() - t0) / e2e_steps)
+    e2e_val = dd.sum(float(B * BUFLEN)) / e2e_s / 1e6
+    # blocking drop-in call (submit+wait per buffer), for the record
+    rx.reset()
+    t0 = time.perf_counter()
+    for b in range(B):
+        rx.process(hin[b % depth], hout[b % depth])
+    blocking_val = B * BUFLEN / (time.perf_counter() - t0) / 1e6
+
+    res = {
+        "metric": "demodulated input MS/s (1000-tone PFB, whole job)", "value": value, "unit": "MS/s",
+        "n_gpus": dd.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"cfg2 TONES PFB: N={NFFT} channels, P={PTAPS} taps, T={NTONES} tones, pf_average={PTAPS}, "
+                               f"{args.streams} x 200 MS/s stream per GPU, {B} transport buffers of 1e6 samples per step",
+                   "streams_per_gpu": args.streams, "buffers_per_step": B, "buffer_len": BUFLEN,
+                   "l2": "inputs larger than L2: two alternating 512 MB device batches per stream",
+                   "kernel": kernel_name},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
+                     "bytes_per_sample": BYTES_PER_SAMPLE, "samples_per_launch": S * B * BUFLEN,
+                     "launch_ms": ms_total / args.steps},
+        "e2e": {"value": e2e_val, "unit": "MS/s", "h2d_bytes_per_step": B * BUFLEN * 8, "d2h_bytes_per_step": d2h_bytes,
+                "api": "gsdr_rx_submit/gsdr_rx_wait (pinned host in/out, depth-3 pipeline)", "steps": e2e_steps,
+                "blocking_process_value": blocking_val},
+        "gpu_launches": int(l1 - l0), "clocks": clocks,
+    }
+    if dd.rank == 0 and dd.world == 1 and not args.no_cpu:
+        res["cpu_baseline"] = cpu_baseline(p)
+    for r in rxs:
+        r.close()
+    return res
+
+
+# ---- reference arm -------------------------------------------------------------------------------
+def run_reference(args, dd: Dist):
+    if dd.rank != 0:
+        return None
+    from tests.common import RefRX, ref_lib  # test infrastructure: the reference's own object code
+    p = workload_param()
+    B = args.buffers
+    lib = ref_lib()
+    cpu = cpu_baseline(p, budget_s=8.0)
+    if lib is None or lib.gsdr_ref_device_count() <= 0:
+        # reference object library not built / no GPU: the oracle port is the only runnable restatement
+        return {"impl": "reference", "metric": "demodulated input MS/s (1000-tone PFB, whole job)", "value": cpu["value"],
+                "unit": "MS/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
+                "ms_per_step": B * BUFLEN / (cpu["value"] * 1e6) * 1e3, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": {"workload": "cfg2 TONES PFB (CPU port; oracle/_ref unavailable)"},
+                "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    ref = RefRX(p)
+    distinct = synth_buffers(p, 4, SEED)
+    hin = []
+    for k in range(4):
+        ptr = lib.gsdr_ref_host_alloc(BUFLEN * 8)
+        a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(2 * BUFLEN,)).view(np.complex64)
+        a[:] = distinct[k]
+        hin.append((ptr, a))
+    cap = NTONES * lib.gsdr_ref_rx_batching(ref.h)
+    optr = lib.gsdr_ref_host_alloc(cap * 8)
+    last = C.c_int(0)
+    steps = max(1, min(args.steps, 10))
+
+    def one_step():
+        tot = 0.0
+        for b in range(B):
+            tot += lib.gsdr_ref_rx_process_timed(ref.h, hin[b % 4][0], optr, 1, C.byref(last))
+        return tot
+
+    for _ in range(max(1, min(args.warmup, 3))):
+        one_step()
+    t = [one_step() for _ in range(steps)]
+    sec = sum(t) / len(t)
+    val = B * BUFLEN / sec / 1e6
+    ref.close()
+    return {"impl": "reference", "metric": "demodulated input MS/s (1000-tone PFB, whole job)", "value": val, "unit": "MS/s",
+            "n_gpus": 1, "steps": steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"cfg2 TONES PFB: N={NFFT}, P={PTAPS}, T={NTONES}, one 200 MS/s stream, {B} transport buffers "
+                                   "of 1e6 samples per step through RX_buffer_demodulator::process (pinned host in/out)",
+                       "reference": "unmodified cpp/kernels.cu + cpp/USRP_demodulator.cpp compiled for sm_100a "
+                                    "(oracle/_ref/libgsdr_ref.so); the reference has no CPU DSP path, so this arm runs "
+                                    "its CUDA path on the same B200"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": val, "unit": "MS/s", "h2d_bytes_per_step": B * BUFLEN * 8, "d2h_bytes_per_step": B * cap * 8},
+            "gpu_launches": 0}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--buffers", type=int, default=64, help="transport buffers per step (batch)")
+    ap.add_argument("--streams", type=int, default=1, help="IQ streams per GPU")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    args.steps = max(args.steps, 1)
+    dd = Dist(args.gpus)
+    try:
+        res = run_reference(args, dd) if args.impl == "reference" else run_ours(args, dd)
+        if dd.rank == 0 and res is not None:
+            print(json.dumps(res), flush=True)
+    finally:
+        dd.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -35,15 +35,20 @@ __device__ __forceinline__ float2 lo_phasor(long long ph, double inv_R) {
     return make_float2(c, -s);
 }
 
+// kStaged: the block's input span is staged in shared memory once and reused by every tone group;
+// otherwise (very long filters) the taps stream straight from global memory through L1/L2.
+template <bool kStaged>
 __global__ void __launch_bounds__(WARPS * 32)
 direct_fir_kernel(const Window w, const float2* __restrict__ g, const int* __restrict__ freq, int T, int M, int ntaps,
                   int rate, long long pos0, long long n_out, int PB, float2* __restrict__ out) {
     extern __shared__ __align__(16) float2 xs[];  // (PB-1)*M + ntaps samples
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long p0 = (long long)blockIdx.x * PB;
-    const int span = (PB - 1) * M + ntaps;
-    for (int i = threadIdx.x; i < span; i += blockDim.x) xs[i] = dev_win_at(w, p0 * M + i);
-    __syncthreads();
+    if (kStaged) {
+        const int span = (PB - 1) * M + ntaps;
+        for (int i = threadIdx.x; i < span; i += blockDim.x) xs[i] = dev_win_at(w, p0 * M + i);
+        __syncthreads();
+    }
 
     const int tone_groups = (T + TC - 1) / TC;
     const int out_groups = PB / TP;
@@ -59,10 +64,11 @@ direct_fir_kernel(const Window w, const float2* __restrict__ g, const int* __res
 #pragma unroll
         for (int b = 0; b < TC; ++b) gbase[b] = g + (long long)min(tg * TC + b, T - 1) * ntaps;
         const float2* xbase = xs + (og * TP) * M;
+        const long long gpos = (p0 + og * TP) * M;
         for (int m = lane; m < ntaps; m += 32) {
             float2 xv[TP], gv[TC];
 #pragma unroll
-            for (int a = 0; a < TP; ++a) xv[a] = xbase[a * M + m];
+            for (int a = 0; a < TP; ++a) xv[a] = kStaged ? xbase[a * M + m] : dev_win_at(w, gpos + (long long)a * M + m);
 #pragma unroll
             for (int b = 0; b < TC; ++b) gv[b] = __ldg(gbase[b] + m);
 #pragma unroll
@@ -152,21 +158,22 @@ int direct_fir_launch(const Window& w, const float2* g, const int* freq_dev, int
     // outputs per block: as many as fit 96 KB of staged input, multiple of TP, at most 64
     int PB = 64;
     while (PB > TP && ((size_t)(PB - 1) * M + ntaps) * sizeof(float2) > 96 * 1024) PB -= TP;
-    const size_t smem = ((size_t)(PB - 1) * M + ntaps) * sizeof(float2);
-    if (smem > 200 * 1024) {
-        set_error("direct_fir_launch: decimation %d x %d taps needs %zu B of shared memory", M, ntaps, smem);
-        return -1;
-    }
+    size_t smem = ((size_t)(PB - 1) * M + ntaps) * sizeof(float2);
+    const bool staged = smem <= 96 * 1024;
+    if (!staged) smem = 0;
     static size_t configured = 0;
     if (smem > configured) {
-        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
     const int units = (PB / TP) * ((T + TC - 1) / TC);
     int gy = (units + WARPS - 1) / WARPS;
     if (gy > 8) gy = 8;
     dim3 grid((unsigned)((n_out + PB - 1) / PB), gy);
-    direct_fir_kernel<<<grid, WARPS * 32, smem, stream>>>(w, g, freq_dev, T, M, ntaps, rate, pos0, n_out, PB, out);
+    if (staged)
+        direct_fir_kernel<true><<<grid, WARPS * 32, smem, stream>>>(w, g, freq_dev, T, M, ntaps, rate, pos0, n_out, PB, out);
+    else
+        direct_fir_kernel<false><<<grid, WARPS * 32, 0, stream>>>(w, g, freq_dev, T, M, ntaps, rate, pos0, n_out, PB, out);
     GSDR_CUDA_OK(cudaGetLastError());
     return 1;
 }

@@ -15,6 +15,7 @@
 #undef private
 
 #include <chrono>
+#include <new>
 #include "../include/gsdr.h"
 
 // ---- non-DSP symbols normally provided by USRP_server_settings.cpp / USRP_server_diagnostic.cpp
@@ -70,7 +71,11 @@ int gsdr_ref_device_count() {
 void* gsdr_ref_rx_create(const gsdr_param* g) {
     ref_rx* r = new ref_rx();
     r->p = make_param(g);
-    r->d = new RX_buffer_demodulator(r->p, false);  // cpp/USRP_server_link_threads.cpp:121
+    // The class leaves several members uninitialised (e.g. `handle`, which close_pfb/close_chirp
+    // pass to cublasDestroy even when no handle was created).  Constructing into zeroed storage
+    // gives them the value a fresh heap page has, so close() is deterministic in a long test run.
+    void* mem = calloc(1, sizeof(RX_buffer_demodulator));
+    r->d = new (mem) RX_buffer_demodulator(r->p, false);  // cpp/USRP_server_link_threads.cpp:121
     cudaDeviceSynchronize();
     return r;
 }
@@ -98,7 +103,8 @@ double gsdr_ref_rx_process_timed(void* h, gsdr_float2* in, gsdr_float2* out, int
 void gsdr_ref_rx_close(void* h) {
     ref_rx* r = (ref_rx*)h;
     r->d->close();
-    delete r->d;
+    r->d->~RX_buffer_demodulator();
+    free(r->d);
     delete r->p;
     delete r;
 }
@@ -134,7 +140,8 @@ void* gsdr_ref_tx_create(const gsdr_param* g) {
     ref_tx* t = new ref_tx();
     t->p = make_param(g);
     t->p->mode = TX;
-    t->g = new TX_buffer_generator(t->p);  // cpp/USRP_server_link_threads.cpp:191
+    void* mem = calloc(1, sizeof(TX_buffer_generator));
+    t->g = new (mem) TX_buffer_generator(t->p);  // cpp/USRP_server_link_threads.cpp:191
     cudaDeviceSynchronize();
     return t;
 }
@@ -157,7 +164,8 @@ int gsdr_ref_tx_chirp_param(void* h, gsdr_chirp_param* out) {
 void gsdr_ref_tx_close(void* h) {
     ref_tx* t = (ref_tx*)h;
     t->g->close();
-    delete t->g;
+    t->g->~TX_buffer_generator();
+    free(t->g);
     delete t->p;
     delete t;
 }

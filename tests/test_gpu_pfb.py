@@ -1,0 +1,195 @@
+"""TONES-mode PFB channelizer: CUDA path (through the C-ABI) vs the fp64 oracle, vs cuFFT, and
+size-independent properties at the full cfg2 size.  Float tolerance: relative L2 <= 1e-5
+(BASELINE.json north_star); valid lengths and bins are integers and must match exactly."""
+import numpy as np
+import pytest
+
+from common import TOL, g, orc, pfb_param, rx_run, tone_stream
+
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("gpu_required")]
+
+
+def check_against_oracle(p, bufs, expect_kernel=None):
+    rx = g.RX_buffer_demodulator(p)
+    if expect_kernel:
+        assert expect_kernel in rx.kernel_name(), rx.kernel_name()
+    o = orc.PFBDemodulator(p.rate, p.fft_tones, p.pf_average, p.buffer_len, p.freq)
+    assert np.array_equal(rx.bins(), np.where(o.bins < 0, 0, o.bins))
+    assert np.array_equal(rx.taps(), o.window32)
+    out = g.pinned_empty(rx.max_output())
+    worst = 0.0
+    for x in bufs:
+        n = rx.process(x, out)
+        want = o.process(x)
+        assert n == len(want)  # integer bookkeeping: exact
+        worst = max(worst, orc.rel_l2(out[:n], want))
+    rx.close()
+    assert worst <= TOL, worst
+    return worst
+
+
+@pytest.mark.parametrize("P", [1, 2, 3, 4])
+@pytest.mark.parametrize("T", [1, 17, 1000])
+def test_fused_2048_vs_oracle(P, T):
+    p = pfb_param(N=2048, P=P, T=T, L=200_000)
+    bufs = [tone_stream(p.rate, p.freq, p.ampl, i * p.buffer_len, p.buffer_len) for i in range(4)]
+    check_against_oracle(p, bufs, "pfb_fused_2048")
+
+
+def test_cfg2_full_size_eight_buffers():
+    """cfg2 exactly: 1e6-sample buffers, 8 of them so the 6-state carry-over cycle is covered."""
+    p = pfb_param()
+    rx = g.RX_buffer_demodulator(p)
+    o = orc.PFBDemodulator(p.rate, 2048, 4, 1_000_000, p.freq)
+    out = g.pinned_empty(rx.max_output())
+    lens = []
+    for i in range(8):
+        x = tone_stream(p.rate, p.freq[:64], p.ampl[:64], i * 1_000_000, 1_000_000)
+        n = rx.process(x, out)
+        want = o.process(x)
+        lens.append(n)
+        assert n == len(want)
+        assert orc.rel_l2(out[:n], want) <= TOL
+    assert lens[:5] == [485000, 488000, 488000, 489000, 488000]
+    rx.close()
+
+
+@pytest.mark.parametrize("N,P,T,L,rate", [(100, 3, 7, 50_000, 1_000_000), (64, 4, 8, 20_000, 1_000_000),
+                                          (10, 1, 3, 50_000, 1_000_000), (2048, 8, 33, 100_000, 200_000_000),
+                                          (4096, 4, 50, 100_000, 200_000_000), (1000, 2, 100, 60_000, 100_000_000),
+                                          (3001, 2, 5, 50_000, 1_000_000)])
+def test_generic_path_vs_oracle(N, P, T, L, rate):
+    p = pfb_param(rate=rate, N=N, P=P, T=T, L=L)
+    bufs = [tone_stream(rate, p.freq, p.ampl, i * L, L) for i in range(3)]
+    check_against_oracle(p, bufs, "generic")
+
+
+def test_odd_buffer_length_uses_unaligned_path():
+    p = pfb_param(N=2048, P=4, T=40, L=100_001)
+    bufs = [tone_stream(p.rate, p.freq, p.ampl, i * p.buffer_len, p.buffer_len) for i in range(5)]
+    check_against_oracle(p, bufs, "pfb_fused_2048")
+
+
+def test_buffer_shorter_than_filter_span():
+    """L < P*N: some calls produce zero frames; the carry-over must keep accumulating."""
+    p = pfb_param(N=2048, P=4, T=9, L=3000)
+    bufs = [tone_stream(p.rate, p.freq, p.ampl, i * 3000, 3000) for i in range(9)]
+    check_against_oracle(p, bufs)
+
+
+def test_known_answer_bin_centre_tone():
+    """A tone exactly on a bin centre comes out as its amplitude in every frame (taps sum to 1)."""
+    rate, N, L = 200_000_000, 2048, 100_000
+    rate, f = 204_800_000, 37 * 100_000  # bin width exactly 100 kHz
+    p = g.param(rate=rate, fft_tones=N, pf_average=4, buffer_len=L, freq=[f, -f], wave_type=[g.TONES] * 2, ampl=[1, 1])
+    n = np.arange(L, dtype=np.int64)
+    x = (0.25 * np.exp(2j * np.pi * ((f * n) % rate) / rate)).astype(np.complex64)
+    out = rx_run(p, [x])[0].reshape(-1, 2)
+    assert np.allclose(np.abs(out[:, 0]), 0.25, rtol=2e-5)
+    assert np.all(np.abs(out[:, 1]) < 1e-3)  # far-away bin: only filter leakage
+
+
+def test_scaling_by_power_of_two_is_bit_exact():
+    """Linearity property at the full cfg2 size: every stage is linear, so x/4 -> out/4 exactly."""
+    p = pfb_param()
+    x = tone_stream(p.rate, p.freq[:16], p.ampl[:16], 0, p.buffer_len)
+    a = rx_run(p, [x])[0]
+    b = rx_run(p, [(x * np.float32(0.25)).astype(np.complex64)])[0]
+    assert np.array_equal(a * np.float32(0.25), b)
+
+
+def test_device_batch_equals_sequential_calls():
+    """process_device over n buffers == n process() calls, bit for bit, including valid lengths."""
+    p = pfb_param(N=2048, P=4, T=100, L=150_000)
+    bufs = [tone_stream(p.rate, p.freq, p.ampl, i * p.buffer_len, p.buffer_len) for i in range(5)]
+    seq = rx_run(p, bufs)
+    rx = g.RX_buffer_demodulator(p)
+    din = g.DeviceBuffer(5 * p.buffer_len)
+    din.upload(np.concatenate(bufs))
+    dout = g.DeviceBuffer(rx.max_output_batch(5))
+    tot, lens = rx.process_device(din.ptr, 5, dout.ptr)
+    rx.sync()
+    got = dout.download(tot)
+    assert lens == [len(s) for s in seq]
+    assert np.array_equal(got, np.concatenate(seq))
+    # two more single-buffer calls continue the stream seamlessly
+    more = [tone_stream(p.rate, p.freq, p.ampl, (5 + i) * p.buffer_len, p.buffer_len) for i in range(2)]
+    out = g.pinned_empty(rx.max_output())
+    o = orc.PFBDemodulator(p.rate, 2048, 4, p.buffer_len, p.freq)
+    for x in bufs:
+        o.process(x)
+    for x in more:
+        n = rx.process(x, out)
+        want = o.process(x)
+        assert n == len(want) and orc.rel_l2(out[:n], want) <= TOL
+    rx.close()
+
+
+def test_group_launch_matches_individual_streams():
+    ps = [pfb_param(N=2048, P=4, T=t, L=120_000, seed=s) for t, s in ((100, 1), (1000, 2), (7, 3))]
+    bufs = [[tone_stream(p.rate, p.freq, p.ampl, i * p.buffer_len, p.buffer_len, seed=10 + j) for i in range(3)]
+            for j, p in enumerate(ps)]
+    want = [np.concatenate(rx_run(p, b)) for p, b in zip(ps, bufs)]
+    rxs = [g.RX_buffer_demodulator(p) for p in ps]
+    grp = g.RxGroup(rxs)
+    dins = []
+    for b in bufs:
+        d = g.DeviceBuffer(3 * 120_000)
+        d.upload(np.concatenate(b))
+        dins.append(d)
+    douts = [g.DeviceBuffer(r.max_output_batch(3)) for r in rxs]
+    tot, lens = grp.process_device([d.ptr for d in dins], 3, [d.ptr for d in douts])
+    grp.sync()
+    for j in range(3):
+        got = douts[j].download(int(lens[j].sum()))
+        assert np.array_equal(got, want[j])
+    assert tot == sum(len(w) for w in want)
+    grp.close()
+    for r in rxs:
+        r.close()
+
+
+def test_noise_mode_full_spectrum():
+    """NOISE (decim=0): every bin in natural order, copy_size = N*current_batch."""
+    rate, N, L = 200_000_000, 2048, 100_000
+    p = g.param(rate=rate, fft_tones=N, pf_average=4, buffer_len=L, freq=[1_000_000], wave_type=[g.NOISE], ampl=[1.0])
+    x = tone_stream(rate, [1_000_000, -30_000_000], [0.3, 0.2], 0, L)
+    out = rx_run(p, [x])[0]
+    o = orc.PFBDemodulator(rate, N, 4, L, list(range(0)))
+    o.bins = np.arange(N, dtype=np.int32)
+    o.T = N
+    want = o.process(x)
+    assert len(out) == len(want) == N * 45
+    assert orc.rel_l2(out, want) <= TOL
+
+
+def test_in_kernel_fft_agrees_with_cufft():
+    """north_star: the in-shared-memory radix FFT is checked against cuFFT (via torch.fft on the GPU)."""
+    torch = pytest.importorskip("torch")
+    p = pfb_param(N=2048, P=4, T=2048 - 1, L=100_000)
+    x = tone_stream(p.rate, p.freq[:50], p.ampl[:50], 0, p.buffer_len)
+    rx = g.RX_buffer_demodulator(p)
+    bins, taps = rx.bins(), rx.taps().reshape(4, 2048)
+    rx.close()
+    ours = rx_run(p, [x])[0].reshape(-1, len(bins))
+    cb = ours.shape[0]
+    rows = x[: (cb + 3) * 2048].reshape(cb + 3, 2048)
+    z = sum(rows[i:i + cb] * taps[i] for i in range(4)).astype(np.complex64)
+    spec = torch.fft.fft(torch.from_numpy(z).cuda(), dim=1).cpu().numpy()
+    assert orc.rel_l2(ours, spec[:, bins]) <= TOL
+
+
+def test_unsupported_configurations_fail_loudly():
+    with pytest.raises(g.GsdrError, match="Mixed RX"):
+        g.RX_buffer_demodulator(g.param(rate=1_000_000, fft_tones=64, buffer_len=10_000, freq=[1, 2], wave_type=[g.TONES, g.DIRECT]))
+    with pytest.raises(g.GsdrError, match="Multiple chirp"):
+        g.RX_buffer_demodulator(g.param(rate=1_000_000, buffer_len=10_000, freq=[1, 2], wave_type=[g.CHIRP, g.CHIRP],
+                                        chirp_t=[1, 1], chirp_f=[2, 2], swipe_s=[3, 3]))
+    with pytest.raises(g.GsdrError):
+        g.RX_buffer_demodulator(g.param(rate=1_000_000, buffer_len=10_000, freq=[1], wave_type=[g.RAMP]))
+
+
+def test_nodsp_passthrough():
+    p = g.param(rate=1_000_000, buffer_len=10_000, wave_type=[])
+    x = tone_stream(1_000_000, [1000], [0.5], 0, 10_000)
+    assert np.array_equal(rx_run(p, [x])[0], x)

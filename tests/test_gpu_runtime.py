@@ -1,0 +1,138 @@
+"""Pinned pool, pipelined submit/wait, replay source, full-duplex loop (cfg4, scaled)."""
+import threading
+
+import numpy as np
+import pytest
+
+from common import TOL, g, orc, pfb_param, rx_run, tone_stream
+
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("gpu_required")]
+
+
+def test_pool_get_trash_close():
+    pool = g.preallocator(10_000, 6)
+    assert pool.size() == 5  # the reference pre-fills pipe_size-1 buffers
+    got = [pool.get() for _ in range(5)]
+    assert len({b.ctypes.data for b in got}) == 5
+    for b in got:
+        b[:] = 1 + 2j
+    extra = pool.get()  # pool dry: the grower thread supplies one more, like the reference's filler
+    assert pool.size() >= 6
+    for b in got + [extra]:
+        pool.trash(b)
+    assert pool.available() == pool.size()
+    pool.close()
+
+
+def test_pool_blocks_until_trash_when_growth_disabled():
+    pool = g.preallocator(1000, 3, prefill_init=False)
+    a, b = pool.get(), pool.get()
+    res = []
+    t = threading.Thread(target=lambda: res.append(pool.get()))
+    t.start()
+    t.join(0.3)
+    assert t.is_alive()
+    pool.trash(a)
+    t.join(2)
+    assert not t.is_alive() and res[0].ctypes.data == a.ctypes.data
+    pool.trash(b)
+    pool.trash(res[0])
+    pool.close()
+
+
+def test_pipelined_submit_wait_matches_blocking():
+    p = pfb_param(N=2048, P=4, T=200, L=200_000)
+    bufs = [tone_stream(p.rate, p.freq, p.ampl, i * p.buffer_len, p.buffer_len) for i in range(7)]
+    want = rx_run(p, bufs)
+    rx = g.RX_buffer_demodulator(p)
+    pool_in, pool_out = g.preallocator(p.buffer_len, 8), g.preallocator(rx.max_output(), 8)
+    pending, got = [], []
+    for x in bufs:
+        hin, hout = pool_in.get(), pool_out.get()
+        hin[:] = x
+        t, n = rx.submit(hin, hout)
+        pending.append((t, n, hin, hout))
+        if len(pending) == 3:
+            t0, n0, i0, o0 = pending.pop(0)
+            rx.wait(t0)
+            got.append(o0[:n0].copy())
+            pool_in.trash(i0)
+            pool_out.trash(o0)
+    for t0, n0, i0, o0 in pending:
+        rx.wait(t0)
+        got.append(o0[:n0].copy())
+    assert all(np.array_equal(a, b) for a, b in zip(got, want))
+    rx.close()
+    pool_in.close()
+    pool_out.close()
+
+
+def test_replay_loopback_tones_known_answer():
+    """Replay source in TX_LOOP mode == --sw_loop: RX sees exactly the TX waveform; with tones on
+    bin centres every selected bin is the tone amplitude in every frame."""
+    rate, N, L, T = 204_800_000 // 100, 2048, 100_000, 16  # 2.048 MS/s: bin width 1 kHz exactly
+    ks = [3, -7, 100, -1000, 511, 77, -300, 900, 12, -13, 640, -641, 1, -1, 250, -999]
+    freq = [k * 1000 for k in ks]
+    p = g.param(mode="RX", rate=rate, fft_tones=N, pf_average=4, buffer_len=L, freq=freq, ampl=[1.0 / T] * T, wave_type=[g.TONES] * T)
+    pool = g.preallocator(L, 8)
+    src = g.ReplaySource(p, pool, kind=g.ReplaySource.TX_LOOP, front_end_code="B")
+    rx = g.RX_buffer_demodulator(p)
+    out = g.pinned_empty(rx.max_output())
+    for k in range(4):
+        pkt, buf = src.next()
+        assert (pkt.packet_number, pkt.length, pkt.errors, pkt.channels, pkt.front_end_code) == (k + 1, L, 0, T, b"B")
+        n = rx.process(buf, out)
+        pool.trash(buf)
+        y = out[:n].reshape(-1, T)
+        assert np.allclose(np.abs(y), 1.0 / T, rtol=1e-4)
+    rx.close()
+    src.close()
+    pool.close()
+
+
+def test_replay_with_noise_is_deterministic_and_parity_holds():
+    p = pfb_param(rate=2_000_000, N=2048, P=4, T=50, L=60_000)
+    outs = []
+    for _ in range(2):
+        pool = g.preallocator(p.buffer_len, 4)
+        src = g.ReplaySource(p, pool, kind=g.ReplaySource.TONES_NOISE, noise_sigma=1e-3, seed=99)
+        bufs = []
+        for _k in range(3):
+            _pkt, b = src.next()
+            bufs.append(b[: p.buffer_len].copy())
+            pool.trash(b)
+        src.close()
+        pool.close()
+        outs.append(bufs)
+    assert all(np.array_equal(a, b) for a, b in zip(*outs))
+    o = orc.PFBDemodulator(p.rate, 2048, 4, p.buffer_len, p.freq)
+    for a, x in zip(rx_run(p, outs[0]), outs[0]):
+        assert orc.rel_l2(a, o.process(x)) <= TOL
+
+
+def test_full_duplex_two_front_ends_concurrently():
+    """cfg4 (scaled): two front-ends, each TX TONES -> loopback -> RX, driven from two threads on one GPU."""
+    rate, L, T = 2_048_000, 100_000, 100
+    results = {}
+
+    def front_end(code, seed):
+        rng = np.random.default_rng(seed)
+        ks = rng.choice(np.arange(-1000, 1000), size=T, replace=False)
+        freq = [int(k) * 1000 for k in ks]
+        p = g.param(mode="RX", rate=rate, fft_tones=2048, pf_average=4, buffer_len=L, freq=freq, ampl=[1.0 / T] * T,
+                    wave_type=[g.TONES] * T)
+        tx = g.TX_buffer_generator(p)
+        rx = g.RX_buffer_demodulator(p)
+        out = g.pinned_empty(rx.max_output())
+        ok = True
+        for _ in range(5):
+            n = rx.process(tx.get(), out)
+            ok = ok and np.allclose(np.abs(out[:n]), 1.0 / T, rtol=1e-4)
+        rx.close()
+        tx.close()
+        results[code] = ok
+
+    th = [threading.Thread(target=front_end, args=(c, s)) for c, s in (("A", 1), ("B", 2))]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert results == {"A": True, "B": True}

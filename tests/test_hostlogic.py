@@ -1,0 +1,147 @@
+"""Host-side logic that defines results: product (libgsdr.so) vs the C oracle vs the golden
+fixtures produced by the reference's own object code -- all BIT-EXACT.  No GPU needed."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+from common import GOLDEN, g, orc, ref_lib
+
+HL = g.hostlogic
+
+
+def golden(name):
+    path = os.path.join(GOLDEN, name)
+    if not os.path.exists(path):
+        pytest.skip(f"{name} not generated yet (tests/golden/make_golden.py)")
+    return np.load(path)
+
+
+def test_survey_worked_values():
+    # ceil-style tone->bin rule
+    assert list(HL.tone_bins(200_000_000, 2048, [292968, -292968, 1, -1, 0])) == [3, 2046, 1, 0, 0]
+    # row a9: cfg2 carry-over sequence (eff, cb, spare, spare_begin)
+    seq = HL.buffer_helper_sequence(2048, 1_000_000, 4, 1000, 5)
+    cols = [HL.BH_FIELDS.index(k) for k in ("eff_length", "current_batch", "spare_samples", "spare_begin")]
+    assert seq[:, cols].tolist() == [[1000000, 485, 6720, 993280], [1006720, 488, 7296, 999424], [1007296, 488, 7872, 999424],
+                                     [1007872, 489, 6400, 1001472], [1006400, 488, 6976, 999424]]
+    assert HL.pfb_batching(1_000_000, 2048, 4) == 498
+    # row a10: cfg3 chirp quantisation; client-side restatement pyUSRP/USRP_VNA.py:740
+    cp = HL.chirp_params(200_000_000, -50_000_000, 50_000_000, 100_000, 1.0)
+    assert (cp.num_steps, cp.length, cp.chirpness, cp.f0) == (100000, 2000, 21475, -1073741823)
+    assert cp.chirpness == int((2**32 - 1) * (50e6 - -50e6) / (100000 - 1) / 200e6)
+    # row a3/KAT 3: 400-tap cfg1 filter
+    taps = HL.make_sinc_window(400, float(np.float32(0.75 / 200)))
+    assert int(np.argmax(taps)) == 199 and abs(float(taps.astype(np.float64).sum()) - 1.0) < 1e-6
+    # make_flat_window zeroes only the LEADING side taps
+    flat = HL.make_flat_window(2000, 200)
+    assert np.all(flat[:200] == 0) and np.all(flat[200:] == np.float32(1.0) / np.float32(1800.0))
+
+
+@pytest.mark.parametrize("L,fc", [(8192, 1.0 / 4096), (400, 0.75 / 200), (401, 0.01), (256, 1.0 / 128), (300, 1.0 / 200),
+                                  (80, 0.75 / 20), (7, 0.2), (2, 0.25), (16384, 1.0 / 8192), (20000, 0.75 / 10000)])
+def test_sinc_window_product_equals_oracle(L, fc):
+    fc = float(np.float32(fc))
+    assert np.array_equal(HL.make_sinc_window(L, fc), orc.make_sinc_window(L, fc))
+
+
+@pytest.mark.parametrize("L,side", [(2000, 200), (6000, 600), (200, 20), (7, 0), (1, 0), (33, 3), (10, 9)])
+def test_flat_window_product_equals_oracle(L, side):
+    assert np.array_equal(HL.make_flat_window(L, side), orc.make_flat_window(L, side))
+
+
+def test_helpers_product_equals_oracle_randomised():
+    rng = np.random.default_rng(7)
+    for _ in range(60):
+        N, P = int(rng.integers(2, 5000)), int(rng.integers(1, 9))
+        L, T = int(rng.integers(max(N, 1000), 2_000_000)), int(rng.integers(1, 50))
+        h = orc.BufferHelper(N, L, P, T)
+        rows = []
+        for _i in range(12):
+            rows.append(h.state())
+            h.update()
+        assert np.array_equal(HL.buffer_helper_sequence(N, L, P, T, 12), np.array(rows))
+        assert HL.pfb_batching(L, N, P) == orc.pfb_batching(L, N, P)
+        ppt = int(rng.integers(1, 3_000_000))
+        v = orc.VNAHelper(ppt, L)
+        rows = []
+        for _i in range(12):
+            rows.append(v.state())
+            v.update()
+        assert np.array_equal(HL.vna_helper_sequence(ppt, L, 12), np.array(rows))
+
+
+def test_tone_bins_product_equals_oracle_randomised():
+    rng = np.random.default_rng(8)
+    for rate, N in ((200_000_000, 2048), (100_000_000, 1000), (1_000_000, 100), (10_000_000, 4096), (250_000_000, 10), (999_983, 77)):
+        freq = rng.integers(-rate // 2 - 10, rate // 2 + 10, size=300).astype(np.int32)
+        bs = rate / N
+        freq[:50] = (rng.integers(-N // 2, N // 2, size=50) * bs).astype(np.int32)  # truncated bin centres
+        assert np.array_equal(HL.tone_bins(rate, N, freq), orc.tone_bins(rate, N, freq))
+
+
+def test_chirp_params_product_equals_oracle_randomised():
+    rng = np.random.default_rng(9)
+    for _ in range(300):
+        rate = int(rng.choice([1_000_000, 100_000_000, 200_000_000, 250_000_000]))
+        f0, f1 = int(rng.integers(-rate // 2, rate // 2)), int(rng.integers(-rate // 2, rate // 2))
+        steps = int(rng.choice([0, 1, 2, 10, 1000, 100_000, 1_000_000]))
+        t = float(np.float32(rng.choice([1e-7, 1e-4, 1e-3, 0.01, 0.5, 1.0, 3.0])))
+        for tx in (False, True):
+            a, b = HL.chirp_params(rate, f0, f1, steps, t, tx), orc.chirp_params(rate, f0, f1, steps, t, tx)
+            assert (a.num_steps, a.length, a.chirpness, a.f0) == (b.num_steps, b.length, b.chirpness, b.f0)
+
+
+# ---- against the reference itself (fixtures made by its object code; live library when built) ----
+def test_golden_windows_and_helpers():
+    z = golden("host_logic.npz")
+    n = 0
+    for key in z.files:
+        kind, *args = key.split("_")
+        if kind == "sinc":
+            L, fc = int(args[0]), float(args[1])
+            assert np.array_equal(HL.make_sinc_window(L, fc), z[key]), key
+            assert np.array_equal(orc.make_sinc_window(L, fc), z[key]), key
+        elif kind == "flat":
+            L, side = int(args[0]), int(args[1])
+            assert np.array_equal(HL.make_flat_window(L, side), z[key]), key
+            assert np.array_equal(orc.make_flat_window(L, side), z[key]), key
+        elif kind == "bh":
+            N, L, P, T = map(int, args)
+            assert np.array_equal(HL.buffer_helper_sequence(N, L, P, T, 16), z[key]), key
+        elif kind == "vna":
+            ppt, L = map(int, args)
+            assert np.array_equal(HL.vna_helper_sequence(ppt, L, 16), z[key]), key
+        n += 1
+    assert n >= 20
+
+
+def test_golden_tone_bins():
+    z = golden("tone_bins.npz")
+    for tag, rate, N in (("edge", 200_000_000, 2048), ("full", 200_000_000, 2048), ("odd", 1_000_000, 100)):
+        f, want = z[tag + "_freq"], z[tag + "_bins"]
+        assert np.array_equal(HL.tone_bins(rate, N, f), want), tag
+        assert np.array_equal(orc.tone_bins(rate, N, f), want), tag
+
+
+@pytest.mark.skipif(ref_lib() is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_live_reference_object_code_host_side():
+    """The reference's own make_sinc_window / buffer_helper / VNA_decimator_helper run on the CPU."""
+    lib = ref_lib()
+    for L, fc in [(8192, 1.0 / 4096), (400, 0.75 / 200), (401, 0.01), (300, 1.0 / 200), (5000, 0.75 / 2500)]:
+        fc = float(np.float32(fc))
+        w = np.empty(L, dtype=np.float32)
+        lib.gsdr_ref_make_sinc_window(L, C.c_float(fc), w.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(HL.make_sinc_window(L, fc), w) and np.array_equal(orc.make_sinc_window(L, fc), w)
+    rng = np.random.default_rng(10)
+    for _ in range(40):
+        N, P = int(rng.integers(2, 5000)), int(rng.integers(1, 9))
+        L, T = int(rng.integers(max(N, 1000), 2_000_000)), int(rng.integers(1, 50))
+        out = np.empty((12, 6), dtype=np.int32)
+        lib.gsdr_ref_buffer_helper_seq(N, L, P, T, 12, out.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(HL.buffer_helper_sequence(N, L, P, T, 12), out)
+        ppt = int(rng.integers(1, 3_000_000))
+        out = np.empty((12, 4), dtype=np.int32)
+        lib.gsdr_ref_vna_helper_seq(ppt, L, 12, out.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(HL.vna_helper_sequence(ppt, L, 12), out)
