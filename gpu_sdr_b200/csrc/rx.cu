@@ -294,13 +294,13 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
                     if (lens) lens[b] = (int)L;
                 total = L * n_buf;
             } else {
-                long long n_out = 0;
+                long long n_out = 0, tail = 0;
                 for (int b = 0; b < n_buf; ++b) {
                     if (lens) lens[b] = rx->vh.valid_size;
                     n_out += rx->vh.valid_size;
+                    tail = rx->vh.new0;  // remainder of THIS buffer (the reference reads new0 before update())
                     vna_helper_update(&rx->vh);
                 }
-                const long long tail = rx->vh.new0;
                 if (w.n_hist + w.n_in - n_out * rx->ppt != tail) {
                     set_error("internal: chirp carry-over mismatch");
                     return -1;
