@@ -255,7 +255,9 @@ class ChirpDemodulator:
             self.helper = VNAHelper(self.ppt, self.L)
             self.profile32 = make_flat_window(self.ppt, self.ppt // 10)  # :246
             self.profile = self.profile32.astype(np.float64)
-            self.buf = np.zeros(3 * self.L, dtype=np.complex128)
+            # the reference's device buffer is 3*buffer_len (USRP_demodulator.cpp:225); it overruns it when
+            # ppt > 2*buffer_len.  The restatement keeps enough room so long integrations stay defined.
+            self.buf = np.zeros(max(3 * self.L, self.ppt + self.L), dtype=np.complex128)
 
     def period(self):
         return int(self.p.num_steps) * int(self.p.length)
