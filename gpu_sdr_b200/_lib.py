@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgsdr.so")
+LIB_PATH = os.environ.get("GSDR_LIB_PATH", os.path.join(_HERE, "libgsdr.so"))  # override: kernel experiments only
 
 
 class GsdrError(RuntimeError):

@@ -16,7 +16,13 @@
 // (N, P, T) the fused kernel is not instantiated for; it is also CUDA -- there is no CPU path.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "common.hpp"
+
+#ifndef GSDR_EXP
+#define GSDR_EXP 0  // bit mask of timing experiments (never set in the product build)
+#endif
 
 namespace gsdr {
 
@@ -112,8 +118,6 @@ struct FusedSmem {
     float2 b[FTEAMS][FBUF];
     float2 tw1[FTW1];
     float2 tw2[FTW2];
-    unsigned short bins[FN];
-    int job_index;
 };
 
 // Load the two float4 (4 samples) of window row `row` that thread t owns.  Uniform fast path when
@@ -150,8 +154,13 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
         else sm.tw2[i - FTW1] = tw_global[i];
     }
 
+    if (GSDR_EXP & 64) {  // experiment: de-phase the SMs so memory and compute phases interleave chip-wide
+        const unsigned int ns = (blockIdx.x & 3u) * 1150u;
+        if (ns) __nanosleep(ns);
+    }
     int loaded_job = -1;
-    float w[P][2][2];  // taps of this thread's 4 columns
+    float w[P][2][2];       // taps of this thread's 4 columns
+    unsigned int bp[8];     // the (up to 16) selected bins this thread gathers, two per register
 
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         // ---- locate the job (stream) this tile belongs to --------------------------------------
@@ -162,8 +171,13 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
         const PfbJob job = (table != nullptr) ? table[j] : single;
         const int tile_in_job = tile - ((table != nullptr) ? tile_begin[j] : 0);
         if (j != loaded_job) {
-            __syncthreads();  // previous tile's gather may still read sm.bins
-            for (int u = t; u < job.T; u += FTHREADS) sm.bins[u] = job.bins ? (unsigned short)job.bins[u] : (unsigned short)u;
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const int u0 = tid + FTEAM_THREADS * (2 * jj), u1 = u0 + FTEAM_THREADS;
+                const unsigned int b0 = u0 < job.T ? (job.bins ? (unsigned int)__ldg(job.bins + u0) : (unsigned int)u0) : 0u;
+                const unsigned int b1 = u1 < job.T ? (job.bins ? (unsigned int)__ldg(job.bins + u1) : (unsigned int)u1) : 0u;
+                bp[jj] = (b0 & 0xffffu) | (b1 << 16);
+            }
 #pragma unroll
             for (int i = 0; i < P; ++i)
 #pragma unroll
@@ -186,42 +200,41 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
         const long long fast_hi = (win.n_hist + win.n_in) / FN;           // first row not fully present
 
         float4 r[FTEAMS + P - 1][2];
-        // prologue: the P-1 rows older than the first new row of iteration 0
+        // rows [row_lo, row_lo+FTEAMS) -> r[P-1 ..]; vector path when they lie inside `in`, aligned
+        auto load_new_rows = [&](long long row_lo) {
+            if (aligned && row_lo >= fast_lo && row_lo + FTEAMS <= fast_hi) {
+#pragma unroll
+                for (int q = 0; q < FTEAMS; ++q) load_row<true>(win, row_lo + q, t, r[P - 1 + q]);
+            } else {
+#pragma unroll
+                for (int q = 0; q < FTEAMS; ++q) load_row<false>(win, row_lo + q, t, r[P - 1 + q]);
+            }
+        };
+        // pull rows [row_lo, row_lo+FTEAMS) towards L2 (one request per 128-byte line)
+        auto prefetch_rows = [&](long long row_lo) {
+            if ((t & 7) != 0 || (GSDR_EXP & 128)) return;
+            const long long s = (row_lo * FN - win.n_hist) + 2 * (long long)t;
+            if (s < 0) return;
+#pragma unroll
+            for (int q = 0; q < FTEAMS; ++q)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const long long sq = s + (long long)q * FN + 2 * c * FTHREADS;
+                    if (sq + 16 <= win.n_in) asm volatile("prefetch.global.L2 [%0];" ::"l"(win.in + sq));
+                }
+        };
+        // prologue: the P-1 rows older than the first new row, then iteration 0's new rows
 #pragma unroll
         for (int i = 0; i < P - 1; ++i) {
             const long long row = frame0 + i;
             if (aligned && row >= fast_lo && row < fast_hi) load_row<true>(win, row, t, r[i]);
             else load_row<false>(win, row, t, r[i]);
         }
+        load_new_rows(frame0 + P - 1);
+        if (n_it > 1) prefetch_rows(frame0 + P - 1 + FTEAMS);
 
         for (int it = 0; it < n_it; ++it) {
             const long long fbase = frame0 + (long long)it * FTEAMS;
-            // ---- new rows of this iteration -----------------------------------------------------
-            {
-                const long long row_lo = fbase + P - 1, row_hi = row_lo + FTEAMS;
-                if (aligned && row_lo >= fast_lo && row_hi <= fast_hi) {
-#pragma unroll
-                    for (int q = 0; q < FTEAMS; ++q) load_row<true>(win, row_lo + q, t, r[P - 1 + q]);
-                } else {
-#pragma unroll
-                    for (int q = 0; q < FTEAMS; ++q) load_row<false>(win, row_lo + q, t, r[P - 1 + q]);
-                }
-                // pull the next iteration's rows towards L2 while the FFTs run
-                if (it + 1 < n_it && (t & 7) == 0) {
-                    const long long s = (row_hi * FN - win.n_hist) + 2 * (long long)t;
-                    if (s >= 0) {
-#pragma unroll
-                        for (int q = 0; q < FTEAMS; ++q) {
-#pragma unroll
-                            for (int c = 0; c < 2; ++c) {
-                                const long long sq = s + (long long)q * FN + 2 * c * FTHREADS;
-                                if (sq + 16 <= win.n_in)
-                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(win.in + sq));
-                            }
-                        }
-                    }
-                }
-            }
             // ---- polyphase FIR: frame (fbase+q) = sum_i row[q+i] * w_i, straight into team q's buffer
 #pragma unroll
             for (int q = 0; q < FTEAMS; ++q) {
@@ -246,10 +259,17 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
                 r[i][1] = r[i + FTEAMS][1];
             }
             __syncthreads();
+            if ((GSDR_EXP & 256) && it + 1 < n_it) {
+                load_new_rows(fbase + FTEAMS + P - 1);
+                if (it + 2 < n_it) prefetch_rows(fbase + 2 * FTEAMS + P - 1);
+            }
 
+            if (GSDR_EXP & 512) { if (team >= 2) __nanosleep(250); }
+            if (GSDR_EXP & 1024) { if (team) __nanosleep(team * 100); }
+            if (GSDR_EXP & 2048) { if (team & 1) __nanosleep(200); }
             // ---- one 2048-point FFT per team ------------------------------------------------------
             const long long frame = fbase + team;
-            if (frame < last_frame) {
+            if (frame < last_frame && !(GSDR_EXP & 16)) {
                 float2* A = sm.a[team];
                 float2* B = sm.b[team];
                 float2 v[16];
@@ -264,7 +284,7 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
                         for (int kb = 0; kb < 4; ++kb) {
                             const int k1 = ka + 4 * kb;
                             float2 x = v[4 * ka + kb];
-                            if (k1 != 0) x = cmul(x, sm.tw1[k1 * 128 + l]);
+                            if (k1 != 0) x = cmul(x, (GSDR_EXP & 1) ? make_float2(0.6f, 0.8f) : sm.tw1[k1 * 128 + l]);
                             B[k1 * 129 + l] = x;
                         }
                 }
@@ -280,7 +300,7 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
                         for (int kb = 0; kb < 4; ++kb) {
                             const int k2 = ka + 4 * kb;
                             float2 x = v[4 * ka + kb];
-                            if (k2 != 0) x = cmul(x, sm.tw2[n3 * 16 + k2]);
+                            if (k2 != 0) x = cmul(x, (GSDR_EXP & 2) ? make_float2(0.6f, 0.8f) : sm.tw2[n3 * 16 + k2]);
                             A[n3 * 256 + k2 * 16 + k1] = x;
                         }
                 }
@@ -298,12 +318,275 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
 #pragma unroll
                         for (int kb = 0; kb < 2; ++kb) A[(ka + 4 * kb) * 256 + g] = u[2 * ka + kb];
                 }
+            }
+            // The FFT registers are dead from here on: issue the next iteration's row loads now so
+            // their latency hides under the barrier, the gather and the next FIR's first FMAs.
+            if (!(GSDR_EXP & 256) && it + 1 < n_it) {
+                load_new_rows(fbase + FTEAMS + P - 1);
+                if (it + 2 < n_it) prefetch_rows(fbase + 2 * FTEAMS + P - 1);
+            }
+            if (frame < last_frame && !(GSDR_EXP & 8)) {
+                float2* A = sm.a[team];
                 team_barrier(team, FTEAM_THREADS);
-                // tone selection: coalesced sample-major store
+                // tone selection: coalesced sample-major store, 8 independent gathers in flight
                 float2* o = job.out + (frame - job.first_frame) * (long long)job.T;
-                for (int u = tid; u < job.T; u += FTEAM_THREADS) o[u] = A[sm.bins[u]];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h * 8 * FTEAM_THREADS < job.T) {
+                        float2 val[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const int j2 = h * 8 + jj;
+                            const unsigned int bin = (GSDR_EXP & 4) ? (unsigned)(tid + FTEAM_THREADS * j2)
+                                                                    : ((bp[j2 >> 1] >> (16 * (j2 & 1))) & 0xffffu);
+                            val[jj] = A[bin];
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const int u = tid + FTEAM_THREADS * (h * 8 + jj);
+                            if (u < job.T) o[u] = val[jj];
+                        }
+                    }
+                }
             }
             __syncthreads();
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
+// warp-specialised fused kernel, N = 2048 = 8 x 16 x 16
+//
+//   FRONT (warps 0-7, 256 threads): thread l owns the 8 polyphase columns l + 256 j.  It keeps the
+//     last P input rows of those columns in a register ring, loads one new row per frame (coalesced
+//     8-byte loads, issued one frame ahead), runs the P-tap FIR and the first FFT stage (radix-8 over
+//     j) in registers, applies the stage-1 twiddles W_2048^(l k1) (per-thread constants, registers)
+//     and writes the result into a ring of exchange buffers.
+//   BACK (2 teams of 128 threads, alternate frames): stage 2 (radix-16, twiddles W_256^(n3 k2) in
+//     registers), exchange, stage 3 (radix-16, in place), gather of the selected bins to global.
+//
+// Compared with the lock-step kernel above this removes the FIR->FFT hand-off through shared
+// memory, every twiddle-table load and every CTA-wide barrier: the producers run ahead through a
+// 4-deep ring guarded by named barriers, so row loads, FIR, FFT passes and output stores of
+// different frames overlap on the SM.  Shared-memory wavefronts drop from 0.65 to ~0.36 per sample.
+// --------------------------------------------------------------------------------------------
+constexpr int WS_FRONT = 256;
+constexpr int WS_TEAM = 128;
+constexpr int WS_TEAMS = 2;
+constexpr int WS_THREADS = WS_FRONT + WS_TEAMS * WS_TEAM;  // 512
+constexpr int WS_D1 = 4;            // exchange-1 ring depth (frames the producers may run ahead)
+constexpr int WS_E1 = 8 * 258;      // [k1][n2*16+n3], k1 stride 258 float2
+constexpr int WS_E2 = 16 * 136;     // [n3][k2*8+k1] / [k3][g], row stride 136 float2
+constexpr int WS_TW1 = 8 * 256;     // W_2048^(l k1) laid out [k1][l]
+constexpr int WS_TW2 = 16 * 16;     // W_256^(n3 k2) laid out [n3][k2]
+
+struct WsSmem {
+    float2 e1[WS_D1][WS_E1];
+    float2 e2[WS_TEAMS][WS_E2];
+};
+
+__device__ __forceinline__ void bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(int id, int count) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+constexpr int WS_BAR_FULL = 1;                   // + slot
+constexpr int WS_BAR_EMPTY = 1 + WS_D1;          // + slot
+constexpr int WS_BAR_TEAM = 1 + 2 * WS_D1;       // + team
+constexpr int WS_PC = WS_FRONT + WS_TEAM;        // participants of a full/empty barrier
+
+// tile -> (job, frame range); identical in every warp role so the frame counters stay in step
+struct WsTile {
+    int job;
+    long long fa, fb;  // window frame indices [fa, fb)
+};
+__device__ __forceinline__ WsTile ws_locate(int tile, const PfbJob& single, const PfbJob* table, const int* tile_begin,
+                                            int n_jobs, int frames_per_tile, PfbJob& job) {
+    int j = 0;
+    if (table != nullptr) {
+        while (j + 1 < n_jobs && tile >= tile_begin[j + 1]) ++j;
+        job = table[j];
+    } else {
+        job = single;
+    }
+    const int tile_in_job = tile - ((table != nullptr) ? tile_begin[j] : 0);
+    WsTile r;
+    r.job = j;
+    r.fa = (long long)job.first_frame + (long long)tile_in_job * frames_per_tile;
+    const long long end = (long long)job.first_frame + job.n_frames;
+    r.fb = r.fa + frames_per_tile < end ? r.fa + frames_per_tile : end;
+    return r;
+}
+
+template <int P>
+__global__ void __launch_bounds__(WS_THREADS, 1)
+pfb_fused_ws_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, const int* __restrict__ tile_begin, int n_jobs,
+                   int frames_per_tile, int total_tiles, const float2* __restrict__ tw_global) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_raw);
+    const int t = threadIdx.x;
+    unsigned int f = 0;  // frames this CTA has started, counted identically by every role
+    PfbJob job;
+
+    if (t < WS_FRONT) {
+        // ======================================= FRONT ===========================================
+        // register split: the producers hold the tap/row state (152 regs), the FFT teams need less (104)
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        const int l = t;
+        // W_2048^(l k1): only k1 = 1, 2, 4 are kept (6 registers); the other four are products
+        const float2 tw1 = __ldg(&tw_global[1 * 256 + l]), tw2 = __ldg(&tw_global[2 * 256 + l]), tw4 = __ldg(&tw_global[4 * 256 + l]);
+        float w[P][8];
+        float2 ring[P][8];
+        int loaded_job = -1;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const WsTile tl = ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
+            if (tl.job != loaded_job) {
+#pragma unroll
+                for (int i = 0; i < P; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w[i][j] = __ldg(job.taps + i * FN + l + 256 * j);
+                loaded_job = tl.job;
+            }
+            const Window win = job.win;
+            const long long fast_lo = (win.n_hist + FN - 1) / FN;  // first row fully inside `in`
+            const long long fast_hi = (win.n_hist + win.n_in) / FN;
+            auto load_row8 = [&](long long row, float2 (&dst)[8]) {
+                if (row >= fast_lo && row < fast_hi) {
+                    const float2* p = win.in + (row * FN - win.n_hist) + l;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = __ldg(p + 256 * j);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = win_at(win, row * FN + l + 256 * j);
+                }
+            };
+            // rows fa .. fa+P-1 fill the ring; row (fa + rho) lives in slot rho % P
+#pragma unroll
+            for (int i = 0; i < P; ++i) load_row8(tl.fa + i, ring[i]);
+
+            for (long long b = tl.fa; b < tl.fb; b += P) {
+#pragma unroll
+                for (int u = 0; u < P; ++u) {
+                    if (b + u < tl.fb) {
+                        // ---- FIR: frame b+u = sum_i row[b+u+i] * w_i, rows in slots (u+i) % P
+                        float2 z[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float ax = 0.f, ay = 0.f;
+#pragma unroll
+                            for (int i = 0; i < P; ++i) {
+                                ax = fmaf(ring[(u + i) % P][j].x, w[i][j], ax);
+                                ay = fmaf(ring[(u + i) % P][j].y, w[i][j], ay);
+                            }
+                            z[j] = make_float2(ax, ay);
+                        }
+                        // the oldest row is dead: fetch row b+u+P into its slot, one frame ahead of its use
+                        if (b + u + 1 < tl.fb) load_row8(b + u + P, ring[u % P]);
+                        // ---- FFT stage 1: radix-8 over j, then twiddle
+                        fft8(z);
+                        const int slot = f % WS_D1;
+                        if (f >= WS_D1) bar_sync(WS_BAR_EMPTY + slot, WS_PC);
+                        float2* E = sm.e1[slot];
+                        // fft8 leaves X[ka + 4 kb] in z[2 ka + kb]
+                        const float2 tw3 = cmul(tw1, tw2), tw5 = cmul(tw1, tw4), tw6 = cmul(tw2, tw4);
+                        E[0 * 258 + l] = z[0];
+                        E[1 * 258 + l] = cmul(z[2], tw1);
+                        E[2 * 258 + l] = cmul(z[4], tw2);
+                        E[3 * 258 + l] = cmul(z[6], tw3);
+                        E[4 * 258 + l] = cmul(z[1], tw4);
+                        E[5 * 258 + l] = cmul(z[3], tw5);
+                        E[6 * 258 + l] = cmul(z[5], tw6);
+                        E[7 * 258 + l] = cmul(z[7], cmul(tw3, tw4));
+                        bar_arrive(WS_BAR_FULL + slot, WS_PC);
+                        ++f;
+                    }
+                }
+            }
+        }
+    } else {
+        // ======================================== BACK ============================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
+        const int q = (t - WS_FRONT) / WS_TEAM;
+        const int tid = (t - WS_FRONT) % WS_TEAM;
+        const int n3 = tid >> 3, k1 = tid & 7;
+        float2 tw2[16];  // W_256^(n3 k2)
+#pragma unroll
+        for (int k2 = 1; k2 < 16; ++k2) tw2[k2] = __ldg(&tw_global[WS_TW1 + n3 * 16 + k2]);
+        unsigned int bp[8];  // padded X indices of the (up to 16) bins this thread gathers
+        int loaded_job = -1;
+        float2* E2 = sm.e2[q];
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const WsTile tl = ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
+            if (tl.job != loaded_job) {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    unsigned int pk = 0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int u = tid + WS_TEAM * (2 * jj + h);
+                        unsigned int bin = 0;
+                        if (u < job.T) bin = job.bins ? (unsigned int)__ldg(job.bins + u) : (unsigned int)u;
+                        bin &= (FN - 1);
+                        const unsigned int idx = (bin >> 7) * 136u + (bin & 127u);
+                        pk |= idx << (16 * h);
+                    }
+                    bp[jj] = pk;
+                }
+                loaded_job = tl.job;
+            }
+            for (long long b = tl.fa; b < tl.fb; ++b, ++f) {
+                if ((int)(f & 1u) != q) continue;
+                const int slot = f % WS_D1;
+                float2 v[16];
+                // ---- stage 2: radix-16 over n2; thread = (n3, k1)
+                bar_sync(WS_BAR_FULL + slot, WS_PC);
+                {
+                    const float2* E = sm.e1[slot];
+#pragma unroll
+                    for (int n2 = 0; n2 < 16; ++n2) v[n2] = E[k1 * 258 + n2 * 16 + n3];
+                }
+                bar_arrive(WS_BAR_EMPTY + slot, WS_PC);
+                fft16(v);
+                bar_sync(WS_BAR_TEAM + q, WS_TEAM);  // the previous frame's gather has left E2
+#pragma unroll
+                for (int ka = 0; ka < 4; ++ka)
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const int k2 = ka + 4 * kb;
+                        float2 x = v[4 * ka + kb];
+                        if (k2 != 0) x = cmul(x, tw2[k2]);
+                        E2[n3 * 136 + k2 * 8 + k1] = x;
+                    }
+                bar_sync(WS_BAR_TEAM + q, WS_TEAM);
+                // ---- stage 3: radix-16 over n3, in place; g = k1 + 8 k2 = tid, bin = g + 128 k3
+#pragma unroll
+                for (int m = 0; m < 16; ++m) v[m] = E2[m * 136 + tid];
+                fft16(v);
+#pragma unroll
+                for (int ka = 0; ka < 4; ++ka)
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) E2[(ka + 4 * kb) * 136 + tid] = v[4 * ka + kb];
+                bar_sync(WS_BAR_TEAM + q, WS_TEAM);
+                // ---- tone selection: 8 independent gathers in flight, coalesced sample-major stores
+                float2* o = job.out + (b - job.first_frame) * (long long)job.T;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (h * 8 * WS_TEAM < job.T) {
+                        float2 val[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const int j2 = h * 8 + jj;
+                            val[jj] = E2[(bp[j2 >> 1] >> (16 * (j2 & 1))) & 0xffffu];
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj) {
+                            const int u = tid + WS_TEAM * (h * 8 + jj);
+                            if (u < job.T) o[u] = val[jj];
+                        }
+                    }
+                }
+            }
         }
     }
 }
@@ -385,8 +668,17 @@ bool pfb_fused_supported(int N, int P, int T, const Window&) {
     return N == FN && P >= 1 && P <= 4 && T >= 1 && T <= FN;
 }
 
+static int pfb_variant();
 const char* pfb_kernel_name(int N, int P, int T) {
     Window w{};
+    if (pfb_fused_supported(N, P, T, w) && pfb_variant() == 1) {
+        switch (P) {
+            case 1: return "pfb_fused_ws_2048_kernel<1>";
+            case 2: return "pfb_fused_ws_2048_kernel<2>";
+            case 3: return "pfb_fused_ws_2048_kernel<3>";
+            default: return "pfb_fused_ws_2048_kernel<4>";
+        }
+    }
     if (pfb_fused_supported(N, P, T, w)) {
         switch (P) {
             case 1: return "pfb_fused_2048_kernel<1>";
@@ -444,12 +736,68 @@ static int launch_fused(const PfbJob* jobs, int n_jobs, void* scratch, const flo
     return 1;
 }
 
+template <int P>
+static int launch_ws(const PfbJob* jobs, int n_jobs, void* scratch, const float2* tw, int sm_count, cudaStream_t stream) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        GSDR_CUDA_OK(cudaFuncSetAttribute(pfb_fused_ws_2048_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSmem)));
+        attr_set = true;
+    }
+    long long total_frames = 0;
+    for (int j = 0; j < n_jobs; ++j) total_frames += jobs[j].n_frames;
+    if (total_frames == 0) return 0;
+    int frames_per_tile = (int)((total_frames + sm_count - 1) / sm_count);
+    if (frames_per_tile < 1) frames_per_tile = 1;
+    std::vector<int> tile_begin(n_jobs + 1, 0);
+    for (int j = 0; j < n_jobs; ++j) tile_begin[j + 1] = tile_begin[j] + (jobs[j].n_frames + frames_per_tile - 1) / frames_per_tile;
+    const int total_tiles = tile_begin[n_jobs];
+    const int grid = total_tiles < sm_count ? total_tiles : sm_count;
+    const PfbJob* table = nullptr;
+    const int* tb = nullptr;
+    if (n_jobs > 1) {
+        if (!scratch) {
+            set_error("pfb_launch: multi-stream launch needs a job table buffer");
+            return -1;
+        }
+        unsigned char* base = static_cast<unsigned char*>(scratch);
+        GSDR_CUDA_OK(cudaMemcpyAsync(base, jobs, sizeof(PfbJob) * n_jobs, cudaMemcpyHostToDevice, stream));
+        const size_t off = (sizeof(PfbJob) * n_jobs + 15) & ~size_t(15);
+        GSDR_CUDA_OK(cudaMemcpyAsync(base + off, tile_begin.data(), sizeof(int) * (n_jobs + 1), cudaMemcpyHostToDevice, stream));
+        table = reinterpret_cast<const PfbJob*>(base);
+        tb = reinterpret_cast<const int*>(base + off);
+    }
+    pfb_fused_ws_2048_kernel<P><<<grid, WS_THREADS, sizeof(WsSmem), stream>>>(jobs[0], table, tb, n_jobs, frames_per_tile, total_tiles, tw);
+    GSDR_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
+// 0 = lock-step kernel, 1 = warp-specialised kernel (default).  GSDR_PFB_VARIANT=lockstep|ws overrides.
+static int pfb_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("GSDR_PFB_VARIANT");
+        v = (e && e[0] == 'l') ? 0 : 1;
+    }
+    return v;
+}
+
+int pfb_fused_twiddle_count() { return FTW1 + FTW2 + WS_TW1 + WS_TW2; }
+
 int pfb_launch(const PfbJob* jobs, int n_jobs, void* scratch, void* workspace, const float2* tw, int sm_count,
                cudaStream_t stream) {
     if (n_jobs <= 0) return 0;
     bool fused = true;
     for (int j = 0; j < n_jobs; ++j)
         fused = fused && pfb_fused_supported(jobs[j].N, jobs[j].P, jobs[j].T, jobs[j].win) && jobs[j].P == jobs[0].P;
+    if (fused && pfb_variant() == 1) {
+        const float2* tws = tw + FTW1 + FTW2;
+        switch (jobs[0].P) {
+            case 1: return launch_ws<1>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            case 2: return launch_ws<2>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            case 3: return launch_ws<3>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            default: return launch_ws<4>(jobs, n_jobs, scratch, tws, sm_count, stream);
+        }
+    }
     if (fused) {
         switch (jobs[0].P) {
             case 1: return launch_fused<1>(jobs, n_jobs, scratch, tw, sm_count, stream);

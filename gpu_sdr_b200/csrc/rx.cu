@@ -97,9 +97,11 @@ int dev_upload(Tp** dst, const Tp* src, size_t n) {
     return 0;
 }
 
-// twiddle tables of the fused 2048-point kernel: [16][128] W_2048^(l k1) then [8][16] W_128^(n3 k2)
+// twiddle tables of the fused 2048-point kernels.  Lock-step kernel (16x16x8): [16][128] W_2048^(l k1)
+// then [8][16] W_128^(n3 k2).  Warp-specialised kernel (8x16x16): [8][256] W_2048^(l k1) then
+// [16][16] W_256^(n3 k2).  All built in double.
 std::vector<float2> fused_twiddles() {
-    std::vector<float2> tw(16 * 128 + 8 * 16);
+    std::vector<float2> tw(16 * 128 + 8 * 16 + 8 * 256 + 16 * 16);
     const double two_pi = 6.283185307179586476925286766559;
     for (int k1 = 0; k1 < 16; ++k1)
         for (int l = 0; l < 128; ++l) {
@@ -110,6 +112,17 @@ std::vector<float2> fused_twiddles() {
         for (int k2 = 0; k2 < 16; ++k2) {
             const double a = -two_pi * (double)((n3 * k2) % 128) / 128.0;
             tw[16 * 128 + n3 * 16 + k2] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+    const int base = 16 * 128 + 8 * 16;
+    for (int k1 = 0; k1 < 8; ++k1)
+        for (int l = 0; l < 256; ++l) {
+            const double a = -two_pi * (double)((l * k1) % 2048) / 2048.0;
+            tw[base + k1 * 256 + l] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+    for (int n3 = 0; n3 < 16; ++n3)
+        for (int k2 = 0; k2 < 16; ++k2) {
+            const double a = -two_pi * (double)((n3 * k2) % 256) / 256.0;
+            tw[base + 8 * 256 + n3 * 16 + k2] = make_float2((float)std::cos(a), (float)std::sin(a));
         }
     return tw;
 }

@@ -33,7 +33,7 @@ def check_against_oracle(p, bufs, expect_kernel=None):
 def test_fused_2048_vs_oracle(P, T):
     p = pfb_param(N=2048, P=P, T=T, L=200_000)
     bufs = [tone_stream(p.rate, p.freq, p.ampl, i * p.buffer_len, p.buffer_len) for i in range(4)]
-    check_against_oracle(p, bufs, "pfb_fused_2048")
+    check_against_oracle(p, bufs, "pfb_fused")
 
 
 def test_cfg2_full_size_eight_buffers():
@@ -67,7 +67,7 @@ def test_generic_path_vs_oracle(N, P, T, L, rate):
 def test_odd_buffer_length_uses_unaligned_path():
     p = pfb_param(N=2048, P=4, T=40, L=100_001)
     bufs = [tone_stream(p.rate, p.freq, p.ampl, i * p.buffer_len, p.buffer_len) for i in range(5)]
-    check_against_oracle(p, bufs, "pfb_fused_2048")
+    check_against_oracle(p, bufs, "pfb_fused")
 
 
 def test_buffer_shorter_than_filter_span():
