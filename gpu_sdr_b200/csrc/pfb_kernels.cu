@@ -437,7 +437,8 @@ pfb_fused_ws_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, 
         // W_2048^(l k1): only k1 = 1, 2, 4 are kept (6 registers); the other four are products
         const float2 tw1 = __ldg(&tw_global[1 * 256 + l]), tw2 = __ldg(&tw_global[2 * 256 + l]), tw4 = __ldg(&tw_global[4 * 256 + l]);
         float w[P][8];
-        float2 ring[P][8];
+        constexpr int RS = P + 1;  // ring slots: P rows in use + one row in flight (two frames of lookahead)
+        float2 ring[RS][8];
         int loaded_job = -1;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const WsTile tl = ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
@@ -451,6 +452,7 @@ pfb_fused_ws_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, 
             const Window win = job.win;
             const long long fast_lo = (win.n_hist + FN - 1) / FN;  // first row fully inside `in`
             const long long fast_hi = (win.n_hist + win.n_in) / FN;
+            const long long last_row = tl.fb + P - 1;             // rows this tile needs: [fa, last_row)
             auto load_row8 = [&](long long row, float2 (&dst)[8]) {
                 if (row >= fast_lo && row < fast_hi) {
                     const float2* p = win.in + (row * FN - win.n_hist) + l;
@@ -461,28 +463,40 @@ pfb_fused_ws_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, 
                     for (int j = 0; j < 8; ++j) dst[j] = win_at(win, row * FN + l + 256 * j);
                 }
             };
-            // rows fa .. fa+P-1 fill the ring; row (fa + rho) lives in slot rho % P
+            // one L2 prefetch per 128-byte line of a row several frames ahead (no registers held)
+            auto prefetch_row = [&](long long row) {
+                if ((l & 15) == 0 && row >= fast_lo && row < fast_hi && row < last_row) {
+                    const float2* p = win.in + (row * FN - win.n_hist) + l;
 #pragma unroll
-            for (int i = 0; i < P; ++i) load_row8(tl.fa + i, ring[i]);
+                    for (int j = 0; j < 8; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 256 * j));
+                }
+            };
+            // row (fa + rho) lives in slot rho % RS; frame 0 needs rows 0..P-1, row P is already in flight
+#pragma unroll
+            for (int i = 0; i < RS; ++i)
+                if (tl.fa + i < last_row) load_row8(tl.fa + i, ring[i]);
+#pragma unroll
+            for (int i = RS; i < RS + 4; ++i) prefetch_row(tl.fa + i);
 
-            for (long long b = tl.fa; b < tl.fb; b += P) {
+            for (long long b = tl.fa; b < tl.fb; b += RS) {
 #pragma unroll
-                for (int u = 0; u < P; ++u) {
+                for (int u = 0; u < RS; ++u) {
                     if (b + u < tl.fb) {
-                        // ---- FIR: frame b+u = sum_i row[b+u+i] * w_i, rows in slots (u+i) % P
+                        // ---- FIR: frame b+u = sum_i row[b+u+i] * w_i, rows in slots (u+i) % RS
                         float2 z[8];
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
                             float ax = 0.f, ay = 0.f;
 #pragma unroll
                             for (int i = 0; i < P; ++i) {
-                                ax = fmaf(ring[(u + i) % P][j].x, w[i][j], ax);
-                                ay = fmaf(ring[(u + i) % P][j].y, w[i][j], ay);
+                                ax = fmaf(ring[(u + i) % RS][j].x, w[i][j], ax);
+                                ay = fmaf(ring[(u + i) % RS][j].y, w[i][j], ay);
                             }
                             z[j] = make_float2(ax, ay);
                         }
-                        // the oldest row is dead: fetch row b+u+P into its slot, one frame ahead of its use
-                        if (b + u + 1 < tl.fb) load_row8(b + u + P, ring[u % P]);
+                        // the oldest row is dead: fetch row b+u+RS into its slot, two frames ahead of its use
+                        if (b + u + RS < last_row) load_row8(b + u + RS, ring[u % RS]);
+                        prefetch_row(b + u + RS + 4);
                         // ---- FFT stage 1: radix-8 over j, then twiddle
                         fft8(z);
                         const int slot = f % WS_D1;
