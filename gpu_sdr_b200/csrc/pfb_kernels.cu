@@ -17,6 +17,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <type_traits>
 
 #include "common.hpp"
 
@@ -450,73 +451,87 @@ pfb_fused_ws_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, 
                 loaded_job = tl.job;
             }
             const Window win = job.win;
-            const long long fast_lo = (win.n_hist + FN - 1) / FN;  // first row fully inside `in`
-            const long long fast_hi = (win.n_hist + win.n_in) / FN;
-            const long long last_row = tl.fb + P - 1;             // rows this tile needs: [fa, last_row)
-            auto load_row8 = [&](long long row, float2 (&dst)[8]) {
-                if (row >= fast_lo && row < fast_hi) {
-                    const float2* p = win.in + (row * FN - win.n_hist) + l;
+            const long long fast_lo = (win.n_hist + FN - 1) / FN;    // first row fully inside `in`
+            const long long fast_hi = (win.n_hist + win.n_in) / FN;  // first row not fully present
+            // The tile body is instantiated twice: kFast when every row it touches lies fully inside the
+            // `in` segment (plain coalesced 8-byte loads, no per-row range logic), general otherwise.
+            auto run_tile = [&](auto fast_tag, const long long fa, const long long fb) {
+                constexpr bool kFast = decltype(fast_tag)::value;
+                const long long last_row = fb + P - 1;  // rows this span needs: [fa, last_row)
+                auto load_row8 = [&](long long row, float2 (&dst)[8]) {
+                    if (kFast) {
+                        const float2* p = win.in + (row * FN - win.n_hist) + l;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = __ldg(p + 256 * j);
-                } else {
+                        for (int j = 0; j < 8; ++j) dst[j] = __ldg(p + 256 * j);
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) dst[j] = win_at(win, row * FN + l + 256 * j);
-                }
-            };
-            // one L2 prefetch per 128-byte line of a row several frames ahead (no registers held)
-            auto prefetch_row = [&](long long row) {
-                if ((l & 15) == 0 && row >= fast_lo && row < fast_hi && row < last_row) {
-                    const float2* p = win.in + (row * FN - win.n_hist) + l;
+                        for (int j = 0; j < 8; ++j) dst[j] = win_at(win, row * FN + l + 256 * j);
+                    }
+                };
+                // warp 0 pulls a whole row (128 lines of 128 bytes) towards L2 several frames ahead
+                auto prefetch_row = [&](long long row) {
+                    if (kFast && l < 32 && row < last_row) {
+                        const float2* p = win.in + (row * FN - win.n_hist) + 16 * l;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 256 * j));
-                }
-            };
-            // row (fa + rho) lives in slot rho % RS; frame 0 needs rows 0..P-1, row P is already in flight
+                        for (int jj = 0; jj < 4; ++jj) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 512 * jj));
+                    }
+                };
+                // row (fa + rho) lives in slot rho % RS; frame 0 needs rows 0..P-1, row P is already in flight
 #pragma unroll
-            for (int i = 0; i < RS; ++i)
-                if (tl.fa + i < last_row) load_row8(tl.fa + i, ring[i]);
+                for (int i = 0; i < RS; ++i)
+                    if (fa + i < last_row) load_row8(fa + i, ring[i]);
 #pragma unroll
-            for (int i = RS; i < RS + 4; ++i) prefetch_row(tl.fa + i);
+                for (int i = RS; i < RS + 4; ++i) prefetch_row(fa + i);
 
-            for (long long b = tl.fa; b < tl.fb; b += RS) {
+                for (long long b = fa; b < fb; b += RS) {
 #pragma unroll
-                for (int u = 0; u < RS; ++u) {
-                    if (b + u < tl.fb) {
-                        // ---- FIR: frame b+u = sum_i row[b+u+i] * w_i, rows in slots (u+i) % RS
-                        float2 z[8];
+                    for (int u = 0; u < RS; ++u) {
+                        if (b + u < fb) {
+                            // ---- FIR: frame b+u = sum_i row[b+u+i] * w_i, rows in slots (u+i) % RS
+                            float2 z[8];
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            float ax = 0.f, ay = 0.f;
+                            for (int j = 0; j < 8; ++j) {
+                                float ax = 0.f, ay = 0.f;
 #pragma unroll
-                            for (int i = 0; i < P; ++i) {
-                                ax = fmaf(ring[(u + i) % RS][j].x, w[i][j], ax);
-                                ay = fmaf(ring[(u + i) % RS][j].y, w[i][j], ay);
+                                for (int i = 0; i < P; ++i) {
+                                    ax = fmaf(ring[(u + i) % RS][j].x, w[i][j], ax);
+                                    ay = fmaf(ring[(u + i) % RS][j].y, w[i][j], ay);
+                                }
+                                z[j] = make_float2(ax, ay);
                             }
-                            z[j] = make_float2(ax, ay);
+                            // the oldest row is dead: fetch row b+u+RS into its slot, two frames ahead of its use
+                            if (b + u + RS < last_row) load_row8(b + u + RS, ring[u % RS]);
+                            prefetch_row(b + u + RS + 4);
+                            // ---- FFT stage 1: radix-8 over j, then twiddle
+                            fft8(z);
+                            const int slot = f % WS_D1;
+                            if (f >= WS_D1) bar_sync(WS_BAR_EMPTY + slot, WS_PC);
+                            float2* E = sm.e1[slot];
+                            // fft8 leaves X[ka + 4 kb] in z[2 ka + kb]
+                            const float2 tw3 = cmul(tw1, tw2), tw5 = cmul(tw1, tw4), tw6 = cmul(tw2, tw4);
+                            E[0 * 258 + l] = z[0];
+                            E[1 * 258 + l] = cmul(z[2], tw1);
+                            E[2 * 258 + l] = cmul(z[4], tw2);
+                            E[3 * 258 + l] = cmul(z[6], tw3);
+                            E[4 * 258 + l] = cmul(z[1], tw4);
+                            E[5 * 258 + l] = cmul(z[3], tw5);
+                            E[6 * 258 + l] = cmul(z[5], tw6);
+                            E[7 * 258 + l] = cmul(z[7], cmul(tw3, tw4));
+                            bar_arrive(WS_BAR_FULL + slot, WS_PC);
+                            ++f;
                         }
-                        // the oldest row is dead: fetch row b+u+RS into its slot, two frames ahead of its use
-                        if (b + u + RS < last_row) load_row8(b + u + RS, ring[u % RS]);
-                        prefetch_row(b + u + RS + 4);
-                        // ---- FFT stage 1: radix-8 over j, then twiddle
-                        fft8(z);
-                        const int slot = f % WS_D1;
-                        if (f >= WS_D1) bar_sync(WS_BAR_EMPTY + slot, WS_PC);
-                        float2* E = sm.e1[slot];
-                        // fft8 leaves X[ka + 4 kb] in z[2 ka + kb]
-                        const float2 tw3 = cmul(tw1, tw2), tw5 = cmul(tw1, tw4), tw6 = cmul(tw2, tw4);
-                        E[0 * 258 + l] = z[0];
-                        E[1 * 258 + l] = cmul(z[2], tw1);
-                        E[2 * 258 + l] = cmul(z[4], tw2);
-                        E[3 * 258 + l] = cmul(z[6], tw3);
-                        E[4 * 258 + l] = cmul(z[1], tw4);
-                        E[5 * 258 + l] = cmul(z[3], tw5);
-                        E[6 * 258 + l] = cmul(z[5], tw6);
-                        E[7 * 258 + l] = cmul(z[7], cmul(tw3, tw4));
-                        bar_arrive(WS_BAR_FULL + slot, WS_PC);
-                        ++f;
                     }
                 }
-            }
+            };
+            // frames whose P rows all lie inside `in` take the fast body; the few that touch the carried-over
+            // history (head of a window) or its ragged end take the general one
+            long long f0 = tl.fa > fast_lo ? tl.fa : fast_lo;
+            long long f1 = tl.fb < fast_hi - P + 1 ? tl.fb : fast_hi - P + 1;
+            if (f0 > tl.fb) f0 = tl.fb;
+            if (f1 < f0) f1 = f0;
+            if (tl.fa < f0) run_tile(std::false_type{}, tl.fa, f0);
+            if (f0 < f1) run_tile(std::true_type{}, f0, f1);
+            if (f1 < tl.fb) run_tile(std::false_type{}, f1, tl.fb);
         }
     } else {
         // ======================================== BACK ============================================
