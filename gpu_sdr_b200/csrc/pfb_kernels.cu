@@ -483,45 +483,54 @@ pfb_fused_ws_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, 
 #pragma unroll
                 for (int i = RS; i < RS + 4; ++i) prefetch_row(fa + i);
 
-                for (long long b = fa; b < fb; b += RS) {
+                // one frame: FIR from the ring, refill the freed slot, radix-8, twiddle, hand over to the teams
+                auto do_frame = [&](const long long fr, auto u_tag, const bool guarded) {
+                    constexpr int u = decltype(u_tag)::value;
+                    // ---- FIR: frame fr = sum_i row[fr+i] * w_i, rows in slots (u+i) % RS
+                    float2 z[8];
 #pragma unroll
-                    for (int u = 0; u < RS; ++u) {
-                        if (b + u < fb) {
-                            // ---- FIR: frame b+u = sum_i row[b+u+i] * w_i, rows in slots (u+i) % RS
-                            float2 z[8];
+                    for (int j = 0; j < 8; ++j) {
+                        float ax = 0.f, ay = 0.f;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float ax = 0.f, ay = 0.f;
-#pragma unroll
-                                for (int i = 0; i < P; ++i) {
-                                    ax = fmaf(ring[(u + i) % RS][j].x, w[i][j], ax);
-                                    ay = fmaf(ring[(u + i) % RS][j].y, w[i][j], ay);
-                                }
-                                z[j] = make_float2(ax, ay);
-                            }
-                            // the oldest row is dead: fetch row b+u+RS into its slot, two frames ahead of its use
-                            if (b + u + RS < last_row) load_row8(b + u + RS, ring[u % RS]);
-                            prefetch_row(b + u + RS + 4);
-                            // ---- FFT stage 1: radix-8 over j, then twiddle
-                            fft8(z);
-                            const int slot = f % WS_D1;
-                            if (f >= WS_D1) bar_sync(WS_BAR_EMPTY + slot, WS_PC);
-                            float2* E = sm.e1[slot];
-                            // fft8 leaves X[ka + 4 kb] in z[2 ka + kb]
-                            const float2 tw3 = cmul(tw1, tw2), tw5 = cmul(tw1, tw4), tw6 = cmul(tw2, tw4);
-                            E[0 * 258 + l] = z[0];
-                            E[1 * 258 + l] = cmul(z[2], tw1);
-                            E[2 * 258 + l] = cmul(z[4], tw2);
-                            E[3 * 258 + l] = cmul(z[6], tw3);
-                            E[4 * 258 + l] = cmul(z[1], tw4);
-                            E[5 * 258 + l] = cmul(z[3], tw5);
-                            E[6 * 258 + l] = cmul(z[5], tw6);
-                            E[7 * 258 + l] = cmul(z[7], cmul(tw3, tw4));
-                            bar_arrive(WS_BAR_FULL + slot, WS_PC);
-                            ++f;
+                        for (int i = 0; i < P; ++i) {
+                            ax = fmaf(ring[(u + i) % RS][j].x, w[i][j], ax);
+                            ay = fmaf(ring[(u + i) % RS][j].y, w[i][j], ay);
                         }
+                        z[j] = make_float2(ax, ay);
                     }
-                }
+                    // the oldest row is dead: fetch row fr+RS into its slot, two frames ahead of its use
+                    if (!guarded || fr + RS < last_row) load_row8(fr + RS, ring[u % RS]);
+                    prefetch_row(fr + RS + 4);
+                    // ---- FFT stage 1: radix-8 over j, then twiddle
+                    fft8(z);
+                    const int slot = f % WS_D1;
+                    if (f >= WS_D1) bar_sync(WS_BAR_EMPTY + slot, WS_PC);
+                    float2* E = sm.e1[slot];
+                    // fft8 leaves X[ka + 4 kb] in z[2 ka + kb]
+                    const float2 tw3 = cmul(tw1, tw2), tw5 = cmul(tw1, tw4), tw6 = cmul(tw2, tw4);
+                    E[0 * 258 + l] = z[0];
+                    E[1 * 258 + l] = cmul(z[2], tw1);
+                    E[2 * 258 + l] = cmul(z[4], tw2);
+                    E[3 * 258 + l] = cmul(z[6], tw3);
+                    E[4 * 258 + l] = cmul(z[1], tw4);
+                    E[5 * 258 + l] = cmul(z[3], tw5);
+                    E[6 * 258 + l] = cmul(z[5], tw6);
+                    E[7 * 258 + l] = cmul(z[7], cmul(tw3, tw4));
+                    bar_arrive(WS_BAR_FULL + slot, WS_PC);
+                    ++f;
+                };
+                auto do_group = [&](const long long b, const bool guarded) {
+                    do_frame(b + 0, std::integral_constant<int, 0>{}, guarded);
+                    if (RS > 1 && (!guarded || b + 1 < fb)) do_frame(b + 1, std::integral_constant<int, 1 % RS>{}, guarded);
+                    if (RS > 2 && (!guarded || b + 2 < fb)) do_frame(b + 2, std::integral_constant<int, 2 % RS>{}, guarded);
+                    if (RS > 3 && (!guarded || b + 3 < fb)) do_frame(b + 3, std::integral_constant<int, 3 % RS>{}, guarded);
+                    if (RS > 4 && (!guarded || b + 4 < fb)) do_frame(b + 4, std::integral_constant<int, 4 % RS>{}, guarded);
+                };
+                long long b = fa;
+                // steady state: whole groups of RS frames whose look-ahead rows all exist -- no per-frame tests
+                for (; b + 2 * RS <= fb + P - 1; b += RS) do_group(b, false);
+                // tail: at most two groups, every frame and every refill guarded
+                for (; b < fb; b += RS) do_group(b, true);
             };
             // frames whose P rows all lie inside `in` take the fast body; the few that touch the carried-over
             // history (head of a window) or its ragged end take the general one
