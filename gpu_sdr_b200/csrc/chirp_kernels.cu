@@ -15,37 +15,59 @@ namespace {
 constexpr int SEG = 8192;  // samples per partial sum when ppt is large
 
 // One warp per (output j, segment): lanes stride the samples, xor-shuffle reduction.
+// profile == nullptr selects the flat lock-in window the reference always uses (make_flat_window:
+// weight 0 for i < side, one constant after): the zero-weight head is skipped -- it is neither read
+// nor demodulated -- and the constant is applied once to the sum.
 __global__ void __launch_bounds__(256)
 chirp_lockin_warp_kernel(const Window w, unsigned long long pos0, const ChirpDev cp, const float* __restrict__ profile,
-                         int ppt, long long n_out, int n_seg, float2* __restrict__ dst /* out or partial */) {
+                         int side, float flat_weight, int ppt, long long n_out, int n_seg, float2* __restrict__ dst) {
     const int lane = threadIdx.x & 31;
     const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
     const long long units = n_out * n_seg;
+    const bool flat = profile == nullptr;
     for (long long unit = warp0; unit < units; unit += n_warps) {
         const long long j = unit / n_seg;
         const int sg = (int)(unit - j * n_seg);
-        const int i0 = sg * SEG;
+        int i0 = sg * SEG;
         const int i1 = min(ppt, i0 + SEG);
+        if (flat && i0 < side) i0 = side;
         float2 acc = make_float2(0.f, 0.f);
         if (i0 + lane < i1) {
-            const long long s0 = j * (long long)ppt + i0 + lane;
+            const long long s0 = j * (long long)ppt;  // window index of the output's first sample
             ChirpWalker cw;
-            cw.seek(pos0 + (unsigned long long)s0, cp);
-            for (int i = i0 + lane; i < i1; i += 32) {
-                const float2 x = dev_win_at(w, j * (long long)ppt + i);
-                const float2 ch = chirp_phasor(cw.idx);
-                const float pw = __ldg(&profile[i]);
-                // out = in * conj(chirp): (cx*ix + cy*iy, cx*iy - cy*ix), cpp/kernels.cu:424-425
-                acc.x = fmaf(fmaf(ch.x, x.x, ch.y * x.y), pw, acc.x);
-                acc.y = fmaf(fmaf(ch.x, x.y, -ch.y * x.x), pw, acc.y);
-                cw.advance(32u, cp);
+            cw.seek(pos0 + (unsigned long long)(s0 + i0 + lane), cp);
+            // every sample of this unit inside the `in` segment: plain pointer walk
+            const bool direct = (s0 + i0 >= w.n_hist) && (s0 + i1 <= w.n_hist + w.n_in);
+            if (direct && flat) {
+                const float2* p = w.in + (s0 - w.n_hist);
+                for (int i = i0 + lane; i < i1; i += 32) {
+                    const float2 x = __ldg(p + i);
+                    const float2 ch = chirp_phasor(cw.idx);
+                    // out = in * conj(chirp): (cx*ix + cy*iy, cx*iy - cy*ix), cpp/kernels.cu:424-425
+                    acc.x = fmaf(ch.x, x.x, fmaf(ch.y, x.y, acc.x));
+                    acc.y = fmaf(ch.x, x.y, fmaf(-ch.y, x.x, acc.y));
+                    cw.advance(32u, cp);
+                }
+            } else {
+                for (int i = i0 + lane; i < i1; i += 32) {
+                    const float2 x = dev_win_at(w, s0 + i);
+                    const float2 ch = chirp_phasor(cw.idx);
+                    const float pw = flat ? 1.f : __ldg(&profile[i]);
+                    acc.x = fmaf(fmaf(ch.x, x.x, ch.y * x.y), pw, acc.x);
+                    acc.y = fmaf(fmaf(ch.x, x.y, -ch.y * x.x), pw, acc.y);
+                    cw.advance(32u, cp);
+                }
             }
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
             acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        }
+        if (flat) {
+            acc.x *= flat_weight;
+            acc.y *= flat_weight;
         }
         if (lane == 0) dst[unit] = acc;
     }
@@ -151,8 +173,9 @@ size_t chirp_partial_count(int ppt, long long n_out, int) {
     return n_seg > 1 ? (size_t)n_out * n_seg : 0;
 }
 
-int chirp_demod_launch(const Window& w, unsigned long long pos0, const ChirpDev& cp, const float* profile, int ppt,
-                       long long n_out, float2* out, float2* partial, int sm_count, cudaStream_t stream) {
+int chirp_demod_launch(const Window& w, unsigned long long pos0, const ChirpDev& cp, const float* profile, int side,
+                       float flat_weight, int ppt, long long n_out, float2* out, float2* partial, int sm_count,
+                       cudaStream_t stream) {
     if (n_out <= 0) return 0;
     int launches = 0;
     if (ppt < 32) {
@@ -164,13 +187,15 @@ int chirp_demod_launch(const Window& w, unsigned long long pos0, const ChirpDev&
         const int n_seg = (ppt + SEG - 1) / SEG;
         const long long units = n_out * n_seg;
         long long blocks = (units + 7) / 8;  // 8 warps per block
-        if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
+        if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
         if (n_seg > 1 && !partial) {
             set_error("chirp_demod_launch: partial buffer missing");
             return -1;
         }
-        chirp_lockin_warp_kernel<<<(int)blocks, 256, 0, stream>>>(w, pos0, cp, profile, ppt, n_out, n_seg,
-                                                                   n_seg > 1 ? partial : out);
+        // the flat window is applied in-kernel (profile pointer not needed); an explicit profile array is only
+        // used when a caller supplies a non-flat one
+        chirp_lockin_warp_kernel<<<(int)blocks, 256, 0, stream>>>(w, pos0, cp, side >= 0 ? nullptr : profile, side, flat_weight, ppt,
+                                                                   n_out, n_seg, n_seg > 1 ? partial : out);
         launches = 1;
         if (n_seg > 1) {
             int fb = (int)((n_out + 255) / 256);

@@ -77,6 +77,9 @@ int pfb_launch(const PfbJob* jobs_host, int n_jobs, void* jobs_dev_scratch, void
                int sm_count, cudaStream_t stream);
 // Copies the last n_tail samples of the window into dst (device), double-buffer safe.
 int window_tail_copy(const Window& w, long long n_tail, float2* dst, cudaStream_t stream);
+int window_tail_copy_multi(const Window* wins, const long long* n_tail, float2* const* dst, int n, void* scratch,
+                           cudaStream_t stream);
+size_t window_tail_multi_scratch_bytes(int n);
 
 // ---- CHIRP launches (chirp_kernels.cu) --------------------------------------------------------
 struct ChirpDev {   // kernel-side copy of gsdr_chirp_param plus derived 32-bit constants
@@ -86,8 +89,9 @@ struct ChirpDev {   // kernel-side copy of gsdr_chirp_param plus derived 32-bit 
     int f0;
 };
 int chirp_demod_launch(const Window& w, unsigned long long pos0 /* chirp position of window sample 0 */,
-                       const ChirpDev& cp, const float* profile, int ppt, long long n_out, float2* out,
-                       float2* partial, int sm_count, cudaStream_t stream);
+                       const ChirpDev& cp, const float* profile, int side /* >=0: flat window, skip [0,side) */,
+                       float flat_weight, int ppt, long long n_out, float2* out, float2* partial, int sm_count,
+                       cudaStream_t stream);
 int chirp_demod_full_launch(const float2* in, long long n, unsigned long long pos0, const ChirpDev& cp, float2* out,
                             cudaStream_t stream);
 int chirp_gen_launch(float2* out, long long n, unsigned long long pos0, const ChirpDev& cp, float scale, cudaStream_t stream);

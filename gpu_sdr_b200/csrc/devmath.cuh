@@ -62,34 +62,28 @@ __device__ __forceinline__ float2 chirp_phasor(unsigned int index_word) {
     return make_float2(s, -c);
 }
 
-// Walks chirp positions pos, pos+stride, pos+2*stride ... without a 64-bit division per sample.
+// Walks chirp positions pos, pos+stride, pos+2*stride ... : inside a frequency step the index is a
+// phase accumulator (one 32-bit multiply-add); the 64-bit division only runs when a step boundary
+// (or the end of the sweep) is crossed.
 struct ChirpWalker {
-    unsigned long long eff, k;
-    unsigned long long r;  // eff - k*length
+    unsigned long long eff, k;   // position and step index at the last (re)seek
+    unsigned int adv;            // samples advanced since then
+    unsigned int r, len32;       // offset inside the step, step length (clamped to 2^31-1)
     unsigned int idx, step;
     __device__ __forceinline__ void seek(unsigned long long pos, const ChirpDev& cp) {
         eff = pos % cp.period;
         k = eff / cp.length;
-        r = eff - k * cp.length;
-        refresh(cp);
-    }
-    __device__ __forceinline__ void refresh(const ChirpDev& cp) {
+        r = (unsigned int)(eff - k * cp.length);
+        len32 = cp.length > 0x7fffffffull ? 0x7fffffffu : (unsigned int)cp.length;
+        adv = 0;
         idx = chirp_index_word(eff, k, cp);
         step = (unsigned int)cp.f0 + (unsigned int)k * cp.chirpness;
     }
     __device__ __forceinline__ void advance(unsigned int stride, const ChirpDev& cp) {
-        eff += stride;
         r += stride;
-        if (eff >= cp.period) {
-            seek(eff, cp);
-        } else if (r >= cp.length) {
-            const unsigned long long dk = r / cp.length;
-            k += dk;
-            r -= dk * cp.length;
-            refresh(cp);
-        } else {
-            idx += stride * step;
-        }
+        adv += stride;
+        if (r < len32) idx += stride * step;
+        else seek(eff + adv, cp);
     }
 };
 

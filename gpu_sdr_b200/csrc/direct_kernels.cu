@@ -17,7 +17,7 @@ namespace gsdr {
 namespace {
 
 constexpr int TP = 4;   // outputs per warp tile
-constexpr int TC = 4;   // tones per warp tile
+constexpr int TC = 8;   // tones per warp tile
 constexpr int WARPS = 8;
 
 // signed LO phase exactly as the reference forms it (C remainder keeps the dividend's sign)
@@ -38,7 +38,7 @@ __device__ __forceinline__ float2 lo_phasor(long long ph, double inv_R) {
 // kStaged: the block's input span is staged in shared memory once and reused by every tone group;
 // otherwise (very long filters) the taps stream straight from global memory through L1/L2.
 template <bool kStaged>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 2)
 direct_fir_kernel(const Window w, const float2* __restrict__ g, const int* __restrict__ freq, int T, int M, int ntaps,
                   int rate, long long pos0, long long n_out, int PB, float2* __restrict__ out) {
     extern __shared__ __align__(16) float2 xs[];  // (PB-1)*M + ntaps samples
@@ -89,7 +89,7 @@ direct_fir_kernel(const Window w, const float2* __restrict__ g, const int* __res
                     acc[a][b].x += __shfl_xor_sync(0xffffffffu, acc[a][b].x, o);
                     acc[a][b].y += __shfl_xor_sync(0xffffffffu, acc[a][b].y, o);
                 }
-        // lanes 0..15 each finish one (output, tone): rotate by the block-start LO phase and store
+        // each lane finishes one (output, tone) of the 4 x 8 tile: rotate by the LO phase of its first tap and store
         float2 mine = make_float2(0.f, 0.f);
 #pragma unroll
         for (int a = 0; a < TP; ++a)
@@ -138,7 +138,11 @@ direct_mix_kernel(const float2* __restrict__ in, long long n, const int* __restr
             if (s0 + i >= n) continue;
             long long tf = freq[c0 + cl] % rate;
             if (tf < 0) tf += rate;
-            const long long ph = (base_ph[cl] + tf * i) % rate;
+            // (base + tf*i) mod R without a 64-bit division: quotient from a double product, then one fix-up
+            long long ph = base_ph[cl] + tf * i;  // < 33 R
+            ph -= (long long)((double)ph * inv_R) * rate;
+            if (ph < 0) ph += rate;
+            if (ph >= rate) ph -= rate;
             out[(s0 + i) * T + c0 + cl] = dev_cmul(xs[i], lo_phasor(ph, inv_R));
         }
     }
@@ -166,10 +170,13 @@ int direct_fir_launch(const Window& w, const float2* g, const int* freq_dev, int
         GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
+    // Split a block's (output group, tone group) units over gridDim.y only when there are too few output
+    // blocks to fill the GPU: every y-slice re-stages the same input span.
     const int units = (PB / TP) * ((T + TC - 1) / TC);
-    int gy = (units + WARPS - 1) / WARPS;
-    if (gy > 8) gy = 8;
-    dim3 grid((unsigned)((n_out + PB - 1) / PB), gy);
+    const long long xblocks = (n_out + PB - 1) / PB;
+    int gy = 1;
+    while (xblocks * gy < 2 * 148 && gy * WARPS < units && gy < 16) gy *= 2;
+    dim3 grid((unsigned)xblocks, gy);
     if (staged)
         direct_fir_kernel<true><<<grid, WARPS * 32, smem, stream>>>(w, g, freq_dev, T, M, ntaps, rate, pos0, n_out, PB, out);
     else

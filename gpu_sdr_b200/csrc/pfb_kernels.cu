@@ -695,6 +695,17 @@ pfb_dft_generic_kernel(const PfbJob job, const float2* __restrict__ z, const flo
     if (live) job.out[(long long)f * job.T + u] = total;
 }
 
+struct TailJob {
+    Window w;
+    long long first, n;
+    float2* dst;
+};
+__global__ void window_tail_multi_kernel(const TailJob* __restrict__ jobs) {
+    const TailJob tj = jobs[blockIdx.y];
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < tj.n; i += (long long)gridDim.x * blockDim.x)
+        tj.dst[i] = win_at(tj.w, tj.first + i);
+}
+
 __global__ void window_tail_kernel(const Window w, long long first, long long n, float2* __restrict__ dst) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
         dst[i] = win_at(w, first + i);
@@ -748,9 +759,12 @@ static int launch_fused(const PfbJob* jobs, int n_jobs, void* scratch, const flo
     int iters_per_tile = (int)((total_iters + sm_count - 1) / sm_count);
     if (iters_per_tile < 1) iters_per_tile = 1;
     std::vector<int> tile_begin(n_jobs + 1, 0);
-    for (int j = 0; j < n_jobs; ++j) {
-        const int it = (jobs[j].n_frames + FTEAMS - 1) / FTEAMS;
-        tile_begin[j + 1] = tile_begin[j] + (it + iters_per_tile - 1) / iters_per_tile;
+    for (;; ++iters_per_tile) {  // keep the launch to one wave (see launch_ws)
+        for (int j = 0; j < n_jobs; ++j) {
+            const int it = (jobs[j].n_frames + FTEAMS - 1) / FTEAMS;
+            tile_begin[j + 1] = tile_begin[j] + (it + iters_per_tile - 1) / iters_per_tile;
+        }
+        if (tile_begin[n_jobs] <= sm_count || n_jobs > sm_count) break;
     }
     const int total_tiles = tile_begin[n_jobs];
     const int grid = total_tiles < sm_count ? total_tiles : sm_count;
@@ -787,7 +801,13 @@ static int launch_ws(const PfbJob* jobs, int n_jobs, void* scratch, const float2
     int frames_per_tile = (int)((total_frames + sm_count - 1) / sm_count);
     if (frames_per_tile < 1) frames_per_tile = 1;
     std::vector<int> tile_begin(n_jobs + 1, 0);
-    for (int j = 0; j < n_jobs; ++j) tile_begin[j + 1] = tile_begin[j] + (jobs[j].n_frames + frames_per_tile - 1) / frames_per_tile;
+    // Tiles never span two streams, so with several jobs the per-job round-up can push the tile count
+    // just past one wave (152 tiles on 148 SMs doubles the makespan): grow the tile until one wave holds it.
+    for (;; ++frames_per_tile) {
+        for (int j = 0; j < n_jobs; ++j)
+            tile_begin[j + 1] = tile_begin[j] + (jobs[j].n_frames + frames_per_tile - 1) / frames_per_tile;
+        if (tile_begin[n_jobs] <= sm_count || n_jobs > sm_count) break;
+    }
     const int total_tiles = tile_begin[n_jobs];
     const int grid = total_tiles < sm_count ? total_tiles : sm_count;
     const PfbJob* table = nullptr;
@@ -864,6 +884,26 @@ int pfb_launch(const PfbJob* jobs, int n_jobs, void* scratch, void* workspace, c
     }
     return launches;
 }
+
+// One launch for the carry-over of every stream of a group.  `scratch` must hold n TailJob (device).
+int window_tail_copy_multi(const Window* wins, const long long* n_tail, float2* const* dst, int n, void* scratch,
+                           cudaStream_t stream) {
+    if (n <= 0) return 0;
+    std::vector<TailJob> tj(n);
+    long long longest = 0;
+    for (int i = 0; i < n; ++i) {
+        tj[i] = TailJob{wins[i], wins[i].n_hist + wins[i].n_in - n_tail[i], n_tail[i], dst[i]};
+        if (n_tail[i] > longest) longest = n_tail[i];
+    }
+    if (longest <= 0) return 0;
+    GSDR_CUDA_OK(cudaMemcpyAsync(scratch, tj.data(), sizeof(TailJob) * n, cudaMemcpyHostToDevice, stream));
+    int bx = (int)((longest + 255) / 256);
+    if (bx > 64) bx = 64;
+    window_tail_multi_kernel<<<dim3(bx, n), 256, 0, stream>>>(static_cast<const TailJob*>(scratch));
+    GSDR_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+size_t window_tail_multi_scratch_bytes(int n) { return sizeof(TailJob) * (size_t)n; }
 
 int window_tail_copy(const Window& w, long long n_tail, float2* dst, cudaStream_t stream) {
     if (n_tail <= 0) return 0;

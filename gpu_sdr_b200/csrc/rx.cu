@@ -331,8 +331,9 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
                 // chirp position of window sample 0 = position of the first new sample minus the carry
                 const unsigned long long per = rx->cdev.period;
                 const unsigned long long pos0 = (rx->last_index + per - ((unsigned long long)w.n_hist % per)) % per;
-                const int nl = chirp_demod_launch(w, pos0, rx->cdev, rx->d_profile, rx->ppt, n_out, d_out, rx->d_partial,
-                                                  rx->sm_count, st);
+                const int side = rx->ppt / 10;  // make_flat_window(ppt, ppt/10): taps [0,side) are zero, the rest equal
+                const int nl = chirp_demod_launch(w, pos0, rx->cdev, rx->d_profile, side, rx->taps_host[rx->ppt - 1], rx->ppt,
+                                                  n_out, d_out, rx->d_partial, rx->sm_count, st);
                 if (nl < 0) return -1;
                 rx->launches += nl;
                 const int tl = window_tail_copy(w, tail, rx->hist[rx->hist_cur ^ 1], st);
@@ -709,6 +710,7 @@ struct gsdr_rx_group {
     cudaStream_t stream = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     void* d_table = nullptr;
+    void* d_tail = nullptr;
     uint64_t launches = 0;
     int device = 0;
 };
@@ -734,6 +736,7 @@ gsdr_rx_group* gsdr_rx_group_create(gsdr_rx** members, int n) {
     GSDR_CUDA_OK_NULL(cudaEventCreate(&g->t0));
     GSDR_CUDA_OK_NULL(cudaEventCreate(&g->t1));
     GSDR_CUDA_OK_NULL(cudaMalloc(&g->d_table, (sizeof(PfbJob) + 64) * (size_t)n + 256));
+    GSDR_CUDA_OK_NULL(cudaMalloc(&g->d_tail, window_tail_multi_scratch_bytes(n)));
     return g.release();
 }
 
@@ -742,6 +745,7 @@ void gsdr_rx_group_destroy(gsdr_rx_group* g) {
     cudaSetDevice(g->device);
     if (g->stream) cudaStreamSynchronize(g->stream);
     if (g->d_table) cudaFree(g->d_table);
+    if (g->d_tail) cudaFree(g->d_tail);
     if (g->t0) cudaEventDestroy(g->t0);
     if (g->t1) cudaEventDestroy(g->t1);
     if (g->stream) cudaStreamDestroy(g->stream);
@@ -776,11 +780,17 @@ int64_t gsdr_rx_group_process_device(gsdr_rx_group* g, const gsdr_float2* const*
     const int nl = pfb_launch(jobs.data(), n, g->d_table, nullptr, g->members[0]->d_tw, g->members[0]->sm_count, g->stream);
     if (nl < 0) return -1;
     g->launches += nl;
+    std::vector<Window> wins(n);
+    std::vector<float2*> dsts(n);
+    for (int i = 0; i < n; ++i) {
+        wins[i] = jobs[i].win;
+        dsts[i] = g->members[i]->hist[g->members[i]->hist_cur ^ 1];
+    }
+    const int tl = window_tail_copy_multi(wins.data(), tails.data(), dsts.data(), n, g->d_tail, g->stream);
+    if (tl < 0) return -1;
+    g->launches += tl;
     for (int i = 0; i < n; ++i) {
         gsdr_rx* rx = g->members[i];
-        const int tl = window_tail_copy(jobs[i].win, tails[i], rx->hist[rx->hist_cur ^ 1], g->stream);
-        if (tl < 0) return -1;
-        g->launches += tl;
         rx->hist_cur ^= 1;
         rx->n_hist = tails[i];
     }
