@@ -53,9 +53,14 @@ chirp_lockin_warp_kernel(const Window w, unsigned long long pos0, const ChirpDev
                 for (int i = i0 + lane; i < i1; i += 32) {
                     const float2 x = dev_win_at(w, s0 + i);
                     const float2 ch = chirp_phasor(cw.idx);
-                    const float pw = flat ? 1.f : __ldg(&profile[i]);
-                    acc.x = fmaf(fmaf(ch.x, x.x, ch.y * x.y), pw, acc.x);
-                    acc.y = fmaf(fmaf(ch.x, x.y, -ch.y * x.x), pw, acc.y);
+                    if (flat) {  // same arithmetic as the pointer walk: results do not depend on the path taken
+                        acc.x = fmaf(ch.x, x.x, fmaf(ch.y, x.y, acc.x));
+                        acc.y = fmaf(ch.x, x.y, fmaf(-ch.y, x.x, acc.y));
+                    } else {
+                        const float pw = __ldg(&profile[i]);
+                        acc.x = fmaf(fmaf(ch.x, x.x, ch.y * x.y), pw, acc.x);
+                        acc.y = fmaf(fmaf(ch.x, x.y, -ch.y * x.x), pw, acc.y);
+                    }
                     cw.advance(32u, cp);
                 }
             }
