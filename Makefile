@@ -13,7 +13,7 @@ OBJS    := $(addprefix $(OBJDIR)/,$(addsuffix .o,$(CU_SRCS))) $(OBJDIR)/hostlogi
 
 all: $(OUT)
 
-$(OBJDIR)/%.o: $(SRC)/%.cu $(SRC)/common.hpp $(SRC)/devmath.cuh include/gsdr.h
+$(OBJDIR)/%.o: $(SRC)/%.cu $(SRC)/common.hpp $(SRC)/devmath.cuh $(SRC)/packed_f32x2.cuh include/gsdr.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
 

@@ -18,8 +18,10 @@
 
 #include <cstdlib>
 #include <type_traits>
+#include <utility>
 
 #include "common.hpp"
+#include "packed_f32x2.cuh"
 
 #ifndef GSDR_EXP
 #define GSDR_EXP 0  // bit mask of timing experiments (never set in the product build)
@@ -630,6 +632,323 @@ pfb_fused_ws_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, 
 }
 
 // --------------------------------------------------------------------------------------------
+// packed warp-specialised fused kernel, N = 2048 = 8 x 16 x 16   (the product default)
+//
+// Same role split as the kernel above, re-derived for the issue and barrier budget:
+//   * all complex arithmetic runs on the packed fp32 pipe (FFMA2 / FADD2 / FMUL2, packed_f32x2.cuh):
+//     the FIR is P packed FMAs per sample with the real tap broadcast, a radix-4 butterfly is 6 packed
+//     + 4 scalar adds, a twiddle is 1 packed multiply + 2 FMAs;
+//   * FRONT keeps all seven stage-1 twiddles W_2048^(l k1) in registers (no per-frame products);
+//   * BACK maps one 256-point sub-transform (fixed k1) onto one HALF-WARP: lane = n3 for stage 2 and
+//     lane = k2 for stage 3, so the stage-2 -> stage-3 exchange is a 16x16 transpose private to the
+//     half-warp (padded tile, __syncwarp) instead of a team-wide buffer behind two named barriers;
+//   * the finished spectrum is written once to a double-buffered [k1][k3][k2] tile, so a team needs a
+//     single named barrier per frame (before the tone gather).
+// --------------------------------------------------------------------------------------------
+constexpr int WP_D1 = 4;         // exchange-1 ring depth
+constexpr int WP_E1 = 8 * 258;   // [k1][n2*16+n3], k1 stride 258 float2
+constexpr int WP_H = 16 * 17;    // one 16x16 transpose tile, row stride 17 float2
+constexpr int WP_X = 8 * 258;    // one frame's spectrum [k1][k3*16+k2], k1 stride 258 float2
+constexpr int WP_THREADS = WS_FRONT + WS_TEAMS * WS_TEAM;  // 512
+constexpr int WP_LAG = WP_D1 + 2;  // FRONT gathers the tones of frame g while it produces frame g + WP_LAG
+#ifndef GSDR_WP_LA
+#define GSDR_WP_LA 1
+#endif
+#ifndef GSDR_WP_HOIST
+#define GSDR_WP_HOIST 0
+#endif
+constexpr int WP_LA = GSDR_WP_LA;
+constexpr bool WP_HOIST = GSDR_WP_HOIST != 0;
+// Register split (setmaxnreg).  The pool is what the CTA got at launch, 512 threads x 128 registers; the
+// split must not exceed it (an `inc` the pool cannot satisfy never returns).  ptxas rounds the launch
+// allocation of a setmaxnreg kernel DOWN to a multiple of 32 registers per thread, so 512 threads is the
+// only CTA shape that owns the whole register file.
+constexpr int WP_FRONT_REGS = 160;
+constexpr int WP_BACK_REGS = 96;
+static_assert(WP_THREADS == 512 && WS_FRONT * WP_FRONT_REGS + WS_TEAMS * WS_TEAM * WP_BACK_REGS <= WP_THREADS * 128,
+              "setmaxnreg split must fit the launch-time register pool");
+
+struct WpSmem {
+    float2 x[WS_TEAMS][WP_X];        // finished spectrum of the team's current frame
+    float2 e1[WP_D1][WP_E1];
+    float2 h[WS_TEAMS * (WS_TEAM / 32)][2][WP_H];
+};
+// named barriers; every one has 384 participants (the 256 producers and one 128-thread team)
+constexpr int WP_BAR_FULL = 1;                    // + slot : FRONT arrives, the frame's BACK team waits
+constexpr int WP_BAR_EMPTY = 1 + WP_D1;           // + slot : BACK team arrives, FRONT waits
+constexpr int WP_BAR_XFULL = 1 + 2 * WP_D1;       // + team : BACK team arrives, FRONT waits
+constexpr int WP_BAR_XEMPTY = 3 + 2 * WP_D1;      // + team : FRONT arrives, BACK team waits
+
+template <typename F, int... I>
+__device__ __forceinline__ void for_each_index(std::integer_sequence<int, I...>, F&& fn) {
+    (fn(std::integral_constant<int, I>{}), ...);
+}
+
+// LA = input rows in flight per producer thread (register look-ahead, in frames); HOIST = keep all seven
+// stage-1 twiddles in registers instead of three plus per-frame products.
+template <int P, int LA, bool HOIST>
+__global__ void __launch_bounds__(WP_THREADS, 1)
+pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, const int* __restrict__ tile_begin, int n_jobs,
+                          int frames_per_tile, int total_tiles, const float2* __restrict__ tw_global) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WpSmem& sm = *reinterpret_cast<WpSmem*>(smem_raw);
+    const int t = threadIdx.x;
+    unsigned int f = 0;  // frames this CTA has started, counted identically by every role
+    PfbJob job;
+
+    if (t < WS_FRONT) {
+        // ======================================= FRONT ===========================================
+        // Transposed-form FIR: each arriving input row updates the P frames it contributes to, so a thread
+        // holds P accumulators (the finished one IS the FFT input) and only the rows still in flight.  The
+        // per-frame FMA chain is the reference's (i = 0..P-1, cpp/kernels.cu:495-506), bit for bit.
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WP_FRONT_REGS));
+        const int l = t;
+        constexpr int NTW = HOIST ? 8 : 5;
+        float2 tw[NTW];  // W_2048^(l k1): k1 = 1..7, or k1 = 1, 2, 4 (slots 1, 2, 4)
+        if (HOIST) {
+#pragma unroll
+            for (int k1 = 1; k1 < 8; ++k1) tw[k1 % NTW] = __ldg(&tw_global[k1 * 256 + l]);
+        } else {
+            tw[1] = __ldg(&tw_global[1 * 256 + l]);
+            tw[2] = __ldg(&tw_global[2 * 256 + l]);
+            tw[4] = __ldg(&tw_global[4 * 256 + l]);
+        }
+        float w[P][8];
+        constexpr int U = (P % LA == 0) ? P : P * LA;  // unroll period: accumulator and landing roles repeat
+        c2 acc[P][8];
+        c2 land[LA][8];
+        // Tone selection (tone_select of the reference, cpp/kernels.cu:531-554) also lives here: the producers
+        // have issue slots to spare, the FFT teams do not.  Thread l stores out[frame*T + l + 256 j], j < 8.
+        constexpr int NU = FN / WS_FRONT;
+        unsigned int bp[NU / 2];  // byte offsets (inside a spectrum tile) of the bins this thread gathers, two per register
+        int nv = 0;               // how many of the NU output slots exist (u < T)
+        const unsigned int x_base = (unsigned int)__cvta_generic_to_shared(sm.x[0]);
+        int loaded_job = -1;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const WsTile tl = ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
+            if (tl.job != loaded_job) {
+#pragma unroll
+                for (int i = 0; i < P; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w[i][j] = __ldg(job.taps + i * FN + l + 256 * j);
+#pragma unroll
+                for (int jj = 0; jj < NU / 2; ++jj) {
+                    unsigned int pk = 0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int u = l + WS_FRONT * (2 * jj + h);
+                        unsigned int bin = 0;
+                        if (u < job.T) bin = job.bins ? (unsigned int)__ldg(job.bins + u) : (unsigned int)u;
+                        bin &= (FN - 1);
+                        const unsigned int idx = (bin & 7u) * 258u + (bin >> 7) * 16u + ((bin >> 3) & 15u);
+                        pk |= (idx * 8u) << (16 * h);
+                    }
+                    bp[jj] = pk;
+                }
+                nv = (job.T - l + WS_FRONT - 1) / WS_FRONT;
+                nv = nv < 0 ? 0 : (nv > NU ? NU : nv);
+                loaded_job = tl.job;
+            }
+            const unsigned int f_tile0 = f;  // CTA frame counter of the tile's first frame
+            int emitted = 0;                 // frames of this tile handed to the FFT teams so far
+            // gather the selected bins of the tile's k-th frame from its team's spectrum tile and store them
+            // sample-major (coalesced 8-byte stores).  Called WP_LAG frames behind production: by then the team
+            // has arrived on EMPTY for a later frame, so its XFULL arrival is long past and this never blocks.
+            auto gather = [&](const int k) {
+                const unsigned int qq = (f_tile0 + (unsigned int)k) & 1u;
+                const unsigned int xa = x_base + qq * (unsigned int)(WP_X * sizeof(float2));
+                c2* o = reinterpret_cast<c2*>(job.out) + ((tl.fa - job.first_frame) + k) * (long long)job.T + l;
+                bar_sync(WP_BAR_XFULL + qq, WS_PC);
+#pragma unroll
+                for (int h = 0; h < NU / 4; ++h) {
+                    if (h * 4 < nv) {
+                        c2 val[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j2 = h * 4 + jj;
+                            const unsigned int off = (j2 & 1) ? (bp[j2 >> 1] >> 16) : (bp[j2 >> 1] & 0xffffu);
+                            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(val[jj]) : "r"(xa + off) : "memory");
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (h * 4 + jj < nv) o[WS_FRONT * (h * 4 + jj)] = val[jj];
+                    }
+                }
+                bar_arrive(WP_BAR_XEMPTY + qq, WS_PC);  // after the stores: they have consumed the gathered values
+            };
+            const Window win = job.win;
+            const long long fast_lo = (win.n_hist + FN - 1) / FN;    // first row fully inside `in`
+            const long long fast_hi = (win.n_hist + win.n_in) / FN;  // first row not fully present
+            // The span body is instantiated twice: kFast when every row it touches lies fully inside the
+            // `in` segment (plain coalesced 8-byte loads, no per-row range logic), general otherwise.
+            auto run_tile = [&](auto fast_tag, const long long fa, const long long fb) {
+                constexpr bool kFast = decltype(fast_tag)::value;
+                const long long last_row = fb + P - 1;      // rows this span needs: [fa, last_row)
+                const long long n_steps = last_row - fa;    // one step per input row
+                auto load_row8 = [&](long long row, c2 (&dst)[8]) {
+                    if (kFast) {
+                        // volatile: the loads stay where the pipeline puts them (after the FIR that frees their
+                        // landing registers) instead of being hoisted into extra registers by the scheduler
+                        const c2* p = reinterpret_cast<const c2*>(win.in + (row * FN - win.n_hist) + l);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            asm volatile("ld.global.L1::no_allocate.b64 %0, [%1];" : "=l"(dst[j]) : "l"(p + 256 * j) : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dst[j] = c2_from(win_at(win, row * FN + l + 256 * j));
+                    }
+                };
+                // warp 0 pulls a whole row (128 lines of 128 bytes) towards L2 several frames ahead
+                auto prefetch_row = [&](long long row) {
+                    if (kFast && l < 32 && row < last_row) {
+                        const float2* p = win.in + (row * FN - win.n_hist) + 16 * l;
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 512 * jj));
+                    }
+                };
+#pragma unroll
+                for (int i = 0; i < LA; ++i)
+                    if (fa + i < last_row) load_row8(fa + i, land[i]);
+#pragma unroll
+                for (int i = LA; i < LA + 4; ++i) prefetch_row(fa + i);
+
+                // one step: row (fa + s) arrives, frame (fa + s - P + 1) completes
+                auto step = [&](const long long s, auto u_tag, const bool guarded, const bool emit) {
+                    constexpr int u = decltype(u_tag)::value;
+                    c2(&x)[8] = land[u % LA];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                        for (int i = P - 1; i >= 1; --i) acc[(u + P * U - i) % P][j] = c2_fma_s(x[j], w[i][j], acc[(u + P * U - i) % P][j]);
+                        acc[u % P][j] = c2_scale(x[j], w[0][j]);
+                    }
+                    if (!guarded || s + LA < n_steps) load_row8(fa + s + LA, x);
+                    prefetch_row(fa + s + LA + 4);
+                    if (!emit) return;
+                    // ---- FFT stage 1: radix-8 over j, then twiddle; X[ka + 4 kb] sits in z[2 ka + kb]
+                    c2 z[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z[j] = acc[(u + 1) % P][j];
+                    c2_fft8(z);
+                    const int slot = f % WP_D1;
+                    if (f >= WP_D1) bar_sync(WP_BAR_EMPTY + slot, WS_PC);
+                    float2* E = sm.e1[slot] + l;
+                    sts_c2(E + 0 * 258, z[0]);
+                    if (HOIST) {
+                        sts_c2(E + 1 * 258, c2_cmul(z[2], tw[1 % NTW].x, tw[1 % NTW].y));
+                        sts_c2(E + 2 * 258, c2_cmul(z[4], tw[2 % NTW].x, tw[2 % NTW].y));
+                        sts_c2(E + 3 * 258, c2_cmul(z[6], tw[3 % NTW].x, tw[3 % NTW].y));
+                        sts_c2(E + 4 * 258, c2_cmul(z[1], tw[4 % NTW].x, tw[4 % NTW].y));
+                        sts_c2(E + 5 * 258, c2_cmul(z[3], tw[5 % NTW].x, tw[5 % NTW].y));
+                        sts_c2(E + 6 * 258, c2_cmul(z[5], tw[6 % NTW].x, tw[6 % NTW].y));
+                        sts_c2(E + 7 * 258, c2_cmul(z[7], tw[7 % NTW].x, tw[7 % NTW].y));
+                    } else {
+                        const float2 t1 = tw[1], t2 = tw[2], t4 = tw[4];
+                        const float2 t3 = cmul(t1, t2), t5 = cmul(t1, t4), t6 = cmul(t2, t4);
+                        const float2 t7 = cmul(t3, t4);
+                        sts_c2(E + 1 * 258, c2_cmul(z[2], t1.x, t1.y));
+                        sts_c2(E + 2 * 258, c2_cmul(z[4], t2.x, t2.y));
+                        sts_c2(E + 3 * 258, c2_cmul(z[6], t3.x, t3.y));
+                        sts_c2(E + 4 * 258, c2_cmul(z[1], t4.x, t4.y));
+                        sts_c2(E + 5 * 258, c2_cmul(z[3], t5.x, t5.y));
+                        sts_c2(E + 6 * 258, c2_cmul(z[5], t6.x, t6.y));
+                        sts_c2(E + 7 * 258, c2_cmul(z[7], t7.x, t7.y));
+                    }
+                    bar_arrive(WP_BAR_FULL + slot, WS_PC);
+                    ++f;
+                    ++emitted;
+                    if (emitted > WP_LAG) gather(emitted - WP_LAG - 1);
+                };
+                auto guarded_group = [&](const long long s0) {
+                    for_each_index(std::make_integer_sequence<int, U>{}, [&](auto u_tag) {
+                        const long long ss = s0 + decltype(u_tag)::value;
+                        if (ss < n_steps) step(ss, u_tag, true, ss >= P - 1);
+                    });
+                };
+                // head: the first P-1 rows only prime the accumulators
+                guarded_group(0);
+                long long s = U;
+                // steady state: whole groups whose frames all emit and whose look-ahead rows all exist
+                for (; s + U - 1 + LA < n_steps; s += U)
+                    for_each_index(std::make_integer_sequence<int, U>{}, [&](auto u_tag) {
+                        step(s + decltype(u_tag)::value, u_tag, false, true);
+                    });
+                // tail
+                for (; s < n_steps; s += U) guarded_group(s);
+            };
+            // frames whose P rows all lie inside `in` take the fast body; the few that touch the carried-over
+            // history (head of a window) or its ragged end take the general one
+            long long f0 = tl.fa > fast_lo ? tl.fa : fast_lo;
+            long long f1 = tl.fb < fast_hi - P + 1 ? tl.fb : fast_hi - P + 1;
+            if (f0 > tl.fb) f0 = tl.fb;
+            if (f1 < f0) f1 = f0;
+            if (tl.fa < f0) run_tile(std::false_type{}, tl.fa, f0);
+            if (f0 < f1) run_tile(std::true_type{}, f0, f1);
+            if (f1 < tl.fb) run_tile(std::false_type{}, f1, tl.fb);
+            // drain: the last WP_LAG frames of the tile
+            for (int k = emitted > WP_LAG ? emitted - WP_LAG : 0; k < emitted; ++k) gather(k);
+        }
+    } else {
+        // ======================================== BACK ============================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WP_BACK_REGS));
+        const int q = (t - WS_FRONT) / WS_TEAM;       // team: frames with (f & 1) == q
+        const int tid = (t - WS_FRONT) % WS_TEAM;
+        const int lane16 = tid & 15;                  // n3 in stage 2, k2 in stage 3
+        const int k1 = tid >> 4;                      // the 256-point sub-transform of this half-warp
+        float2 tw2[16];  // W_256^(n3 k2)
+#pragma unroll
+        for (int k2 = 1; k2 < 16; ++k2) tw2[k2] = __ldg(&tw_global[WS_TW1 + lane16 * 16 + k2]);
+        float2* H = sm.h[(t - WS_FRONT) >> 5][(tid >> 4) & 1];
+        bool x_used = false;  // the team's spectrum tile holds a frame the producers may still be gathering from
+        const unsigned int xw = (unsigned int)__cvta_generic_to_shared(sm.x[q]) + (unsigned int)((k1 * 258 + lane16) * sizeof(float2));
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const WsTile tl = ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
+            const int nf = (int)(tl.fb - tl.fa);
+            for (int i = (int)((q - f) & 1u); i < nf; i += 2) {
+                const int slot = (f + i) % WP_D1;
+                c2 v[16];
+                // ---- stage 2: radix-16 over n2; lane = n3
+                bar_sync(WP_BAR_FULL + slot, WS_PC);
+                {
+                    const float2* E = sm.e1[slot] + k1 * 258 + lane16;
+#pragma unroll
+                    for (int n2 = 0; n2 < 16; ++n2) v[n2] = lds_c2(E + n2 * 16);
+                }
+                c2_fft16_first(v);  // consumes every loaded value: the slot can go back to the producers
+                bar_arrive(WP_BAR_EMPTY + slot, WS_PC);
+                c2_fft16_second(v);
+#pragma unroll
+                for (int ka = 0; ka < 4; ++ka)
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const int k2 = ka + 4 * kb;
+                        c2 x = v[4 * ka + kb];
+                        if (k2 != 0) x = c2_cmul(x, tw2[k2].x, tw2[k2].y);
+                        sts_c2(H + k2 * 17 + lane16, x);
+                    }
+                __syncwarp();
+                // ---- stage 3: radix-16 over n3; lane = k2; bin = k1 + 8 k2 + 128 k3
+#pragma unroll
+                for (int m = 0; m < 16; ++m) v[m] = lds_c2(H + lane16 * 17 + m);
+                __syncwarp();
+                c2_fft16(v);
+                if (x_used) bar_sync(WP_BAR_XEMPTY + q, WS_PC);  // the previous frame's tones have left the tile
+#pragma unroll
+                for (int ka = 0; ka < 4; ++ka)
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb)
+                        asm volatile("st.shared.b64 [%0], %1;" ::"r"(xw + (unsigned int)((ka + 4 * kb) * 16 * sizeof(float2))),
+                                     "l"(v[4 * ka + kb])
+                                     : "memory");
+                bar_arrive(WP_BAR_XFULL + q, WS_PC);
+                x_used = true;
+            }
+            f += nf;
+        }
+    }
+}
+
+// --------------------------------------------------------------------------------------------
 // generic path: any N, P, T
 // --------------------------------------------------------------------------------------------
 __global__ void pfb_fir_generic_kernel(const PfbJob job, float2* __restrict__ z) {
@@ -720,6 +1039,14 @@ bool pfb_fused_supported(int N, int P, int T, const Window&) {
 static int pfb_variant();
 const char* pfb_kernel_name(int N, int P, int T) {
     Window w{};
+    if (pfb_fused_supported(N, P, T, w) && pfb_variant() == 2) {
+        switch (P) {
+            case 1: return "pfb_fused_wsp_2048_kernel<1>";
+            case 2: return "pfb_fused_wsp_2048_kernel<2>";
+            case 3: return "pfb_fused_wsp_2048_kernel<3>";
+            default: return "pfb_fused_wsp_2048_kernel<4>";
+        }
+    }
     if (pfb_fused_supported(N, P, T, w) && pfb_variant() == 1) {
         switch (P) {
             case 1: return "pfb_fused_ws_2048_kernel<1>";
@@ -788,11 +1115,13 @@ static int launch_fused(const PfbJob* jobs, int n_jobs, void* scratch, const flo
     return 1;
 }
 
-template <int P>
+template <int P, bool kPacked>
 static int launch_ws(const PfbJob* jobs, int n_jobs, void* scratch, const float2* tw, int sm_count, cudaStream_t stream) {
     static bool attr_set = false;
+    constexpr size_t smem_bytes = kPacked ? sizeof(WpSmem) : sizeof(WsSmem);
+    auto kernel = kPacked ? pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST> : pfb_fused_ws_2048_kernel<P>;
     if (!attr_set) {
-        GSDR_CUDA_OK(cudaFuncSetAttribute(pfb_fused_ws_2048_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(WsSmem)));
+        GSDR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         attr_set = true;
     }
     long long total_frames = 0;
@@ -824,17 +1153,20 @@ static int launch_ws(const PfbJob* jobs, int n_jobs, void* scratch, const float2
         table = reinterpret_cast<const PfbJob*>(base);
         tb = reinterpret_cast<const int*>(base + off);
     }
-    pfb_fused_ws_2048_kernel<P><<<grid, WS_THREADS, sizeof(WsSmem), stream>>>(jobs[0], table, tb, n_jobs, frames_per_tile, total_tiles, tw);
+    kernel<<<grid, WS_THREADS, smem_bytes, stream>>>(jobs[0], table, tb, n_jobs, frames_per_tile, total_tiles, tw);
     GSDR_CUDA_OK(cudaGetLastError());
     return 1;
 }
 
-// 0 = lock-step kernel, 1 = warp-specialised kernel (default).  GSDR_PFB_VARIANT=lockstep|ws overrides.
+// 0 = lock-step kernel, 1 = warp-specialised scalar kernel, 2 = packed warp-specialised kernel (default).
+// GSDR_PFB_VARIANT=lockstep|ws|wsp overrides (timing comparisons only).
 static int pfb_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("GSDR_PFB_VARIANT");
-        v = (e && e[0] == 'l') ? 0 : 1;
+        if (e && e[0] == 'l') v = 0;
+        else if (e && e[0] == 'w' && e[1] == 's' && e[2] == 0) v = 1;
+        else v = 2;
     }
     return v;
 }
@@ -847,13 +1179,22 @@ int pfb_launch(const PfbJob* jobs, int n_jobs, void* scratch, void* workspace, c
     bool fused = true;
     for (int j = 0; j < n_jobs; ++j)
         fused = fused && pfb_fused_supported(jobs[j].N, jobs[j].P, jobs[j].T, jobs[j].win) && jobs[j].P == jobs[0].P;
+    if (fused && pfb_variant() == 2) {
+        const float2* tws = tw + FTW1 + FTW2;
+        switch (jobs[0].P) {
+            case 1: return launch_ws<1, true>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            case 2: return launch_ws<2, true>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            case 3: return launch_ws<3, true>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            default: return launch_ws<4, true>(jobs, n_jobs, scratch, tws, sm_count, stream);
+        }
+    }
     if (fused && pfb_variant() == 1) {
         const float2* tws = tw + FTW1 + FTW2;
         switch (jobs[0].P) {
-            case 1: return launch_ws<1>(jobs, n_jobs, scratch, tws, sm_count, stream);
-            case 2: return launch_ws<2>(jobs, n_jobs, scratch, tws, sm_count, stream);
-            case 3: return launch_ws<3>(jobs, n_jobs, scratch, tws, sm_count, stream);
-            default: return launch_ws<4>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            case 1: return launch_ws<1, false>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            case 2: return launch_ws<2, false>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            case 3: return launch_ws<3, false>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            default: return launch_ws<4, false>(jobs, n_jobs, scratch, tws, sm_count, stream);
         }
     }
     if (fused) {
