@@ -42,6 +42,7 @@ void make_sinc_window(int length, float fc, float* out);
 void make_flat_window(int length, int side, float* out);
 int pfb_batching(int buffer_len, int fft_tones, int pf_average);
 void tone_bins(int rate, int fft_tones, const int32_t* freq, int n, int32_t* bins);
+void pfb_gather_coloring(const int32_t* bins /* nullptr: all bins in order */, int T, uint8_t* perm /* [2048] */);
 void buffer_helper_init(gsdr_buffer_helper* h, int n_tones, int buffer_len, int average, int n_eff_tones);
 void buffer_helper_update(gsdr_buffer_helper* h);
 void vna_helper_init(gsdr_vna_helper* h, int ppt, int buffer_len);
@@ -67,6 +68,7 @@ struct PfbJob {          // one stream's share of a launch
     int first_frame;     // frame index within the window (0 = window start)
     int n_frames;
     int N, P, T;
+    const unsigned char* xperm = nullptr;  // [2048] in-row position of each bin (pfb_gather_coloring); nullptr => k2
 };
 // Returns the number of kernel launches issued (>0) or -1.  `workspace` is device scratch of at
 // least pfb_workspace_bytes() for the generic path (may be null for the fused path).

@@ -270,6 +270,11 @@ int gsdr_tone_bins(int rate, int fft_tones, const int32_t* freq, int n, int32_t*
     tone_bins(rate, fft_tones, freq, n, bins);
     return n;
 }
+int gsdr_pfb_gather_layout(const int32_t* bins, int n_tones, uint8_t* pos_out) {
+    if (n_tones < 0 || n_tones > 2048 || !pos_out) return -1;
+    pfb_gather_coloring(bins, n_tones, pos_out);
+    return n_tones;
+}
 void gsdr_buffer_helper_init(gsdr_buffer_helper* h, int n_tones, int buffer_len, int average, int n_eff) {
     buffer_helper_init(h, n_tones, buffer_len, average, n_eff);
 }

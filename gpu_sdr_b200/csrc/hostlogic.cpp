@@ -3,6 +3,7 @@
 // reference bit for bit (taps: float32; the rest: integers), so each routine documents the
 // reference lines whose arithmetic it reproduces (paths relative to the reference tree).
 // Built WITHOUT fast-math / FMA contraction (see Makefile) for the same reason.
+#include <algorithm>
 #include <cmath>
 #include <limits>
 
@@ -149,6 +150,117 @@ void chirp_params(int rate, int freq0, int chirp_f0, int swipe_s0, float chirp_t
     out->length = len;
     out->chirpness = wrap_u32((full * (chirp_f0 - freq0) / (static_cast<double>(steps) - 1.)) / static_cast<double>(rate));
     out->f0 = trunc_i32(full * (static_cast<double>(freq0) / static_cast<double>(rate)));
+}
+
+
+// Bank-conflict-free tone gather for the fused 2048-channel kernel.
+//
+// The kernel parks a frame's spectrum in shared memory as rows of 16 bins: row (k1, k3) holds the bins
+// k1 + 8 k2 + 128 k3 (k2 = 0..15), 128 bytes, one 8-byte bank pair per bin.  Inside a row the FFT team may
+// place the 16 bins in ANY order without hurting its own (half-warp, one row per store) accesses.  The
+// producers then read the selected bins 16 at a time (tones 16 h .. 16 h + 15 per half-warp) -- in the
+// caller's tone order, i.e. scattered rows.  That read is conflict-free iff its 16 bins sit in 16 different
+// bank pairs.  Rows on one side, half-warp reads on the other, selected bins as edges: a bipartite multigraph
+// of maximum degree 16, and by Koenig's theorem it always has a proper edge colouring with 16 colours
+// (colour = bank pair).  Built with alternating-path recolouring; O(T * 16).
+// perm[bin] = position (0..15) of the bin inside its row.  Duplicate tones (same bin twice) share the first
+// occurrence's position; they are read by broadcast or, at worst, with a conflict -- never wrongly.
+void pfb_gather_coloring(const int32_t* bins, int T, uint8_t* perm /* [2048] */) {
+    constexpr int NB = 2048, NL = 128, NC = 16, FIXED = 1 << 29;
+    const int nR = (T + 15) / 16;
+    struct Edge { int l, r, bin, color; };
+    std::vector<Edge> edges;
+    edges.reserve(T);
+    std::vector<std::vector<int>> reads(NB);  // the 16-tone reads each bin takes part in
+    for (int u = 0; u < T; ++u) {
+        const int bin = (bins ? bins[u] : u) & (NB - 1);
+        if (reads[bin].empty() || reads[bin].back() != (u >> 4)) reads[bin].push_back(u >> 4);
+    }
+    std::vector<int> colL(NL * NC, -1), colR((size_t)(nR > 0 ? nR : 1) * NC, -1);
+    std::vector<int> bin_color(NB, -1);
+    // A tone list may name a bin more than once (two tones in one channel).  Such a bin is read by several
+    // half-warps but lives in one slot: give it a slot that is free in its row and in all of its reads FIRST,
+    // while almost everything is free, and never recolour it afterwards.
+    for (int bin = 0; bin < NB; ++bin) {
+        if (reads[bin].size() < 2) continue;
+        const int x = (bin & 7) * 16 + (bin >> 7);
+        int best = -1, best_clash = 1 << 30;
+        for (int cdt = 0; cdt < NC; ++cdt) {
+            if (colL[x * NC + cdt] >= 0) continue;
+            int clash = 0;
+            for (int y : reads[bin]) clash += colR[y * NC + cdt] >= 0;
+            if (clash < best_clash) best_clash = clash, best = cdt;
+        }
+        bin_color[bin] = best;
+        colL[x * NC + best] = FIXED;
+        for (int y : reads[bin])
+            if (colR[y * NC + best] < 0) colR[y * NC + best] = FIXED;
+    }
+    for (int bin = 0; bin < NB; ++bin)
+        if (reads[bin].size() == 1) edges.push_back(Edge{(bin & 7) * 16 + (bin >> 7), reads[bin][0], bin, -1});
+    // order of the caller's tone list (deterministic, and the test reproduces it)
+    std::sort(edges.begin(), edges.end(), [](const Edge& p, const Edge& q) { return p.r != q.r ? p.r < q.r : p.bin < q.bin; });
+    std::vector<int> path;
+    for (int e = 0; e < (int)edges.size(); ++e) {
+        const int x = edges[e].l, y = edges[e].r;
+        int chosen = -1;
+        // a colour free on both sides needs no work
+        for (int a = 0; a < NC && chosen < 0; ++a)
+            if (colL[x * NC + a] < 0 && colR[y * NC + a] < 0) chosen = a;
+        // otherwise: a free at the row, b free at the read; swap a <-> b along the alternating path that starts at
+        // the read with colour a.  Bipartite + a free at x => the path never returns to x.  A path through a
+        // pinned (duplicate) bin is not flipped; another (a, b) pair is tried.
+        for (int a = 0; a < NC && chosen < 0; ++a) {
+            if (colL[x * NC + a] >= 0) continue;
+            for (int b = 0; b < NC && chosen < 0; ++b) {
+                if (colR[y * NC + b] >= 0) continue;
+                path.clear();
+                int c = a, node = y;
+                bool at_right = true, ok = true;
+                for (;;) {
+                    const int pe = at_right ? colR[node * NC + c] : colL[node * NC + c];
+                    if (pe < 0) break;
+                    if (pe >= FIXED) { ok = false; break; }
+                    path.push_back(pe);
+                    node = at_right ? edges[pe].l : edges[pe].r;
+                    at_right = !at_right;
+                    c = (c == a) ? b : a;
+                }
+                if (!ok) continue;
+                for (int pe : path) {
+                    colL[edges[pe].l * NC + edges[pe].color] = -1;
+                    colR[edges[pe].r * NC + edges[pe].color] = -1;
+                }
+                for (int pe : path) {
+                    edges[pe].color = (edges[pe].color == a) ? b : a;
+                    colL[edges[pe].l * NC + edges[pe].color] = pe;
+                    colR[edges[pe].r * NC + edges[pe].color] = pe;
+                }
+                chosen = a;
+            }
+        }
+        if (chosen < 0) {  // only reachable around pinned bins: accept one conflict rather than fail
+            for (int a = 0; a < NC && chosen < 0; ++a)
+                if (colL[x * NC + a] < 0) chosen = a;
+        }
+        edges[e].color = chosen;
+        colL[x * NC + chosen] = e;
+        if (colR[y * NC + chosen] < 0) colR[y * NC + chosen] = e;
+    }
+    for (const Edge& ed : edges) bin_color[ed.bin] = ed.color;
+    // unselected bins take the positions their row has left
+    for (int l = 0; l < NL; ++l) {
+        const int k1 = l / 16, k3 = l % 16;
+        int next = 0;
+        for (int k2 = 0; k2 < 16; ++k2) {
+            const int bin = k1 + 8 * k2 + 128 * k3;
+            if (bin_color[bin] >= 0) continue;
+            while (colL[l * NC + next] >= 0) ++next;
+            bin_color[bin] = next;
+            colL[l * NC + next] = FIXED;
+        }
+    }
+    for (int bin = 0; bin < NB; ++bin) perm[bin] = (uint8_t)bin_color[bin];
 }
 
 }  // namespace gsdr

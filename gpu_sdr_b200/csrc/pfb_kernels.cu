@@ -645,12 +645,18 @@ pfb_fused_ws_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, 
 //   * the finished spectrum is written once to a double-buffered [k1][k3][k2] tile, so a team needs a
 //     single named barrier per frame (before the tone gather).
 // --------------------------------------------------------------------------------------------
-constexpr int WP_D1 = 4;         // exchange-1 ring depth
+#ifndef GSDR_WP_D1
+#define GSDR_WP_D1 4
+#endif
+#ifndef GSDR_WP_XB
+#define GSDR_WP_XB 2
+#endif
+constexpr int WP_D1 = GSDR_WP_D1;  // exchange-1 ring depth
 constexpr int WP_E1 = 8 * 258;   // [k1][n2*16+n3], k1 stride 258 float2
 constexpr int WP_H = 16 * 17;    // one 16x16 transpose tile, row stride 17 float2
-constexpr int WP_X = 8 * 258;    // one frame's spectrum [k1][k3*16+k2], k1 stride 258 float2
+constexpr int WP_X = 8 * 256;    // one frame's spectrum: rows (k1, k3) of 16 bins, in-row order from PfbJob::xperm
 constexpr int WP_THREADS = WS_FRONT + WS_TEAMS * WS_TEAM;  // 512
-constexpr int WP_LAG = WP_D1 + 2;  // FRONT gathers the tones of frame g while it produces frame g + WP_LAG
+constexpr int WP_XB = GSDR_WP_XB;   // spectrum tiles per team (a team may finish two frames before a gather frees one)
 #ifndef GSDR_WP_LA
 #define GSDR_WP_LA 1
 #endif
@@ -663,21 +669,58 @@ constexpr bool WP_HOIST = GSDR_WP_HOIST != 0;
 // split must not exceed it (an `inc` the pool cannot satisfy never returns).  ptxas rounds the launch
 // allocation of a setmaxnreg kernel DOWN to a multiple of 32 registers per thread, so 512 threads is the
 // only CTA shape that owns the whole register file.
-constexpr int WP_FRONT_REGS = 160;
-constexpr int WP_BACK_REGS = 96;
+#ifndef GSDR_WP_FRONT_REGS
+#define GSDR_WP_FRONT_REGS 160
+#endif
+constexpr int WP_FRONT_REGS = GSDR_WP_FRONT_REGS;
+constexpr int WP_BACK_REGS = 256 - WP_FRONT_REGS;
 static_assert(WP_THREADS == 512 && WS_FRONT * WP_FRONT_REGS + WS_TEAMS * WS_TEAM * WP_BACK_REGS <= WP_THREADS * 128,
               "setmaxnreg split must fit the launch-time register pool");
 
 struct WpSmem {
-    float2 x[WS_TEAMS][WP_X];        // finished spectrum of the team's current frame
+    float2 x[WS_TEAMS][WP_XB][WP_X];  // finished spectra, [team][tile]
+    unsigned long long xfull[WS_TEAMS][WP_XB];   // mbarrier: the team's 4 warps have written the tile
+    unsigned long long xempty[WS_TEAMS][WP_XB];  // mbarrier: the 8 producer warps have gathered from it
     float2 e1[WP_D1][WP_E1];
     float2 h[WS_TEAMS * (WS_TEAM / 32)][2][WP_H];
 };
-// named barriers; every one has 384 participants (the 256 producers and one 128-thread team)
+// named barriers of the exchange-1 ring; each has 384 participants (the 256 producers and one 128-thread team)
 constexpr int WP_BAR_FULL = 1;                    // + slot : FRONT arrives, the frame's BACK team waits
 constexpr int WP_BAR_EMPTY = 1 + WP_D1;           // + slot : BACK team arrives, FRONT waits
-constexpr int WP_BAR_XFULL = 1 + 2 * WP_D1;       // + team : BACK team arrives, FRONT waits
-constexpr int WP_BAR_XEMPTY = 3 + 2 * WP_D1;      // + team : FRONT arrives, BACK team waits
+
+// mbarriers guard the spectrum tiles: unlike a named barrier they can be POLLED, so the producers gather a
+// finished frame whenever one is ready instead of at a fixed distance behind production.
+__device__ __forceinline__ void mbar_init(unsigned int addr, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned int addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+// One arrival for the whole warp: 32 lanes arriving on one address would serialise into 32 shared-memory
+// atomics.  __syncwarp orders the lanes' earlier shared-memory accesses before the elected lane's release.
+// (Predicated inside the asm statement: a C-level `if (lane == 0)` is a branch, and ptxas then spills around it.)
+__device__ __forceinline__ void mbar_arrive_warp(unsigned int addr) {
+    __syncwarp();
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.eq.u32 p, %1, 0;\n\t@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(addr),
+        "r"(threadIdx.x & 31u)
+        : "memory");
+}
+__device__ __forceinline__ bool mbar_test(unsigned int addr, unsigned int parity) {
+    unsigned int ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(unsigned int addr, unsigned int parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@!p bra WAIT_%=;\n\t}" ::"r"(addr),
+        "r"(parity)
+        : "memory");
+}
 
 template <typename F, int... I>
 __device__ __forceinline__ void for_each_index(std::integer_sequence<int, I...>, F&& fn) {
@@ -695,6 +738,17 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
     const int t = threadIdx.x;
     unsigned int f = 0;  // frames this CTA has started, counted identically by every role
     PfbJob job;
+    const unsigned int xfull0 = (unsigned int)__cvta_generic_to_shared(&sm.xfull[0][0]);
+    const unsigned int xempty0 = (unsigned int)__cvta_generic_to_shared(&sm.xempty[0][0]);
+    if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < WS_TEAMS * WP_XB; ++i) {
+            mbar_init(xfull0 + 8 * i, WS_TEAM / 32);   // one arrival per warp (see mbar_arrive_warp)
+            mbar_init(xempty0 + 8 * i, WS_FRONT / 32);
+        }
+    }
+    __syncthreads();
+    // frame number n (per CTA) -> team n & 1, that team's frame c = n >> 1, tile c % WP_XB, use c / WP_XB of the tile
 
     if (t < WS_FRONT) {
         // ======================================= FRONT ===========================================
@@ -722,7 +776,7 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
         constexpr int NU = FN / WS_FRONT;
         unsigned int bp[NU / 2];  // byte offsets (inside a spectrum tile) of the bins this thread gathers, two per register
         int nv = 0;               // how many of the NU output slots exist (u < T)
-        const unsigned int x_base = (unsigned int)__cvta_generic_to_shared(sm.x[0]);
+        const unsigned int x_base = (unsigned int)__cvta_generic_to_shared(&sm.x[0][0][0]);
         int loaded_job = -1;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const WsTile tl = ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
@@ -740,7 +794,8 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
                         unsigned int bin = 0;
                         if (u < job.T) bin = job.bins ? (unsigned int)__ldg(job.bins + u) : (unsigned int)u;
                         bin &= (FN - 1);
-                        const unsigned int idx = (bin & 7u) * 258u + (bin >> 7) * 16u + ((bin >> 3) & 15u);
+                        const unsigned int pos = job.xperm ? (unsigned int)__ldg(job.xperm + bin) : ((bin >> 3) & 15u);
+                        const unsigned int idx = (bin & 7u) * 256u + (bin >> 7) * 16u + (pos & 15u);
                         pk |= (idx * 8u) << (16 * h);
                     }
                     bp[jj] = pk;
@@ -750,15 +805,21 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
                 loaded_job = tl.job;
             }
             const unsigned int f_tile0 = f;  // CTA frame counter of the tile's first frame
-            int emitted = 0;                 // frames of this tile handed to the FFT teams so far
-            // gather the selected bins of the tile's k-th frame from its team's spectrum tile and store them
-            // sample-major (coalesced 8-byte stores).  Called WP_LAG frames behind production: by then the team
-            // has arrived on EMPTY for a later frame, so its XFULL arrival is long past and this never blocks.
-            auto gather = [&](const int k) {
-                const unsigned int qq = (f_tile0 + (unsigned int)k) & 1u;
-                const unsigned int xa = x_base + qq * (unsigned int)(WP_X * sizeof(float2));
-                c2* o = reinterpret_cast<c2*>(job.out) + ((tl.fa - job.first_frame) + k) * (long long)job.T + l;
-                bar_sync(WP_BAR_XFULL + qq, WS_PC);
+            unsigned int g = f;              // next frame whose tones are still to be stored
+            // Gather the selected bins of frame n (CTA numbering) from its team's spectrum tile and store them
+            // sample-major (coalesced 8-byte stores).  `block` = wait for the tile; otherwise poll once and
+            // return false when the team has not finished the frame yet.
+            auto gather = [&](const unsigned int n, const bool block) -> bool {
+                const unsigned int qq = n & 1u, cc = n >> 1;
+                const unsigned int tile_i = qq * WP_XB + (cc % WP_XB), par = (cc / WP_XB) & 1u;
+                if (block) {
+                    mbar_wait(xfull0 + 8 * tile_i, par);
+                } else {
+                    // warp-uniform decision (lanes can observe the phase flip at different times)
+                    if (!__all_sync(0xffffffffu, mbar_test(xfull0 + 8 * tile_i, par))) return false;
+                }
+                const unsigned int xa = x_base + tile_i * (unsigned int)(WP_X * sizeof(float2));
+                c2* o = reinterpret_cast<c2*>(job.out) + ((tl.fa - job.first_frame) + (long long)(n - f_tile0)) * (long long)job.T + l;
 #pragma unroll
                 for (int h = 0; h < NU / 4; ++h) {
                     if (h * 4 < nv) {
@@ -774,7 +835,8 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
                             if (h * 4 + jj < nv) o[WS_FRONT * (h * 4 + jj)] = val[jj];
                     }
                 }
-                bar_arrive(WP_BAR_XEMPTY + qq, WS_PC);  // after the stores: they have consumed the gathered values
+                mbar_arrive_warp(xempty0 + 8 * tile_i);  // after the stores: they have consumed the gathered values
+                return true;
             };
             const Window win = job.win;
             const long long fast_lo = (win.n_hist + FN - 1) / FN;    // first row fully inside `in`
@@ -856,8 +918,10 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
                     }
                     bar_arrive(WP_BAR_FULL + slot, WS_PC);
                     ++f;
-                    ++emitted;
-                    if (emitted > WP_LAG) gather(emitted - WP_LAG - 1);
+                    // One poll per produced frame keeps the stores a frame or two behind the teams.  (Polling once
+                    // per unrolled group instead -- smaller hot code -- measured 8 % slower: the stores then come in
+                    // bursts and the teams wait for their tiles.)
+                    if (g + 1 < f && gather(g, false)) ++g;
                 };
                 auto guarded_group = [&](const long long s0) {
                     for_each_index(std::make_integer_sequence<int, U>{}, [&](auto u_tag) {
@@ -885,8 +949,8 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
             if (tl.fa < f0) run_tile(std::false_type{}, tl.fa, f0);
             if (f0 < f1) run_tile(std::true_type{}, f0, f1);
             if (f1 < tl.fb) run_tile(std::false_type{}, f1, tl.fb);
-            // drain: the last WP_LAG frames of the tile
-            for (int k = emitted > WP_LAG ? emitted - WP_LAG : 0; k < emitted; ++k) gather(k);
+            // drain: what the polls have not stored yet
+            for (; g < f; ++g) gather(g, true);
         }
     } else {
         // ======================================== BACK ============================================
@@ -899,10 +963,26 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
 #pragma unroll
         for (int k2 = 1; k2 < 16; ++k2) tw2[k2] = __ldg(&tw_global[WS_TW1 + lane16 * 16 + k2]);
         float2* H = sm.h[(t - WS_FRONT) >> 5][(tid >> 4) & 1];
-        bool x_used = false;  // the team's spectrum tile holds a frame the producers may still be gathering from
-        const unsigned int xw = (unsigned int)__cvta_generic_to_shared(sm.x[q]) + (unsigned int)((k1 * 258 + lane16) * sizeof(float2));
+        unsigned int c = 0;  // frames this team has finished
+        const unsigned int xw0 = (unsigned int)__cvta_generic_to_shared(&sm.x[q][0][0]) + (unsigned int)(k1 * 256 * sizeof(float2));
+        unsigned int xo[4];  // byte offset inside row (k1, k3) of this thread's bin k1 + 8 k2 + 128 k3, one byte per k3
+        int loaded_job = -1;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const WsTile tl = ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
+            if (tl.job != loaded_job) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    unsigned int pk = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int bin = k1 + 8 * lane16 + 128 * (4 * i + b);
+                        const unsigned int pos = job.xperm ? (unsigned int)__ldg(job.xperm + bin) : (unsigned int)lane16;
+                        pk |= ((pos & 15u) * 8u) << (8 * b);
+                    }
+                    xo[i] = pk;
+                }
+                loaded_job = tl.job;
+            }
             const int nf = (int)(tl.fb - tl.fa);
             for (int i = (int)((q - f) & 1u); i < nf; i += 2) {
                 const int slot = (f + i) % WP_D1;
@@ -932,16 +1012,21 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
                 for (int m = 0; m < 16; ++m) v[m] = lds_c2(H + lane16 * 17 + m);
                 __syncwarp();
                 c2_fft16(v);
-                if (x_used) bar_sync(WP_BAR_XEMPTY + q, WS_PC);  // the previous frame's tones have left the tile
+                const unsigned int tile_i = q * WP_XB + (c % WP_XB), use = c / WP_XB;
+                if (use > 0) mbar_wait(xempty0 + 8 * tile_i, (use - 1) & 1u);  // the tile's previous frame has been gathered
+                const unsigned int xw = xw0 + (c % WP_XB) * (unsigned int)(WP_X * sizeof(float2));
 #pragma unroll
                 for (int ka = 0; ka < 4; ++ka)
 #pragma unroll
                     for (int kb = 0; kb < 4; ++kb)
-                        asm volatile("st.shared.b64 [%0], %1;" ::"r"(xw + (unsigned int)((ka + 4 * kb) * 16 * sizeof(float2))),
-                                     "l"(v[4 * ka + kb])
+                    {
+                        const int k3 = ka + 4 * kb;
+                        const unsigned int off = __byte_perm(xo[k3 >> 2], 0u, 0x4440u + (k3 & 3));
+                        asm volatile("st.shared.b64 [%0], %1;" ::"r"(xw + off + (unsigned int)(k3 * 16 * sizeof(float2))), "l"(v[4 * ka + kb])
                                      : "memory");
-                bar_arrive(WP_BAR_XFULL + q, WS_PC);
-                x_used = true;
+                    }
+                mbar_arrive_warp(xfull0 + 8 * tile_i);
+                ++c;
             }
             f += nf;
         }

@@ -59,6 +59,7 @@ struct gsdr_rx {
     std::vector<int32_t> bins_host;
     float* d_taps = nullptr;
     int* d_bins = nullptr;
+    unsigned char* d_xperm = nullptr;  // fused kernel: in-row placement that makes the tone gather conflict-free
     float2* d_tw = nullptr;
     void* d_work = nullptr;
     size_t work_bytes = 0;
@@ -165,6 +166,9 @@ int init_pfb(gsdr_rx* rx, bool all_bins) {
     if (rx->fused) {
         auto tw = fused_twiddles();
         if (dev_upload(&rx->d_tw, tw.data(), tw.size())) return -1;
+        std::vector<uint8_t> perm(2048);
+        pfb_gather_coloring(all_bins ? nullptr : rx->bins_host.data(), rx->T_sel, perm.data());
+        if (dev_upload(&rx->d_xperm, perm.data(), perm.size())) return -1;
     } else {
         auto tw = generic_twiddles(N);
         if (dev_upload(&rx->d_tw, tw.data(), tw.size())) return -1;
@@ -275,7 +279,7 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
                 set_error("internal: PFB carry-over mismatch (%lld vs %lld)", w.n_hist + w.n_in - frames * rx->N, tail);
                 return -1;
             }
-            PfbJob job{w, rx->d_taps, rx->d_bins, d_out, 0, (int)frames, rx->N, (int)rx->P, rx->T_sel};
+            PfbJob job{w, rx->d_taps, rx->d_bins, d_out, 0, (int)frames, rx->N, (int)rx->P, rx->T_sel, rx->d_xperm};
             if (!rx->fused) {
                 const size_t need = pfb_workspace_bytes(rx->N, (int)rx->P, (int)frames);
                 if (need > rx->work_bytes) {
@@ -395,6 +399,7 @@ void free_all(gsdr_rx* rx) {
         if (rx->hist[i]) cudaFree(rx->hist[i]);
     if (rx->d_taps) cudaFree(rx->d_taps);
     if (rx->d_bins) cudaFree(rx->d_bins);
+    if (rx->d_xperm) cudaFree(rx->d_xperm);
     if (rx->d_tw) cudaFree(rx->d_tw);
     if (rx->d_work) cudaFree(rx->d_work);
     if (rx->d_profile) cudaFree(rx->d_profile);
@@ -775,7 +780,7 @@ int64_t gsdr_rx_group_process_device(gsdr_rx_group* g, const gsdr_float2* const*
             buffer_helper_update(&rx->bh);
         }
         tails[i] = rx->bh.new_0;
-        jobs[i] = PfbJob{w, rx->d_taps, rx->d_bins, reinterpret_cast<float2*>(out_dev[i]), 0, (int)frames, rx->N, (int)rx->P, rx->T_sel};
+        jobs[i] = PfbJob{w, rx->d_taps, rx->d_bins, reinterpret_cast<float2*>(out_dev[i]), 0, (int)frames, rx->N, (int)rx->P, rx->T_sel, rx->d_xperm};
     }
     const int nl = pfb_launch(jobs.data(), n, g->d_table, nullptr, g->members[0]->d_tw, g->members[0]->sm_count, g->stream);
     if (nl < 0) return -1;

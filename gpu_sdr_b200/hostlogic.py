@@ -35,6 +35,18 @@ def tone_bins(rate, fft_tones, freq) -> np.ndarray:
     return out
 
 
+def pfb_gather_layout(bins, n_tones=None) -> np.ndarray:
+    """Slot (0..15) of every one of the 2048 bins inside its shared-memory row; bins=None: all bins in order."""
+    out = np.empty(2048, dtype=np.uint8)
+    if bins is None:
+        n, ptr = int(n_tones if n_tones is not None else 2048), None
+    else:
+        b = np.ascontiguousarray(bins, dtype=np.int32)
+        n, ptr = len(b), b.ctypes.data_as(C.c_void_p)
+    check(_lib.load().gsdr_pfb_gather_layout(ptr, n, out.ctypes.data_as(C.c_void_p)), "gsdr_pfb_gather_layout")
+    return out
+
+
 BH_FIELDS = ("eff_length", "new_0", "copy_size", "current_batch", "spare_samples", "spare_begin")
 VH_FIELDS = ("valid_size", "new0", "total_len", "spare_begin")
 

@@ -162,6 +162,10 @@ int gsdr_make_sinc_window(int length, float fc, float *taps_out);          /* re
 int gsdr_make_flat_window(int length, int side, float *taps_out);
 int gsdr_pfb_batching(int buffer_len, int fft_tones, int pf_average);
 int gsdr_tone_bins(int rate, int fft_tones, const int32_t *freq, int n, int32_t *bins_out); /* -1: unmatched */
+/* Shared-memory placement the fused 2048-channel kernel uses so that tone_select (cpp/kernels.cu:531-554)
+ * reads its bins without bank conflicts: pos_out[bin] = slot 0..15 of the bin inside its 16-bin row
+ * (bin & 7, bin >> 7).  bins == NULL means all 2048 bins in order (NOISE).  Diagnostic/test hook. */
+int gsdr_pfb_gather_layout(const int32_t *bins, int n_tones, uint8_t *pos_out /* [2048] */);
 
 typedef struct gsdr_buffer_helper {
     int n_tones, eff_length, buffer_len, average, n_eff_tones;
