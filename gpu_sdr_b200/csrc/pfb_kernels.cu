@@ -358,35 +358,22 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
 }
 
 // --------------------------------------------------------------------------------------------
-// warp-specialised fused kernel, N = 2048 = 8 x 16 x 16
+// warp-specialised fused kernel, N = 2048 = 8 x 16 x 16: shared definitions
 //
-//   FRONT (warps 0-7, 256 threads): thread l owns the 8 polyphase columns l + 256 j.  It keeps the
-//     last P input rows of those columns in a register ring, loads one new row per frame (coalesced
-//     8-byte loads, issued one frame ahead), runs the P-tap FIR and the first FFT stage (radix-8 over
-//     j) in registers, applies the stage-1 twiddles W_2048^(l k1) (per-thread constants, registers)
-//     and writes the result into a ring of exchange buffers.
-//   BACK (2 teams of 128 threads, alternate frames): stage 2 (radix-16, twiddles W_256^(n3 k2) in
-//     registers), exchange, stage 3 (radix-16, in place), gather of the selected bins to global.
-//
-// Compared with the lock-step kernel above this removes the FIR->FFT hand-off through shared
-// memory, every twiddle-table load and every CTA-wide barrier: the producers run ahead through a
-// 4-deep ring guarded by named barriers, so row loads, FIR, FFT passes and output stores of
-// different frames overlap on the SM.  Shared-memory wavefronts drop from 0.65 to ~0.36 per sample.
+//   FRONT (warps 0-7, 256 threads): thread l owns the 8 polyphase columns l + 256 j: P-tap FIR, first FFT
+//     stage (radix-8 over j), stage-1 twiddles W_2048^(l k1), hand-over through a ring of exchange buffers.
+//   BACK (2 teams of 128 threads, alternate frames): stage 2 (radix-16, twiddles W_256^(n3 k2)), exchange,
+//     stage 3 (radix-16).
+// The producers run ahead through a 4-deep ring guarded by named barriers, so row loads, FIR, FFT passes and
+// output stores of different frames overlap on the SM.
 // --------------------------------------------------------------------------------------------
 constexpr int WS_FRONT = 256;
 constexpr int WS_TEAM = 128;
 constexpr int WS_TEAMS = 2;
 constexpr int WS_THREADS = WS_FRONT + WS_TEAMS * WS_TEAM;  // 512
-constexpr int WS_D1 = 4;            // exchange-1 ring depth (frames the producers may run ahead)
-constexpr int WS_E1 = 8 * 258;      // [k1][n2*16+n3], k1 stride 258 float2
-constexpr int WS_E2 = 16 * 136;     // [n3][k2*8+k1] / [k3][g], row stride 136 float2
 constexpr int WS_TW1 = 8 * 256;     // W_2048^(l k1) laid out [k1][l]
 constexpr int WS_TW2 = 16 * 16;     // W_256^(n3 k2) laid out [n3][k2]
 
-struct WsSmem {
-    float2 e1[WS_D1][WS_E1];
-    float2 e2[WS_TEAMS][WS_E2];
-};
 
 __device__ __forceinline__ void bar_sync(int id, int count) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
@@ -394,9 +381,6 @@ __device__ __forceinline__ void bar_sync(int id, int count) {
 __device__ __forceinline__ void bar_arrive(int id, int count) {
     asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
 }
-constexpr int WS_BAR_FULL = 1;                   // + slot
-constexpr int WS_BAR_EMPTY = 1 + WS_D1;          // + slot
-constexpr int WS_BAR_TEAM = 1 + 2 * WS_D1;       // + team
 constexpr int WS_PC = WS_FRONT + WS_TEAM;        // participants of a full/empty barrier
 
 // tile -> (job, frame range); identical in every warp role so the frame counters stay in step
@@ -420,215 +404,6 @@ __device__ __forceinline__ WsTile ws_locate(int tile, const PfbJob& single, cons
     const long long end = (long long)job.first_frame + job.n_frames;
     r.fb = r.fa + frames_per_tile < end ? r.fa + frames_per_tile : end;
     return r;
-}
-
-template <int P>
-__global__ void __launch_bounds__(WS_THREADS, 1)
-pfb_fused_ws_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, const int* __restrict__ tile_begin, int n_jobs,
-                   int frames_per_tile, int total_tiles, const float2* __restrict__ tw_global) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    WsSmem& sm = *reinterpret_cast<WsSmem*>(smem_raw);
-    const int t = threadIdx.x;
-    unsigned int f = 0;  // frames this CTA has started, counted identically by every role
-    PfbJob job;
-
-    if (t < WS_FRONT) {
-        // ======================================= FRONT ===========================================
-        // register split: the producers hold the tap/row state (152 regs), the FFT teams need less (104)
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
-        const int l = t;
-        // W_2048^(l k1): only k1 = 1, 2, 4 are kept (6 registers); the other four are products
-        const float2 tw1 = __ldg(&tw_global[1 * 256 + l]), tw2 = __ldg(&tw_global[2 * 256 + l]), tw4 = __ldg(&tw_global[4 * 256 + l]);
-        float w[P][8];
-        constexpr int RS = P + 1;  // ring slots: P rows in use + one row in flight (two frames of lookahead)
-        float2 ring[RS][8];
-        int loaded_job = -1;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const WsTile tl = ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
-            if (tl.job != loaded_job) {
-#pragma unroll
-                for (int i = 0; i < P; ++i)
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) w[i][j] = __ldg(job.taps + i * FN + l + 256 * j);
-                loaded_job = tl.job;
-            }
-            const Window win = job.win;
-            const long long fast_lo = (win.n_hist + FN - 1) / FN;    // first row fully inside `in`
-            const long long fast_hi = (win.n_hist + win.n_in) / FN;  // first row not fully present
-            // The tile body is instantiated twice: kFast when every row it touches lies fully inside the
-            // `in` segment (plain coalesced 8-byte loads, no per-row range logic), general otherwise.
-            auto run_tile = [&](auto fast_tag, const long long fa, const long long fb) {
-                constexpr bool kFast = decltype(fast_tag)::value;
-                const long long last_row = fb + P - 1;  // rows this span needs: [fa, last_row)
-                auto load_row8 = [&](long long row, float2 (&dst)[8]) {
-                    if (kFast) {
-                        const float2* p = win.in + (row * FN - win.n_hist) + l;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) dst[j] = __ldg(p + 256 * j);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) dst[j] = win_at(win, row * FN + l + 256 * j);
-                    }
-                };
-                // warp 0 pulls a whole row (128 lines of 128 bytes) towards L2 several frames ahead
-                auto prefetch_row = [&](long long row) {
-                    if (kFast && l < 32 && row < last_row) {
-                        const float2* p = win.in + (row * FN - win.n_hist) + 16 * l;
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 512 * jj));
-                    }
-                };
-                // row (fa + rho) lives in slot rho % RS; frame 0 needs rows 0..P-1, row P is already in flight
-#pragma unroll
-                for (int i = 0; i < RS; ++i)
-                    if (fa + i < last_row) load_row8(fa + i, ring[i]);
-#pragma unroll
-                for (int i = RS; i < RS + 4; ++i) prefetch_row(fa + i);
-
-                // one frame: FIR from the ring, refill the freed slot, radix-8, twiddle, hand over to the teams
-                auto do_frame = [&](const long long fr, auto u_tag, const bool guarded) {
-                    constexpr int u = decltype(u_tag)::value;
-                    // ---- FIR: frame fr = sum_i row[fr+i] * w_i, rows in slots (u+i) % RS
-                    float2 z[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float ax = 0.f, ay = 0.f;
-#pragma unroll
-                        for (int i = 0; i < P; ++i) {
-                            ax = fmaf(ring[(u + i) % RS][j].x, w[i][j], ax);
-                            ay = fmaf(ring[(u + i) % RS][j].y, w[i][j], ay);
-                        }
-                        z[j] = make_float2(ax, ay);
-                    }
-                    // the oldest row is dead: fetch row fr+RS into its slot, two frames ahead of its use
-                    if (!guarded || fr + RS < last_row) load_row8(fr + RS, ring[u % RS]);
-                    prefetch_row(fr + RS + 4);
-                    // ---- FFT stage 1: radix-8 over j, then twiddle
-                    fft8(z);
-                    const int slot = f % WS_D1;
-                    if (f >= WS_D1) bar_sync(WS_BAR_EMPTY + slot, WS_PC);
-                    float2* E = sm.e1[slot];
-                    // fft8 leaves X[ka + 4 kb] in z[2 ka + kb]
-                    const float2 tw3 = cmul(tw1, tw2), tw5 = cmul(tw1, tw4), tw6 = cmul(tw2, tw4);
-                    E[0 * 258 + l] = z[0];
-                    E[1 * 258 + l] = cmul(z[2], tw1);
-                    E[2 * 258 + l] = cmul(z[4], tw2);
-                    E[3 * 258 + l] = cmul(z[6], tw3);
-                    E[4 * 258 + l] = cmul(z[1], tw4);
-                    E[5 * 258 + l] = cmul(z[3], tw5);
-                    E[6 * 258 + l] = cmul(z[5], tw6);
-                    E[7 * 258 + l] = cmul(z[7], cmul(tw3, tw4));
-                    bar_arrive(WS_BAR_FULL + slot, WS_PC);
-                    ++f;
-                };
-                auto do_group = [&](const long long b, const bool guarded) {
-                    do_frame(b + 0, std::integral_constant<int, 0>{}, guarded);
-                    if (RS > 1 && (!guarded || b + 1 < fb)) do_frame(b + 1, std::integral_constant<int, 1 % RS>{}, guarded);
-                    if (RS > 2 && (!guarded || b + 2 < fb)) do_frame(b + 2, std::integral_constant<int, 2 % RS>{}, guarded);
-                    if (RS > 3 && (!guarded || b + 3 < fb)) do_frame(b + 3, std::integral_constant<int, 3 % RS>{}, guarded);
-                    if (RS > 4 && (!guarded || b + 4 < fb)) do_frame(b + 4, std::integral_constant<int, 4 % RS>{}, guarded);
-                };
-                long long b = fa;
-                // steady state: whole groups of RS frames whose look-ahead rows all exist -- no per-frame tests
-                for (; b + 2 * RS <= fb + P - 1; b += RS) do_group(b, false);
-                // tail: at most two groups, every frame and every refill guarded
-                for (; b < fb; b += RS) do_group(b, true);
-            };
-            // frames whose P rows all lie inside `in` take the fast body; the few that touch the carried-over
-            // history (head of a window) or its ragged end take the general one
-            long long f0 = tl.fa > fast_lo ? tl.fa : fast_lo;
-            long long f1 = tl.fb < fast_hi - P + 1 ? tl.fb : fast_hi - P + 1;
-            if (f0 > tl.fb) f0 = tl.fb;
-            if (f1 < f0) f1 = f0;
-            if (tl.fa < f0) run_tile(std::false_type{}, tl.fa, f0);
-            if (f0 < f1) run_tile(std::true_type{}, f0, f1);
-            if (f1 < tl.fb) run_tile(std::false_type{}, f1, tl.fb);
-        }
-    } else {
-        // ======================================== BACK ============================================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 104;");
-        const int q = (t - WS_FRONT) / WS_TEAM;
-        const int tid = (t - WS_FRONT) % WS_TEAM;
-        const int n3 = tid >> 3, k1 = tid & 7;
-        float2 tw2[16];  // W_256^(n3 k2)
-#pragma unroll
-        for (int k2 = 1; k2 < 16; ++k2) tw2[k2] = __ldg(&tw_global[WS_TW1 + n3 * 16 + k2]);
-        unsigned int bp[8];  // padded X indices of the (up to 16) bins this thread gathers
-        int loaded_job = -1;
-        float2* E2 = sm.e2[q];
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const WsTile tl = ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
-            if (tl.job != loaded_job) {
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                    unsigned int pk = 0;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int u = tid + WS_TEAM * (2 * jj + h);
-                        unsigned int bin = 0;
-                        if (u < job.T) bin = job.bins ? (unsigned int)__ldg(job.bins + u) : (unsigned int)u;
-                        bin &= (FN - 1);
-                        const unsigned int idx = (bin >> 7) * 136u + (bin & 127u);
-                        pk |= idx << (16 * h);
-                    }
-                    bp[jj] = pk;
-                }
-                loaded_job = tl.job;
-            }
-            for (long long b = tl.fa; b < tl.fb; ++b, ++f) {
-                if ((int)(f & 1u) != q) continue;
-                const int slot = f % WS_D1;
-                float2 v[16];
-                // ---- stage 2: radix-16 over n2; thread = (n3, k1)
-                bar_sync(WS_BAR_FULL + slot, WS_PC);
-                {
-                    const float2* E = sm.e1[slot];
-#pragma unroll
-                    for (int n2 = 0; n2 < 16; ++n2) v[n2] = E[k1 * 258 + n2 * 16 + n3];
-                }
-                bar_arrive(WS_BAR_EMPTY + slot, WS_PC);
-                fft16(v);
-                bar_sync(WS_BAR_TEAM + q, WS_TEAM);  // the previous frame's gather has left E2
-#pragma unroll
-                for (int ka = 0; ka < 4; ++ka)
-#pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) {
-                        const int k2 = ka + 4 * kb;
-                        float2 x = v[4 * ka + kb];
-                        if (k2 != 0) x = cmul(x, tw2[k2]);
-                        E2[n3 * 136 + k2 * 8 + k1] = x;
-                    }
-                bar_sync(WS_BAR_TEAM + q, WS_TEAM);
-                // ---- stage 3: radix-16 over n3, in place; g = k1 + 8 k2 = tid, bin = g + 128 k3
-#pragma unroll
-                for (int m = 0; m < 16; ++m) v[m] = E2[m * 136 + tid];
-                fft16(v);
-#pragma unroll
-                for (int ka = 0; ka < 4; ++ka)
-#pragma unroll
-                    for (int kb = 0; kb < 4; ++kb) E2[(ka + 4 * kb) * 136 + tid] = v[4 * ka + kb];
-                bar_sync(WS_BAR_TEAM + q, WS_TEAM);
-                // ---- tone selection: 8 independent gathers in flight, coalesced sample-major stores
-                float2* o = job.out + (b - job.first_frame) * (long long)job.T;
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    if (h * 8 * WS_TEAM < job.T) {
-                        float2 val[8];
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) {
-                            const int j2 = h * 8 + jj;
-                            val[jj] = E2[(bp[j2 >> 1] >> (16 * (j2 & 1))) & 0xffffu];
-                        }
-#pragma unroll
-                        for (int jj = 0; jj < 8; ++jj) {
-                            const int u = tid + WS_TEAM * (h * 8 + jj);
-                            if (u < job.T) o[u] = val[jj];
-                        }
-                    }
-                }
-            }
-        }
-    }
 }
 
 // --------------------------------------------------------------------------------------------
@@ -1124,20 +899,12 @@ bool pfb_fused_supported(int N, int P, int T, const Window&) {
 static int pfb_variant();
 const char* pfb_kernel_name(int N, int P, int T) {
     Window w{};
-    if (pfb_fused_supported(N, P, T, w) && pfb_variant() == 2) {
+    if (pfb_fused_supported(N, P, T, w) && pfb_variant() == 1) {
         switch (P) {
             case 1: return "pfb_fused_wsp_2048_kernel<1>";
             case 2: return "pfb_fused_wsp_2048_kernel<2>";
             case 3: return "pfb_fused_wsp_2048_kernel<3>";
             default: return "pfb_fused_wsp_2048_kernel<4>";
-        }
-    }
-    if (pfb_fused_supported(N, P, T, w) && pfb_variant() == 1) {
-        switch (P) {
-            case 1: return "pfb_fused_ws_2048_kernel<1>";
-            case 2: return "pfb_fused_ws_2048_kernel<2>";
-            case 3: return "pfb_fused_ws_2048_kernel<3>";
-            default: return "pfb_fused_ws_2048_kernel<4>";
         }
     }
     if (pfb_fused_supported(N, P, T, w)) {
@@ -1200,11 +967,11 @@ static int launch_fused(const PfbJob* jobs, int n_jobs, void* scratch, const flo
     return 1;
 }
 
-template <int P, bool kPacked>
+template <int P>
 static int launch_ws(const PfbJob* jobs, int n_jobs, void* scratch, const float2* tw, int sm_count, cudaStream_t stream) {
     static bool attr_set = false;
-    constexpr size_t smem_bytes = kPacked ? sizeof(WpSmem) : sizeof(WsSmem);
-    auto kernel = kPacked ? pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST> : pfb_fused_ws_2048_kernel<P>;
+    constexpr size_t smem_bytes = sizeof(WpSmem);
+    auto kernel = pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST>;
     if (!attr_set) {
         GSDR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         attr_set = true;
@@ -1243,15 +1010,13 @@ static int launch_ws(const PfbJob* jobs, int n_jobs, void* scratch, const float2
     return 1;
 }
 
-// 0 = lock-step kernel, 1 = warp-specialised scalar kernel, 2 = packed warp-specialised kernel (default).
-// GSDR_PFB_VARIANT=lockstep|ws|wsp overrides (timing comparisons only).
+// 0 = lock-step kernel (kept as an independent second implementation for cross-checks),
+// 1 = packed warp-specialised kernel (default).  GSDR_PFB_VARIANT=lockstep selects 0.
 static int pfb_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("GSDR_PFB_VARIANT");
-        if (e && e[0] == 'l') v = 0;
-        else if (e && e[0] == 'w' && e[1] == 's' && e[2] == 0) v = 1;
-        else v = 2;
+        v = (e && e[0] == 'l') ? 0 : 1;
     }
     return v;
 }
@@ -1264,22 +1029,13 @@ int pfb_launch(const PfbJob* jobs, int n_jobs, void* scratch, void* workspace, c
     bool fused = true;
     for (int j = 0; j < n_jobs; ++j)
         fused = fused && pfb_fused_supported(jobs[j].N, jobs[j].P, jobs[j].T, jobs[j].win) && jobs[j].P == jobs[0].P;
-    if (fused && pfb_variant() == 2) {
-        const float2* tws = tw + FTW1 + FTW2;
-        switch (jobs[0].P) {
-            case 1: return launch_ws<1, true>(jobs, n_jobs, scratch, tws, sm_count, stream);
-            case 2: return launch_ws<2, true>(jobs, n_jobs, scratch, tws, sm_count, stream);
-            case 3: return launch_ws<3, true>(jobs, n_jobs, scratch, tws, sm_count, stream);
-            default: return launch_ws<4, true>(jobs, n_jobs, scratch, tws, sm_count, stream);
-        }
-    }
     if (fused && pfb_variant() == 1) {
         const float2* tws = tw + FTW1 + FTW2;
         switch (jobs[0].P) {
-            case 1: return launch_ws<1, false>(jobs, n_jobs, scratch, tws, sm_count, stream);
-            case 2: return launch_ws<2, false>(jobs, n_jobs, scratch, tws, sm_count, stream);
-            case 3: return launch_ws<3, false>(jobs, n_jobs, scratch, tws, sm_count, stream);
-            default: return launch_ws<4, false>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            case 1: return launch_ws<1>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            case 2: return launch_ws<2>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            case 3: return launch_ws<3>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            default: return launch_ws<4>(jobs, n_jobs, scratch, tws, sm_count, stream);
         }
     }
     if (fused) {
