@@ -41,7 +41,22 @@ chirp_lockin_warp_kernel(const Window w, unsigned long long pos0, const ChirpDev
             const bool direct = (s0 + i0 >= w.n_hist) && (s0 + i1 <= w.n_hist + w.n_in);
             if (direct && flat) {
                 const float2* p = w.in + (s0 - w.n_hist);
-                for (int i = i0 + lane; i < i1; i += 32) {
+                int i = i0 + lane;
+                // four independent 256-byte warp loads in flight per iteration (one load per iteration leaves the
+                // SM with too few bytes outstanding to cover HBM latency); same per-lane summation order
+                for (; i + 96 < i1; i += 128) {
+                    float2 x[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) x[u] = __ldg(p + i + 32 * u);
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float2 ch = chirp_phasor(cw.idx);
+                        acc.x = fmaf(ch.x, x[u].x, fmaf(ch.y, x[u].y, acc.x));
+                        acc.y = fmaf(ch.x, x[u].y, fmaf(-ch.y, x[u].x, acc.y));
+                        cw.advance(32u, cp);
+                    }
+                }
+                for (; i < i1; i += 32) {
                     const float2 x = __ldg(p + i);
                     const float2 ch = chirp_phasor(cw.idx);
                     // out = in * conj(chirp): (cx*ix + cy*iy, cx*iy - cy*ix), cpp/kernels.cu:424-425
@@ -111,24 +126,30 @@ __global__ void chirp_lockin_finalize_kernel(const float2* __restrict__ partial,
 }
 
 // decim == 0: plain demodulation, one output per input (cpp/USRP_demodulator.cpp:384-391).
-// Each thread owns RUN consecutive samples so the phase walk is incremental.
+// A warp owns a tile of 32 x RUN consecutive samples, lanes stride it: every load and store of the warp is one
+// contiguous 256-byte line pair, all RUN loads are issued before the first is used.
 constexpr int RUN = 8;
 __global__ void __launch_bounds__(256)
 chirp_demod_full_kernel(const float2* __restrict__ in, long long n, unsigned long long pos0, const ChirpDev cp,
                         float2* __restrict__ out) {
-    const long long n_runs = (n + RUN - 1) / RUN;
-    for (long long rn = blockIdx.x * (long long)blockDim.x + threadIdx.x; rn < n_runs; rn += (long long)gridDim.x * blockDim.x) {
-        const long long s0 = rn * RUN;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    constexpr int TILE = 32 * RUN;
+    const long long tiles = (n + TILE - 1) / TILE;
+    for (long long tile = warp0; tile < tiles; tile += n_warps) {
+        const long long s0 = tile * TILE + lane;
+        if (s0 >= n) continue;
+        float2 x[RUN];
+#pragma unroll
+        for (int i = 0; i < RUN; ++i) x[i] = (s0 + 32 * i < n) ? __ldg(in + s0 + 32 * i) : make_float2(0.f, 0.f);
         ChirpWalker cw;
         cw.seek(pos0 + (unsigned long long)s0, cp);
 #pragma unroll
         for (int i = 0; i < RUN; ++i) {
-            if (s0 + i < n) {
-                const float2 x = in[s0 + i];
-                const float2 ch = chirp_phasor(cw.idx);
-                out[s0 + i] = make_float2(fmaf(ch.x, x.x, ch.y * x.y), fmaf(ch.x, x.y, -ch.y * x.x));
-                cw.advance(1u, cp);
-            }
+            const float2 ch = chirp_phasor(cw.idx);
+            if (s0 + 32 * i < n) out[s0 + 32 * i] = make_float2(fmaf(ch.x, x[i].x, ch.y * x[i].y), fmaf(ch.x, x[i].y, -ch.y * x[i].x));
+            cw.advance(32u, cp);
         }
     }
 }
@@ -216,7 +237,7 @@ int chirp_demod_launch(const Window& w, unsigned long long pos0, const ChirpDev&
 int chirp_demod_full_launch(const float2* in, long long n, unsigned long long pos0, const ChirpDev& cp, float2* out,
                             cudaStream_t stream) {
     if (n <= 0) return 0;
-    long long blocks = ((n + RUN - 1) / RUN + 255) / 256;
+    long long blocks = ((n + 32 * RUN - 1) / (32 * RUN) + 7) / 8;  // 8 warps per block, one tile per warp and pass
     if (blocks > 148 * 16) blocks = 148 * 16;
     chirp_demod_full_kernel<<<(int)blocks, 256, 0, stream>>>(in, n, pos0, cp, out);
     GSDR_CUDA_OK(cudaGetLastError());

@@ -89,6 +89,7 @@ struct ChirpDev {   // kernel-side copy of gsdr_chirp_param plus derived 32-bit 
     unsigned long long length;
     unsigned int chirpness;
     int f0;
+    unsigned long long num_steps;  // period / length
 };
 int chirp_demod_launch(const Window& w, unsigned long long pos0 /* chirp position of window sample 0 */,
                        const ChirpDev& cp, const float* profile, int side /* >=0: flat window, skip [0,side) */,

@@ -63,27 +63,44 @@ __device__ __forceinline__ float2 chirp_phasor(unsigned int index_word) {
 }
 
 // Walks chirp positions pos, pos+stride, pos+2*stride ... : inside a frequency step the index is a
-// phase accumulator (one 32-bit multiply-add); the 64-bit division only runs when a step boundary
-// (or the end of the sweep) is crossed.
+// phase accumulator (one 32-bit multiply-add).  Crossing a step boundary costs one 32-bit division and a
+// re-evaluation of the closed form -- no 64-bit division -- so short steps (a true chirp has length 1: every
+// advance crosses) stay cheap.  64-bit divisions only run in seek() and when the sweep wraps around.
 struct ChirpWalker {
-    unsigned long long eff, k;   // position and step index at the last (re)seek
-    unsigned int adv;            // samples advanced since then
+    unsigned long long k;        // step index
     unsigned int r, len32;       // offset inside the step, step length (clamped to 2^31-1)
     unsigned int idx, step;
+    bool huge;                   // step length does not fit 31 bits: the walk never leaves the step in practice
+    unsigned long long eff0, adv;  // only used when `huge`
     __device__ __forceinline__ void seek(unsigned long long pos, const ChirpDev& cp) {
-        eff = pos % cp.period;
+        const unsigned long long eff = pos % cp.period;
         k = eff / cp.length;
-        r = (unsigned int)(eff - k * cp.length);
-        len32 = cp.length > 0x7fffffffull ? 0x7fffffffu : (unsigned int)cp.length;
+        huge = cp.length > 0x7fffffffull;
+        r = huge ? 0u : (unsigned int)(eff - k * cp.length);
+        len32 = huge ? 0x7fffffffu : (unsigned int)cp.length;
+        eff0 = eff;
         adv = 0;
         idx = chirp_index_word(eff, k, cp);
         step = (unsigned int)cp.f0 + (unsigned int)k * cp.chirpness;
     }
     __device__ __forceinline__ void advance(unsigned int stride, const ChirpDev& cp) {
+        if (huge) {  // rare configuration (a step longer than 2^31 samples): exact but slow
+            adv += stride;
+            seek(eff0 + adv, cp);
+            return;
+        }
         r += stride;
-        adv += stride;
-        if (r < len32) idx += stride * step;
-        else seek(eff + adv, cp);
+        if (r < len32) {
+            idx += stride * step;
+            return;
+        }
+        const unsigned int dk = (len32 == 1u) ? r : r / len32;  // a true chirp (one sample per step) needs no division
+        r -= dk * len32;
+        k += dk;
+        if (k >= cp.num_steps) k %= cp.num_steps;
+        // chirp_index_word only uses the low 32 bits of the position
+        idx = chirp_index_word((unsigned long long)((unsigned int)k * len32 + r), k, cp);
+        step = (unsigned int)cp.f0 + (unsigned int)k * cp.chirpness;
     }
 };
 

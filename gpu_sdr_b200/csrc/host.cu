@@ -293,7 +293,7 @@ int gsdr_probe_chirp_index(int device, const gsdr_chirp_param* p, uint64_t last_
         return -1;
     }
     GSDR_CUDA_OK(cudaSetDevice(device));
-    ChirpDev cd{p->num_steps * p->length, p->length, p->chirpness, p->f0};
+    ChirpDev cd{p->num_steps * p->length, p->length, p->chirpness, p->f0, p->num_steps};
     int* d = nullptr;
     GSDR_CUDA_OK(cudaMalloc(&d, sizeof(int) * (n ? n : 1)));
     const int rc = chirp_index_probe_launch(d, n, last_index, cd, 0);

@@ -192,6 +192,7 @@ int init_chirp(gsdr_rx* rx, const gsdr_param* p) {
     rx->cdev.length = rx->cpar.length;
     rx->cdev.chirpness = rx->cpar.chirpness;
     rx->cdev.f0 = rx->cpar.f0;
+    rx->cdev.num_steps = rx->cpar.num_steps;
     rx->last_index = 0;
     rx->kernel_name = "chirp_demod_full_kernel";
     rx->max_out = (size_t)rx->L;

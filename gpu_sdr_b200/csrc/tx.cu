@@ -120,6 +120,7 @@ int init_chirp(gsdr_tx* tx, const gsdr_param* p) {
     tx->cdev.length = tx->cpar.length;
     tx->cdev.chirpness = tx->cpar.chirpness;
     tx->cdev.f0 = tx->cpar.f0;
+    tx->cdev.num_steps = tx->cpar.num_steps;
     tx->scale = p->ampl[0];
     tx->last_index = 0;
     GSDR_CUDA_OK(cudaMalloc(&tx->d_buf, sizeof(float2) * tx->L));
