@@ -12,6 +12,7 @@
 // phases) followed by one rotation per OUTPUT sample.  No trig and no 64-bit remainder per input
 // sample remain, and nothing but the decimated, sample-major result is written.
 #include "devmath.cuh"
+#include "packed_f32x2.cuh"
 
 namespace gsdr {
 namespace {
@@ -112,6 +113,92 @@ direct_fir_kernel(const Window w, const float2* __restrict__ g, const int* __res
     }
 }
 
+// --------------------------------------------------------------------------------------------
+// Register-tiled version (the default): lane = output, 16 tones per thread.
+//
+// The filter is M x f taps: y[p] = sum_{i<f} sum_{k<M} x[(p+i) M + k] g[i M + k].  A block owns 32*NW consecutive
+// outputs and one group of 16 tones and walks the taps in chunks of KC columns k: the chunk's input columns of all
+// PB+f-1 rows go to shared memory with an ODD row stride (KC+1), so the 32 lanes -- 32 consecutive outputs, M samples
+// apart -- read 32 different bank pairs; the chunk's taps go to shared memory tone-fastest, so one tap of two tones is
+// ONE broadcast 16-byte load.  Per tap and thread: 1 + 8 shared loads feed 32 packed FMAs (acc += x*gr + (j x)*gi),
+// i.e. the kernel is bound by the fp32 pipe (16 T real FMAs per input sample), not by loads or shuffles; there is no
+// cross-lane reduction at all.  The previous kernel (lanes stride the taps, 320 shuffles per 4 x 8 tile) stays as the
+// fallback for filters with more than D_FMAX blocks.
+// --------------------------------------------------------------------------------------------
+constexpr int D_TC = 16;    // tones per thread
+constexpr int D_KC = 32;    // tap columns per staged chunk
+constexpr int D_GST = 18;   // float2 stride of one staged tap (16 tones + 2 pad: 16-byte aligned, spreads the staging stores)
+constexpr int D_FMAX = 8;
+
+template <int NW>
+__global__ void __launch_bounds__(32 * NW, 4)
+direct_fir_tiled_kernel(const Window w, const float2* __restrict__ g, const int* __restrict__ freq, int T, int M, int f, int rate,
+                        long long pos0, long long n_out, float2* __restrict__ out) {
+    extern __shared__ __align__(16) float2 dsm[];
+    constexpr int PB = 32 * NW;
+    const int rows = PB + f - 1;
+    float2* xs = dsm;                              // [rows][D_KC + 1]
+    float2* gs = dsm + rows * (D_KC + 1);          // [f][D_KC][D_GST]
+    if ((reinterpret_cast<uintptr_t>(gs) & 15) != 0) gs += 1;  // 16-byte alignment for the broadcast loads
+    const int tid = threadIdx.x;
+    const long long p0 = (long long)blockIdx.x * PB;
+    const int ch0 = blockIdx.y * D_TC;
+    const int ntaps = f * M;
+
+    c2 acc[D_TC];
+#pragma unroll
+    for (int b = 0; b < D_TC; ++b) acc[b] = c2_pack(0.f, 0.f);
+
+    for (int k0 = 0; k0 < M; k0 += D_KC) {
+        const int kc = min(D_KC, M - k0);
+        __syncthreads();
+        for (int e = tid; e < rows * kc; e += PB) {
+            const int r = e / kc, kk = e - r * kc;
+            xs[r * (D_KC + 1) + kk] = dev_win_at(w, (p0 + r) * (long long)M + k0 + kk);
+        }
+        for (int e = tid; e < f * D_TC * kc; e += PB) {
+            const int kk = e % kc, ch = (e / kc) % D_TC, i = e / (kc * D_TC);
+            float2 v = make_float2(0.f, 0.f);
+            if (ch0 + ch < T) v = __ldg(g + (long long)(ch0 + ch) * ntaps + i * M + k0 + kk);
+            gs[(i * D_KC + kk) * D_GST + ch] = v;
+        }
+        __syncthreads();
+        for (int i = 0; i < f; ++i) {
+            const float2* xr = xs + (tid + i) * (D_KC + 1);
+            const float4* gr = reinterpret_cast<const float4*>(gs + i * D_KC * D_GST);
+#pragma unroll 4
+            for (int kk = 0; kk < kc; ++kk) {
+                const float2 xv = xr[kk];
+                const c2 x = c2_pack(xv.x, xv.y), jx = c2_pack(-xv.y, xv.x);
+#pragma unroll
+                for (int b2 = 0; b2 < D_TC / 2; ++b2) {
+                    const float4 gg = gr[kk * (D_GST / 2) + b2];  // taps of two tones, same address in every lane
+                    acc[2 * b2] = c2_fma_s(x, gg.x, acc[2 * b2]);
+                    acc[2 * b2] = c2_fma_s(jx, gg.y, acc[2 * b2]);
+                    acc[2 * b2 + 1] = c2_fma_s(x, gg.z, acc[2 * b2 + 1]);
+                    acc[2 * b2 + 1] = c2_fma_s(jx, gg.w, acc[2 * b2 + 1]);
+                }
+            }
+        }
+    }
+    // rotate by the LO phase of the output's first tap (integer phase, cpp/kernels.cu:59-75) and store sample-major
+    const long long p = p0 + tid;
+    if (p < n_out) {
+        const double inv_R = 1.0 / (double)rate;
+        long long n0 = (pos0 + p * (long long)M) % rate;
+        if (n0 < 0) n0 += rate;
+#pragma unroll
+        for (int b = 0; b < D_TC; ++b) {
+            const int ch = ch0 + b;
+            if (ch < T) {
+                long long ph = direct_phase_signed(freq[ch], (unsigned long long)n0, rate);
+                if (ph < 0) ph += rate;  // same residue class; the reference keeps the sign
+                out[p * T + ch] = dev_cmul(c2_to(acc[b]), lo_phasor(ph, inv_R));
+            }
+        }
+    }
+}
+
 // decim == 0: pure mixing, out[n*T + ch] = x[n] e^{-j theta_ch n} (cpp/USRP_demodulator.cpp:442-457).
 constexpr int MIX_S = 32;  // samples per block
 __global__ void __launch_bounds__(256)
@@ -159,6 +246,28 @@ __global__ void direct_phase_probe_kernel(long long* __restrict__ out, unsigned 
 int direct_fir_launch(const Window& w, const float2* g, const int* freq_dev, int T, int M, int ntaps, int rate,
                       long long pos0, long long n_out, float2* out, cudaStream_t stream) {
     if (n_out <= 0) return 0;
+    const int f = M > 0 ? ntaps / M : 0;
+    if (M >= 1 && f >= 1 && f <= D_FMAX && f * M == ntaps) {
+        // register-tiled kernel; 64-output blocks when 128-output blocks would leave SMs idle
+        const int tone_groups = (T + D_TC - 1) / D_TC;
+        const bool small = ((n_out + 127) / 128) * tone_groups < 2 * 148;
+        const int PB2 = small ? 64 : 128;
+        const size_t smem = ((size_t)(PB2 + f - 1) * (D_KC + 1) + (size_t)f * D_KC * D_GST + 2) * sizeof(float2);
+        dim3 grid((unsigned)((n_out + PB2 - 1) / PB2), (unsigned)tone_groups);
+        static bool attr_set = false;
+        if (!attr_set) {
+            const int cap = (int)(((size_t)(128 + D_FMAX - 1) * (D_KC + 1) + (size_t)D_FMAX * D_KC * D_GST + 2) * sizeof(float2));
+            GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_tiled_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
+            attr_set = true;
+        }
+        if (small)
+            direct_fir_tiled_kernel<2><<<grid, 64, smem, stream>>>(w, g, freq_dev, T, M, f, rate, pos0, n_out, out);
+        else
+            direct_fir_tiled_kernel<4><<<grid, 128, smem, stream>>>(w, g, freq_dev, T, M, f, rate, pos0, n_out, out);
+        GSDR_CUDA_OK(cudaGetLastError());
+        return 1;
+    }
     // outputs per block: as many as fit 96 KB of staged input, multiple of TP, at most 64
     int PB = 64;
     while (PB > TP && ((size_t)(PB - 1) * M + ntaps) * sizeof(float2) > 96 * 1024) PB -= TP;

@@ -4,8 +4,7 @@
 // the channelizer (cpp/USRP_demodulator.cpp:501 -- cufftExecC2C in the reference) and its polyphase
 // FIR (cpp/kernels.cu:495-506) are issue-bound on CUDA cores, not FMA-pipe bound.
 //
-// Every packed op is the same IEEE fp32 operation per component as its scalar twin, so results are
-// bit-identical to the unpacked formulation.
+// Every packed op is the same IEEE fp32 operation per component as its scalar twin.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -61,52 +60,99 @@ __device__ __forceinline__ c2 c2_fma_s(c2 a, float s, c2 c) {
     return r;
 }
 
-// a * (bx + j by): one packed multiply and two scalar FMAs (a swap of the halves is not free in the
-// packed form, so the cross terms stay scalar).
+// Multiplication by -j / +j: a swap of the halves plus one sign flip.  ptxas folds the pair below into OPERAND
+// MODIFIERS of the consuming packed instruction (SASS `R.F32x2.LO_HI.NP`), so quarter-turn rotations are free.
+__device__ __forceinline__ c2 c2_mj(c2 a) {
+    float x, y;
+    c2_unpack(a, x, y);
+    return c2_pack(y, -x);
+}
+__device__ __forceinline__ c2 c2_pj(c2 a) {
+    float x, y;
+    c2_unpack(a, x, y);
+    return c2_pack(-y, x);
+}
+// Packed instructions execute on the fmaheavy pipe only, two cycles each; scalar FADD/FFMA can also use fmalite.
+// An all-packed FFT therefore trades issue slots for fmaheavy cycles.  GSDR_PK_MODE picks the mix (measured on the
+// fused PFB kernel, bench.py --profile): bit 0 = butterflies fully packed (8 instructions instead of 6 packed + 4
+// scalar), bit 1 = twiddles fully packed (2 instructions instead of 1 packed + 2 scalar).
+#ifndef GSDR_PK_MODE
+#define GSDR_PK_MODE 0
+#endif
+// a * (bx + j by)
 __device__ __forceinline__ c2 c2_cmul(c2 a, float bx, float by) {
+#if GSDR_PK_MODE & 2
+    return c2_fma_s(c2_pj(a), by, c2_scale(a, bx));
+#elif GSDR_PK_MODE & 4
+    float ax, ay;
+    c2_unpack(a, ax, ay);
+    return c2_pack(fmaf(-ay, by, ax * bx), fmaf(ax, by, ay * bx));
+#else
     float ax, ay, mx, my;
     c2_unpack(a, ax, ay);
     c2_unpack(c2_scale(a, bx), mx, my);
     return c2_pack(fmaf(-ay, by, mx), fmaf(ax, by, my));
+#endif
 }
 // a * sqrt(1/2) (1 - j)  =  W8^1
 __device__ __forceinline__ c2 c2_mul_w8_1(c2 a) {
+#if GSDR_PK_MODE & 2
+    return c2_fma_s(c2_mj(a), 0.70710678118654752f, c2_scale(a, 0.70710678118654752f));
+#else
     float mx, my;
     c2_unpack(c2_scale(a, 0.70710678118654752f), mx, my);
     return c2_pack(mx + my, my - mx);
+#endif
 }
 // a * sqrt(1/2) (-1 - j)  =  W8^3
 __device__ __forceinline__ c2 c2_mul_w8_3(c2 a) {
+#if GSDR_PK_MODE & 2
+    return c2_fma_s(c2_mj(a), 0.70710678118654752f, c2_scale(a, -0.70710678118654752f));
+#else
     float mx, my;
     c2_unpack(c2_scale(a, 0.70710678118654752f), mx, my);
     return c2_pack(my - mx, -mx - my);
+#endif
 }
 
-// 4-point forward DFT in place, natural order out: 6 packed + 4 scalar adds.
+// t + (-j) d and t - (-j) d
+__device__ __forceinline__ void c2_rot_pair(c2 t, c2 d, c2& plus, c2& minus) {
+#if GSDR_PK_MODE & 1
+    const c2 r = c2_mj(d);
+    plus = c2_add(t, r);
+    minus = c2_sub(t, r);
+#else
+    float tx, ty, dx, dy;
+    c2_unpack(t, tx, ty);
+    c2_unpack(d, dx, dy);
+    plus = c2_pack(tx + dy, ty - dx);
+    minus = c2_pack(tx - dy, ty + dx);
+#endif
+}
+
+// 4-point forward DFT in place, natural order out.
 __device__ __forceinline__ void c2_fft4(c2& a0, c2& a1, c2& a2, c2& a3) {
     const c2 t0 = c2_add(a0, a2), t1 = c2_sub(a0, a2), t2 = c2_add(a1, a3), d = c2_sub(a1, a3);
-    float t1x, t1y, dx, dy;
-    c2_unpack(t1, t1x, t1y);
-    c2_unpack(d, dx, dy);
+#if GSDR_PK_MODE & 16
+    float ux, uy, vx, vy;
+    c2_unpack(t0, ux, uy);
+    c2_unpack(t2, vx, vy);
+    a0 = c2_pack(ux + vx, uy + vy);
+    a2 = c2_pack(ux - vx, uy - vy);
+#else
     a0 = c2_add(t0, t2);
     a2 = c2_sub(t0, t2);
-    a1 = c2_pack(t1x + dy, t1y - dx);  // t1 + (-j) d
-    a3 = c2_pack(t1x - dy, t1y + dx);  // t1 - (-j) d
+#endif
+    c2_rot_pair(t1, d, a1, a3);
 }
 // same with a2 pre-multiplied by -j (folds the W16^4 twiddle of the 16-point transform)
 __device__ __forceinline__ void c2_fft4_a2mj(c2& a0, c2& a1, c2& a2, c2& a3) {
-    float a0x, a0y, a2x, a2y;
-    c2_unpack(a0, a0x, a0y);
-    c2_unpack(a2, a2x, a2y);
-    const c2 t0 = c2_pack(a0x + a2y, a0y - a2x), t1 = c2_pack(a0x - a2y, a0y + a2x);
+    c2 t0, t1;
+    c2_rot_pair(a0, a2, t0, t1);
     const c2 t2 = c2_add(a1, a3), d = c2_sub(a1, a3);
-    float t1x, t1y, dx, dy;
-    c2_unpack(t1, t1x, t1y);
-    c2_unpack(d, dx, dy);
     a0 = c2_add(t0, t2);
     a2 = c2_sub(t0, t2);
-    a1 = c2_pack(t1x + dy, t1y - dx);
-    a3 = c2_pack(t1x - dy, t1y + dx);
+    c2_rot_pair(t1, d, a1, a3);
 }
 
 #define GSDR_PK_C1 0.92387953251128674f /* cos(pi/8) */
@@ -154,13 +200,7 @@ __device__ __forceinline__ void c2_fft8(c2 (&v)[8]) {
         v[2] = c2_add(a, b);
         v[3] = c2_sub(a, b);
     }
-    {   // odd input carries W8^2 = -j
-        float ax, ay, bx, by;
-        c2_unpack(v[4], ax, ay);
-        c2_unpack(v[5], bx, by);
-        v[4] = c2_pack(ax + by, ay - bx);
-        v[5] = c2_pack(ax - by, ay + bx);
-    }
+    c2_rot_pair(v[4], v[5], v[4], v[5]);  // odd input carries W8^2 = -j
     {
         const c2 a = v[6], b = v[7];
         v[6] = c2_add(a, b);

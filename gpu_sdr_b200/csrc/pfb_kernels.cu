@@ -655,9 +655,21 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
                     c2(&x)[8] = land[u % LA];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
+#if GSDR_PK_MODE & 8
+                        float xr, xi;
+                        c2_unpack(x[j], xr, xi);
+#pragma unroll
+                        for (int i = P - 1; i >= 1; --i) {
+                            float ar, ai;
+                            c2_unpack(acc[(u + P * U - i) % P][j], ar, ai);
+                            acc[(u + P * U - i) % P][j] = c2_pack(fmaf(xr, w[i][j], ar), fmaf(xi, w[i][j], ai));
+                        }
+                        acc[u % P][j] = c2_pack(xr * w[0][j], xi * w[0][j]);
+#else
 #pragma unroll
                         for (int i = P - 1; i >= 1; --i) acc[(u + P * U - i) % P][j] = c2_fma_s(x[j], w[i][j], acc[(u + P * U - i) % P][j]);
                         acc[u % P][j] = c2_scale(x[j], w[0][j]);
+#endif
                     }
                     if (!guarded || s + LA < n_steps) load_row8(fa + s + LA, x);
                     prefetch_row(fa + s + LA + 4);

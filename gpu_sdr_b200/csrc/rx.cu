@@ -252,7 +252,7 @@ int init_direct(gsdr_rx* rx) {
         rx->hist_cap = (f - 1) * M + 16;
         rx->n_hist = (f - 1) * M;  // FIR history starts as zeros (cpp/fir.cu:23-26)
         rx->max_out = (size_t)(rx->L / M) * T;
-        rx->kernel_name = "direct_fir_kernel";
+        rx->kernel_name = (rx->P >= 1 && rx->P <= 8) ? "direct_fir_tiled_kernel" : "direct_fir_kernel";
     }
     return 0;
 }
