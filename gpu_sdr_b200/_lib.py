@@ -68,6 +68,8 @@ SIGNATURES = {
     "gsdr_rx_destroy": (None, [C.c_void_p]),
     "gsdr_rx_process": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsdr_rx_submit": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "gsdr_rx_submit_sc16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
+    "gsdr_rx_process_sc16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "gsdr_rx_wait": (C.c_int, [C.c_void_p, C.c_int]),
     "gsdr_rx_input_consumed": (C.c_int, [C.c_void_p, C.c_int]),
     "gsdr_rx_pipeline_depth": (C.c_int, [C.c_void_p]),

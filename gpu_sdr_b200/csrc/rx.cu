@@ -24,9 +24,38 @@ namespace {
 struct Slot {
     float2* d_in = nullptr;
     float2* d_out = nullptr;
+    short2* d_raw = nullptr;  // sc16 ingest: the wire-format copy of the buffer (allocated on first use)
     cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
     bool used = false;
 };
+
+// sc16 -> fc32 on the device.  With a USRP the wire format is sc16 and UHD converts to fc32 on the host CPU (the
+// reference asks for stream_args_t("fc32"), cpp/USRP_hardware_manager.cpp:764-820; "The UHD libraries use the CPU to
+// convert the data", server_docs/01_installation.md:9) with the scale factor 1/32767.  Doing it here halves the bytes
+// that cross PCIe and the pinned-pool footprint.  4 samples per thread: one 16-byte load, two 16-byte stores.
+constexpr float kSc16Scale = 1.0f / 32767.0f;
+__global__ void __launch_bounds__(256)
+sc16_to_fc32_kernel(const short2* __restrict__ in, long long n, float2* __restrict__ out) {
+    const long long n4 = n >> 2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const int4 v = __ldg(reinterpret_cast<const int4*>(in) + i);
+        const int w[4] = {v.x, v.y, v.z, v.w};
+        float4 o[2];
+        float* of = reinterpret_cast<float*>(o);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            of[2 * k] = (float)(short)(w[k] & 0xffff) * kSc16Scale;
+            of[2 * k + 1] = (float)(short)(w[k] >> 16) * kSc16Scale;
+        }
+        reinterpret_cast<float4*>(out)[2 * i] = o[0];
+        reinterpret_cast<float4*>(out)[2 * i + 1] = o[1];
+    }
+    // ragged tail (buffer_len not a multiple of 4)
+    for (long long i = (n4 << 2) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const short2 v = in[i];
+        out[i] = make_float2((float)v.x * kSc16Scale, (float)v.y * kSc16Scale);
+    }
+}
 
 }  // namespace
 
@@ -392,6 +421,7 @@ void free_all(gsdr_rx* rx) {
     for (auto& s : rx->slots) {
         if (s.d_in) cudaFree(s.d_in);
         if (s.d_out) cudaFree(s.d_out);
+        if (s.d_raw) cudaFree(s.d_raw);
         if (s.in_done) cudaEventDestroy(s.in_done);
         if (s.comp_done) cudaEventDestroy(s.comp_done);
         if (s.out_done) cudaEventDestroy(s.out_done);
@@ -607,6 +637,54 @@ int gsdr_rx_pipeline_depth(const gsdr_rx* rx) { return rx ? (int)(rx->slots.empt
 int gsdr_rx_process(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* out) {
     int len = 0;
     const int ticket = gsdr_rx_submit(rx, in, out, &len);
+    if (ticket < 0) return -1;
+    if (gsdr_rx_wait(rx, ticket)) return -1;
+    return len;
+}
+
+int gsdr_rx_submit_sc16(gsdr_rx* rx, const int16_t* in_iq, gsdr_float2* out, int* valid_len) {
+    if (!rx || !in_iq || !out) {
+        set_error("gsdr_rx_submit_sc16: null argument");
+        return -1;
+    }
+    if (set_dev(rx)) return -1;
+    if (rx->mode == GSDR_NODSP) {  // no GPU work in this mode: convert while copying
+        float* o = reinterpret_cast<float*>(out);
+        for (long long i = 0; i < 2 * rx->L; ++i) o[i] = (float)in_iq[i] * kSc16Scale;
+        if (valid_len) *valid_len = (int)rx->L;
+        return (int)(rx->tickets++ % 0x40000000u);
+    }
+    const int ticket = (int)(rx->tickets++ % 0x40000000u);
+    Slot& s = rx->slots[(size_t)ticket % rx->slots.size()];
+    if (s.used) GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));
+    if (!s.d_raw) GSDR_CUDA_OK(cudaMalloc(&s.d_raw, sizeof(short2) * rx->L));
+    GSDR_CUDA_OK(cudaMemcpyAsync(s.d_raw, in_iq, sizeof(short2) * rx->L, cudaMemcpyHostToDevice, rx->s_in));
+    GSDR_CUDA_OK(cudaEventRecord(s.in_done, rx->s_in));
+    GSDR_CUDA_OK(cudaStreamWaitEvent(rx->s_comp, s.in_done, 0));
+    {
+        long long blocks = ((rx->L >> 2) + 255) / 256;
+        if (blocks < 1) blocks = 1;
+        if (blocks > (long long)rx->sm_count * 8) blocks = (long long)rx->sm_count * 8;
+        sc16_to_fc32_kernel<<<(int)blocks, 256, 0, rx->s_comp>>>(s.d_raw, rx->L, s.d_in);
+        GSDR_CUDA_OK(cudaGetLastError());
+        rx->launches++;
+    }
+    int len = 0;
+    const long long total = enqueue_compute(rx, s.d_in, 1, s.d_out, &len);
+    if (total < 0) return -1;
+    GSDR_CUDA_OK(cudaEventRecord(s.comp_done, rx->s_comp));
+    GSDR_CUDA_OK(cudaStreamWaitEvent(rx->s_out, s.comp_done, 0));
+    if (total > 0)
+        GSDR_CUDA_OK(cudaMemcpyAsync(out, s.d_out, sizeof(float2) * total, cudaMemcpyDeviceToHost, rx->s_out));
+    GSDR_CUDA_OK(cudaEventRecord(s.out_done, rx->s_out));
+    s.used = true;
+    if (valid_len) *valid_len = len;
+    return ticket;
+}
+
+int gsdr_rx_process_sc16(gsdr_rx* rx, const int16_t* in_iq, gsdr_float2* out) {
+    int len = 0;
+    const int ticket = gsdr_rx_submit_sc16(rx, in_iq, out, &len);
     if (ticket < 0) return -1;
     if (gsdr_rx_wait(rx, ticket)) return -1;
     return len;

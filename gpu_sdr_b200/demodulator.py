@@ -33,6 +33,12 @@ def _ptr(a: np.ndarray):
     return a.ctypes.data_as(C.c_void_p)
 
 
+def _ptr_i16(a: np.ndarray):
+    if a.dtype != np.int16 or not a.flags["C_CONTIGUOUS"]:
+        raise TypeError("sc16 buffers must be C-contiguous int16 arrays (interleaved I/Q)")
+    return a.ctypes.data_as(C.c_void_p)
+
+
 class _Pinned:
     """Owner of one cudaMallocHost block exposed as a complex64 numpy array."""
 
@@ -101,6 +107,20 @@ class RX_buffer_demodulator:
 
     def wait(self, ticket: int) -> None:
         check(self.lib.gsdr_rx_wait(self._h, int(ticket)), "gsdr_rx_wait")
+
+    # -- sc16 ingest: the USRP wire format goes to the GPU as is --------
+    def process_sc16(self, iq: np.ndarray, output_buffer: np.ndarray) -> int:
+        """iq: int16 array of 2*buffer_len interleaved I/Q.  Same result as process(iq_as_float / 32767)."""
+        if iq.dtype != np.int16 or iq.size < 2 * self.parameters.buffer_len:
+            raise ValueError("iq must be int16 with 2*buffer_len elements")
+        if output_buffer.size < self.max_output():
+            raise ValueError(f"output buffer holds {output_buffer.size} < {self.max_output()} samples")
+        return check(self.lib.gsdr_rx_process_sc16(self._h, _ptr_i16(iq), _ptr(output_buffer)), "gsdr_rx_process_sc16")
+
+    def submit_sc16(self, iq, output_buffer):
+        n = C.c_int(0)
+        t = check(self.lib.gsdr_rx_submit_sc16(self._h, _ptr_i16(iq), _ptr(output_buffer), C.byref(n)), "gsdr_rx_submit_sc16")
+        return t, n.value
 
     def process_device(self, in_dev: int, n_buffers: int, out_dev: int):
         lens = (C.c_int * n_buffers)()

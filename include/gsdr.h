@@ -94,6 +94,14 @@ int gsdr_rx_wait(gsdr_rx *rx, int ticket);
 int gsdr_rx_input_consumed(gsdr_rx *rx, int ticket);
 int gsdr_rx_pipeline_depth(const gsdr_rx *rx);
 
+/* sc16 ingest.  `in_iq` = buffer_len interleaved int16 I/Q pairs, the USRP wire
+ * format; the sc16 -> fc32 conversion that UHD does on the host CPU for the reference
+ * (stream_args_t("fc32"), cpp/USRP_hardware_manager.cpp:764-820; scale 1/32767) runs on the GPU instead, so half
+ * the bytes cross PCIe.  Results equal gsdr_rx_process on (float)iq * (1.0f/32767.0f) bit for bit.  Same ticket /
+ * wait protocol and output contract as gsdr_rx_submit / gsdr_rx_process. */
+int gsdr_rx_submit_sc16(gsdr_rx *rx, const int16_t *in_iq, gsdr_float2 *out, int *valid_len);
+int gsdr_rx_process_sc16(gsdr_rx *rx, const int16_t *in_iq, gsdr_float2 *out);
+
 /* Device-resident batched variant (inputs already in HBM): `in_dev` holds n_buffers consecutive
  * transport buffers of this stream (n_buffers*buffer_len float2, contiguous), `out_dev` receives
  * the concatenated valid outputs; valid_lens[i] gets buffer i's valid float2 count (host array,

@@ -136,3 +136,68 @@ def test_full_duplex_two_front_ends_concurrently():
     [t.start() for t in th]
     [t.join() for t in th]
     assert results == {"A": True, "B": True}
+
+
+@pytest.mark.parametrize("mode", ["tones", "direct", "chirp", "nodsp"])
+def test_sc16_ingest_equals_host_side_conversion(mode):
+    """gsdr_rx_process_sc16 (wire-format int16 I/Q, converted on the GPU) must equal gsdr_rx_process on the buffer a
+    host would have produced with UHD's sc16 -> fc32 rule, (float)v * (1/32767), bit for bit -- and the fp64 oracle."""
+    from common import chirp_param, direct_param
+    L = 100_003 if mode == "nodsp" else 100_000  # the ragged tail of the conversion kernel is exercised by nodsp only
+    if mode == "tones":
+        p = pfb_param(N=2048, P=4, T=300, L=L)
+        o = orc.PFBDemodulator(p.rate, p.fft_tones, p.pf_average, L, p.freq)
+    elif mode == "direct":
+        p = direct_param(rate=10_000_000, T=5, decim=50, f=4, L=L)
+        o = orc.DirectDemodulator(p.rate, p.freq, p.decim, p.pf_average, L)
+    elif mode == "chirp":
+        p = chirp_param(steps=1000, t=0.01, decim=2, L=L)
+        o = orc.ChirpDemodulator(p.rate, p.freq[0], p.chirp_f[0], p.swipe_s[0], p.chirp_t[0], p.decim, L)
+    else:
+        p = g.param(rate=1_000_000, buffer_len=L, wave_type=[g.NODSP], freq=[0], ampl=[1.0])
+        o = None
+    rng = np.random.default_rng(99)
+    raws = [rng.integers(-20000, 20000, size=2 * L, dtype=np.int16) for _ in range(3)]
+    as_float = [(r.astype(np.float32) * np.float32(1.0 / 32767.0)).view(np.complex64) for r in raws]
+    want = rx_run(p, as_float)
+    rx = g.RX_buffer_demodulator(p)
+    out = g.pinned_empty(rx.max_output())
+    pinned_raw = g.pinned_empty((L + 1) // 2 + 1).view(np.int16)
+    try:
+        for r, w, xf in zip(raws, want, as_float):
+            pinned_raw[:2 * L] = r
+            n = rx.process_sc16(pinned_raw, out)
+            assert n == len(w)
+            assert np.array_equal(out[:n].view(np.uint32), w.view(np.uint32))
+            if o is not None:
+                assert orc.rel_l2(out[:n], o.process(xf)) <= TOL
+    finally:
+        rx.close()
+
+
+def test_sc16_pipelined_submit_wait():
+    p = pfb_param(N=2048, P=4, T=100, L=150_000)
+    L = p.buffer_len
+    rng = np.random.default_rng(5)
+    raws = [rng.integers(-8000, 8000, size=2 * L, dtype=np.int16) for _ in range(6)]
+    want = rx_run(p, [(r.astype(np.float32) * np.float32(1.0 / 32767.0)).view(np.complex64) for r in raws])
+    rx = g.RX_buffer_demodulator(p)
+    ins = [g.pinned_empty(L // 2).view(np.int16) for _ in range(3)]
+    outs = [g.pinned_empty(rx.max_output()) for _ in range(3)]
+    pending, got = [], []
+    for i, r in enumerate(raws):
+        if len(pending) == 3:
+            t0, n0, k0 = pending.pop(0)
+            rx.wait(t0)
+            got.append(outs[k0][:n0].copy())
+        k = i % 3
+        ins[k][:] = r
+        t, n = rx.submit_sc16(ins[k], outs[k])
+        pending.append((t, n, k))
+    for t0, n0, k0 in pending:
+        rx.wait(t0)
+        got.append(outs[k0][:n0].copy())
+    rx.close()
+    assert len(got) == len(want)
+    for a, b in zip(got, want):
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
