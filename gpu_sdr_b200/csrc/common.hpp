@@ -77,6 +77,9 @@ const char* pfb_kernel_name(int N, int P, int T);
 size_t pfb_workspace_bytes(int N, int P, int max_frames);
 int pfb_launch(const PfbJob* jobs_host, int n_jobs, void* jobs_dev_scratch, void* workspace, const float2* twiddle_dev,
                int sm_count, cudaStream_t stream);
+// NOISE + decim: average every d consecutive N-bin spectra; `acc` (2*N float2, device) carries the open group.
+int spectra_decimate_launch(const float2* spec, long long n_frames, int N, int d, int carried, float2* acc, float2* out,
+                            long long n_groups, int sm_count, cudaStream_t stream);
 // Copies the last n_tail samples of the window into dst (device), double-buffer safe.
 int window_tail_copy(const Window& w, long long n_tail, float2* dst, cudaStream_t stream);
 int window_tail_copy_multi(const Window* wins, const long long* n_tail, float2* const* dst, int n, void* scratch,

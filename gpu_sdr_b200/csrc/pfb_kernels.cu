@@ -886,6 +886,41 @@ pfb_dft_generic_kernel(const PfbJob job, const float2* __restrict__ z, const flo
     if (live) job.out[(long long)f * job.T + u] = total;
 }
 
+// NOISE mode with decim > 0 (process_pfb_spec + decimate_spectra, cpp/USRP_demodulator.cpp:568-649,
+// cpp/kernels.cu:704-749): every `d` consecutive spectra are averaged bin by bin.  The reference accumulates with
+// float atomics into a buffer it never zeroes and scales on another stream; what is built here is the function it
+// is meant to compute, out[g][k] = (1/d) sum_{j<d} X[g d + j][k], with the running sum carried across calls so group
+// boundaries do not depend on how the stream was cut into buffers.  One thread per (group, bin), sequential in j:
+// coalesced across bins, deterministic, bit-identical for any buffering.
+__global__ void __launch_bounds__(256)
+spectra_decimate_kernel(const float2* __restrict__ spec, long long n_frames, int N, int d, int carried /* frames already in acc */,
+                        float2* __restrict__ acc /* [N] running sum of the open group */, float2* __restrict__ out, long long n_groups) {
+    const float inv_d = 1.0f / (float)d;
+    // units 0..n_groups-1 close a group; unit n_groups folds the remaining frames into acc
+    const long long units = (n_groups + 1) * (long long)N;
+    for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < units; e += (long long)gridDim.x * blockDim.x) {
+        const long long grp = e / N;
+        const int k = (int)(e - grp * N);
+        long long f0 = grp * d - carried, f1 = f0 + d;
+        if (grp == n_groups) f1 = n_frames;
+        float2 sum = make_float2(0.f, 0.f);
+        if (f0 < 0) {  // the open group starts in an earlier call
+            f0 = 0;
+            if (carried > 0) sum = acc[k];
+        }
+        for (long long fr = f0; fr < f1; ++fr) {
+            const float2 v = spec[fr * N + k];
+            sum.x += v.x;
+            sum.y += v.y;
+        }
+        if (grp < n_groups) out[grp * N + k] = make_float2(sum.x * inv_d, sum.y * inv_d);
+        else acc[N + k] = sum;  // staged: group 0's threads may still be reading acc[k]; spectra_commit_kernel moves it
+    }
+}
+__global__ void spectra_commit_kernel(float2* __restrict__ acc, int N) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < N; k += gridDim.x * blockDim.x) acc[k] = acc[N + k];
+}
+
 struct TailJob {
     Window w;
     long long first, n;
@@ -1077,6 +1112,19 @@ int pfb_launch(const PfbJob* jobs, int n_jobs, void* scratch, void* workspace, c
         launches += 2;
     }
     return launches;
+}
+
+// acc: device buffer of 2*N float2 (running sum + staging).  Returns launches or -1.
+int spectra_decimate_launch(const float2* spec, long long n_frames, int N, int d, int carried, float2* acc, float2* out,
+                            long long n_groups, int sm_count, cudaStream_t stream) {
+    if (n_frames <= 0) return 0;
+    const long long units = (n_groups + 1) * (long long)N;
+    long long blocks = (units + 255) / 256;
+    if (blocks > (long long)sm_count * 16) blocks = (long long)sm_count * 16;
+    spectra_decimate_kernel<<<(int)blocks, 256, 0, stream>>>(spec, n_frames, N, d, carried, acc, out, n_groups);
+    spectra_commit_kernel<<<(N + 255) / 256, 256, 0, stream>>>(acc, N);
+    GSDR_CUDA_OK(cudaGetLastError());
+    return 2;
 }
 
 // One launch for the carry-over of every stream of a group.  `scratch` must hold n TailJob (device).

@@ -92,6 +92,11 @@ struct gsdr_rx {
     float2* d_tw = nullptr;
     void* d_work = nullptr;
     size_t work_bytes = 0;
+    // NOISE with decim > 0: spectra of the current call, running sum of the open group, frames already in it
+    float2* d_spec = nullptr;
+    size_t spec_bytes = 0;
+    float2* d_spec_acc = nullptr;
+    int spec_carried = 0;
     int batching = 0, T_sel = 0;
     bool fused = false;
     gsdr_buffer_helper bh{};
@@ -297,12 +302,35 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
         case GSDR_TONES:
         case GSDR_NOISE: {
             long long frames = 0;
+            const bool spec_decim = rx->mode == GSDR_NOISE && rx->decim > 0;
+            long long groups = 0;
+            int carried = rx->spec_carried;
             for (int b = 0; b < n_buf; ++b) {
-                const int v = rx->T_sel * rx->bh.current_batch;
+                int v = rx->T_sel * rx->bh.current_batch;
+                if (spec_decim) {  // complete groups of `decim` spectra that end inside this buffer
+                    const long long gb = ((long long)carried + rx->bh.current_batch) / rx->decim;
+                    carried = (int)((long long)carried + rx->bh.current_batch - gb * rx->decim);
+                    groups += gb;
+                    v = (int)(gb * rx->N);
+                }
                 if (lens) lens[b] = v;
                 frames += rx->bh.current_batch;
                 total += v;
                 buffer_helper_update(&rx->bh);
+            }
+            float2* const final_out = d_out;
+            if (spec_decim) {
+                const size_t need = sizeof(float2) * (size_t)(frames > 0 ? frames : 1) * rx->N;
+                if (need > rx->spec_bytes) {
+                    if (rx->d_spec) cudaFree(rx->d_spec);
+                    rx->d_spec = nullptr;
+                    if (cudaMalloc(&rx->d_spec, need) != cudaSuccess) {
+                        set_error("cudaMalloc(%zu) for the spectra buffer failed", need);
+                        return -1;
+                    }
+                    rx->spec_bytes = need;
+                }
+                d_out = rx->d_spec;
             }
             const long long tail = rx->bh.new_0;  // spare samples to carry into the next call
             if (w.n_hist + w.n_in - frames * rx->N != tail) {
@@ -325,6 +353,13 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
             const int nl = pfb_launch(&job, 1, nullptr, rx->d_work, rx->d_tw, rx->sm_count, st);
             if (nl < 0) return -1;
             rx->launches += nl;
+            if (spec_decim) {
+                const int dl = spectra_decimate_launch(rx->d_spec, frames, rx->N, rx->decim, rx->spec_carried, rx->d_spec_acc, final_out,
+                                                       groups, rx->sm_count, st);
+                if (dl < 0) return -1;
+                rx->launches += dl;
+                rx->spec_carried = carried;
+            }
             const int tl = window_tail_copy(w, tail, rx->hist[rx->hist_cur ^ 1], st);
             if (tl < 0) return -1;
             rx->launches += tl;
@@ -433,6 +468,8 @@ void free_all(gsdr_rx* rx) {
     if (rx->d_xperm) cudaFree(rx->d_xperm);
     if (rx->d_tw) cudaFree(rx->d_tw);
     if (rx->d_work) cudaFree(rx->d_work);
+    if (rx->d_spec) cudaFree(rx->d_spec);
+    if (rx->d_spec_acc) cudaFree(rx->d_spec_acc);
     if (rx->d_profile) cudaFree(rx->d_profile);
     if (rx->d_partial) cudaFree(rx->d_partial);
     if (rx->d_g) cudaFree(rx->d_g);
@@ -513,11 +550,16 @@ gsdr_rx* gsdr_rx_create(const gsdr_param* p, int device, int diagnostic) {
             rc = init_pfb(rx.get(), false);
             break;
         case GSDR_NOISE:
-            if (rx->decim > 0) {
-                set_error("NOISE (full spectrum) with decim>0 is not implemented (SURVEY 8f)");
-                return nullptr;
-            }
             rc = init_pfb(rx.get(), true);
+            if (rc == 0 && rx->decim > 0) {
+                // spectral decimation (cpp/USRP_demodulator.cpp:596-624): running sum + staging row
+                if (cudaMalloc(&rx->d_spec_acc, sizeof(float2) * 2 * rx->N) != cudaSuccess ||
+                    cudaMemset(rx->d_spec_acc, 0, sizeof(float2) * 2 * rx->N) != cudaSuccess) {
+                    set_error("cudaMalloc for the spectral accumulator failed");
+                    rc = -1;
+                }
+                rx->kernel_name = "pfb_fused_wsp_2048_kernel<P> + spectra_decimate_kernel";
+            }
             break;
         case GSDR_CHIRP:
             rc = init_chirp(rx.get(), p);
@@ -725,6 +767,8 @@ int gsdr_rx_reset(gsdr_rx* rx) {
         case GSDR_TONES:
         case GSDR_NOISE:
             buffer_helper_init(&rx->bh, rx->N, (int)rx->L, (int)rx->P, rx->T_sel);
+            rx->spec_carried = 0;
+            if (rx->d_spec_acc) GSDR_CUDA_OK(cudaMemset(rx->d_spec_acc, 0, sizeof(float2) * 2 * rx->N));
             break;
         case GSDR_CHIRP:
             rx->last_index = 0;
@@ -807,7 +851,7 @@ gsdr_rx_group* gsdr_rx_group_create(gsdr_rx** members, int n) {
     for (int i = 0; i < n; ++i) {
         gsdr_rx* m = members[i];
         if (!m || (m->mode != GSDR_TONES && m->mode != GSDR_NOISE) || !m->fused || m->device != members[0]->device ||
-            m->N != members[0]->N || m->P != members[0]->P) {
+            m->N != members[0]->N || m->P != members[0]->P || (m->mode == GSDR_NOISE && m->decim > 0)) {
             set_error("gsdr_rx_group_create: member %d is not a fused TONES/NOISE stream compatible with member 0", i);
             return nullptr;
         }

@@ -193,3 +193,47 @@ def test_nodsp_passthrough():
     p = g.param(rate=1_000_000, buffer_len=10_000, wave_type=[])
     x = tone_stream(1_000_000, [1000], [0.5], 0, 10_000)
     assert np.array_equal(rx_run(p, [x])[0], x)
+
+
+@pytest.mark.parametrize("decim,L", [(4, 100_000), (7, 60_000), (100, 100_000)])
+def test_noise_mode_spectral_decimation(decim, L):
+    """NOISE with decim > 0 (process_pfb_spec + decimate_spectra, cpp/USRP_demodulator.cpp:568-649): the mean of every
+    `decim` consecutive spectra, groups running across buffer boundaries.  The reference's own version accumulates
+    into a never-zeroed buffer with float atomics, so the check is against the function it is meant to
+    compute, evaluated in fp64 on the oracle's spectra."""
+    rate, N = 200_000_000, 2048
+    p = g.param(rate=rate, fft_tones=N, pf_average=4, buffer_len=L, decim=decim, freq=[1_000_000], wave_type=[g.NOISE], ampl=[1.0])
+    # tones on bin centres (multiples of 4 bins are integer Hz): their phase is the same in every frame, so the
+    # coherent mean does not cancel and the float32 comparison is meaningful for large `decim` too
+    tones = [12 * 97_656.25, -300 * 97_656.25, 800 * 97_656.25]
+    bufs = [tone_stream(rate, [int(t) for t in tones], [0.3, 0.2, 0.1], i * L, L) for i in range(5)]
+    outs = rx_run(p, bufs)
+    o = orc.PFBDemodulator(rate, N, 4, L, [])
+    o.bins = np.arange(N, dtype=np.int32)
+    o.T = N
+    spectra = [o.process(x).reshape(-1, N) for x in bufs]
+    # per-buffer valid lengths: groups that complete inside each buffer
+    carried, want_lens = 0, []
+    for s in spectra:
+        gb = (carried + len(s)) // decim
+        carried = carried + len(s) - gb * decim
+        want_lens.append(gb * N)
+    assert [len(x) for x in outs] == want_lens
+    allspec = np.concatenate(spectra)
+    ng = len(allspec) // decim
+    want = allspec[: ng * decim].reshape(ng, decim, N).mean(axis=1).reshape(-1)
+    got = np.concatenate(outs)
+    assert len(got) == len(want) and len(got) > 0
+    assert orc.rel_l2(got, want) <= TOL
+    # the result must not depend on how the stream was cut into calls: one device-resident batch of all buffers
+    rx = g.RX_buffer_demodulator(p)
+    d_in = g.DeviceBuffer(len(bufs) * L)
+    for i, x in enumerate(bufs):
+        d_in.upload(x, offset=i * L)
+    d_out = g.DeviceBuffer(rx.max_output_batch(len(bufs)))
+    total, lens = rx.process_device(d_in.ptr, len(bufs), d_out.ptr)
+    rx.sync()
+    batch = d_out.download(total)
+    rx.close()
+    assert list(lens) == want_lens
+    assert np.array_equal(batch.view(np.uint32), got.view(np.uint32))
