@@ -136,6 +136,9 @@ SIGNATURES = {
     "gsdr_replay_create": (C.c_void_p, [C.POINTER(CParam), C.c_int, C.c_float, C.c_uint64, C.c_void_p, C.c_char,
                                         C.c_double, C.c_int]),
     "gsdr_replay_next": (C.c_int, [C.c_void_p, C.POINTER(RxPacket)]),
+    "gsdr_packet_header_write": (C.c_int, [C.POINTER(RxPacket), C.c_void_p]),
+    "gsdr_packet_header_read": (C.c_int, [C.c_void_p, C.POINTER(RxPacket)]),
+    "gsdr_packet_frame": (C.c_int, [C.POINTER(RxPacket), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "gsdr_replay_destroy": (None, [C.c_void_p]),
     "gsdr_replay_packets": (C.c_uint64, [C.c_void_p]),
 }

@@ -32,11 +32,14 @@ struct gsdr_pool {
     std::thread grower;
     bool closing = false;
 
+    // Every buffer has GSDR_POOL_HEADROOM bytes in front of it, so the data-socket header can be written directly
+    // before the payload and the whole frame leaves with one send() (gsdr_packet_frame).
     gsdr_float2* alloc_one() {
         void* p = nullptr;
-        if (cudaMallocHost(&p, vector_size * sizeof(gsdr_float2)) != cudaSuccess) return nullptr;
-        return static_cast<gsdr_float2*>(p);
+        if (cudaMallocHost(&p, vector_size * sizeof(gsdr_float2) + GSDR_POOL_HEADROOM) != cudaSuccess) return nullptr;
+        return reinterpret_cast<gsdr_float2*>(static_cast<char*>(p) + GSDR_POOL_HEADROOM);
     }
+    static void free_one(gsdr_float2* b) { cudaFreeHost(reinterpret_cast<char*>(b) - GSDR_POOL_HEADROOM); }
     void grow_loop() {
         std::unique_lock<std::mutex> lk(m);
         while (!closing) {
@@ -69,7 +72,7 @@ gsdr_pool* gsdr_pool_create(size_t vector_size, int pipe_size, int prefill) {
         gsdr_float2* b = pool->alloc_one();
         if (!b) {
             set_error("Memory manager cannot allocate pinned host memory!");
-            for (auto* q : pool->all) cudaFreeHost(q);
+            for (auto* q : pool->all) gsdr_pool::free_one(q);
             return nullptr;
         }
         pool->all.push_back(b);
@@ -109,7 +112,7 @@ void gsdr_pool_close(gsdr_pool* pool) {
     pool->cv_grow.notify_all();
     pool->cv_free.notify_all();
     if (pool->grower.joinable()) pool->grower.join();
-    for (auto* b : pool->all) cudaFreeHost(b);
+    for (auto* b : pool->all) gsdr_pool::free_one(b);
     delete pool;
 }
 
@@ -327,6 +330,44 @@ int gsdr_probe_direct_phase(int device, int tone_freq, int rate, uint64_t index_
     }
     cudaFree(d);
     return rc < 0 ? -1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Data-socket framing.  Reference: Sync_server::format_net_buffer (cpp/USRP_server_network.cpp:164-191) packs
+// usrp_number | front_end_code | packet_number | length | errors | channels (4+1+4+4+4+4 = 21 bytes, host byte order,
+// no padding) and then memcpy's `length` float2 behind it into a malloc'd staging buffer for every packet
+// (cpp/USRP_server_network.cpp:187,215).  The client reads it with the packed dtype of pyUSRP/USRP_low_level.py:63-70.
+// ------------------------------------------------------------------------------------------------
+int gsdr_packet_header_write(const gsdr_rx_packet* pkt, uint8_t* dst) {
+    if (!pkt || !dst) return -1;
+    std::memcpy(dst + 0, &pkt->usrp_number, 4);
+    std::memcpy(dst + 4, &pkt->front_end_code, 1);
+    std::memcpy(dst + 5, &pkt->packet_number, 4);
+    std::memcpy(dst + 9, &pkt->length, 4);
+    std::memcpy(dst + 13, &pkt->errors, 4);
+    std::memcpy(dst + 17, &pkt->channels, 4);
+    return GSDR_PACKET_HEADER_BYTES;
+}
+int gsdr_packet_header_read(const uint8_t* src, gsdr_rx_packet* pkt) {
+    if (!pkt || !src) return -1;
+    std::memcpy(&pkt->usrp_number, src + 0, 4);
+    std::memcpy(&pkt->front_end_code, src + 4, 1);
+    std::memcpy(&pkt->packet_number, src + 5, 4);
+    std::memcpy(&pkt->length, src + 9, 4);
+    std::memcpy(&pkt->errors, src + 13, 4);
+    std::memcpy(&pkt->channels, src + 17, 4);
+    return GSDR_PACKET_HEADER_BYTES;
+}
+int gsdr_packet_frame(const gsdr_rx_packet* pkt, const void** frame, size_t* frame_bytes) {
+    if (!pkt || !pkt->buffer || !frame || !frame_bytes || pkt->length < 0) {
+        set_error("gsdr_packet_frame: bad argument");
+        return -1;
+    }
+    uint8_t* hdr = reinterpret_cast<uint8_t*>(pkt->buffer) - GSDR_PACKET_HEADER_BYTES;  // inside the pool headroom
+    gsdr_packet_header_write(pkt, hdr);
+    *frame = hdr;
+    *frame_bytes = GSDR_PACKET_HEADER_BYTES + sizeof(gsdr_float2) * (size_t)pkt->length;
+    return 0;
 }
 
 void* gsdr_host_alloc(size_t bytes) {

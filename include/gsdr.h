@@ -223,6 +223,19 @@ typedef struct gsdr_rx_packet {   /* == RX_wrapper, headers/USRP_server_settings
     gsdr_float2 *buffer; int32_t usrp_number; char front_end_code; int32_t packet_number;
     int32_t length; int32_t errors; int32_t channels;
 } gsdr_rx_packet;
+/* Data-socket framing.  The wire frame of Sync_server::format_net_buffer
+ * (cpp/USRP_server_network.cpp:164-191; client side pyUSRP/USRP_low_level.py:63-70) is a packed 21-byte header
+ * followed by `length` float2.  header_write/read are pure.  gsdr_packet_frame builds the frame IN PLACE: every
+ * gsdr_pool buffer is preceded by GSDR_POOL_HEADROOM writable bytes, the header goes directly in front of the payload
+ * and *frame / *frame_bytes describe one contiguous region to hand to send() -- no per-packet staging copy
+ * (the reference memcpy's every payload into a malloc'd buffer, cpp/USRP_server_network.cpp:187,215).
+ * pkt->buffer must come from gsdr_pool_get. */
+#define GSDR_PACKET_HEADER_BYTES 21
+#define GSDR_POOL_HEADROOM 32
+int gsdr_packet_header_write(const gsdr_rx_packet *pkt, uint8_t *dst21);
+int gsdr_packet_header_read(const uint8_t *src21, gsdr_rx_packet *pkt);
+int gsdr_packet_frame(const gsdr_rx_packet *pkt, const void **frame, size_t *frame_bytes);
+
 typedef enum gsdr_replay_kind {
     GSDR_REPLAY_TONES_NOISE = 0,  /* sum of param tones (ampl) + complex gaussian noise of given sigma */
     GSDR_REPLAY_TX_LOOP = 1       /* loop back a gsdr_tx of the same param (the --sw_loop identity) */

@@ -201,3 +201,32 @@ def test_sc16_pipelined_submit_wait():
     assert len(got) == len(want)
     for a, b in zip(got, want):
         assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_packet_frame_in_place_is_one_contiguous_wire_frame():
+    """gsdr_packet_frame writes the 21-byte header into the pool headroom directly in front of the payload: the frame
+    the client expects (header dtype + length complex64, pyUSRP/USRP_connections.py:814-970) without a staging copy."""
+    import ctypes as C
+    from gpu_sdr_b200 import _lib
+    lib = _lib.load()
+    pool = g.preallocator(5000, 3)
+    buf = pool.get()
+    rng = np.random.default_rng(1)
+    buf[:] = (rng.standard_normal(5000) + 1j * rng.standard_normal(5000)).astype(np.complex64)
+    pkt = _lib.RxPacket()
+    pkt.buffer = buf.ctypes.data
+    pkt.usrp_number, pkt.front_end_code, pkt.packet_number, pkt.length, pkt.errors, pkt.channels = 0, b"D", 7, 4000, 0, 8
+    frame, nbytes = C.c_void_p(), C.c_size_t()
+    assert lib.gsdr_packet_frame(C.byref(pkt), C.byref(frame), C.byref(nbytes)) == 0
+    assert nbytes.value == 21 + 8 * 4000 and frame.value == buf.ctypes.data - 21
+    wire = C.string_at(frame.value, nbytes.value)
+    header_type = np.dtype([("usrp_number", np.int32), ("front_end_code", np.dtype("|S1")), ("packet_number", np.int32),
+                            ("length", np.int32), ("errors", np.int32), ("channels", np.int32)])
+    h = np.frombuffer(wire[:21], dtype=header_type)[0]
+    assert h["length"] == 4000 and h["front_end_code"] == b"D" and h["channels"] == 8 and h["packet_number"] == 7
+    data = np.frombuffer(wire[21:], dtype=np.complex64)
+    assert np.array_equal(data, buf[:4000])
+    # client-side de-interleave (pyUSRP/USRP_connections.py:157)
+    assert np.reshape(data, (4000 // 8, 8)).T.shape == (8, 500)
+    pool.trash(buf)
+    pool.close()

@@ -177,3 +177,26 @@ def test_pfb_gather_layout_is_conflict_free(T, seed, order):
     # repeated tones are pinned first and everything else is coloured around them; a clash is only possible
     # next to a pinned bin and should not occur on a list like this one
     assert clashes == 0, clashes
+
+
+def test_packet_header_matches_the_client_dtype():
+    """The 21-byte data-socket header (Sync_server::format_net_buffer, cpp/USRP_server_network.cpp:164-191) as the
+    client parses it (pyUSRP/USRP_low_level.py:63-70: a packed numpy dtype)."""
+    import ctypes as C
+    from gpu_sdr_b200 import _lib
+    header_type = np.dtype([("usrp_number", np.int32), ("front_end_code", np.dtype("|S1")), ("packet_number", np.int32),
+                            ("length", np.int32), ("errors", np.int32), ("channels", np.int32)])
+    assert header_type.itemsize == 21
+    lib = _lib.load()
+    pkt = _lib.RxPacket()
+    pkt.usrp_number, pkt.front_end_code, pkt.packet_number = 3, b"B", 123456
+    pkt.length, pkt.errors, pkt.channels = 488000, -2, 1000
+    raw = np.zeros(21, dtype=np.uint8)
+    assert lib.gsdr_packet_header_write(C.byref(pkt), raw.ctypes.data_as(C.c_void_p)) == 21
+    h = np.frombuffer(raw.tobytes(), dtype=header_type)[0]
+    assert (h["usrp_number"], h["front_end_code"], h["packet_number"], h["length"], h["errors"], h["channels"]) == \
+        (3, b"B", 123456, 488000, -2, 1000)
+    back = _lib.RxPacket()
+    assert lib.gsdr_packet_header_read(raw.ctypes.data_as(C.c_void_p), C.byref(back)) == 21
+    assert (back.usrp_number, back.front_end_code, back.packet_number, back.length, back.errors, back.channels) == \
+        (3, b"B", 123456, 488000, -2, 1000)
