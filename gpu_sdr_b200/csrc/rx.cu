@@ -93,6 +93,8 @@ struct gsdr_rx {
     void* d_work = nullptr;
     size_t work_bytes = 0;
     // NOISE with decim > 0: spectra of the current call, running sum of the open group, frames already in it
+    // blocking process(): chunk events (H2D of chunk c done / kernels of chunk c done)
+    std::vector<cudaEvent_t> ev_chunk_in, ev_chunk_comp;
     float2* d_spec = nullptr;
     size_t spec_bytes = 0;
     float2* d_spec_acc = nullptr;
@@ -468,6 +470,8 @@ void free_all(gsdr_rx* rx) {
     if (rx->d_xperm) cudaFree(rx->d_xperm);
     if (rx->d_tw) cudaFree(rx->d_tw);
     if (rx->d_work) cudaFree(rx->d_work);
+    for (auto e : rx->ev_chunk_in) cudaEventDestroy(e);
+    for (auto e : rx->ev_chunk_comp) cudaEventDestroy(e);
     if (rx->d_spec) cudaFree(rx->d_spec);
     if (rx->d_spec_acc) cudaFree(rx->d_spec_acc);
     if (rx->d_profile) cudaFree(rx->d_profile);
@@ -676,7 +680,84 @@ int gsdr_rx_input_consumed(gsdr_rx* rx, int ticket) {
 
 int gsdr_rx_pipeline_depth(const gsdr_rx* rx) { return rx ? (int)(rx->slots.empty() ? 1 : rx->slots.size()) : 0; }
 
+// Blocking call, fused filter bank: the buffer is uploaded in kChunks pieces and every piece's frames are launched
+// and downloaded as soon as their samples are on the device, so H2D, kernels and D2H of ONE buffer overlap.  The
+// reference's process_pfb (cpp/USRP_demodulator.cpp:486-565) and a naive port serialise the three (8 MB up, kernels,
+// 3.9 MB down); this makes the unchanged blocking drop-in call run at the speed of the slower PCIe direction.
+// Results are identical to the one-launch path: same frames, same kernel, same carry-over.
+static int process_pfb_chunked(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* out) {
+    constexpr int kChunks = 4;
+    const long long L = rx->L, N = rx->N, P = rx->P;
+    Slot& s = rx->slots[0];
+    if (s.used) GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));
+    if (rx->ev_chunk_in.empty()) {
+        rx->ev_chunk_in.resize(kChunks);
+        rx->ev_chunk_comp.resize(kChunks);
+        for (int c = 0; c < kChunks; ++c) {
+            GSDR_CUDA_OK(cudaEventCreateWithFlags(&rx->ev_chunk_in[c], cudaEventDisableTiming));
+            GSDR_CUDA_OK(cudaEventCreateWithFlags(&rx->ev_chunk_comp[c], cudaEventDisableTiming));
+        }
+    }
+    const Window w{rx->hist[rx->hist_cur], s.d_in, rx->n_hist, L};
+    const long long frames = rx->bh.current_batch;
+    const int len = rx->T_sel * rx->bh.current_batch;
+    buffer_helper_update(&rx->bh);
+    const long long tail = rx->bh.new_0;
+    if (w.n_hist + w.n_in - frames * N != tail) {
+        set_error("internal: PFB carry-over mismatch (%lld vs %lld)", w.n_hist + w.n_in - frames * N, tail);
+        return -1;
+    }
+    const long long Lc = ((L / kChunks) + 1) & ~1LL;  // even: chunk starts stay 16-byte aligned
+    long long done = 0;
+    for (int c = 0; c < kChunks; ++c) {
+        const long long off = c * Lc;
+        if (off >= L) break;
+        const long long n = (c == kChunks - 1 || off + Lc > L) ? L - off : Lc;
+        GSDR_CUDA_OK(cudaMemcpyAsync(s.d_in + off, reinterpret_cast<const float2*>(in) + off, sizeof(float2) * n, cudaMemcpyHostToDevice,
+                                     rx->s_in));
+        GSDR_CUDA_OK(cudaEventRecord(rx->ev_chunk_in[c], rx->s_in));
+        const long long avail = rx->n_hist + off + n;  // window samples on the device once this chunk has landed
+        long long fa = avail / N - (P - 1);
+        if (fa < 0) fa = 0;
+        if (fa > frames || off + n >= L) fa = frames;
+        GSDR_CUDA_OK(cudaStreamWaitEvent(rx->s_comp, rx->ev_chunk_in[c], 0));
+        if (fa > done) {
+            PfbJob job{w, rx->d_taps, rx->d_bins, s.d_out + done * rx->T_sel, (int)done, (int)(fa - done), rx->N, (int)rx->P, rx->T_sel,
+                       rx->d_xperm};
+            const int nl = pfb_launch(&job, 1, nullptr, nullptr, rx->d_tw, rx->sm_count, rx->s_comp);
+            if (nl < 0) return -1;
+            rx->launches += nl;
+            GSDR_CUDA_OK(cudaEventRecord(rx->ev_chunk_comp[c], rx->s_comp));
+            GSDR_CUDA_OK(cudaStreamWaitEvent(rx->s_out, rx->ev_chunk_comp[c], 0));
+            GSDR_CUDA_OK(cudaMemcpyAsync(reinterpret_cast<float2*>(out) + done * rx->T_sel, s.d_out + done * rx->T_sel,
+                                         sizeof(float2) * (size_t)(fa - done) * rx->T_sel, cudaMemcpyDeviceToHost, rx->s_out));
+            done = fa;
+        }
+    }
+    const int tl = window_tail_copy(w, tail, rx->hist[rx->hist_cur ^ 1], rx->s_comp);  // after the last chunk's wait on s_comp
+    if (tl < 0) return -1;
+    rx->launches += tl;
+    rx->hist_cur ^= 1;
+    rx->n_hist = tail;
+    GSDR_CUDA_OK(cudaEventRecord(s.in_done, rx->s_in));
+    GSDR_CUDA_OK(cudaEventRecord(s.comp_done, rx->s_comp));
+    GSDR_CUDA_OK(cudaEventRecord(s.out_done, rx->s_out));
+    s.used = true;
+    rx->tickets++;
+    GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));
+    GSDR_CUDA_OK(cudaEventSynchronize(s.comp_done));  // carry-over written, input fully consumed
+    return len;
+}
+
 int gsdr_rx_process(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* out) {
+    if (rx && in && out && rx->fused && !rx->slots.empty() && rx->L >= 64LL * rx->N &&
+        (rx->mode == GSDR_TONES || (rx->mode == GSDR_NOISE && rx->decim <= 0))) {
+        if (set_dev(rx)) return -1;
+        // keep the ticket/slot rotation of submit() intact: the blocking path always uses slot 0 and leaves every slot idle
+        for (auto& sl : rx->slots)
+            if (sl.used) GSDR_CUDA_OK(cudaEventSynchronize(sl.out_done));
+        return process_pfb_chunked(rx, in, out);
+    }
     int len = 0;
     const int ticket = gsdr_rx_submit(rx, in, out, &len);
     if (ticket < 0) return -1;
