@@ -1037,7 +1037,16 @@ static int launch_ws(const PfbJob* jobs, int n_jobs, void* scratch, const float2
         if (tile_begin[n_jobs] <= sm_count || n_jobs > sm_count) break;
     }
     const int total_tiles = tile_begin[n_jobs];
-    const int grid = total_tiles < sm_count ? total_tiles : sm_count;
+    int grid = total_tiles < sm_count ? total_tiles : sm_count;
+    {   // test hook: a smaller grid makes every CTA walk several tiles (the path a launch of more than sm_count
+        // streams takes); results must not change
+        static int cap = -1;
+        if (cap < 0) {
+            const char* e = getenv("GSDR_PFB_MAX_GRID");
+            cap = e ? atoi(e) : 0;
+        }
+        if (cap > 0 && grid > cap) grid = cap;
+    }
     const PfbJob* table = nullptr;
     const int* tb = nullptr;
     if (n_jobs > 1) {

@@ -237,3 +237,47 @@ def test_noise_mode_spectral_decimation(decim, L):
     rx.close()
     assert list(lens) == want_lens
     assert np.array_equal(batch.view(np.uint32), got.view(np.uint32))
+
+
+def test_several_tiles_per_cta_same_results():
+    """A launch over more streams than SMs makes every persistent CTA walk several tiles (frame counters, ring slots
+    and spectrum-tile parities run on across tile boundaries, tone stores are drained per tile).  The same path is
+    forced here with a capped grid (GSDR_PFB_MAX_GRID, read once per process -> subprocess) on a group of 3 streams with
+    different tone lists, and must reproduce the full-grid results bit for bit."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+    code = r"""
+import sys, numpy as np
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+from common import g, pfb_param, tone_stream
+L, nb = 150_000, 3
+ps = [pfb_param(N=2048, P=4, T=t, L=L, seed=s) for t, s in ((1000, 1), (37, 2), (513, 3))]
+rxs = [g.RX_buffer_demodulator(p) for p in ps]
+grp = g.RxGroup(rxs)
+ins, outs = [], []
+for p in ps:
+    d = g.DeviceBuffer(nb * L)
+    for b in range(nb):
+        d.upload(tone_stream(p.rate, p.freq[:20], p.ampl[:20], b * L, L), offset=b * L)
+    ins.append(d)
+    outs.append(g.DeviceBuffer(rxs[0].max_output_batch(nb) * 2))
+res = []
+for rep in range(2):  # second call: carried-over history
+    tot, lens = grp.process_device([d.ptr for d in ins], nb, [o.ptr for o in outs])
+    grp.sync()
+    res += [o.download(int(l.sum())) for o, l in zip(outs, lens)]
+np.savez(sys.argv[1], *res)
+""" % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as td:
+        files = []
+        for cap in ("0", "5"):
+            f = os.path.join(td, f"out_{cap}.npz")
+            env = dict(os.environ, GSDR_PFB_MAX_GRID=cap)
+            subprocess.run([sys.executable, "-c", code, f], check=True, env=env, timeout=300)
+            files.append(np.load(f))
+        a, b = files
+        assert len(a.files) == len(b.files) == 6
+        for k in a.files:
+            assert a[k].size > 0 and np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
