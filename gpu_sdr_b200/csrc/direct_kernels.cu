@@ -11,6 +11,8 @@
 // i.e. a bank of per-tone complex FIRs g_ch[m] (built once, in double, from the same integer
 // phases) followed by one rotation per OUTPUT sample.  No trig and no 64-bit remainder per input
 // sample remain, and nothing but the decimated, sample-major result is written.
+#include <cmath>
+
 #include "devmath.cuh"
 #include "packed_f32x2.cuh"
 
@@ -149,18 +151,53 @@ direct_fir_tiled_kernel(const Window w, const float2* __restrict__ g, const int*
 #pragma unroll
     for (int b = 0; b < D_TC; ++b) acc[b] = c2_pack(0.f, 0.f);
 
-    for (int k0 = 0; k0 < M; k0 += D_KC) {
-        const int kc = min(D_KC, M - k0);
+    // equal chunks (M = 100 -> 4 x 25 rather than 32 + 32 + 32 + 4: every chunk pays the same staging round trip)
+    const int n_chunks = (M + D_KC - 1) / D_KC;
+    const int kstep = (M + n_chunks - 1) / n_chunks;
+    for (int k0 = 0; k0 < M; k0 += kstep) {
+        const int kc = min(kstep, M - k0);
         __syncthreads();
-        for (int e = tid; e < rows * kc; e += PB) {
-            const int r = e / kc, kk = e - r * kc;
-            xs[r * (D_KC + 1) + kk] = dev_win_at(w, (p0 + r) * (long long)M + k0 + kk);
-        }
-        for (int e = tid; e < f * D_TC * kc; e += PB) {
-            const int kk = e % kc, ch = (e / kc) % D_TC, i = e / (kc * D_TC);
-            float2 v = make_float2(0.f, 0.f);
-            if (ch0 + ch < T) v = __ldg(g + (long long)(ch0 + ch) * ntaps + i * M + k0 + kk);
-            gs[(i * D_KC + kk) * D_GST + ch] = v;
+        // Staging: eight independent loads in flight per thread before the first store (one load -> one store per
+        // iteration serialises ~50 global-memory latencies per chunk).  `inside`: the block's whole input span lies in
+        // the `in` segment, plain pointer arithmetic instead of the history/zero-padding logic.
+        {
+            const int cnt = rows * kc;
+            const long long span_lo = p0 * (long long)M, span_hi = (p0 + rows) * (long long)M;
+            const bool inside = span_lo >= w.n_hist && span_hi <= w.n_hist + w.n_in;
+            const float2* xin = w.in + (span_lo - w.n_hist) + k0;
+            for (int base = 0; base < cnt; base += PB * 8) {
+                float2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = base + tid + u * PB;
+                    const int r = e / kc, kk = e - r * kc;
+                    v[u] = make_float2(0.f, 0.f);
+                    if (e < cnt) v[u] = inside ? __ldg(xin + (long long)r * M + kk) : dev_win_at(w, span_lo + (long long)r * M + k0 + kk);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = base + tid + u * PB;
+                    const int r = e / kc, kk = e - r * kc;
+                    if (e < cnt) xs[r * (D_KC + 1) + kk] = v[u];
+                }
+            }
+            const int gcnt = f * D_TC * kc;
+            for (int base = 0; base < gcnt; base += PB * 8) {
+                float2 v[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = base + tid + u * PB;
+                    const int kk = e % kc, ch = (e / kc) % D_TC, i = e / (kc * D_TC);
+                    v[u] = make_float2(0.f, 0.f);
+                    if (e < gcnt && ch0 + ch < T) v[u] = __ldg(g + (long long)(ch0 + ch) * ntaps + i * M + k0 + kk);
+                }
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int e = base + tid + u * PB;
+                    const int kk = e % kc, ch = (e / kc) % D_TC, i = e / (kc * D_TC);
+                    if (e < gcnt) gs[(i * D_KC + kk) * D_GST + ch] = v[u];
+                }
+            }
         }
         __syncthreads();
         for (int i = 0; i < f; ++i) {
@@ -250,7 +287,13 @@ int direct_fir_launch(const Window& w, const float2* g, const int* freq_dev, int
     if (M >= 1 && f >= 1 && f <= D_FMAX && f * M == ntaps) {
         // register-tiled kernel; 64-output blocks when 128-output blocks would leave SMs idle
         const int tone_groups = (T + D_TC - 1) / D_TC;
-        const bool small = ((n_out + 127) / 128) * tone_groups < 2 * 148;
+        // 128- or 64-output blocks, whichever fills its waves better (a 64-output block needs 36 KB of shared memory:
+        // 6 per SM; a 128-output block 53 KB: 4 per SM).  Ties go to the larger block (taps are staged once per block).
+        auto wave_eff = [&](int pb, int per_sm) {
+            const double tiles = (double)((n_out + pb - 1) / pb) * tone_groups, slots = 148.0 * per_sm;
+            return tiles / (std::ceil(tiles / slots) * slots);
+        };
+        const bool small = wave_eff(64, 6) > wave_eff(128, 4) + 0.02;
         const int PB2 = small ? 64 : 128;
         const size_t smem = ((size_t)(PB2 + f - 1) * (D_KC + 1) + (size_t)f * D_KC * D_GST + 2) * sizeof(float2);
         dim3 grid((unsigned)((n_out + PB2 - 1) / PB2), (unsigned)tone_groups);
