@@ -7,12 +7,15 @@
 // accumulator: within a frequency step the int32 phase index advances by a constant, so the
 // per-sample cost is one integer add plus an exact-range-reduced float32 sincos.
 // TX: chirp_gen (cpp/kernels.cu:335-372) is the same phase walk with a store instead of a load.
+#include <type_traits>
+
 #include "devmath.cuh"
 
 namespace gsdr {
 namespace {
 
 constexpr int SEG = 8192;  // samples per partial sum when ppt is large
+
 
 // One warp per (output j, segment): lanes stride the samples, xor-shuffle reduction.
 // profile == nullptr selects the flat lock-in window the reference always uses (make_flat_window:
@@ -42,20 +45,25 @@ chirp_lockin_warp_kernel(const Window w, unsigned long long pos0, const ChirpDev
             if (direct && flat) {
                 const float2* p = w.in + (s0 - w.n_hist);
                 int i = i0 + lane;
-                // four independent 256-byte warp loads in flight per iteration (one load per iteration leaves the
-                // SM with too few bytes outstanding to cover HBM latency); same per-lane summation order
-                for (; i + 96 < i1; i += 128) {
-                    float2 x[4];
+                // Eight, then four independent 256-byte warp loads in flight per iteration (one load per iteration
+                // leaves the SM with too few bytes outstanding to cover HBM latency); same per-lane summation order.
+                auto burst = [&](auto width_tag) {
+                    constexpr int W = decltype(width_tag)::value;
+                    for (; i + 32 * (W - 1) < i1; i += 32 * W) {
+                        float2 x[W];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) x[u] = __ldg(p + i + 32 * u);
+                        for (int u = 0; u < W; ++u) x[u] = __ldg(p + i + 32 * u);
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float2 ch = chirp_phasor(cw.idx);
-                        acc.x = fmaf(ch.x, x[u].x, fmaf(ch.y, x[u].y, acc.x));
-                        acc.y = fmaf(ch.x, x[u].y, fmaf(-ch.y, x[u].x, acc.y));
-                        cw.advance(32u, cp);
+                        for (int u = 0; u < W; ++u) {
+                            const float2 ch = chirp_phasor(cw.idx);
+                            acc.x = fmaf(ch.x, x[u].x, fmaf(ch.y, x[u].y, acc.x));
+                            acc.y = fmaf(ch.x, x[u].y, fmaf(-ch.y, x[u].x, acc.y));
+                            cw.advance(32u, cp);
+                        }
                     }
-                }
+                };
+                burst(std::integral_constant<int, 8>{});
+                burst(std::integral_constant<int, 4>{});
                 for (; i < i1; i += 32) {
                     const float2 x = __ldg(p + i);
                     const float2 ch = chirp_phasor(cw.idx);
