@@ -14,6 +14,7 @@
 #include <cmath>
 
 #include "devmath.cuh"
+#include "direct_common.cuh"
 #include "packed_f32x2.cuh"
 
 namespace gsdr {
@@ -22,21 +23,6 @@ namespace {
 constexpr int TP = 4;   // outputs per warp tile
 constexpr int TC = 8;   // tones per warp tile
 constexpr int WARPS = 8;
-
-// signed LO phase exactly as the reference forms it (C remainder keeps the dividend's sign)
-__device__ __forceinline__ long long direct_phase_signed(long long tf, unsigned long long stream_index, long long R) {
-    const long long ii = (long long)(stream_index % (unsigned long long)R);
-    return (tf * ii) % R;
-}
-
-// e^{-2 pi j ph / R} for ph in [0, R): double divide, 32-bit phase word, exact-reduction sincos
-__device__ __forceinline__ float2 lo_phasor(long long ph, double inv_R) {
-    const double turns = (double)ph * inv_R;                       // [0,1)
-    const unsigned int word = (unsigned int)(long long)(turns * 4294967296.0);
-    float s, c;
-    sincos_phase32(word, s, c);
-    return make_float2(c, -s);
-}
 
 // kStaged: the block's input span is staged in shared memory once and reused by every tone group;
 // otherwise (very long filters) the taps stream straight from global memory through L1/L2.

@@ -1,0 +1,479 @@
+// DIRECT-mode demodulator on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+//
+// Same function as direct_fir_tiled_kernel (direct_kernels.cu), i.e. the reference's
+// direct_demodulator_integer + T x FIR::run_fir + cublasCgeam (cpp/kernels.cu:45-86, cpp/fir.cu:44-88,
+// cpp/USRP_demodulator.cpp:400-464), as a GEMM.  The filter has F blocks of M taps and the decimation is M, so
+//     y[p,t] = rot(p,t) * sum_{i<F} Z_i[p+i, t],      Z_i[r, t] = sum_{k<M} w[r M + k] g_t[i M + k]
+// where w is the stream window cut into rows of M samples -- rows do NOT overlap, the window IS the A operand:
+//     A [rows x 2M]      = the input samples, re/im interleaved, exactly as they lie in memory,
+//     B [2M x F*TG*2]    = (g_r, g_i ; -g_i, g_r) per (FIR block i, tone t): complex multiply as a real GEMM,
+//     D [rows x F*TG*2]  = all F partial filters Z_i of TG tones at once (N = 128 columns for every supported F).
+// The F-term sum over neighbouring ROWS (the reference's overlap-add, cpp/fir.cu:55-69) is a lane shift in the
+// epilogue, followed by the per-output LO rotation from the integer phase (cpp/kernels.cu:59-75).
+//
+// Precision: the tolerance is 1e-5 relative L2 against fp64 and one TF32 product has a 2^-11 relative error, so both
+// operands are split x = hi + lo (hi = x rounded to TF32, lo = x - hi, exact) and three MMAs are issued per k-step:
+// hi*hi into one TMEM accumulator, lo*hi + hi*lo into a second one (kept apart so that the small terms are not
+// absorbed by the truncating tensor-core accumulation); the dropped lo*lo term is 2^-22 relative.
+//
+// Warp roles (one persistent CTA per SM, static tile scheduler over (row tile, tone group)):
+//   warps 0-3   epilogue: tcgen05.ld of the two accumulators, row shift-and-add, LO rotation, sample-major store
+//   warp  4     TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, M=128, N=128, K=8)
+//   warps 5-12  operand producers: coalesced global loads of the window rows and of the tone filters, hi/lo split,
+//               stores into the 128-byte-swizzled K-major operand tiles, fence.proxy.async, mbarrier arrive
+// Three operand stages (64 KB each: A_hi, A_lo, B_hi, B_lo for 16 complex taps), two accumulator stages (512 TMEM
+// columns), so the epilogue of tile n overlaps the MMAs of tile n+1.
+#include <cstdlib>
+
+#include "devmath.cuh"
+#include "direct_common.cuh"
+
+namespace gsdr {
+namespace {
+
+constexpr int TC_ROWS = 128;                       // window rows per tile = UMMA M
+constexpr int TC_N = 128;                          // accumulator columns = F * TG * 2
+constexpr int TC_KC = 16;                          // complex taps per K block: 32 floats = one 128-byte swizzle row
+constexpr int TC_STAGES = 3;
+constexpr int TC_EPI_WARPS = 4;
+constexpr int TC_LOAD_WARPS = 8;
+constexpr int TC_LOAD_THREADS = 32 * TC_LOAD_WARPS;
+constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 1 + TC_LOAD_WARPS);
+constexpr int TC_OPER_BYTES = TC_ROWS * 128;       // one operand part of one stage (128 rows x 128 bytes)
+constexpr int TC_STAGE_BYTES = 4 * TC_OPER_BYTES;  // A_hi, A_lo, B_hi, B_lo
+constexpr int TC_XCH_FLOATS = 7 * 7 * 16;          // per epilogue warp: (F-1) lanes x (F-1) blocks x chunk, F <= 8
+constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_A_PER_THREAD = TC_ROWS * TC_KC / TC_LOAD_THREADS;        // 8
+constexpr int TC_B_PER_THREAD = (TC_N / 2) * TC_KC / TC_LOAD_THREADS;     // 4
+
+struct TcShared {
+    unsigned long long full[TC_STAGES];
+    unsigned long long empty[TC_STAGES];
+    unsigned long long tmem_full[2];
+    unsigned long long tmem_empty[2];
+    unsigned int tmem_base;
+    unsigned int pad;
+    long long ph_base[64];   // LO phase of the tile's first row, per tone of the group
+    long long ph_step[64];   // (tf * M) mod rate
+    alignas(16) float xch[TC_EPI_WARPS][TC_XCH_FLOATS];
+};
+constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(TcShared);
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned int addr, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned int addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+// Bounded wait: a protocol error traps (the launch fails) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned int addr, unsigned int parity) {
+    long long t0 = 0;
+    for (unsigned int spins = 0;; ++spins) {
+        unsigned int done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins == 64) t0 = clock64();
+        if (spins > 64 && (spins & 255u) == 0 && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned int mbar_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_addr) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread
+__device__ __forceinline__ void tc_mma_tf32(unsigned int d_tmem, unsigned long long a_desc, unsigned long long b_desc,
+                                            unsigned int idesc, unsigned int accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30) = 1, SBO>>4 [32,46) = 64, version [46,48) = 1,
+// layout [61,64) = 2 (SWIZZLE_128B)).
+__device__ __forceinline__ unsigned long long tc_smem_desc(unsigned int saddr) {
+    const unsigned int lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+    const unsigned int hi = 64u | (1u << 14) | (2u << 29);
+    return ((unsigned long long)hi << 32) | lo;
+}
+// cute::UMMA::InstrDescriptor: D = f32 (1 @4), A = B = tf32 (2 @7, 2 @10), K-major both, N>>3 @17, M>>4 @24
+constexpr unsigned int TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TC_N >> 3) << 17) | ((unsigned)(TC_ROWS >> 4) << 24);
+
+template <int CW>
+__device__ __forceinline__ void tmem_ld(unsigned int taddr, float* v);
+template <>
+__device__ __forceinline__ void tmem_ld<32>(unsigned int taddr, float* v) {
+    unsigned int* r = reinterpret_cast<unsigned int*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_ld<16>(unsigned int taddr, float* v) {
+    unsigned int* r = reinterpret_cast<unsigned int*>(v);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory"); }
+
+// x = hi + lo with hi = x rounded to TF32 (10 explicit mantissa bits); lo = x - hi is exact in fp32
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+    unsigned int h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    lo = x - hi;
+}
+
+// byte offset of (row, complex tap kc) inside a 128-row K-major SWIZZLE_128B operand tile
+__device__ __forceinline__ unsigned int tc_swz(unsigned int row, unsigned int kc) {
+    return (row >> 3) * 1024u + (row & 7u) * 128u + ((((kc >> 1) ^ row) & 7u) << 4) + ((kc & 1u) << 3);
+}
+
+struct TcTile {
+    long long row0;   // first window row of the tile
+    int ch0;          // first tone of the group
+};
+
+// F = FIR blocks (pf_average); TG = 64 / F tones per group; outputs per tile = 128 - (F - 1)
+template <int F>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+direct_fir_tc_kernel(const Window w, const float2* __restrict__ g, const int* __restrict__ freq, int T, int M, int rate,
+                     long long pos0, long long n_out, int n_row_tiles, int n_tone_groups, float2* __restrict__ out) {
+    constexpr int TG = 64 / F;
+    constexpr int RB = TC_ROWS - (F - 1);
+    constexpr int TCW = TG < 16 ? TG : 16;     // tones per epilogue chunk
+    constexpr int CW = 2 * TCW;                // accumulator columns per chunk and FIR block
+    constexpr int NCHUNK = TG / TCW;
+
+    extern __shared__ unsigned char tc_smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    TcShared* sh = reinterpret_cast<TcShared*>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
+    const unsigned int smem_base = smem_u32(smem);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntaps = F * M;
+    const int KB = (M + TC_KC - 1) / TC_KC;           // K blocks per tile
+    const int ksteps_total = (M + 3) / 4;             // MMA k-steps (4 complex taps = 8 tf32) per tile
+    const int n_tiles = n_row_tiles * n_tone_groups;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(smem_u32(&sh->full[s]), TC_LOAD_THREADS);
+            mbar_init(smem_u32(&sh->empty[s]), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&sh->tmem_full[a]), 1);
+            mbar_init(smem_u32(&sh->tmem_empty[a]), 32 * TC_EPI_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == TC_EPI_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                     "r"(TC_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned int tmem_base = sh->tmem_base;
+
+    auto tile_of = [&](int n) {
+        const int id = (int)blockIdx.x + n * (int)gridDim.x;
+        TcTile t;
+        t.row0 = (long long)(id / n_tone_groups) * RB;
+        t.ch0 = (id % n_tone_groups) * TG;
+        return t;
+    };
+
+    if (warp < TC_EPI_WARPS) {
+        // ======================================= EPILOGUE =======================================
+        const int row_in_tile = warp * 32 + lane;
+        const double inv_R = 1.0 / (double)rate;
+        float* xw = sh->xch[warp];
+        const float* xn = sh->xch[(warp + 1) & 3];
+        for (int n = 0; n < my_tiles; ++n) {
+            const TcTile tl = tile_of(n);
+            const unsigned int as = n & 1, aph = (n >> 1) & 1;
+            // LO phase of the tile's first output for each tone of the group, and its step per output
+            if (threadIdx.x < TG) {
+                const int ch = tl.ch0 + (int)threadIdx.x;
+                long long base = 0, step = 0;
+                if (ch < T) {
+                    long long tf = (long long)freq[ch] % rate;
+                    if (tf < 0) tf += rate;   // same residue class as the reference's signed remainder
+                    long long n0 = (pos0 + tl.row0 * (long long)M) % rate;
+                    if (n0 < 0) n0 += rate;
+                    base = (long long)(((unsigned long long)tf * (unsigned long long)n0) % (unsigned long long)rate);
+                    step = (long long)(((unsigned long long)tf * (unsigned long long)(M % rate)) % (unsigned long long)rate);
+                }
+                sh->ph_base[threadIdx.x] = base;
+                sh->ph_step[threadIdx.x] = step;
+            }
+            mbar_wait(smem_u32(&sh->tmem_full[as]), aph);
+            tc_fence_after();
+            const unsigned int t_main = tmem_base + ((unsigned int)(warp * 32) << 16) + as * 256u;
+            const unsigned int t_corr = t_main + 128u;
+            const long long p = tl.row0 + row_in_tile;
+#pragma unroll 1
+            for (int c = 0; c < NCHUNK; ++c) {
+                float y[CW], za[CW], zb[CW];
+                tmem_ld<CW>(t_main + (unsigned)(c * CW), y);
+                tmem_ld<CW>(t_corr + (unsigned)(c * CW), zb);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < CW; ++j) y[j] += zb[j];
+#pragma unroll
+                for (int i = 1; i < F; ++i) {
+                    const unsigned int col = (unsigned)((i * TG + c * TCW) * 2);
+                    tmem_ld<CW>(t_main + col, za);
+                    tmem_ld<CW>(t_corr + col, zb);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) za[j] += zb[j];
+                    if (lane < F - 1) {
+                        float4* dst = reinterpret_cast<float4*>(xw + (lane * (F - 1) + (i - 1)) * CW);
+#pragma unroll
+                        for (int j = 0; j < CW / 4; ++j) dst[j] = make_float4(za[4 * j], za[4 * j + 1], za[4 * j + 2], za[4 * j + 3]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) {
+                        const float v = __shfl_down_sync(0xffffffffu, za[j], i);
+                        if (lane + i < 32) y[j] += v;
+                    }
+                }
+                if (F > 1) {
+                    epi_bar();
+#pragma unroll
+                    for (int i = 1; i < F; ++i) {
+                        if (lane + i >= 32) {   // rows of the next warp (meaningless for the last warp: those outputs belong to the next tile)
+                            const float4* src = reinterpret_cast<const float4*>(xn + ((lane + i - 32) * (F - 1) + (i - 1)) * CW);
+#pragma unroll
+                            for (int j = 0; j < CW / 4; ++j) {
+                                const float4 v = src[j];
+                                y[4 * j] += v.x, y[4 * j + 1] += v.y, y[4 * j + 2] += v.z, y[4 * j + 3] += v.w;
+                            }
+                        }
+                    }
+                } else if (c == 0) {
+                    epi_bar();   // publishes ph_base / ph_step
+                }
+                if (row_in_tile < RB && p < n_out) {
+#pragma unroll
+                    for (int t = 0; t < TCW; ++t) {
+                        const int tg_idx = c * TCW + t;
+                        const int ch = tl.ch0 + tg_idx;
+                        if (ch < T) {
+                            long long ph = sh->ph_base[tg_idx] + (long long)row_in_tile * sh->ph_step[tg_idx];   // < 128 * rate
+                            ph -= (long long)((double)ph * inv_R) * rate;
+                            if (ph < 0) ph += rate;
+                            if (ph >= rate) ph -= rate;
+                            out[p * T + ch] = dev_cmul(make_float2(y[2 * t], y[2 * t + 1]), lo_phasor(ph, inv_R));
+                        }
+                    }
+                }
+                if (F > 1) epi_bar();   // the exchange buffer (and ph_base after the last chunk) may be rewritten
+            }
+            if (F == 1) epi_bar();
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(smem_u32(&sh->tmem_empty[as]));
+        }
+    } else if (warp == TC_EPI_WARPS) {
+        // ======================================= MMA ISSUE =======================================
+        int it = 0;
+        for (int n = 0; n < my_tiles; ++n) {
+            const unsigned int as = n & 1, aph = (n >> 1) & 1;
+            mbar_wait(smem_u32(&sh->tmem_empty[as]), aph ^ 1u);
+            tc_fence_after();
+            const unsigned int d_main = tmem_base + as * 256u, d_corr = d_main + 128u;
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int s = it % TC_STAGES;
+                const unsigned int ph = (unsigned)(it / TC_STAGES) & 1u;
+                mbar_wait(smem_u32(&sh->full[s]), ph);
+                tc_fence_after();
+                if (lane == 0) {
+                    const unsigned int a0 = smem_base + (unsigned)s * TC_STAGE_BYTES;
+                    const unsigned long long a_hi = tc_smem_desc(a0), a_lo = tc_smem_desc(a0 + TC_OPER_BYTES);
+                    const unsigned long long b_hi = tc_smem_desc(a0 + 2 * TC_OPER_BYTES), b_lo = tc_smem_desc(a0 + 3 * TC_OPER_BYTES);
+                    const int ks_n = min(4, ksteps_total - 4 * kb);
+                    for (int ks = 0; ks < ks_n; ++ks) {
+                        const unsigned long long adv = (unsigned long long)(2 * ks);   // 32 bytes >> 4 per k-step
+                        const unsigned int acc = (kb | ks) ? 1u : 0u;
+                        tc_mma_tf32(d_main, a_hi + adv, b_hi + adv, TC_IDESC, acc);
+                        tc_mma_tf32(d_corr, a_lo + adv, b_hi + adv, TC_IDESC, acc);
+                        tc_mma_tf32(d_corr, a_hi + adv, b_lo + adv, TC_IDESC, 1u);
+                    }
+                    tc_commit(smem_u32(&sh->empty[s]));
+                    if (kb == KB - 1) tc_commit(smem_u32(&sh->tmem_full[as]));
+                }
+                __syncwarp();
+            }
+        }
+    } else {
+        // ======================================= OPERAND PRODUCERS =======================================
+        const int lt = threadIdx.x - 32 * (TC_EPI_WARPS + 1);   // 0..255
+        const unsigned int kc = (unsigned)lt & 15u, sub = (unsigned)lt >> 4;   // tap inside the K block, row / (block,tone) slot
+        const unsigned int a_off = tc_swz(sub, kc);                 // + u * 2048   (row = u*16 + sub)
+        const unsigned int b_off_re = tc_swz(2u * sub, kc);         // + u * 4096   (row n = 2*(u*16 + sub) + {0,1})
+        const unsigned int b_off_im = tc_swz(2u * sub + 1u, kc);
+        const int total_it = my_tiles * KB;
+        float2 xa[TC_A_PER_THREAD], xb[TC_B_PER_THREAD];
+
+        auto issue_loads = [&](int iter, float2* va, float2* vb) {
+            const int n = iter / KB, kb = iter - n * KB;
+            const TcTile tl = tile_of(n);
+            const int k = kb * TC_KC + (int)kc;
+            const bool kvalid = k < M;
+            const long long s0 = (tl.row0 + sub) * (long long)M + k;
+#pragma unroll
+            for (int u = 0; u < TC_A_PER_THREAD; ++u) {
+                va[u] = make_float2(0.f, 0.f);
+                if (kvalid) {
+                    long long s = s0 + (long long)(u * 16) * M;
+                    if (s < w.n_hist) va[u] = __ldg(w.hist + s);
+                    else if (s - w.n_hist < w.n_in) va[u] = __ldg(w.in + (s - w.n_hist));
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < TC_B_PER_THREAD; ++u) {
+                const int slot = u * 16 + (int)sub;            // (block i, tone t) = (slot / TG, slot % TG)
+                const int i = slot / TG, t = slot - i * TG;
+                const int ch = tl.ch0 + t;
+                vb[u] = make_float2(0.f, 0.f);
+                if (kvalid && ch < T) vb[u] = __ldg(g + (long long)ch * ntaps + i * M + k);
+            }
+        };
+
+        if (total_it > 0) issue_loads(0, xa, xb);
+        for (int it = 0; it < total_it; ++it) {
+            float2 na[TC_A_PER_THREAD], nb[TC_B_PER_THREAD];
+            if (it + 1 < total_it) issue_loads(it + 1, na, nb);
+            const int s = it % TC_STAGES;
+            const unsigned int ph = (unsigned)(it / TC_STAGES) & 1u;
+            mbar_wait(smem_u32(&sh->empty[s]), ph ^ 1u);
+            unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
+#pragma unroll
+            for (int u = 0; u < TC_A_PER_THREAD; ++u) {
+                float2 hi, lo;
+                tf32_split(xa[u].x, hi.x, lo.x);
+                tf32_split(xa[u].y, hi.y, lo.y);
+                *reinterpret_cast<float2*>(st + a_off + u * 2048) = hi;
+                *reinterpret_cast<float2*>(st + TC_OPER_BYTES + a_off + u * 2048) = lo;
+            }
+#pragma unroll
+            for (int u = 0; u < TC_B_PER_THREAD; ++u) {
+                float2 hi, lo;
+                tf32_split(xb[u].x, hi.x, lo.x);
+                tf32_split(xb[u].y, hi.y, lo.y);
+                unsigned char* bh = st + 2 * TC_OPER_BYTES + u * 4096;
+                unsigned char* bl = st + 3 * TC_OPER_BYTES + u * 4096;
+                *reinterpret_cast<float2*>(bh + b_off_re) = make_float2(hi.x, -hi.y);   // Re(x g): x_r g_r - x_i g_i
+                *reinterpret_cast<float2*>(bh + b_off_im) = make_float2(hi.y, hi.x);    // Im(x g): x_r g_i + x_i g_r
+                *reinterpret_cast<float2*>(bl + b_off_re) = make_float2(lo.x, -lo.y);
+                *reinterpret_cast<float2*>(bl + b_off_im) = make_float2(lo.y, lo.x);
+            }
+            fence_proxy_async();
+            mbar_arrive(smem_u32(&sh->full[s]));
+            if (it + 1 < total_it) {
+#pragma unroll
+                for (int u = 0; u < TC_A_PER_THREAD; ++u) xa[u] = na[u];
+#pragma unroll
+                for (int u = 0; u < TC_B_PER_THREAD; ++u) xb[u] = nb[u];
+            }
+        }
+    }
+
+    // teardown: every MMA has completed before the last tmem_full arrival, every tcgen05.ld before this barrier
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == TC_EPI_WARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TC_TMEM_COLS) : "memory");
+    }
+}
+
+template <int F>
+int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int M, int rate, long long pos0, long long n_out,
+              float2* out, int sm_count, cudaStream_t stream) {
+    constexpr int TG = 64 / F, RB = TC_ROWS - (F - 1);
+    const int row_tiles = (int)((n_out + RB - 1) / RB), tone_groups = (T + TG - 1) / TG;
+    static bool attr_set = false;
+    if (!attr_set) {
+        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+        attr_set = true;
+    }
+    const long long tiles = (long long)row_tiles * tone_groups;
+    const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+    direct_fir_tc_kernel<F><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(w, g, freq_dev, T, M, rate, pos0, n_out, row_tiles,
+                                                                         tone_groups, out);
+    GSDR_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
+}  // namespace
+
+// F in {1, 2, 4, 8} so that F * TG * 2 = 128 accumulator columns; the LO phase arithmetic needs 128 * rate < 2^53.
+// M <= 128: the tensor-core accumulation truncates (measured on B200: about 1.6e-7 relative per accumulated k-step
+// when every term has the same sign, 4e-5 at M = 1000), so one accumulation chain is kept to 32 k-steps.
+constexpr int TC_MAX_M = 128;
+bool direct_fir_tc_supported(int T, int M, int ntaps, long long n_out) {
+    if (M < 1 || M > TC_MAX_M || T < 1 || n_out < 1 || ntaps % M != 0) return false;
+    const int f = ntaps / M;
+    if (!(f == 1 || f == 2 || f == 4 || f == 8)) return false;
+    const long long rb = TC_ROWS - (f - 1), tg = 64 / f;
+    const long long tiles = ((n_out + rb - 1) / rb) * ((T + tg - 1) / tg);
+    return tiles < (1ll << 30);
+}
+
+// Worth it when there are enough (row tile, tone group) tiles to occupy a good part of the GPU; small problems
+// (few outputs per buffer, i.e. very large decimation) stay on the fp32 kernel.
+bool direct_fir_tc_preferred(int T, int M, int ntaps, long long n_out) {
+    if (!direct_fir_tc_supported(T, M, ntaps, n_out)) return false;
+    const int f = ntaps / M;
+    const long long rb = TC_ROWS - (f - 1), tg = 64 / f;
+    const long long tiles = ((n_out + rb - 1) / rb) * ((T + tg - 1) / tg);
+    return tiles >= 64;
+}
+
+int direct_fir_tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int M, int ntaps, int rate, long long pos0,
+                         long long n_out, float2* out, int sm_count, cudaStream_t stream) {
+    if (n_out <= 0) return 0;
+    if (!direct_fir_tc_supported(T, M, ntaps, n_out)) {
+        set_error("direct_fir_tc_launch: unsupported shape (T=%d M=%d ntaps=%d)", T, M, ntaps);
+        return -1;
+    }
+    switch (ntaps / M) {
+        case 1: return tc_launch<1>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream);
+        case 2: return tc_launch<2>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream);
+        case 4: return tc_launch<4>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream);
+        default: return tc_launch<8>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream);
+    }
+}
+
+}  // namespace gsdr

@@ -118,6 +118,7 @@ struct gsdr_rx {
     int* d_freq = nullptr;
     int ntaps = 0;
     long long index_counter = 0;
+    bool direct_tc = false;
 };
 
 namespace {
@@ -289,6 +290,13 @@ int init_direct(gsdr_rx* rx) {
         rx->n_hist = (f - 1) * M;  // FIR history starts as zeros (cpp/fir.cu:23-26)
         rx->max_out = (size_t)(rx->L / M) * T;
         rx->kernel_name = (rx->P >= 1 && rx->P <= 8) ? "direct_fir_tiled_kernel" : "direct_fir_kernel";
+        // tensor-core path (direct_tc_kernels.cu): default when the shape fills the GPU; GSDR_DIRECT_VARIANT=tc|fp32 forces
+        const long long n_out1 = rx->L / M;
+        const char* e = getenv("GSDR_DIRECT_VARIANT");
+        rx->direct_tc = direct_fir_tc_preferred(T, (int)M, rx->ntaps, n_out1);
+        if (e && !strcmp(e, "tc")) rx->direct_tc = direct_fir_tc_supported(T, (int)M, rx->ntaps, n_out1);
+        if (e && !strcmp(e, "fp32")) rx->direct_tc = false;
+        if (rx->direct_tc) rx->kernel_name = "direct_fir_tc_kernel";
     }
     return 0;
 }
@@ -430,8 +438,10 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
                 const long long n_out = (L / M) * n_buf;
                 long long pos0 = (rx->index_counter - w.n_hist) % rx->rate;
                 if (pos0 < 0) pos0 += rx->rate;
-                const int nl = direct_fir_launch(w, rx->d_g, rx->d_freq, rx->T, (int)M, rx->ntaps, rx->rate, pos0, n_out,
-                                                 d_out, st);
+                const int nl = rx->direct_tc ? direct_fir_tc_launch(w, rx->d_g, rx->d_freq, rx->T, (int)M, rx->ntaps, rx->rate, pos0,
+                                                                    n_out, d_out, rx->sm_count, st)
+                                             : direct_fir_launch(w, rx->d_g, rx->d_freq, rx->T, (int)M, rx->ntaps, rx->rate, pos0, n_out,
+                                                                 d_out, st);
                 if (nl < 0) return -1;
                 rx->launches += nl;
                 const long long tail = w.n_hist;  // (f-1)*M samples, constant

@@ -1,0 +1,109 @@
+"""DIRECT mode on the tensor cores (direct_fir_tc_kernel, tcgen05 + TMEM, 3xTF32 split GEMM): the same parity bar
+as the fp32 kernel -- relative L2 <= 1e-5 against the fp64 oracle -- over every supported filter shape."""
+import os
+
+import numpy as np
+import pytest
+
+from common import TOL, direct_param, g, orc, rx_run, tone_stream
+
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("gpu_required")]
+
+
+@pytest.fixture(autouse=True)
+def force_tc(monkeypatch):
+    monkeypatch.setenv("GSDR_DIRECT_VARIANT", "tc")
+    yield
+
+
+def run_case(p, nbuf, noise=1e-3, expect_tc=True):
+    rx = g.RX_buffer_demodulator(p)
+    name = rx.kernel_name()
+    rx.close()
+    assert (name == "direct_fir_tc_kernel") == expect_tc, name
+    bufs = [tone_stream(p.rate, p.freq, p.ampl, i * p.buffer_len, p.buffer_len, noise=noise) for i in range(nbuf)]
+    ours = rx_run(p, bufs)
+    o = orc.DirectDemodulator(p.rate, p.freq, p.decim, p.pf_average, p.buffer_len)
+    worst = 0.0
+    for a, x in zip(ours, bufs):
+        want = o.process(x)
+        assert len(a) == len(want)
+        worst = max(worst, orc.rel_l2(a, want))
+    assert worst <= TOL, worst
+    return ours, worst
+
+
+def test_cfg1_full_size_tc():
+    out, worst = run_case(direct_param(), 3)
+    assert all(len(o) == 160_000 for o in out)
+    assert worst <= 3e-6, worst   # the 3xTF32 split is expected well inside the 1e-5 bar
+
+
+@pytest.mark.parametrize("T,decim,f,L,rate", [
+    (5, 10, 8, 50_000, 1_000_000),          # M < one K block, 8 FIR blocks (8 tones per group, 16-column chunks)
+    (1, 100, 4, 100_000, 100_000_000),      # one tone: every product has the same sign (worst case for the truncating accumulation)
+    (33, 50, 2, 50_000, 10_000_000),        # two tone groups of 32, the second almost empty
+    (4, 7, 1, 70_000, 1_000_000),           # f = 1 (no row exchange), M odd and not a multiple of 4
+    (70, 25, 1, 50_000, 10_000_000),        # f = 1, two tone groups of 64, four epilogue chunks
+    (16, 100, 4, 1_000_000, 100_000_000),   # cfg1 shape
+    (40, 13, 4, 65_000, 5_000_000),         # three tone groups, M odd
+    (2, 128, 4, 128_000, 200_000_000),      # the longest accumulation chain the path accepts
+    (3, 1, 2, 4_096, 1_000_000),            # decim = 1
+])
+def test_tc_vs_oracle(T, decim, f, L, rate):
+    run_case(direct_param(rate=rate, T=T, decim=decim, f=f, L=L), 3)
+
+
+@pytest.mark.parametrize("T,decim,f,L,rate", [(1, 1000, 4, 100_000, 100_000_000), (2, 5000, 4, 100_000, 200_000_000)])
+def test_long_decimation_stays_on_fp32(T, decim, f, L, rate):
+    """decim > 128 would need accumulation chains long enough for the tensor cores' truncating accumulate to show
+    (4e-5 at decim = 1000): those shapes run the fp32 kernel even when the tensor-core path is forced."""
+    run_case(direct_param(rate=rate, T=T, decim=decim, f=f, L=L), 2, expect_tc=False)
+
+
+def test_unsupported_block_count_falls_back():
+    """pf_average = 3 has no 128-column tiling: the fp32 kernel runs even when the tensor-core path is forced."""
+    run_case(direct_param(rate=1_000_000, T=4, decim=10, f=3, L=50_000), 2, expect_tc=False)
+
+
+def test_known_answer_single_tone_goes_to_dc_tc():
+    rate, L, f = 100_000_000, 100_000, -12_345_677
+    p = g.param(rate=rate, decim=100, pf_average=4, buffer_len=L, freq=[f], wave_type=[g.DIRECT], ampl=[1.0])
+    n = np.arange(2 * L, dtype=np.int64)
+    x = (0.3 * np.exp(2j * np.pi * ((f * n) % rate) / rate)).astype(np.complex64)
+    out = rx_run(p, [x[:L], x[L:]])
+    assert np.allclose(out[1], 0.3, atol=3e-6)
+    assert np.allclose(out[0][4:], 0.3, atol=3e-6)
+
+
+def test_phase_continuity_across_rate_wrap_tc():
+    run_case(direct_param(rate=1_000_000, T=3, decim=10, f=4, L=50_000), 30, noise=0.0)
+
+
+def test_device_batch_equals_sequential_tc():
+    """Results do not depend on where a row falls inside a tile: a 4-buffer device batch is bit-identical to four
+    single-buffer calls."""
+    p = direct_param(rate=10_000_000, T=6, decim=20, f=4, L=40_000)
+    bufs = [tone_stream(p.rate, p.freq, p.ampl, i * p.buffer_len, p.buffer_len) for i in range(4)]
+    seq = rx_run(p, bufs)
+    rx = g.RX_buffer_demodulator(p)
+    assert rx.kernel_name() == "direct_fir_tc_kernel"
+    din = g.DeviceBuffer(4 * p.buffer_len)
+    din.upload(np.concatenate(bufs))
+    dout = g.DeviceBuffer(rx.max_output_batch(4))
+    tot, lens = rx.process_device(din.ptr, 4, dout.ptr)
+    rx.sync()
+    assert lens == [len(s) for s in seq]
+    assert np.array_equal(dout.download(tot), np.concatenate(seq))
+    rx.close()
+
+
+def test_tc_matches_fp32_kernel(monkeypatch):
+    """The two CUDA implementations agree far inside the tolerance on the same buffers."""
+    p = direct_param(rate=10_000_000, T=16, decim=100, f=4, L=200_000)
+    bufs = [tone_stream(p.rate, p.freq, p.ampl, i * p.buffer_len, p.buffer_len) for i in range(2)]
+    tc = rx_run(p, bufs)
+    monkeypatch.setenv("GSDR_DIRECT_VARIANT", "fp32")
+    fp = rx_run(p, bufs)
+    for a, b in zip(tc, fp):
+        assert orc.rel_l2(a, b) <= 3e-6
