@@ -19,10 +19,16 @@
 // Warp roles (one persistent CTA per SM, static tile scheduler over (row tile, tone group)):
 //   warps 0-3   epilogue: tcgen05.ld of the two accumulators, row shift-and-add, LO rotation, sample-major store
 //   warp  4     TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, M=128, N=128, K=8)
-//   warps 5-12  operand producers: coalesced global loads of the window rows and of the tone filters, hi/lo split,
-//               stores into the 128-byte-swizzled K-major operand tiles, fence.proxy.async, mbarrier arrive
+//   warps 5-12  operand producers: hi/lo split of the window rows and of the tone filters into the 128-byte-swizzled
+//               K-major operand tiles, fence.proxy.async, mbarrier arrive.  The filters come through registers (L2
+//               hits); the window rows are put into the A_hi tile by TMA and split in place (shared -> shared), or,
+//               for rows that touch the carried-over history or a mis-aligned stream, loaded through registers
+//   warp  13    TMA issue: one cp.async.bulk.tensor (128 rows x 32 floats, SWIZZLE_128B) per K block, as far ahead
+//               as there are free stages
 // Three operand stages (64 KB each: A_hi, A_lo, B_hi, B_lo for 16 complex taps), two accumulator stages (512 TMEM
 // columns), so the epilogue of tile n overlaps the MMAs of tile n+1.
+#include <cuda.h>
+
 #include <cstdlib>
 
 #include "devmath.cuh"
@@ -38,16 +44,19 @@ constexpr int TC_STAGES = 3;
 constexpr int TC_EPI_WARPS = 4;
 constexpr int TC_LOAD_WARPS = 8;
 constexpr int TC_LOAD_THREADS = 32 * TC_LOAD_WARPS;
-constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 1 + TC_LOAD_WARPS);
+constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 1 + TC_LOAD_WARPS + 1);
+constexpr int TC_TMA_WARP = TC_EPI_WARPS + 1 + TC_LOAD_WARPS;
 constexpr int TC_OPER_BYTES = TC_ROWS * 128;       // one operand part of one stage (128 rows x 128 bytes)
 constexpr int TC_STAGE_BYTES = 4 * TC_OPER_BYTES;  // A_hi, A_lo, B_hi, B_lo
 constexpr int TC_XCH_FLOATS = 7 * 7 * 16;          // per epilogue warp: (F-1) lanes x (F-1) blocks x chunk, F <= 8
 constexpr int TC_TMEM_COLS = 512;
+constexpr int TC_L2_AHEAD = 8;                     // K blocks between the L2 prefetch of a box and its TMA load
 constexpr int TC_A_PER_THREAD = TC_ROWS * TC_KC / TC_LOAD_THREADS;        // 8
 constexpr int TC_B_PER_THREAD = (TC_N / 2) * TC_KC / TC_LOAD_THREADS;     // 4
 
 struct TcShared {
     unsigned long long full[TC_STAGES];
+    unsigned long long raw_full[TC_STAGES];   // the stage is free and (TMA tiles) the raw window rows have landed
     unsigned long long empty[TC_STAGES];
     unsigned long long tmem_full[2];
     unsigned long long tmem_empty[2];
@@ -82,6 +91,21 @@ __device__ __forceinline__ void mbar_wait(unsigned int addr, unsigned int parity
         if (spins == 64) t0 = clock64();
         if (spins > 64 && (spins & 255u) == 0 && clock64() - t0 > 4000000000LL) __trap();
     }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned int addr, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+// 2-D tiled TMA load: box (32 floats x 128 rows) at (c0 = float column, c1 = row), completion on an mbarrier
+__device__ __forceinline__ void tma_load_2d(unsigned int dst, const CUtensorMap* map, int c0, int c1, unsigned int mbar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(mbar)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(reinterpret_cast<unsigned long long>(map)),
+                 "r"(c0), "r"(c1)
+                 : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -140,11 +164,11 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory"); }
 
-// x = hi + lo with hi = x rounded to TF32 (10 explicit mantissa bits); lo = x - hi is exact in fp32
+// x = hi + lo with hi = x rounded to TF32 (10 explicit mantissa bits, half away from zero: one integer add and a
+// mask on the sign-magnitude bits); lo = x - hi is exact in fp32.  The tensor core drops the low 13 bits of lo, an
+// error of at most 2^-21 |x| with the sign of lo, i.e. unbiased.  (cvt.rna.tf32.f32 costs six instructions on sm_100a.)
 __device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
-    unsigned int h;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-    hi = __uint_as_float(h);
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
     lo = x - hi;
 }
 
@@ -161,8 +185,9 @@ struct TcTile {
 // F = FIR blocks (pf_average); TG = 64 / F tones per group; outputs per tile = 128 - (F - 1)
 template <int F>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-direct_fir_tc_kernel(const Window w, const float2* __restrict__ g, const int* __restrict__ freq, int T, int M, int rate,
-                     long long pos0, long long n_out, int n_row_tiles, int n_tone_groups, float2* __restrict__ out) {
+direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma, const Window w, const float2* __restrict__ g,
+                     const int* __restrict__ freq, int T, int M, int rate, long long pos0, long long n_out, int n_row_tiles,
+                     int n_tone_groups, float2* __restrict__ out) {
     constexpr int TG = 64 / F;
     constexpr int RB = TC_ROWS - (F - 1);
     constexpr int TCW = TG < 16 ? TG : 16;     // tones per epilogue chunk
@@ -170,7 +195,8 @@ direct_fir_tc_kernel(const Window w, const float2* __restrict__ g, const int* __
     constexpr int NCHUNK = TG / TCW;
 
     extern __shared__ unsigned char tc_smem_raw[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(tc_smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space: LDS/STS, not generic)
+    unsigned char* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
     TcShared* sh = reinterpret_cast<TcShared*>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
     const unsigned int smem_base = smem_u32(smem);
 
@@ -184,6 +210,7 @@ direct_fir_tc_kernel(const Window w, const float2* __restrict__ g, const int* __
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
             mbar_init(smem_u32(&sh->full[s]), TC_LOAD_THREADS);
+            mbar_init(smem_u32(&sh->raw_full[s]), 1);
             mbar_init(smem_u32(&sh->empty[s]), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -203,6 +230,8 @@ direct_fir_tc_kernel(const Window w, const float2* __restrict__ g, const int* __
     tc_fence_after();
     const unsigned int tmem_base = sh->tmem_base;
 
+    // TMA tiles: every window row of the tile lies in the `in` segment (tensor row = window row - hist_rows)
+    const long long hist_rows = w.n_hist / M;
     auto tile_of = [&](int n) {
         const int id = (int)blockIdx.x + n * (int)gridDim.x;
         TcTile t;
@@ -306,15 +335,14 @@ direct_fir_tc_kernel(const Window w, const float2* __restrict__ g, const int* __
         }
     } else if (warp == TC_EPI_WARPS) {
         // ======================================= MMA ISSUE =======================================
-        int it = 0;
+        int s = 0;
+        unsigned int ph = 0;
         for (int n = 0; n < my_tiles; ++n) {
             const unsigned int as = n & 1, aph = (n >> 1) & 1;
             mbar_wait(smem_u32(&sh->tmem_empty[as]), aph ^ 1u);
             tc_fence_after();
             const unsigned int d_main = tmem_base + as * 256u, d_corr = d_main + 128u;
-            for (int kb = 0; kb < KB; ++kb, ++it) {
-                const int s = it % TC_STAGES;
-                const unsigned int ph = (unsigned)(it / TC_STAGES) & 1u;
+            for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(smem_u32(&sh->full[s]), ph);
                 tc_fence_after();
                 if (lane == 0) {
@@ -333,58 +361,91 @@ direct_fir_tc_kernel(const Window w, const float2* __restrict__ g, const int* __
                     if (kb == KB - 1) tc_commit(smem_u32(&sh->tmem_full[as]));
                 }
                 __syncwarp();
+                if (++s == TC_STAGES) s = 0, ph ^= 1u;
             }
         }
-    } else {
+    } else if (warp < TC_TMA_WARP) {
         // ======================================= OPERAND PRODUCERS =======================================
         const int lt = threadIdx.x - 32 * (TC_EPI_WARPS + 1);   // 0..255
         const unsigned int kc = (unsigned)lt & 15u, sub = (unsigned)lt >> 4;   // tap inside the K block, row / (block,tone) slot
         const unsigned int a_off = tc_swz(sub, kc);                 // + u * 2048   (row = u*16 + sub)
         const unsigned int b_off_re = tc_swz(2u * sub, kc);         // + u * 4096   (row n = 2*(u*16 + sub) + {0,1})
         const unsigned int b_off_im = tc_swz(2u * sub + 1u, kc);
-        const int total_it = my_tiles * KB;
         float2 xa[TC_A_PER_THREAD], xb[TC_B_PER_THREAD];
+        // (block i, tone t) of this thread's four filter taps: slot = u * 16 + sub, i = slot / TG, t = slot % TG
+        int g_off[TC_B_PER_THREAD], g_t[TC_B_PER_THREAD];
+#pragma unroll
+        for (int u = 0; u < TC_B_PER_THREAD; ++u) {
+            const int slot = u * 16 + (int)sub;
+            g_t[u] = slot % TG;
+            g_off[u] = (slot / TG) * M + g_t[u] * ntaps;
+        }
 
-        auto issue_loads = [&](int iter, float2* va, float2* vb) {
-            const int n = iter / KB, kb = iter - n * KB;
-            const TcTile tl = tile_of(n);
+        auto issue_loads = [&](const TcTile& tl, bool tma, int kb, float2* va, float2* vb) {
             const int k = kb * TC_KC + (int)kc;
             const bool kvalid = k < M;
-            const long long s0 = (tl.row0 + sub) * (long long)M + k;
+            if (!tma) {
+                const long long s0 = (tl.row0 + sub) * (long long)M + k;
 #pragma unroll
-            for (int u = 0; u < TC_A_PER_THREAD; ++u) {
-                va[u] = make_float2(0.f, 0.f);
-                if (kvalid) {
-                    long long s = s0 + (long long)(u * 16) * M;
-                    if (s < w.n_hist) va[u] = __ldg(w.hist + s);
-                    else if (s - w.n_hist < w.n_in) va[u] = __ldg(w.in + (s - w.n_hist));
+                for (int u = 0; u < TC_A_PER_THREAD; ++u) {
+                    va[u] = make_float2(0.f, 0.f);
+                    if (kvalid) {
+                        long long s = s0 + (long long)(u * 16) * M;
+                        if (s < w.n_hist) va[u] = __ldg(w.hist + s);
+                        else if (s - w.n_hist < w.n_in) va[u] = __ldg(w.in + (s - w.n_hist));
+                    }
                 }
             }
+            const float2* gk = g + (long long)tl.ch0 * ntaps + k;
 #pragma unroll
             for (int u = 0; u < TC_B_PER_THREAD; ++u) {
-                const int slot = u * 16 + (int)sub;            // (block i, tone t) = (slot / TG, slot % TG)
-                const int i = slot / TG, t = slot - i * TG;
-                const int ch = tl.ch0 + t;
                 vb[u] = make_float2(0.f, 0.f);
-                if (kvalid && ch < T) vb[u] = __ldg(g + (long long)ch * ntaps + i * M + k);
+                if (kvalid && tl.ch0 + g_t[u] < T) vb[u] = __ldg(gk + g_off[u]);
             }
         };
 
-        if (total_it > 0) issue_loads(0, xa, xb);
-        for (int it = 0; it < total_it; ++it) {
+        // (tile, K block) of the iteration being stored and of the one being loaded, advanced without divisions
+        int n_cur = 0, kb_cur = 0, n_nxt = 0, kb_nxt = 0, s = 0;
+        unsigned int ph = 0;
+        TcTile t_cur = tile_of(0), t_nxt = t_cur;
+        bool tma_cur = use_tma && t_cur.row0 >= hist_rows, tma_nxt = tma_cur;
+        if (my_tiles > 0) issue_loads(t_cur, tma_cur, 0, xa, xb);
+        while (n_cur < my_tiles) {
             float2 na[TC_A_PER_THREAD], nb[TC_B_PER_THREAD];
-            if (it + 1 < total_it) issue_loads(it + 1, na, nb);
-            const int s = it % TC_STAGES;
-            const unsigned int ph = (unsigned)(it / TC_STAGES) & 1u;
-            mbar_wait(smem_u32(&sh->empty[s]), ph ^ 1u);
+            if (++kb_nxt == KB) {
+                kb_nxt = 0;
+                ++n_nxt;
+                t_nxt = tile_of(n_nxt);
+                tma_nxt = use_tma && t_nxt.row0 >= hist_rows;
+            }
+            const bool more = n_nxt < my_tiles;
+            if (more) issue_loads(t_nxt, tma_nxt, kb_nxt, na, nb);
+            mbar_wait(smem_u32(&sh->raw_full[s]), ph);
             unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
+            if (tma_cur) {
+                // the raw rows are in the A_hi tile: split in place, same (swizzled) position in both tiles
+                float4 v[TC_OPER_BYTES / 16 / TC_LOAD_THREADS];
 #pragma unroll
-            for (int u = 0; u < TC_A_PER_THREAD; ++u) {
-                float2 hi, lo;
-                tf32_split(xa[u].x, hi.x, lo.x);
-                tf32_split(xa[u].y, hi.y, lo.y);
-                *reinterpret_cast<float2*>(st + a_off + u * 2048) = hi;
-                *reinterpret_cast<float2*>(st + TC_OPER_BYTES + a_off + u * 2048) = lo;
+                for (int u = 0; u < TC_OPER_BYTES / 16 / TC_LOAD_THREADS; ++u) v[u] = *(reinterpret_cast<const float4*>(st) + u * TC_LOAD_THREADS + lt);
+#pragma unroll
+                for (int u = 0; u < TC_OPER_BYTES / 16 / TC_LOAD_THREADS; ++u) {
+                    float4 hi, lo;
+                    tf32_split(v[u].x, hi.x, lo.x);
+                    tf32_split(v[u].y, hi.y, lo.y);
+                    tf32_split(v[u].z, hi.z, lo.z);
+                    tf32_split(v[u].w, hi.w, lo.w);
+                    *(reinterpret_cast<float4*>(st) + u * TC_LOAD_THREADS + lt) = hi;
+                    *(reinterpret_cast<float4*>(st + TC_OPER_BYTES) + u * TC_LOAD_THREADS + lt) = lo;
+                }
+            } else {
+#pragma unroll
+                for (int u = 0; u < TC_A_PER_THREAD; ++u) {
+                    float2 hi, lo;
+                    tf32_split(xa[u].x, hi.x, lo.x);
+                    tf32_split(xa[u].y, hi.y, lo.y);
+                    *reinterpret_cast<float2*>(st + a_off + u * 2048) = hi;
+                    *reinterpret_cast<float2*>(st + TC_OPER_BYTES + a_off + u * 2048) = lo;
+                }
             }
 #pragma unroll
             for (int u = 0; u < TC_B_PER_THREAD; ++u) {
@@ -400,11 +461,50 @@ direct_fir_tc_kernel(const Window w, const float2* __restrict__ g, const int* __
             }
             fence_proxy_async();
             mbar_arrive(smem_u32(&sh->full[s]));
-            if (it + 1 < total_it) {
+            if (more) {
 #pragma unroll
                 for (int u = 0; u < TC_A_PER_THREAD; ++u) xa[u] = na[u];
 #pragma unroll
                 for (int u = 0; u < TC_B_PER_THREAD; ++u) xb[u] = nb[u];
+            }
+            if (++s == TC_STAGES) s = 0, ph ^= 1u;
+            n_cur = n_nxt, kb_cur = kb_nxt, t_cur = t_nxt, tma_cur = tma_nxt;
+        }
+        (void)kb_cur;
+    } else if (warp == TC_TMA_WARP) {
+        // ======================================= TMA ISSUE =======================================
+        // One lane.  Besides the load of the K block into its stage, the box TC_L2_AHEAD iterations further on is
+        // prefetched into L2, so that the load proper finds its rows there: three stages cannot cover the HBM latency.
+        if (lane == 0) {
+            int s = 0;
+            unsigned int ph = 0;
+            int n_pf = 0, kb_pf = 0;   // (tile, K block) of the next L2 prefetch
+            TcTile t_pf = tile_of(0);
+            auto prefetch_next = [&]() {
+                if (n_pf >= my_tiles) return;
+                if (use_tma && t_pf.row0 >= hist_rows) tma_prefetch_2d(&tmap, kb_pf * 2 * TC_KC, (int)(t_pf.row0 - hist_rows));
+                if (++kb_pf == KB) {
+                    kb_pf = 0;
+                    ++n_pf;
+                    t_pf = tile_of(n_pf);
+                }
+            };
+            for (int j = 0; j < TC_L2_AHEAD; ++j) prefetch_next();
+            for (int n = 0; n < my_tiles; ++n) {
+                const TcTile tl = tile_of(n);
+                const bool tma = use_tma && tl.row0 >= hist_rows;
+                for (int kb = 0; kb < KB; ++kb) {
+                    prefetch_next();
+                    mbar_wait(smem_u32(&sh->empty[s]), ph ^ 1u);
+                    const unsigned int bar = smem_u32(&sh->raw_full[s]);
+                    if (tma) {
+                        mbar_arrive_expect_tx(bar, TC_OPER_BYTES);
+                        tma_load_2d(smem_base + (unsigned)s * TC_STAGE_BYTES, &tmap, kb * 2 * TC_KC, (int)(tl.row0 - hist_rows), bar);
+                    } else {
+                        mbar_arrive(bar);
+                    }
+                    if (++s == TC_STAGES) s = 0, ph ^= 1u;
+                }
             }
         }
     }
@@ -418,6 +518,44 @@ direct_fir_tc_kernel(const Window w, const float2* __restrict__ g, const int* __
     }
 }
 
+typedef CUresult (*TcEncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// cuTensorMapEncodeTiled through the runtime (libgsdr.so does not link libcuda)
+TcEncodeTiledFn tc_encode_fn() {
+    static TcEncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<TcEncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// The `in` segment as a 2-D tensor [rows][2 M floats] (row pitch M * 8 bytes), box = 128 rows x 32 floats, 128-byte
+// swizzle: exactly the K-major operand tile of one K block.  Needs a 16-byte-aligned base and pitch.
+bool tc_make_tensor_map(const Window& w, int M, CUtensorMap* map) {
+    const char* e = getenv("GSDR_DIRECT_TC_TMA");   // =0: every tile through the register path (tests)
+    const bool off = e && e[0] == '0';
+    if (off || M < TC_KC || (M & 1) || w.n_hist % M != 0 || w.n_in < M || w.n_in % M != 0) return false;
+    if (reinterpret_cast<uintptr_t>(w.in) & 15) return false;
+    TcEncodeTiledFn enc = tc_encode_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)(2 * M), (cuuint64_t)(w.n_in / M)};
+    const cuuint64_t strides[1] = {(cuuint64_t)M * 8};
+    const cuuint32_t box[2] = {2 * TC_KC, TC_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(w.in), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int F>
 int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int M, int rate, long long pos0, long long n_out,
               float2* out, int sm_count, cudaStream_t stream) {
@@ -428,10 +566,13 @@ int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int 
         GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
         attr_set = true;
     }
+    CUtensorMap map;
+    memset(&map, 0, sizeof(map));
+    const int use_tma = tc_make_tensor_map(w, M, &map) ? 1 : 0;
     const long long tiles = (long long)row_tiles * tone_groups;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
-    direct_fir_tc_kernel<F><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(w, g, freq_dev, T, M, rate, pos0, n_out, row_tiles,
-                                                                         tone_groups, out);
+    direct_fir_tc_kernel<F><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, use_tma, w, g, freq_dev, T, M, rate, pos0, n_out,
+                                                                         row_tiles, tone_groups, out);
     GSDR_CUDA_OK(cudaGetLastError());
     return 1;
 }

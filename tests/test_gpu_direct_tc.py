@@ -107,3 +107,15 @@ def test_tc_matches_fp32_kernel(monkeypatch):
     fp = rx_run(p, bufs)
     for a, b in zip(tc, fp):
         assert orc.rel_l2(a, b) <= 3e-6
+
+
+def test_tma_and_register_operand_paths_are_identical(monkeypatch):
+    """Window rows reach the A operand either by TMA (split in place) or through registers (history rows, mis-aligned
+    streams); both must give the same bits."""
+    p = direct_param(rate=10_000_000, T=16, decim=100, f=4, L=400_000)
+    bufs = [tone_stream(p.rate, p.freq, p.ampl, i * p.buffer_len, p.buffer_len) for i in range(2)]
+    a = rx_run(p, bufs)
+    monkeypatch.setenv("GSDR_DIRECT_TC_TMA", "0")
+    b = rx_run(p, bufs)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
