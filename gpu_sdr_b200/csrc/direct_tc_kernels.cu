@@ -62,8 +62,7 @@ struct TcShared {
     unsigned long long tmem_empty[2];
     unsigned int tmem_base;
     unsigned int pad;
-    long long ph_base[64];   // LO phase of the tile's first row, per tone of the group
-    long long ph_step[64];   // (tf * M) mod rate
+    double2 ph[64];          // per tone of the group: (LO phase of the tile's first row, phase step per row), integers < rate
     alignas(16) float xch[TC_EPI_WARPS][TC_XCH_FLOATS];
 };
 constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(TcShared);
@@ -107,6 +106,16 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, 
                  "r"(c0), "r"(c1)
                  : "memory");
 }
+// debug builds of the schedule: cycles spent in a wait, accumulated per role (dbg == nullptr in production)
+__device__ __forceinline__ void mbar_wait_t(unsigned int addr, unsigned int parity, long long& acc, bool on) {
+    if (!on) {
+        mbar_wait(addr, parity);
+        return;
+    }
+    const long long t0 = clock64();
+    mbar_wait(addr, parity);
+    acc += clock64() - t0;
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -131,7 +140,9 @@ __device__ __forceinline__ unsigned long long tc_smem_desc(unsigned int saddr) {
     return ((unsigned long long)hi << 32) | lo;
 }
 // cute::UMMA::InstrDescriptor: D = f32 (1 @4), A = B = tf32 (2 @7, 2 @10), K-major both, N>>3 @17, M>>4 @24
-constexpr unsigned int TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(TC_N >> 3) << 17) | ((unsigned)(TC_ROWS >> 4) << 24);
+constexpr unsigned int tc_idesc(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(TC_ROWS >> 4) << 24); }
+constexpr unsigned int TC_IDESC = tc_idesc(TC_N);
+constexpr unsigned int TC_IDESC_WIDE = tc_idesc(2 * TC_N);   // B = [B_hi ; B_lo] (256 rows, contiguous tiles): main and corr side by side
 
 template <int CW>
 __device__ __forceinline__ void tmem_ld(unsigned int taddr, float* v);
@@ -187,7 +198,7 @@ template <int F>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma, const Window w, const float2* __restrict__ g,
                      const int* __restrict__ freq, int T, int M, int rate, long long pos0, long long n_out, int n_row_tiles,
-                     int n_tone_groups, float2* __restrict__ out) {
+                     int n_tone_groups, float2* __restrict__ out, long long* __restrict__ dbg) {
     constexpr int TG = 64 / F;
     constexpr int RB = TC_ROWS - (F - 1);
     constexpr int TCW = TG < 16 ? TG : 16;     // tones per epilogue chunk
@@ -243,28 +254,32 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
     if (warp < TC_EPI_WARPS) {
         // ======================================= EPILOGUE =======================================
         const int row_in_tile = warp * 32 + lane;
-        const double inv_R = 1.0 / (double)rate;
+        const double row_d = (double)row_in_tile;
+        const double word_per_phase = 4294967296.0 / (double)rate;
         float* xw = sh->xch[warp];
         const float* xn = sh->xch[(warp + 1) & 3];
+        long long w_acc0 = 0;
+        const long long t_role0 = clock64();
         for (int n = 0; n < my_tiles; ++n) {
             const TcTile tl = tile_of(n);
             const unsigned int as = n & 1, aph = (n >> 1) & 1;
-            // LO phase of the tile's first output for each tone of the group, and its step per output
+            // LO phase (cpp/kernels.cu:59-75) of the tile's first output for each tone of the group, and its step per
+            // output, as exact integers; row r of the tile then has phase base + r * step < 128 * rate < 2^53, formed
+            // exactly by one DFMA.
             if (threadIdx.x < TG) {
                 const int ch = tl.ch0 + (int)threadIdx.x;
-                long long base = 0, step = 0;
+                double base = 0.0, step = 0.0;
                 if (ch < T) {
                     long long tf = (long long)freq[ch] % rate;
                     if (tf < 0) tf += rate;   // same residue class as the reference's signed remainder
                     long long n0 = (pos0 + tl.row0 * (long long)M) % rate;
                     if (n0 < 0) n0 += rate;
-                    base = (long long)(((unsigned long long)tf * (unsigned long long)n0) % (unsigned long long)rate);
-                    step = (long long)(((unsigned long long)tf * (unsigned long long)(M % rate)) % (unsigned long long)rate);
+                    base = (double)(((unsigned long long)tf * (unsigned long long)n0) % (unsigned long long)rate);
+                    step = (double)(((unsigned long long)tf * (unsigned long long)(M % rate)) % (unsigned long long)rate);
                 }
-                sh->ph_base[threadIdx.x] = base;
-                sh->ph_step[threadIdx.x] = step;
+                sh->ph[threadIdx.x] = make_double2(base, step);
             }
-            mbar_wait(smem_u32(&sh->tmem_full[as]), aph);
+            mbar_wait_t(smem_u32(&sh->tmem_full[as]), aph, w_acc0, dbg != nullptr);
             tc_fence_after();
             const unsigned int t_main = tmem_base + ((unsigned int)(warp * 32) << 16) + as * 256u;
             const unsigned int t_corr = t_main + 128u;
@@ -310,52 +325,68 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                         }
                     }
                 } else if (c == 0) {
-                    epi_bar();   // publishes ph_base / ph_step
+                    epi_bar();   // publishes sh->ph
+                }
+                // every accumulator column of the tile is in registers: the MMA warp may start tile n + 2 in this stage
+                if (c == NCHUNK - 1) {
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&sh->tmem_empty[as]));
                 }
                 if (row_in_tile < RB && p < n_out) {
+                    // phase word = round(phase * 2^32 / rate) mod 2^32: the low mantissa bits of phase * c + 1.5 * 2^52
+                    float2 o[TCW];
 #pragma unroll
                     for (int t = 0; t < TCW; ++t) {
-                        const int tg_idx = c * TCW + t;
-                        const int ch = tl.ch0 + tg_idx;
-                        if (ch < T) {
-                            long long ph = sh->ph_base[tg_idx] + (long long)row_in_tile * sh->ph_step[tg_idx];   // < 128 * rate
-                            ph -= (long long)((double)ph * inv_R) * rate;
-                            if (ph < 0) ph += rate;
-                            if (ph >= rate) ph -= rate;
-                            out[p * T + ch] = dev_cmul(make_float2(y[2 * t], y[2 * t + 1]), lo_phasor(ph, inv_R));
-                        }
+                        const double2 bs = sh->ph[c * TCW + t];
+                        const double r = fma(row_d, bs.y, bs.x);
+                        const unsigned int word = (unsigned int)__double2loint(fma(r, word_per_phase, 6755399441055744.0));
+                        float sn, cs;
+                        sincos_phase32(word, sn, cs);
+                        o[t] = dev_cmul(make_float2(y[2 * t], y[2 * t + 1]), make_float2(cs, -sn));
+                    }
+                    float2* dst = out + p * T + tl.ch0 + c * TCW;
+                    const int n_valid = T - (tl.ch0 + c * TCW);   // tones of this chunk that exist
+                    if (n_valid >= TCW && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                        for (int t = 0; t < TCW; t += 2) *reinterpret_cast<float4*>(dst + t) = make_float4(o[t].x, o[t].y, o[t + 1].x, o[t + 1].y);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < TCW; ++t)
+                            if (t < n_valid) dst[t] = o[t];
                     }
                 }
-                if (F > 1) epi_bar();   // the exchange buffer (and ph_base after the last chunk) may be rewritten
+                if (F > 1) epi_bar();   // the exchange buffer (and sh->ph after the last chunk) may be rewritten
             }
             if (F == 1) epi_bar();
-            tmem_ld_wait();
-            tc_fence_before();
-            mbar_arrive(smem_u32(&sh->tmem_empty[as]));
+        }
+        if (dbg && threadIdx.x == 0) {
+            atomicAdd((unsigned long long*)&dbg[0], (unsigned long long)w_acc0);                      // epilogue: wait for accumulators
+            atomicAdd((unsigned long long*)&dbg[1], (unsigned long long)(clock64() - t_role0));       // epilogue: role time
         }
     } else if (warp == TC_EPI_WARPS) {
         // ======================================= MMA ISSUE =======================================
         int s = 0;
         unsigned int ph = 0;
+        long long w_acc0 = 0, w_acc1 = 0;
+        const long long t_role0 = clock64();
         for (int n = 0; n < my_tiles; ++n) {
             const unsigned int as = n & 1, aph = (n >> 1) & 1;
-            mbar_wait(smem_u32(&sh->tmem_empty[as]), aph ^ 1u);
+            mbar_wait_t(smem_u32(&sh->tmem_empty[as]), aph ^ 1u, w_acc1, dbg != nullptr);
             tc_fence_after();
             const unsigned int d_main = tmem_base + as * 256u, d_corr = d_main + 128u;
             for (int kb = 0; kb < KB; ++kb) {
-                mbar_wait(smem_u32(&sh->full[s]), ph);
+                mbar_wait_t(smem_u32(&sh->full[s]), ph, w_acc0, dbg != nullptr);
                 tc_fence_after();
                 if (lane == 0) {
                     const unsigned int a0 = smem_base + (unsigned)s * TC_STAGE_BYTES;
                     const unsigned long long a_hi = tc_smem_desc(a0), a_lo = tc_smem_desc(a0 + TC_OPER_BYTES);
-                    const unsigned long long b_hi = tc_smem_desc(a0 + 2 * TC_OPER_BYTES), b_lo = tc_smem_desc(a0 + 3 * TC_OPER_BYTES);
+                    const unsigned long long b_hi = tc_smem_desc(a0 + 2 * TC_OPER_BYTES);   // B_lo follows B_hi: rows 128..255
                     const int ks_n = min(4, ksteps_total - 4 * kb);
                     for (int ks = 0; ks < ks_n; ++ks) {
                         const unsigned long long adv = (unsigned long long)(2 * ks);   // 32 bytes >> 4 per k-step
-                        const unsigned int acc = (kb | ks) ? 1u : 0u;
-                        tc_mma_tf32(d_main, a_hi + adv, b_hi + adv, TC_IDESC, acc);
-                        tc_mma_tf32(d_corr, a_lo + adv, b_hi + adv, TC_IDESC, acc);
-                        tc_mma_tf32(d_corr, a_hi + adv, b_lo + adv, TC_IDESC, 1u);
+                        // [main | corr] (+)= A_hi [B_hi | B_lo] in one N = 256 instruction (A_hi is read once), corr += A_lo B_hi
+                        tc_mma_tf32(d_main, a_hi + adv, b_hi + adv, TC_IDESC_WIDE, (kb | ks) ? 1u : 0u);
+                        tc_mma_tf32(d_corr, a_lo + adv, b_hi + adv, TC_IDESC, 1u);
                     }
                     tc_commit(smem_u32(&sh->empty[s]));
                     if (kb == KB - 1) tc_commit(smem_u32(&sh->tmem_full[as]));
@@ -363,6 +394,11 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                 __syncwarp();
                 if (++s == TC_STAGES) s = 0, ph ^= 1u;
             }
+        }
+        if (dbg && lane == 0) {
+            atomicAdd((unsigned long long*)&dbg[2], (unsigned long long)w_acc0);                      // MMA: wait for operands
+            atomicAdd((unsigned long long*)&dbg[3], (unsigned long long)w_acc1);                      // MMA: wait for a free accumulator
+            atomicAdd((unsigned long long*)&dbg[4], (unsigned long long)(clock64() - t_role0));       // MMA: role time
         }
     } else if (warp < TC_TMA_WARP) {
         // ======================================= OPERAND PRODUCERS =======================================
@@ -408,6 +444,8 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
         int n_cur = 0, kb_cur = 0, n_nxt = 0, kb_nxt = 0, s = 0;
         unsigned int ph = 0;
         TcTile t_cur = tile_of(0), t_nxt = t_cur;
+        long long w_acc0 = 0;
+        const long long t_role0 = clock64();
         bool tma_cur = use_tma && t_cur.row0 >= hist_rows, tma_nxt = tma_cur;
         if (my_tiles > 0) issue_loads(t_cur, tma_cur, 0, xa, xb);
         while (n_cur < my_tiles) {
@@ -420,7 +458,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
             }
             const bool more = n_nxt < my_tiles;
             if (more) issue_loads(t_nxt, tma_nxt, kb_nxt, na, nb);
-            mbar_wait(smem_u32(&sh->raw_full[s]), ph);
+            mbar_wait_t(smem_u32(&sh->raw_full[s]), ph, w_acc0, dbg != nullptr);
             unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
             if (tma_cur) {
                 // the raw rows are in the A_hi tile: split in place, same (swizzled) position in both tiles
@@ -471,6 +509,10 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
             n_cur = n_nxt, kb_cur = kb_nxt, t_cur = t_nxt, tma_cur = tma_nxt;
         }
         (void)kb_cur;
+        if (dbg && lt == 0) {
+            atomicAdd((unsigned long long*)&dbg[5], (unsigned long long)w_acc0);                      // producers: wait for raw rows / a free stage
+            atomicAdd((unsigned long long*)&dbg[6], (unsigned long long)(clock64() - t_role0));       // producers: role time
+        }
     } else if (warp == TC_TMA_WARP) {
         // ======================================= TMA ISSUE =======================================
         // One lane.  Besides the load of the K block into its stage, the box TC_L2_AHEAD iterations further on is
@@ -479,6 +521,8 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
             int s = 0;
             unsigned int ph = 0;
             int n_pf = 0, kb_pf = 0;   // (tile, K block) of the next L2 prefetch
+            long long w_acc0 = 0;
+            const long long t_role0 = clock64();
             TcTile t_pf = tile_of(0);
             auto prefetch_next = [&]() {
                 if (n_pf >= my_tiles) return;
@@ -495,7 +539,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                 const bool tma = use_tma && tl.row0 >= hist_rows;
                 for (int kb = 0; kb < KB; ++kb) {
                     prefetch_next();
-                    mbar_wait(smem_u32(&sh->empty[s]), ph ^ 1u);
+                    mbar_wait_t(smem_u32(&sh->empty[s]), ph ^ 1u, w_acc0, dbg != nullptr);
                     const unsigned int bar = smem_u32(&sh->raw_full[s]);
                     if (tma) {
                         mbar_arrive_expect_tx(bar, TC_OPER_BYTES);
@@ -505,6 +549,11 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                     }
                     if (++s == TC_STAGES) s = 0, ph ^= 1u;
                 }
+            }
+            if (dbg) {
+                atomicAdd((unsigned long long*)&dbg[7], (unsigned long long)w_acc0);                  // TMA: wait for a free stage
+                atomicAdd((unsigned long long*)&dbg[8], (unsigned long long)(clock64() - t_role0));   // TMA: role time
+                atomicAdd((unsigned long long*)&dbg[9], (unsigned long long)(my_tiles * KB));         // stage iterations
             }
         }
     }
@@ -571,9 +620,27 @@ int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int 
     const int use_tma = tc_make_tensor_map(w, M, &map) ? 1 : 0;
     const long long tiles = (long long)row_tiles * tone_groups;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+    // GSDR_DIRECT_TC_DEBUG=1: per-role wait / run cycles of this launch on stderr (synchronises; schedule tuning only)
+    const char* de = getenv("GSDR_DIRECT_TC_DEBUG");
+    long long* dbg = nullptr;
+    if (de && de[0] == '1') {
+        GSDR_CUDA_OK(cudaMalloc(&dbg, 16 * sizeof(long long)));
+        GSDR_CUDA_OK(cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), stream));
+    }
     direct_fir_tc_kernel<F><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, use_tma, w, g, freq_dev, T, M, rate, pos0, n_out,
-                                                                         row_tiles, tone_groups, out);
+                                                                         row_tiles, tone_groups, out, dbg);
     GSDR_CUDA_OK(cudaGetLastError());
+    if (dbg) {
+        long long h[16];
+        GSDR_CUDA_OK(cudaStreamSynchronize(stream));
+        GSDR_CUDA_OK(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(dbg);
+        const double it = h[9] > 0 ? (double)h[9] : 1.0;
+        fprintf(stderr,
+                "[direct_tc] grid %d tiles %lld use_tma %d | per stage iteration (cycles): epi wait %.0f of %.0f | mma wait-operands %.0f "
+                "wait-acc %.0f of %.0f | producers wait %.0f of %.0f | tma wait %.0f of %.0f\n",
+                grid, tiles, use_tma, h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[4] / it, h[5] / it, h[6] / it, h[7] / it, h[8] / it);
+    }
     return 1;
 }
 
