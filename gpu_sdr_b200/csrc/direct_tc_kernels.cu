@@ -51,8 +51,12 @@ constexpr int TC_STAGE_BYTES = 4 * TC_OPER_BYTES;  // A_hi, A_lo, B_hi, B_lo
 constexpr int TC_XCH_FLOATS = 7 * 7 * 16;          // per epilogue warp: (F-1) lanes x (F-1) blocks x chunk, F <= 8
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_L2_AHEAD = 8;                     // K blocks between the L2 prefetch of a box and its TMA load
-constexpr int TC_A_PER_THREAD = TC_ROWS * TC_KC / TC_LOAD_THREADS;        // 8
-constexpr int TC_B_PER_THREAD = (TC_N / 2) * TC_KC / TC_LOAD_THREADS;     // 4
+constexpr int TC_GROUPS = 2;                       // producer groups, alternate K blocks
+constexpr int TC_GROUP_WARPS = TC_LOAD_WARPS / TC_GROUPS;
+constexpr int TC_GROUP_THREADS = 32 * TC_GROUP_WARPS;
+constexpr int TC_A_PER_THREAD = TC_OPER_BYTES / 16 / TC_GROUP_THREADS;    // 8 chunks of 16 bytes (two complex taps)
+constexpr int TC_B_PER_THREAD = (TC_N / 2) * TC_KC / TC_GROUP_THREADS;    // 8 filter taps
+static_assert(TC_STAGES == 3 && TC_GROUPS == 2, "the producers' stage / parity walk assumes 3 stages and 2 groups");
 
 struct TcShared {
     unsigned long long full[TC_STAGES];
@@ -220,7 +224,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(smem_u32(&sh->full[s]), TC_LOAD_THREADS);
+            mbar_init(smem_u32(&sh->full[s]), TC_GROUP_THREADS);
             mbar_init(smem_u32(&sh->raw_full[s]), 1);
             mbar_init(smem_u32(&sh->empty[s]), 1);
         }
@@ -402,87 +406,93 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
         }
     } else if (warp < TC_TMA_WARP) {
         // ======================================= OPERAND PRODUCERS =======================================
-        const int lt = threadIdx.x - 32 * (TC_EPI_WARPS + 1);   // 0..255
-        const unsigned int kc = (unsigned)lt & 15u, sub = (unsigned)lt >> 4;   // tap inside the K block, row / (block,tone) slot
-        const unsigned int a_off = tc_swz(sub, kc);                 // + u * 2048   (row = u*16 + sub)
-        const unsigned int b_off_re = tc_swz(2u * sub, kc);         // + u * 4096   (row n = 2*(u*16 + sub) + {0,1})
+        // Two groups of four warps take alternate K blocks, so that the fence / arrive / wait latency of one group
+        // overlaps the shared-memory traffic of the other.
+        const int grp = (warp - (TC_EPI_WARPS + 1)) / TC_GROUP_WARPS;
+        const int lt = (int)threadIdx.x - 32 * (TC_EPI_WARPS + 1) - grp * TC_GROUP_THREADS;   // 0..127 inside the group
+        const unsigned int kc = (unsigned)lt & 15u, sub = (unsigned)lt >> 4;   // tap inside the K block, (block,tone) slot
+        const unsigned int b_off_re = tc_swz(2u * sub, kc);         // + u * 2048   (row n = 2*(u*8 + sub) + {0,1})
         const unsigned int b_off_im = tc_swz(2u * sub + 1u, kc);
-        float2 xa[TC_A_PER_THREAD], xb[TC_B_PER_THREAD];
-        // (block i, tone t) of this thread's four filter taps: slot = u * 16 + sub, i = slot / TG, t = slot % TG
+        // (block i, tone t) of this thread's eight filter taps: slot = u * 8 + sub, i = slot / TG, t = slot % TG
         int g_off[TC_B_PER_THREAD], g_t[TC_B_PER_THREAD];
 #pragma unroll
         for (int u = 0; u < TC_B_PER_THREAD; ++u) {
-            const int slot = u * 16 + (int)sub;
+            const int slot = u * 8 + (int)sub;
             g_t[u] = slot % TG;
             g_off[u] = (slot / TG) * M + g_t[u] * ntaps;
         }
+        // A: this thread owns the 16-byte chunks e = u * 128 + lt of the stage's A tiles.  Chunk e is two complex taps
+        // of window row a_row(u) = u * 16 + (lt >> 3) at logical chunk (lt ^ (lt >> 3)) & 7 of the K block.
+        const int a_row0 = lt >> 3;
+        const int a_k = 2 * ((lt ^ (lt >> 3)) & 7);
 
-        auto issue_loads = [&](const TcTile& tl, bool tma, int kb, float2* va, float2* vb) {
-            const int k = kb * TC_KC + (int)kc;
-            const bool kvalid = k < M;
-            if (!tma) {
-                const long long s0 = (tl.row0 + sub) * (long long)M + k;
-#pragma unroll
-                for (int u = 0; u < TC_A_PER_THREAD; ++u) {
-                    va[u] = make_float2(0.f, 0.f);
-                    if (kvalid) {
-                        long long s = s0 + (long long)(u * 16) * M;
-                        if (s < w.n_hist) va[u] = __ldg(w.hist + s);
-                        else if (s - w.n_hist < w.n_in) va[u] = __ldg(w.in + (s - w.n_hist));
-                    }
-                }
+        float2 xb[TC_B_PER_THREAD];
+        float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);   // history patch (TMA mode): chunk u = 0 of a tile that starts inside the history
+
+        auto load_pair = [&](long long sidx, int k) {   // two consecutive window samples, zero beyond the taps / the window
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < M) {
+                const float2 a = dev_win_at(w, sidx);
+                v.x = a.x, v.y = a.y;
             }
+            if (k + 1 < M) {
+                const float2 a = dev_win_at(w, sidx + 1);
+                v.z = a.x, v.w = a.y;
+            }
+            return v;
+        };
+        auto issue_loads = [&](const TcTile& tl, int kb, float2* vb, float4& h) {
+            const int k = kb * TC_KC + (int)kc;
             const float2* gk = g + (long long)tl.ch0 * ntaps + k;
 #pragma unroll
             for (int u = 0; u < TC_B_PER_THREAD; ++u) {
                 vb[u] = make_float2(0.f, 0.f);
-                if (kvalid && tl.ch0 + g_t[u] < T) vb[u] = __ldg(gk + g_off[u]);
+                if (k < M && tl.ch0 + g_t[u] < T) vb[u] = __ldg(gk + g_off[u]);
             }
+            // rows of the tile that lie in the carried-over history are not in the TMA tensor (it zero-fills them)
+            if (use_tma && tl.row0 + a_row0 < hist_rows) h = load_pair((tl.row0 + a_row0) * (long long)M + kb * TC_KC + a_k, kb * TC_KC + a_k);
         };
 
-        // (tile, K block) of the iteration being stored and of the one being loaded, advanced without divisions
-        int n_cur = 0, kb_cur = 0, n_nxt = 0, kb_nxt = 0, s = 0;
+        // this group's iterations: it = grp, grp + 2, ...; (tile, K block) advanced without divisions
+        int n_cur = 0, kb_cur = grp, s = grp;
         unsigned int ph = 0;
-        TcTile t_cur = tile_of(0), t_nxt = t_cur;
+        while (kb_cur >= KB) kb_cur -= KB, ++n_cur;
+        TcTile t_cur = tile_of(n_cur);
         long long w_acc0 = 0;
         const long long t_role0 = clock64();
-        bool tma_cur = use_tma && t_cur.row0 >= hist_rows, tma_nxt = tma_cur;
-        if (my_tiles > 0) issue_loads(t_cur, tma_cur, 0, xa, xb);
+        if (n_cur < my_tiles) issue_loads(t_cur, kb_cur, xb, hv);
         while (n_cur < my_tiles) {
-            float2 na[TC_A_PER_THREAD], nb[TC_B_PER_THREAD];
-            if (++kb_nxt == KB) {
-                kb_nxt = 0;
-                ++n_nxt;
-                t_nxt = tile_of(n_nxt);
-                tma_nxt = use_tma && t_nxt.row0 >= hist_rows;
-            }
+            int n_nxt = n_cur, kb_nxt = kb_cur + TC_GROUPS;
+            while (kb_nxt >= KB) kb_nxt -= KB, ++n_nxt;
+            const TcTile t_nxt = (n_nxt == n_cur) ? t_cur : tile_of(n_nxt);
+            float2 nb[TC_B_PER_THREAD];
+            float4 nh = make_float4(0.f, 0.f, 0.f, 0.f);
             const bool more = n_nxt < my_tiles;
-            if (more) issue_loads(t_nxt, tma_nxt, kb_nxt, na, nb);
+            if (more) issue_loads(t_nxt, kb_nxt, nb, nh);
             mbar_wait_t(smem_u32(&sh->raw_full[s]), ph, w_acc0, dbg != nullptr);
             unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
-            if (tma_cur) {
-                // the raw rows are in the A_hi tile: split in place, same (swizzled) position in both tiles
-                float4 v[TC_OPER_BYTES / 16 / TC_LOAD_THREADS];
+            {
+                float4 v[TC_A_PER_THREAD];
+                if (use_tma) {
+                    // the raw rows are in the A_hi tile (TMA): split in place, same swizzled position in both tiles
 #pragma unroll
-                for (int u = 0; u < TC_OPER_BYTES / 16 / TC_LOAD_THREADS; ++u) v[u] = *(reinterpret_cast<const float4*>(st) + u * TC_LOAD_THREADS + lt);
+                    for (int u = 0; u < TC_A_PER_THREAD; ++u) v[u] = *(reinterpret_cast<const float4*>(st) + u * TC_GROUP_THREADS + lt);
+                    if (t_cur.row0 + a_row0 < hist_rows) v[0] = hv;
+                } else {
+                    // mis-aligned stream or odd decimation: the same chunks straight from global memory
 #pragma unroll
-                for (int u = 0; u < TC_OPER_BYTES / 16 / TC_LOAD_THREADS; ++u) {
+                    for (int u = 0; u < TC_A_PER_THREAD; ++u)
+                        v[u] = load_pair((t_cur.row0 + u * 16 + a_row0) * (long long)M + kb_cur * TC_KC + a_k, kb_cur * TC_KC + a_k);
+                }
+#pragma unroll
+                for (int u = 0; u < TC_A_PER_THREAD; ++u) {
                     float4 hi, lo;
                     tf32_split(v[u].x, hi.x, lo.x);
                     tf32_split(v[u].y, hi.y, lo.y);
                     tf32_split(v[u].z, hi.z, lo.z);
                     tf32_split(v[u].w, hi.w, lo.w);
-                    *(reinterpret_cast<float4*>(st) + u * TC_LOAD_THREADS + lt) = hi;
-                    *(reinterpret_cast<float4*>(st + TC_OPER_BYTES) + u * TC_LOAD_THREADS + lt) = lo;
-                }
-            } else {
-#pragma unroll
-                for (int u = 0; u < TC_A_PER_THREAD; ++u) {
-                    float2 hi, lo;
-                    tf32_split(xa[u].x, hi.x, lo.x);
-                    tf32_split(xa[u].y, hi.y, lo.y);
-                    *reinterpret_cast<float2*>(st + a_off + u * 2048) = hi;
-                    *reinterpret_cast<float2*>(st + TC_OPER_BYTES + a_off + u * 2048) = lo;
+                    *(reinterpret_cast<float4*>(st) + u * TC_GROUP_THREADS + lt) = hi;
+                    *(reinterpret_cast<float4*>(st + TC_OPER_BYTES) + u * TC_GROUP_THREADS + lt) = lo;
                 }
             }
 #pragma unroll
@@ -490,8 +500,8 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                 float2 hi, lo;
                 tf32_split(xb[u].x, hi.x, lo.x);
                 tf32_split(xb[u].y, hi.y, lo.y);
-                unsigned char* bh = st + 2 * TC_OPER_BYTES + u * 4096;
-                unsigned char* bl = st + 3 * TC_OPER_BYTES + u * 4096;
+                unsigned char* bh = st + 2 * TC_OPER_BYTES + u * 2048;
+                unsigned char* bl = st + 3 * TC_OPER_BYTES + u * 2048;
                 *reinterpret_cast<float2*>(bh + b_off_re) = make_float2(hi.x, -hi.y);   // Re(x g): x_r g_r - x_i g_i
                 *reinterpret_cast<float2*>(bh + b_off_im) = make_float2(hi.y, hi.x);    // Im(x g): x_r g_i + x_i g_r
                 *reinterpret_cast<float2*>(bl + b_off_re) = make_float2(lo.x, -lo.y);
@@ -501,15 +511,15 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
             mbar_arrive(smem_u32(&sh->full[s]));
             if (more) {
 #pragma unroll
-                for (int u = 0; u < TC_A_PER_THREAD; ++u) xa[u] = na[u];
-#pragma unroll
                 for (int u = 0; u < TC_B_PER_THREAD; ++u) xb[u] = nb[u];
+                hv = nh;
             }
-            if (++s == TC_STAGES) s = 0, ph ^= 1u;
-            n_cur = n_nxt, kb_cur = kb_nxt, t_cur = t_nxt, tma_cur = tma_nxt;
+            // two iterations on: stage (s + 2) mod 3, parity flips when the stage index wraps
+            s += TC_GROUPS;
+            if (s >= TC_STAGES) s -= TC_STAGES, ph ^= 1u;
+            n_cur = n_nxt, kb_cur = kb_nxt, t_cur = t_nxt;
         }
-        (void)kb_cur;
-        if (dbg && lt == 0) {
+        if (dbg && lt == 0 && grp == 0) {
             atomicAdd((unsigned long long*)&dbg[5], (unsigned long long)w_acc0);                      // producers: wait for raw rows / a free stage
             atomicAdd((unsigned long long*)&dbg[6], (unsigned long long)(clock64() - t_role0));       // producers: role time
         }
@@ -526,7 +536,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
             TcTile t_pf = tile_of(0);
             auto prefetch_next = [&]() {
                 if (n_pf >= my_tiles) return;
-                if (use_tma && t_pf.row0 >= hist_rows) tma_prefetch_2d(&tmap, kb_pf * 2 * TC_KC, (int)(t_pf.row0 - hist_rows));
+                if (use_tma) tma_prefetch_2d(&tmap, kb_pf * 2 * TC_KC, (int)(t_pf.row0 - hist_rows));
                 if (++kb_pf == KB) {
                     kb_pf = 0;
                     ++n_pf;
@@ -536,7 +546,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
             for (int j = 0; j < TC_L2_AHEAD; ++j) prefetch_next();
             for (int n = 0; n < my_tiles; ++n) {
                 const TcTile tl = tile_of(n);
-                const bool tma = use_tma && tl.row0 >= hist_rows;
+                const bool tma = use_tma != 0;   // history rows have negative tensor coordinates: zero-filled, patched by the producers
                 for (int kb = 0; kb < KB; ++kb) {
                     prefetch_next();
                     mbar_wait_t(smem_u32(&sh->empty[s]), ph ^ 1u, w_acc0, dbg != nullptr);
