@@ -13,20 +13,29 @@
 //
 // Precision: the tolerance is 1e-5 relative L2 against fp64 and one TF32 product has a 2^-11 relative error, so both
 // operands are split x = hi + lo (hi = x rounded to TF32, lo = x - hi, exact) and three MMAs are issued per k-step:
-// hi*hi into one TMEM accumulator, lo*hi + hi*lo into a second one (kept apart so that the small terms are not
-// absorbed by the truncating tensor-core accumulation); the dropped lo*lo term is 2^-22 relative.
+// hi*hi into the `main` TMEM accumulator, lo*hi + hi*lo into a second one (`corr`: kept apart so that the small
+// terms do not add truncating accumulation steps to the long chain); the dropped lo*lo term is 2^-22 relative.
+//
+// What bounds the kernel is shared-memory bandwidth (128 B/clk/SM), which the operand fetch of tcgen05.mma shares
+// with TMA writes and LDS/STS.  So the A operand (the samples) is fed from TENSOR MEMORY, written there by the
+// producers with tcgen05.st straight from registers: it never exists in shared memory in operand form, and per
+// 16-tap K block shared memory carries 16 KB (TMA landing) + 16 KB (one read of it) + 32 KB (B tiles written) +
+// 48 KB (B read by the MMAs) instead of 176 KB.
 //
 // Warp roles (one persistent CTA per SM, static tile scheduler over (row tile, tone group)):
-//   warps 0-3   epilogue: tcgen05.ld of the two accumulators, row shift-and-add, LO rotation, sample-major store
-//   warp  4     TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, M=128, N=128, K=8)
-//   warps 5-12  operand producers: hi/lo split of the window rows and of the tone filters into the 128-byte-swizzled
-//               K-major operand tiles, fence.proxy.async, mbarrier arrive.  The filters come through registers (L2
-//               hits); the window rows are put into the A_hi tile by TMA and split in place (shared -> shared), or,
-//               for rows that touch the carried-over history or a mis-aligned stream, loaded through registers
-//   warp  13    TMA issue: one cp.async.bulk.tensor (128 rows x 32 floats, SWIZZLE_128B) per K block, as far ahead
-//               as there are free stages
-// Three operand stages (64 KB each: A_hi, A_lo, B_hi, B_lo for 16 complex taps), two accumulator stages (512 TMEM
-// columns), so the epilogue of tile n overlaps the MMAs of tile n+1.
+//   warps 0-3   epilogue: fold corr into main in TMEM (frees corr for the next tile), tcgen05.ld, row shift-and-add,
+//               LO rotation, sample-major store
+//   warp  4     TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, M=128, N=128, K=8, A from TMEM)
+//   warps 5-12  operand producers, two groups of four warps on alternate K blocks, each group owning one operand
+//               stage: thread = one window row (TMEM lane); 8 x LDS.128 of the row from the TMA landing slot,
+//               hi/lo split, tcgen05.st; the tone filters come through registers (L2 hits) and are split into the
+//               128-byte-swizzled K-major B tiles
+//   warp  13    TMA issue: one cp.async.bulk.tensor (128 rows x 32 floats, SWIZZLE_128B) per K block into a ring of
+//               four landing slots, each box prefetched into L2 eight K blocks earlier
+// TMEM columns: main x 2 (the epilogue of tile n overlaps the MMAs of tile n+1), corr x 1, A (hi, lo) x 2 stages.
+// From the second K block of a tile on, A_hi [B_hi | B_lo] is ONE N = 256 instruction into [main | corr] (the B tiles
+// are laid out in the order of the accumulators), so a K block is 8 MMAs, not 12: the issuing thread spends ~60 cycles
+// per instruction, about what a 128 x 128 x 8 MMA takes to execute.
 #include <cuda.h>
 
 #include <cstdlib>
@@ -40,36 +49,42 @@ namespace {
 constexpr int TC_ROWS = 128;                       // window rows per tile = UMMA M
 constexpr int TC_N = 128;                          // accumulator columns = F * TG * 2
 constexpr int TC_KC = 16;                          // complex taps per K block: 32 floats = one 128-byte swizzle row
-constexpr int TC_STAGES = 3;
+constexpr int TC_RAW = 4;                          // TMA landing slots
+constexpr int TC_GROUPS = 2;                       // producer groups == operand stages, alternate K blocks
 constexpr int TC_EPI_WARPS = 4;
-constexpr int TC_LOAD_WARPS = 8;
-constexpr int TC_LOAD_THREADS = 32 * TC_LOAD_WARPS;
+constexpr int TC_GROUP_WARPS = 4;                  // one warp per TMEM lane quarter
+constexpr int TC_GROUP_THREADS = 32 * TC_GROUP_WARPS;
+constexpr int TC_LOAD_WARPS = TC_GROUPS * TC_GROUP_WARPS;
 constexpr int TC_THREADS = 32 * (TC_EPI_WARPS + 1 + TC_LOAD_WARPS + 1);
 constexpr int TC_TMA_WARP = TC_EPI_WARPS + 1 + TC_LOAD_WARPS;
-constexpr int TC_OPER_BYTES = TC_ROWS * 128;       // one operand part of one stage (128 rows x 128 bytes)
-constexpr int TC_STAGE_BYTES = 4 * TC_OPER_BYTES;  // A_hi, A_lo, B_hi, B_lo
+constexpr int TC_RAW_BYTES = TC_ROWS * 128;        // one landing slot: 128 rows x 128 bytes
+constexpr int TC_B_BYTES = 2 * TC_N * 128;         // B_hi and B_lo tiles of one stage (128 rows x 128 bytes each)
 constexpr int TC_XCH_FLOATS = 7 * 7 * 16;          // per epilogue warp: (F-1) lanes x (F-1) blocks x chunk, F <= 8
 constexpr int TC_TMEM_COLS = 512;
+constexpr unsigned int TC_COL_CORR = 128;          // main(0) at 0, corr at 128, main(1) at 256: [main(0) | corr] and [corr | main(1)] are
+                                                   // both 256 contiguous columns, the D operand of one N = 256 MMA
+constexpr unsigned int TC_COL_A = 384;             // A stage g: hi at +64 g, lo at +64 g + 32
 constexpr int TC_L2_AHEAD = 8;                     // K blocks between the L2 prefetch of a box and its TMA load
-constexpr int TC_GROUPS = 2;                       // producer groups, alternate K blocks
-constexpr int TC_GROUP_WARPS = TC_LOAD_WARPS / TC_GROUPS;
-constexpr int TC_GROUP_THREADS = 32 * TC_GROUP_WARPS;
-constexpr int TC_A_PER_THREAD = TC_OPER_BYTES / 16 / TC_GROUP_THREADS;    // 8 chunks of 16 bytes (two complex taps)
 constexpr int TC_B_PER_THREAD = (TC_N / 2) * TC_KC / TC_GROUP_THREADS;    // 8 filter taps
-static_assert(TC_STAGES == 3 && TC_GROUPS == 2, "the producers' stage / parity walk assumes 3 stages and 2 groups");
+constexpr int TC_MAX_M = 128;                      // longest accumulation chain accepted (see direct_fir_tc_supported)
+constexpr int TC_HIST_MAX = 7 * TC_MAX_M;          // carried-over samples: (F - 1) * M
+static_assert((TC_EPI_WARPS + 1) % 4 == 1 && TC_GROUP_WARPS == 4, "producer warp w owns TMEM lane quarter w % 4");
 
 struct TcShared {
-    unsigned long long full[TC_STAGES];
-    unsigned long long raw_full[TC_STAGES];   // the stage is free and (TMA tiles) the raw window rows have landed
-    unsigned long long empty[TC_STAGES];
-    unsigned long long tmem_full[2];
-    unsigned long long tmem_empty[2];
+    unsigned long long raw_full[TC_RAW];     // TMA -> producers: the window rows of a K block have landed
+    unsigned long long raw_empty[TC_RAW];    // producers -> TMA
+    unsigned long long full[TC_GROUPS];      // producers -> MMA: A in TMEM and B in shared memory are ready
+    unsigned long long empty[TC_GROUPS];     // MMA (tcgen05.commit) -> producers
+    unsigned long long tmem_full[2];         // MMA -> epilogue: main(as) and corr hold the tile
+    unsigned long long tmem_empty[2];        // epilogue -> MMA: main(as) has been read
+    unsigned long long corr_empty;           // epilogue -> MMA: corr has been folded into main
     unsigned int tmem_base;
     unsigned int pad;
     double2 ph[64];          // per tone of the group: (LO phase of the tile's first row, phase step per row), integers < rate
     alignas(16) float xch[TC_EPI_WARPS][TC_XCH_FLOATS];
+    alignas(16) float2 hist[TC_HIST_MAX];    // copy of the carried-over samples (rows the TMA tensor does not hold)
 };
-constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + sizeof(TcShared);
+constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)TC_RAW * TC_RAW_BYTES + (size_t)TC_GROUPS * TC_B_BYTES + sizeof(TcShared);
 
 // ---- PTX wrappers ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
@@ -126,14 +141,36 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(unsigned int mbar_addr) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_addr) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], kind::tf32, issued by one thread
-__device__ __forceinline__ void tc_mma_tf32(unsigned int d_tmem, unsigned long long a_desc, unsigned long long b_desc,
-                                            unsigned int idesc, unsigned int accumulate) {
+// cute::UMMA::InstrDescriptor: D = f32 (1 @4), A = B = tf32 (2 @7, 2 @10), K-major both, N>>3 @17, M>>4 @24
+constexpr unsigned int tc_idesc(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(TC_ROWS >> 4) << 24); }
+constexpr unsigned int TC_IDESC = tc_idesc(TC_N);
+constexpr unsigned int TC_IDESC_WIDE = tc_idesc(2 * TC_N);
+
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 8 columns of tf32.  The accumulate flag is a compile-time constant
+// (the predicate folds away): the single issuing thread is the kernel's critical path, ~10 instructions per MMA count.
+template <bool kAccumulate>
+__device__ __forceinline__ void tc_mma_tf32_ts(unsigned int d_tmem, unsigned int a_tmem, unsigned long long b_desc, unsigned int idesc) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "n"(kAccumulate ? 1 : 0)
         : "memory");
+}
+// one k-step, wide form: [main | corr] += A_hi [B_hi | B_lo] (d_wide / b_wide in the accumulators' order); corr += A_lo B_hi
+__device__ __forceinline__ void tc_kstep_wide(unsigned int d_wide, unsigned int d_corr, unsigned int a_hi, unsigned long long b_wide,
+                                              unsigned long long b_hi, int ks) {
+    const unsigned long long adv = (unsigned long long)(2 * ks);
+    tc_mma_tf32_ts<true>(d_wide, a_hi + 8u * ks, b_wide + adv, TC_IDESC_WIDE);
+    tc_mma_tf32_ts<true>(d_corr, a_hi + 32u + 8u * ks, b_hi + adv, TC_IDESC);
+}
+// one k-step: main (+)= A_hi B_hi; small (+)= A_lo B_hi; small += A_hi B_lo
+template <bool kAccMain, bool kAccSmall>
+__device__ __forceinline__ void tc_kstep(unsigned int d_main, unsigned int d_small, unsigned int a_hi, unsigned long long b_hi,
+                                         unsigned long long b_lo, int ks) {
+    const unsigned long long adv = (unsigned long long)(2 * ks);   // 32 bytes >> 4 per k-step
+    tc_mma_tf32_ts<kAccMain>(d_main, a_hi + 8u * ks, b_hi + adv, TC_IDESC);
+    tc_mma_tf32_ts<kAccSmall>(d_small, a_hi + 32u + 8u * ks, b_hi + adv, TC_IDESC);
+    tc_mma_tf32_ts<true>(d_small, a_hi + 8u * ks, b_lo + adv, TC_IDESC);
 }
 // K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
 // (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30) = 1, SBO>>4 [32,46) = 64, version [46,48) = 1,
@@ -143,11 +180,6 @@ __device__ __forceinline__ unsigned long long tc_smem_desc(unsigned int saddr) {
     const unsigned int hi = 64u | (1u << 14) | (2u << 29);
     return ((unsigned long long)hi << 32) | lo;
 }
-// cute::UMMA::InstrDescriptor: D = f32 (1 @4), A = B = tf32 (2 @7, 2 @10), K-major both, N>>3 @17, M>>4 @24
-constexpr unsigned int tc_idesc(int n) { return (1u << 4) | (2u << 7) | (2u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(TC_ROWS >> 4) << 24); }
-constexpr unsigned int TC_IDESC = tc_idesc(TC_N);
-constexpr unsigned int TC_IDESC_WIDE = tc_idesc(2 * TC_N);   // B = [B_hi ; B_lo] (256 rows, contiguous tiles): main and corr side by side
-
 template <int CW>
 __device__ __forceinline__ void tmem_ld(unsigned int taddr, float* v);
 template <>
@@ -175,6 +207,20 @@ __device__ __forceinline__ void tmem_ld<16>(unsigned int taddr, float* v) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_st16(unsigned int taddr, const float* v) {
+    const unsigned int* r = reinterpret_cast<const unsigned int*>(v);
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(unsigned int taddr, const float* v) {
+    tmem_st16(taddr, v);
+    tmem_st16(taddr + 16u, v + 16);
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * TC_EPI_WARPS) : "memory"); }
@@ -212,7 +258,8 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
     extern __shared__ unsigned char tc_smem_raw[];
     // 1024-byte alignment by pointer arithmetic on the __shared__ array (keeps the address space: LDS/STS, not generic)
     unsigned char* smem = tc_smem_raw + ((1024u - (smem_u32(tc_smem_raw) & 1023u)) & 1023u);
-    TcShared* sh = reinterpret_cast<TcShared*>(smem + (size_t)TC_STAGES * TC_STAGE_BYTES);
+    unsigned char* smem_b = smem + (size_t)TC_RAW * TC_RAW_BYTES;
+    TcShared* sh = reinterpret_cast<TcShared*>(smem_b + (size_t)TC_GROUPS * TC_B_BYTES);
     const unsigned int smem_base = smem_u32(smem);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -221,17 +268,20 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
     const int ksteps_total = (M + 3) / 4;             // MMA k-steps (4 complex taps = 8 tf32) per tile
     const int n_tiles = n_row_tiles * n_tone_groups;
     const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const bool timed = dbg != nullptr;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
-            mbar_init(smem_u32(&sh->full[s]), TC_GROUP_THREADS);
+        for (int s = 0; s < TC_RAW; ++s) {
             mbar_init(smem_u32(&sh->raw_full[s]), 1);
-            mbar_init(smem_u32(&sh->empty[s]), 1);
+            mbar_init(smem_u32(&sh->raw_empty[s]), TC_GROUP_THREADS);
         }
         for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&sh->full[a]), TC_GROUP_THREADS);
+            mbar_init(smem_u32(&sh->empty[a]), 1);
             mbar_init(smem_u32(&sh->tmem_full[a]), 1);
             mbar_init(smem_u32(&sh->tmem_empty[a]), 32 * TC_EPI_WARPS);
         }
+        mbar_init(smem_u32(&sh->corr_empty), 32 * TC_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == TC_EPI_WARPS) {
@@ -240,13 +290,25 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // the carried-over samples: the first window rows of the stream, which the TMA tensor (the `in` segment) lacks
+    const long long hist_rows = w.n_hist / M;
+
+    for (int i = threadIdx.x; i < TC_HIST_MAX && i < w.n_hist; i += TC_THREADS) sh->hist[i] = w.hist[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const unsigned int tmem_base = sh->tmem_base;
+    if (warp < TC_EPI_WARPS) {   // corr starts at zero: tiles only ever accumulate into it
+        float z[32];
+#pragma unroll
+        for (int e = 0; e < 32; ++e) z[e] = 0.f;
+        for (int j = 0; j < TC_N / 32; ++j) tmem_st32(tmem_base + ((unsigned int)(warp * 32) << 16) + TC_COL_CORR + 32u * j, z);
+        tmem_st_wait();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
 
-    // TMA tiles: every window row of the tile lies in the `in` segment (tensor row = window row - hist_rows)
-    const long long hist_rows = w.n_hist / M;
     auto tile_of = [&](int n) {
         const int id = (int)blockIdx.x + n * (int)gridDim.x;
         TcTile t;
@@ -262,7 +324,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
         const double word_per_phase = 4294967296.0 / (double)rate;
         float* xw = sh->xch[warp];
         const float* xn = sh->xch[(warp + 1) & 3];
-        long long w_acc0 = 0;
+        long long w_acc0 = 0, e_fold = 0, e_gather = 0, e_rot = 0;
         const long long t_role0 = clock64();
         for (int n = 0; n < my_tiles; ++n) {
             const TcTile tl = tile_of(n);
@@ -283,27 +345,42 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                 }
                 sh->ph[threadIdx.x] = make_double2(base, step);
             }
-            mbar_wait_t(smem_u32(&sh->tmem_full[as]), aph, w_acc0, dbg != nullptr);
+            mbar_wait_t(smem_u32(&sh->tmem_full[as]), aph, w_acc0, timed);
             tc_fence_after();
             const unsigned int t_main = tmem_base + ((unsigned int)(warp * 32) << 16) + as * 256u;
-            const unsigned int t_corr = t_main + 128u;
+            const long long te0 = timed ? clock64() : 0;
+            if (KB > 1) {
+                // main += corr, in place, and corr = 0: corr is free for the next tile long before this one has been written out
+                const unsigned int t_corr = tmem_base + ((unsigned int)(warp * 32) << 16) + TC_COL_CORR;
+#pragma unroll 1
+                for (int j = 0; j < TC_N / 32; ++j) {
+                    float a[32], b[32];
+                    tmem_ld<32>(t_main + 32u * j, a);
+                    tmem_ld<32>(t_corr + 32u * j, b);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e) a[e] += b[e], b[e] = 0.f;
+                    tmem_st32(t_main + 32u * j, a);
+                    tmem_st32(t_corr + 32u * j, b);   // the next tile accumulates into corr from its second K block on
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(smem_u32(&sh->corr_empty));
+            }
             const long long p = tl.row0 + row_in_tile;
+            const long long te1 = timed ? clock64() : 0;
+            e_fold += te1 - te0;
 #pragma unroll 1
             for (int c = 0; c < NCHUNK; ++c) {
-                float y[CW], za[CW], zb[CW];
+                const long long tc0 = timed ? clock64() : 0;
+                float y[CW], za[CW];
                 tmem_ld<CW>(t_main + (unsigned)(c * CW), y);
-                tmem_ld<CW>(t_corr + (unsigned)(c * CW), zb);
                 tmem_ld_wait();
-#pragma unroll
-                for (int j = 0; j < CW; ++j) y[j] += zb[j];
 #pragma unroll
                 for (int i = 1; i < F; ++i) {
                     const unsigned int col = (unsigned)((i * TG + c * TCW) * 2);
                     tmem_ld<CW>(t_main + col, za);
-                    tmem_ld<CW>(t_corr + col, zb);
                     tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < CW; ++j) za[j] += zb[j];
                     if (lane < F - 1) {
                         float4* dst = reinterpret_cast<float4*>(xw + (lane * (F - 1) + (i - 1)) * CW);
 #pragma unroll
@@ -314,6 +391,11 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                         const float v = __shfl_down_sync(0xffffffffu, za[j], i);
                         if (lane + i < 32) y[j] += v;
                     }
+                }
+                // every accumulator column of the tile is in registers: the MMA warp may start tile n + 2 in this stage
+                if (c == NCHUNK - 1) {
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&sh->tmem_empty[as]));
                 }
                 if (F > 1) {
                     epi_bar();
@@ -331,11 +413,8 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                 } else if (c == 0) {
                     epi_bar();   // publishes sh->ph
                 }
-                // every accumulator column of the tile is in registers: the MMA warp may start tile n + 2 in this stage
-                if (c == NCHUNK - 1) {
-                    tc_fence_before();
-                    mbar_arrive(smem_u32(&sh->tmem_empty[as]));
-                }
+                const long long tc1 = timed ? clock64() : 0;
+                e_gather += tc1 - tc0;
                 if (row_in_tile < RB && p < n_out) {
                     // phase word = round(phase * 2^32 / rate) mod 2^32: the low mantissa bits of phase * c + 1.5 * 2^52
                     float2 o[TCW];
@@ -359,6 +438,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                             if (t < n_valid) dst[t] = o[t];
                     }
                 }
+                if (timed) e_rot += clock64() - tc1;
                 if (F > 1) epi_bar();   // the exchange buffer (and sh->ph after the last chunk) may be rewritten
             }
             if (F == 1) epi_bar();
@@ -366,53 +446,71 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
         if (dbg && threadIdx.x == 0) {
             atomicAdd((unsigned long long*)&dbg[0], (unsigned long long)w_acc0);                      // epilogue: wait for accumulators
             atomicAdd((unsigned long long*)&dbg[1], (unsigned long long)(clock64() - t_role0));       // epilogue: role time
+            atomicAdd((unsigned long long*)&dbg[11], (unsigned long long)e_fold);                     // epilogue: corr fold
+            atomicAdd((unsigned long long*)&dbg[12], (unsigned long long)e_gather);                   // epilogue: TMEM loads, row shift, exchange
+            atomicAdd((unsigned long long*)&dbg[13], (unsigned long long)e_rot);                      // epilogue: LO rotation + store
         }
     } else if (warp == TC_EPI_WARPS) {
         // ======================================= MMA ISSUE =======================================
-        int s = 0;
-        unsigned int ph = 0;
-        long long w_acc0 = 0, w_acc1 = 0;
+        // Stage g = iteration & 1 (the producer groups alternate).  The first K block of a tile sends its two
+        // small products into `main` (the chain is short and small there), so that the epilogue has a whole K
+        // block of time to fold the previous tile's corr before this tile overwrites it.
+        int it = 0;
+        long long w_acc0 = 0, w_acc1 = 0, w_issue = 0;
         const long long t_role0 = clock64();
         for (int n = 0; n < my_tiles; ++n) {
             const unsigned int as = n & 1, aph = (n >> 1) & 1;
-            mbar_wait_t(smem_u32(&sh->tmem_empty[as]), aph ^ 1u, w_acc1, dbg != nullptr);
+            mbar_wait_t(smem_u32(&sh->tmem_empty[as]), aph ^ 1u, w_acc1, timed);
             tc_fence_after();
-            const unsigned int d_main = tmem_base + as * 256u, d_corr = d_main + 128u;
-            for (int kb = 0; kb < KB; ++kb) {
-                mbar_wait_t(smem_u32(&sh->full[s]), ph, w_acc0, dbg != nullptr);
+            const unsigned int d_main = tmem_base + as * 256u, d_corr = tmem_base + TC_COL_CORR;
+            const unsigned int d_wide = tmem_base + as * 128u;   // [main(0) | corr] or [corr | main(1)]
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int gst = it & 1;
+                mbar_wait_t(smem_u32(&sh->full[gst]), (unsigned)(it >> 1) & 1u, w_acc0, timed);
+                if (kb == 1) mbar_wait_t(smem_u32(&sh->corr_empty), (unsigned)(n & 1) ^ 1u, w_acc1, timed);
                 tc_fence_after();
                 if (lane == 0) {
-                    const unsigned int a0 = smem_base + (unsigned)s * TC_STAGE_BYTES;
-                    const unsigned long long a_hi = tc_smem_desc(a0), a_lo = tc_smem_desc(a0 + TC_OPER_BYTES);
-                    const unsigned long long b_hi = tc_smem_desc(a0 + 2 * TC_OPER_BYTES);   // B_lo follows B_hi: rows 128..255
+                    const long long ti0 = timed ? clock64() : 0;
+                    const unsigned int a_hi = tmem_base + TC_COL_A + 64u * gst;
+                    const unsigned int b0 = smem_u32(smem_b) + (unsigned)gst * TC_B_BYTES;
+                    // B tiles of the stage lie in the order of the accumulators: [B_hi | B_lo] for as = 0, [B_lo | B_hi] for as = 1
+                    const unsigned long long b_x = tc_smem_desc(b0), b_y = tc_smem_desc(b0 + TC_B_BYTES / 2);
+                    const unsigned long long b_hi = as ? b_y : b_x, b_lo = as ? b_x : b_y;
                     const int ks_n = min(4, ksteps_total - 4 * kb);
-                    for (int ks = 0; ks < ks_n; ++ks) {
-                        const unsigned long long adv = (unsigned long long)(2 * ks);   // 32 bytes >> 4 per k-step
-                        // [main | corr] (+)= A_hi [B_hi | B_lo] in one N = 256 instruction (A_hi is read once), corr += A_lo B_hi
-                        tc_mma_tf32(d_main, a_hi + adv, b_hi + adv, TC_IDESC_WIDE, (kb | ks) ? 1u : 0u);
-                        tc_mma_tf32(d_corr, a_lo + adv, b_hi + adv, TC_IDESC, 1u);
+                    if (kb == 0) {          // first K block: every product into main, which the first MMA initialises
+                        tc_kstep<false, true>(d_main, d_main, a_hi, b_hi, b_lo, 0);
+                        for (int ks = 1; ks < ks_n; ++ks) tc_kstep<true, true>(d_main, d_main, a_hi, b_hi, b_lo, ks);
+                    } else if (ks_n == 4) { // corr was zeroed by the epilogue's fold
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) tc_kstep_wide(d_wide, d_corr, a_hi, b_x, b_hi, ks);
+                    } else {
+                        for (int ks = 0; ks < ks_n; ++ks) tc_kstep_wide(d_wide, d_corr, a_hi, b_x, b_hi, ks);
                     }
-                    tc_commit(smem_u32(&sh->empty[s]));
+                    tc_commit(smem_u32(&sh->empty[gst]));
                     if (kb == KB - 1) tc_commit(smem_u32(&sh->tmem_full[as]));
+                    if (timed) w_issue += clock64() - ti0;
                 }
                 __syncwarp();
-                if (++s == TC_STAGES) s = 0, ph ^= 1u;
             }
         }
         if (dbg && lane == 0) {
             atomicAdd((unsigned long long*)&dbg[2], (unsigned long long)w_acc0);                      // MMA: wait for operands
             atomicAdd((unsigned long long*)&dbg[3], (unsigned long long)w_acc1);                      // MMA: wait for a free accumulator
             atomicAdd((unsigned long long*)&dbg[4], (unsigned long long)(clock64() - t_role0));       // MMA: role time
+            atomicAdd((unsigned long long*)&dbg[10], (unsigned long long)w_issue);                    // MMA: inside the issue block
         }
     } else if (warp < TC_TMA_WARP) {
         // ======================================= OPERAND PRODUCERS =======================================
-        // Two groups of four warps take alternate K blocks, so that the fence / arrive / wait latency of one group
-        // overlaps the shared-memory traffic of the other.
-        const int grp = (warp - (TC_EPI_WARPS + 1)) / TC_GROUP_WARPS;
-        const int lt = (int)threadIdx.x - 32 * (TC_EPI_WARPS + 1) - grp * TC_GROUP_THREADS;   // 0..127 inside the group
+        const int grp = (warp - (TC_EPI_WARPS + 1)) / TC_GROUP_WARPS;     // operand stage of this group
+        const int q = warp & 3;                                           // TMEM lane quarter this warp may access
+        const int row = 32 * q + lane;                                    // window row of the tile == TMEM lane
+        const int lt = (warp - (TC_EPI_WARPS + 1) - grp * TC_GROUP_WARPS) * 32 + lane;   // 0..127 inside the group
         const unsigned int kc = (unsigned)lt & 15u, sub = (unsigned)lt >> 4;   // tap inside the K block, (block,tone) slot
         const unsigned int b_off_re = tc_swz(2u * sub, kc);         // + u * 2048   (row n = 2*(u*8 + sub) + {0,1})
         const unsigned int b_off_im = tc_swz(2u * sub + 1u, kc);
+        const unsigned int a_rowoff = (unsigned)(row >> 3) * 1024u + (unsigned)(row & 7) * 128u;
+        const unsigned int a_tmem = tmem_base + ((unsigned int)(32 * q) << 16) + TC_COL_A + 64u * grp;
+        unsigned char* const bst = smem_b + (size_t)grp * TC_B_BYTES;
         // (block i, tone t) of this thread's eight filter taps: slot = u * 8 + sub, i = slot / TG, t = slot % TG
         int g_off[TC_B_PER_THREAD], g_t[TC_B_PER_THREAD];
 #pragma unroll
@@ -421,27 +519,8 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
             g_t[u] = slot % TG;
             g_off[u] = (slot / TG) * M + g_t[u] * ntaps;
         }
-        // A: this thread owns the 16-byte chunks e = u * 128 + lt of the stage's A tiles.  Chunk e is two complex taps
-        // of window row a_row(u) = u * 16 + (lt >> 3) at logical chunk (lt ^ (lt >> 3)) & 7 of the K block.
-        const int a_row0 = lt >> 3;
-        const int a_k = 2 * ((lt ^ (lt >> 3)) & 7);
-
         float2 xb[TC_B_PER_THREAD];
-        float4 hv = make_float4(0.f, 0.f, 0.f, 0.f);   // history patch (TMA mode): chunk u = 0 of a tile that starts inside the history
-
-        auto load_pair = [&](long long sidx, int k) {   // two consecutive window samples, zero beyond the taps / the window
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < M) {
-                const float2 a = dev_win_at(w, sidx);
-                v.x = a.x, v.y = a.y;
-            }
-            if (k + 1 < M) {
-                const float2 a = dev_win_at(w, sidx + 1);
-                v.z = a.x, v.w = a.y;
-            }
-            return v;
-        };
-        auto issue_loads = [&](const TcTile& tl, int kb, float2* vb, float4& h) {
+        auto issue_loads = [&](const TcTile& tl, int kb, float2* vb) {
             const int k = kb * TC_KC + (int)kc;
             const float2* gk = g + (long long)tl.ch0 * ntaps + k;
 #pragma unroll
@@ -449,74 +528,79 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                 vb[u] = make_float2(0.f, 0.f);
                 if (k < M && tl.ch0 + g_t[u] < T) vb[u] = __ldg(gk + g_off[u]);
             }
-            // rows of the tile that lie in the carried-over history are not in the TMA tensor (it zero-fills them)
-            if (use_tma && tl.row0 + a_row0 < hist_rows) h = load_pair((tl.row0 + a_row0) * (long long)M + kb * TC_KC + a_k, kb * TC_KC + a_k);
         };
 
-        // this group's iterations: it = grp, grp + 2, ...; (tile, K block) advanced without divisions
-        int n_cur = 0, kb_cur = grp, s = grp;
-        unsigned int ph = 0;
+        // this group's iterations: it = grp, grp + 2, ...; (tile, K block) advanced without divisions.
+        // Landing slot r = it mod 4 alternates between grp and grp + 2; the operand stage is always `grp`.
+        int n_cur = 0, kb_cur = grp, r = grp;
+        unsigned int rph = 0, oph = 0;
         while (kb_cur >= KB) kb_cur -= KB, ++n_cur;
         TcTile t_cur = tile_of(n_cur);
         long long w_acc0 = 0;
         const long long t_role0 = clock64();
-        if (n_cur < my_tiles) issue_loads(t_cur, kb_cur, xb, hv);
+        if (n_cur < my_tiles) issue_loads(t_cur, kb_cur, xb);
         while (n_cur < my_tiles) {
             int n_nxt = n_cur, kb_nxt = kb_cur + TC_GROUPS;
             while (kb_nxt >= KB) kb_nxt -= KB, ++n_nxt;
             const TcTile t_nxt = (n_nxt == n_cur) ? t_cur : tile_of(n_nxt);
             float2 nb[TC_B_PER_THREAD];
-            float4 nh = make_float4(0.f, 0.f, 0.f, 0.f);
             const bool more = n_nxt < my_tiles;
-            if (more) issue_loads(t_nxt, kb_nxt, nb, nh);
-            mbar_wait_t(smem_u32(&sh->raw_full[s]), ph, w_acc0, dbg != nullptr);
-            unsigned char* st = smem + (size_t)s * TC_STAGE_BYTES;
-            {
-                float4 v[TC_A_PER_THREAD];
-                if (use_tma) {
-                    // the raw rows are in the A_hi tile (TMA): split in place, same swizzled position in both tiles
+            if (more) issue_loads(t_nxt, kb_nxt, nb);
+            mbar_wait_t(smem_u32(&sh->empty[grp]), oph ^ 1u, w_acc0, timed);     // the MMAs of this stage's previous use are done
+            mbar_wait_t(smem_u32(&sh->raw_full[r]), rph, w_acc0, timed);
+            tc_fence_after();
+            const unsigned char* raw = smem + (size_t)r * TC_RAW_BYTES;
+            const bool from_smem = use_tma && t_cur.row0 + row >= hist_rows;   // else: history row, or no TMA at all
+            const long long s_row = (t_cur.row0 + row) * (long long)M + kb_cur * TC_KC;
 #pragma unroll
-                    for (int u = 0; u < TC_A_PER_THREAD; ++u) v[u] = *(reinterpret_cast<const float4*>(st) + u * TC_GROUP_THREADS + lt);
-                    if (t_cur.row0 + a_row0 < hist_rows) v[0] = hv;
+            for (int h = 0; h < 2; ++h) {
+                float v[16], hi[16], lo[16];
+                if (from_smem) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 x = *reinterpret_cast<const float4*>(raw + a_rowoff + ((unsigned)((4 * h + c4) ^ (row & 7)) << 4));
+                        v[4 * c4] = x.x, v[4 * c4 + 1] = x.y, v[4 * c4 + 2] = x.z, v[4 * c4 + 3] = x.w;
+                    }
                 } else {
-                    // mis-aligned stream or odd decimation: the same chunks straight from global memory
 #pragma unroll
-                    for (int u = 0; u < TC_A_PER_THREAD; ++u)
-                        v[u] = load_pair((t_cur.row0 + u * 16 + a_row0) * (long long)M + kb_cur * TC_KC + a_k, kb_cur * TC_KC + a_k);
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = kb_cur * TC_KC + 8 * h + j;
+                        float2 a = make_float2(0.f, 0.f);
+                        if (k < M) a = (use_tma && s_row + 8 * h + j < TC_HIST_MAX) ? sh->hist[s_row + 8 * h + j] : dev_win_at(w, s_row + 8 * h + j);
+                        v[2 * j] = a.x, v[2 * j + 1] = a.y;
+                    }
                 }
 #pragma unroll
-                for (int u = 0; u < TC_A_PER_THREAD; ++u) {
-                    float4 hi, lo;
-                    tf32_split(v[u].x, hi.x, lo.x);
-                    tf32_split(v[u].y, hi.y, lo.y);
-                    tf32_split(v[u].z, hi.z, lo.z);
-                    tf32_split(v[u].w, hi.w, lo.w);
-                    *(reinterpret_cast<float4*>(st) + u * TC_GROUP_THREADS + lt) = hi;
-                    *(reinterpret_cast<float4*>(st + TC_OPER_BYTES) + u * TC_GROUP_THREADS + lt) = lo;
-                }
+                for (int e = 0; e < 16; ++e) tf32_split(v[e], hi[e], lo[e]);
+                __syncwarp();   // tcgen05.st is warp-collective: reconverge after the per-lane source selection
+                tmem_st16(a_tmem + 16u * h, hi);
+                tmem_st16(a_tmem + 32u + 16u * h, lo);
             }
+            const int b_hi_off = (n_cur & 1) ? TC_B_BYTES / 2 : 0;   // accumulator order: [main(0) | corr], [corr | main(1)]
+            mbar_arrive(smem_u32(&sh->raw_empty[r]));   // this thread's reads of the landing slot are complete (values consumed)
 #pragma unroll
             for (int u = 0; u < TC_B_PER_THREAD; ++u) {
                 float2 hi, lo;
                 tf32_split(xb[u].x, hi.x, lo.x);
                 tf32_split(xb[u].y, hi.y, lo.y);
-                unsigned char* bh = st + 2 * TC_OPER_BYTES + u * 2048;
-                unsigned char* bl = st + 3 * TC_OPER_BYTES + u * 2048;
+                unsigned char* bh = bst + b_hi_off + u * 2048;
+                unsigned char* bl = bst + (TC_B_BYTES / 2 - b_hi_off) + u * 2048;
                 *reinterpret_cast<float2*>(bh + b_off_re) = make_float2(hi.x, -hi.y);   // Re(x g): x_r g_r - x_i g_i
                 *reinterpret_cast<float2*>(bh + b_off_im) = make_float2(hi.y, hi.x);    // Im(x g): x_r g_i + x_i g_r
                 *reinterpret_cast<float2*>(bl + b_off_re) = make_float2(lo.x, -lo.y);
                 *reinterpret_cast<float2*>(bl + b_off_im) = make_float2(lo.y, lo.x);
             }
+            tmem_st_wait();
             fence_proxy_async();
-            mbar_arrive(smem_u32(&sh->full[s]));
+            tc_fence_before();
+            mbar_arrive(smem_u32(&sh->full[grp]));
             if (more) {
 #pragma unroll
                 for (int u = 0; u < TC_B_PER_THREAD; ++u) xb[u] = nb[u];
-                hv = nh;
             }
-            // two iterations on: stage (s + 2) mod 3, parity flips when the stage index wraps
-            s += TC_GROUPS;
-            if (s >= TC_STAGES) s -= TC_STAGES, ph ^= 1u;
+            oph ^= 1u;
+            r += TC_GROUPS;
+            if (r >= TC_RAW) r -= TC_RAW, rph ^= 1u;
             n_cur = n_nxt, kb_cur = kb_nxt, t_cur = t_nxt;
         }
         if (dbg && lt == 0 && grp == 0) {
@@ -525,8 +609,9 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
         }
     } else if (warp == TC_TMA_WARP) {
         // ======================================= TMA ISSUE =======================================
-        // One lane.  Besides the load of the K block into its stage, the box TC_L2_AHEAD iterations further on is
-        // prefetched into L2, so that the load proper finds its rows there: three stages cannot cover the HBM latency.
+        // One lane.  Besides the load of the K block into its landing slot, the box TC_L2_AHEAD iterations further on
+        // is prefetched into L2, so that the load proper finds its rows there.  History rows have negative tensor
+        // coordinates: TMA zero-fills them and the producers take them from sh->hist.
         if (lane == 0) {
             int s = 0;
             unsigned int ph = 0;
@@ -546,22 +631,21 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
             for (int j = 0; j < TC_L2_AHEAD; ++j) prefetch_next();
             for (int n = 0; n < my_tiles; ++n) {
                 const TcTile tl = tile_of(n);
-                const bool tma = use_tma != 0;   // history rows have negative tensor coordinates: zero-filled, patched by the producers
                 for (int kb = 0; kb < KB; ++kb) {
                     prefetch_next();
-                    mbar_wait_t(smem_u32(&sh->empty[s]), ph ^ 1u, w_acc0, dbg != nullptr);
+                    mbar_wait_t(smem_u32(&sh->raw_empty[s]), ph ^ 1u, w_acc0, timed);
                     const unsigned int bar = smem_u32(&sh->raw_full[s]);
-                    if (tma) {
-                        mbar_arrive_expect_tx(bar, TC_OPER_BYTES);
-                        tma_load_2d(smem_base + (unsigned)s * TC_STAGE_BYTES, &tmap, kb * 2 * TC_KC, (int)(tl.row0 - hist_rows), bar);
+                    if (use_tma) {
+                        mbar_arrive_expect_tx(bar, TC_RAW_BYTES);
+                        tma_load_2d(smem_base + (unsigned)s * TC_RAW_BYTES, &tmap, kb * 2 * TC_KC, (int)(tl.row0 - hist_rows), bar);
                     } else {
                         mbar_arrive(bar);
                     }
-                    if (++s == TC_STAGES) s = 0, ph ^= 1u;
+                    if (++s == TC_RAW) s = 0, ph ^= 1u;
                 }
             }
             if (dbg) {
-                atomicAdd((unsigned long long*)&dbg[7], (unsigned long long)w_acc0);                  // TMA: wait for a free stage
+                atomicAdd((unsigned long long*)&dbg[7], (unsigned long long)w_acc0);                  // TMA: wait for a free slot
                 atomicAdd((unsigned long long*)&dbg[8], (unsigned long long)(clock64() - t_role0));   // TMA: role time
                 atomicAdd((unsigned long long*)&dbg[9], (unsigned long long)(my_tiles * KB));         // stage iterations
             }
@@ -602,7 +686,7 @@ TcEncodeTiledFn tc_encode_fn() {
 bool tc_make_tensor_map(const Window& w, int M, CUtensorMap* map) {
     const char* e = getenv("GSDR_DIRECT_TC_TMA");   // =0: every tile through the register path (tests)
     const bool off = e && e[0] == '0';
-    if (off || M < TC_KC || (M & 1) || w.n_hist % M != 0 || w.n_in < M || w.n_in % M != 0) return false;
+    if (off || M < TC_KC || (M & 1) || w.n_hist % M != 0 || w.n_hist > TC_HIST_MAX || w.n_in < M || w.n_in % M != 0) return false;
     if (reinterpret_cast<uintptr_t>(w.in) & 15) return false;
     TcEncodeTiledFn enc = tc_encode_fn();
     if (!enc) return false;
@@ -648,8 +732,9 @@ int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int 
         const double it = h[9] > 0 ? (double)h[9] : 1.0;
         fprintf(stderr,
                 "[direct_tc] grid %d tiles %lld use_tma %d | per stage iteration (cycles): epi wait %.0f of %.0f | mma wait-operands %.0f "
-                "wait-acc %.0f of %.0f | producers wait %.0f of %.0f | tma wait %.0f of %.0f\n",
-                grid, tiles, use_tma, h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[4] / it, h[5] / it, h[6] / it, h[7] / it, h[8] / it);
+                "wait-acc %.0f issue %.0f of %.0f | producers wait %.0f of %.0f | tma wait %.0f of %.0f | epi fold %.0f gather %.0f rotate+store %.0f\n",
+                grid, tiles, use_tma, h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[10] / it, h[4] / it, h[5] / it, h[6] / it, h[7] / it, h[8] / it,
+                h[11] / it, h[12] / it, h[13] / it);
     }
     return 1;
 }
@@ -659,7 +744,6 @@ int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int 
 // F in {1, 2, 4, 8} so that F * TG * 2 = 128 accumulator columns; the LO phase arithmetic needs 128 * rate < 2^53.
 // M <= 128: the tensor-core accumulation truncates (measured on B200: about 1.6e-7 relative per accumulated k-step
 // when every term has the same sign, 4e-5 at M = 1000), so one accumulation chain is kept to 32 k-steps.
-constexpr int TC_MAX_M = 128;
 bool direct_fir_tc_supported(int T, int M, int ntaps, long long n_out) {
     if (M < 1 || M > TC_MAX_M || T < 1 || n_out < 1 || ntaps % M != 0) return false;
     const int f = ntaps / M;
