@@ -26,10 +26,9 @@
 //   warps 0-3   epilogue: fold corr into main in TMEM (frees corr for the next tile), tcgen05.ld, row shift-and-add,
 //               LO rotation, sample-major store
 //   warp  4     TMEM allocation + single-thread tcgen05.mma issue (kind::tf32, M=128, N=128, K=8, A from TMEM)
-//   warps 5-12  operand producers, two groups of four warps on alternate K blocks, each group owning one operand
-//               stage: thread = one window row (TMEM lane); 8 x LDS.128 of the row from the TMA landing slot,
-//               hi/lo split, tcgen05.st; the tone filters come through registers (L2 hits) and are split into the
-//               128-byte-swizzled K-major B tiles
+//   warps 5-12  operand producers: thread = one window row (TMEM lane) and one half of its K block; 4 x LDS.128 of the
+//               row from the TMA landing slot, hi/lo split, tcgen05.st; the tone filters come through registers (L2
+//               hits) and are split into the 128-byte-swizzled K-major B tiles; two operand stages
 //   warp  13    TMA issue: one cp.async.bulk.tensor (128 rows x 32 floats, SWIZZLE_128B) per K block into a ring of
 //               four landing slots, each box prefetched into L2 eight K blocks earlier
 // TMEM columns: main x 2 (the epilogue of tile n overlaps the MMAs of tile n+1), corr x 1, A (hi, lo) x 2 stages.
@@ -65,7 +64,7 @@ constexpr unsigned int TC_COL_CORR = 128;          // main(0) at 0, corr at 128,
                                                    // both 256 contiguous columns, the D operand of one N = 256 MMA
 constexpr unsigned int TC_COL_A = 384;             // A stage g: hi at +64 g, lo at +64 g + 32
 constexpr int TC_L2_AHEAD = 8;                     // K blocks between the L2 prefetch of a box and its TMA load
-constexpr int TC_B_PER_THREAD = (TC_N / 2) * TC_KC / TC_GROUP_THREADS;    // 8 filter taps
+constexpr int TC_B_PER_THREAD = (TC_N / 2) * TC_KC / (32 * TC_LOAD_WARPS);   // 4 filter taps
 constexpr int TC_MAX_M = 128;                      // longest accumulation chain accepted (see direct_fir_tc_supported)
 constexpr int TC_HIST_MAX = 7 * TC_MAX_M;          // carried-over samples: (F - 1) * M
 static_assert((TC_EPI_WARPS + 1) % 4 == 1 && TC_GROUP_WARPS == 4, "producer warp w owns TMEM lane quarter w % 4");
@@ -273,10 +272,10 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_RAW; ++s) {
             mbar_init(smem_u32(&sh->raw_full[s]), 1);
-            mbar_init(smem_u32(&sh->raw_empty[s]), TC_GROUP_THREADS);
+            mbar_init(smem_u32(&sh->raw_empty[s]), 32 * TC_LOAD_WARPS);
         }
         for (int a = 0; a < 2; ++a) {
-            mbar_init(smem_u32(&sh->full[a]), TC_GROUP_THREADS);
+            mbar_init(smem_u32(&sh->full[a]), 32 * TC_LOAD_WARPS);
             mbar_init(smem_u32(&sh->empty[a]), 1);
             mbar_init(smem_u32(&sh->tmem_full[a]), 1);
             mbar_init(smem_u32(&sh->tmem_empty[a]), 32 * TC_EPI_WARPS);
@@ -293,7 +292,8 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
     // the carried-over samples: the first window rows of the stream, which the TMA tensor (the `in` segment) lacks
     const long long hist_rows = w.n_hist / M;
 
-    for (int i = threadIdx.x; i < TC_HIST_MAX && i < w.n_hist; i += TC_THREADS) sh->hist[i] = w.hist[i];
+    if ((int)blockIdx.x < n_tone_groups)   // only the CTAs that own a tile of the first row tile meet history rows
+        for (int i = threadIdx.x; i < TC_HIST_MAX && i < w.n_hist; i += TC_THREADS) sh->hist[i] = w.hist[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -501,25 +501,25 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
         }
     } else if (warp < TC_TMA_WARP) {
         // ======================================= OPERAND PRODUCERS =======================================
-        const int grp = (warp - (TC_EPI_WARPS + 1)) / TC_GROUP_WARPS;     // operand stage of this group
+        // Eight warps, every K block: warp w owns TMEM lane quarter w % 4 (thread = one window row); the two warps of a
+        // quarter take one half (16 floats) of the row's K block each.  Stage = iteration & 1.
+        const int half = (warp - (TC_EPI_WARPS + 1)) / TC_GROUP_WARPS;    // which 16 floats of the 32-float K block
         const int q = warp & 3;                                           // TMEM lane quarter this warp may access
         const int row = 32 * q + lane;                                    // window row of the tile == TMEM lane
-        const int lt = (warp - (TC_EPI_WARPS + 1) - grp * TC_GROUP_WARPS) * 32 + lane;   // 0..127 inside the group
+        const int lt = (int)threadIdx.x - 32 * (TC_EPI_WARPS + 1);        // 0..255
         const unsigned int kc = (unsigned)lt & 15u, sub = (unsigned)lt >> 4;   // tap inside the K block, (block,tone) slot
-        const unsigned int b_off_re = tc_swz(2u * sub, kc);         // + u * 2048   (row n = 2*(u*8 + sub) + {0,1})
+        const unsigned int b_off_re = tc_swz(2u * sub, kc);         // + u * 4096   (row n = 2*(u*16 + sub) + {0,1})
         const unsigned int b_off_im = tc_swz(2u * sub + 1u, kc);
         const unsigned int a_rowoff = (unsigned)(row >> 3) * 1024u + (unsigned)(row & 7) * 128u;
-        const unsigned int a_tmem = tmem_base + ((unsigned int)(32 * q) << 16) + TC_COL_A + 64u * grp;
-        unsigned char* const bst = smem_b + (size_t)grp * TC_B_BYTES;
-        // (block i, tone t) of this thread's eight filter taps: slot = u * 8 + sub, i = slot / TG, t = slot % TG
+        const unsigned int a_tmem0 = tmem_base + ((unsigned int)(32 * q) << 16) + TC_COL_A + 16u * half;
+        // (block i, tone t) of this thread's four filter taps: slot = u * 16 + sub, i = slot / TG, t = slot % TG
         int g_off[TC_B_PER_THREAD], g_t[TC_B_PER_THREAD];
 #pragma unroll
         for (int u = 0; u < TC_B_PER_THREAD; ++u) {
-            const int slot = u * 8 + (int)sub;
+            const int slot = u * 16 + (int)sub;
             g_t[u] = slot % TG;
             g_off[u] = (slot / TG) * M + g_t[u] * ntaps;
         }
-        float2 xb[TC_B_PER_THREAD];
         auto issue_loads = [&](const TcTile& tl, int kb, float2* vb) {
             const int k = kb * TC_KC + (int)kc;
             const float2* gk = g + (long long)tl.ch0 * ntaps + k;
@@ -530,82 +530,88 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
             }
         };
 
-        // this group's iterations: it = grp, grp + 2, ...; (tile, K block) advanced without divisions.
-        // Landing slot r = it mod 4 alternates between grp and grp + 2; the operand stage is always `grp`.
-        int n_cur = 0, kb_cur = grp, r = grp;
-        unsigned int rph = 0, oph = 0;
-        while (kb_cur >= KB) kb_cur -= KB, ++n_cur;
-        TcTile t_cur = tile_of(n_cur);
-        long long w_acc0 = 0;
+        int n_cur = 0, kb_cur = 0, it = 0;
+        TcTile t_cur = tile_of(0);
+        long long w_acc0 = 0, p_a = 0, p_b = 0, p_stw = 0, p_fence = 0;
         const long long t_role0 = clock64();
-        if (n_cur < my_tiles) issue_loads(t_cur, kb_cur, xb);
-        while (n_cur < my_tiles) {
-            int n_nxt = n_cur, kb_nxt = kb_cur + TC_GROUPS;
-            while (kb_nxt >= KB) kb_nxt -= KB, ++n_nxt;
+        // One K block: prefetch the next block's filter taps into `nb`, convert this block from `cb`.  Called with the
+        // two buffers swapped on alternate iterations: a register copy of `nb` would wait for the loads to land.
+        auto k_block = [&](float2* cb, float2* nb) {
+            int n_nxt = n_cur, kb_nxt = kb_cur + 1;
+            if (kb_nxt == KB) kb_nxt = 0, ++n_nxt;
             const TcTile t_nxt = (n_nxt == n_cur) ? t_cur : tile_of(n_nxt);
-            float2 nb[TC_B_PER_THREAD];
-            const bool more = n_nxt < my_tiles;
-            if (more) issue_loads(t_nxt, kb_nxt, nb);
-            mbar_wait_t(smem_u32(&sh->empty[grp]), oph ^ 1u, w_acc0, timed);     // the MMAs of this stage's previous use are done
-            mbar_wait_t(smem_u32(&sh->raw_full[r]), rph, w_acc0, timed);
+            if (n_nxt < my_tiles) issue_loads(t_nxt, kb_nxt, nb);
+            const int st = it & 1, r = it & (TC_RAW - 1);
+            mbar_wait_t(smem_u32(&sh->empty[st]), ((unsigned)(it >> 1) & 1u) ^ 1u, w_acc0, timed);   // the MMAs of this stage's previous use are done
+            mbar_wait_t(smem_u32(&sh->raw_full[r]), (unsigned)(it >> 2) & 1u, w_acc0, timed);
             tc_fence_after();
+            const long long tp0 = timed ? clock64() : 0;
             const unsigned char* raw = smem + (size_t)r * TC_RAW_BYTES;
             const bool from_smem = use_tma && t_cur.row0 + row >= hist_rows;   // else: history row, or no TMA at all
-            const long long s_row = (t_cur.row0 + row) * (long long)M + kb_cur * TC_KC;
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
+            const long long s_row = (t_cur.row0 + row) * (long long)M + kb_cur * TC_KC + 8 * half;
+            {
                 float v[16], hi[16], lo[16];
                 if (from_smem) {
 #pragma unroll
                     for (int c4 = 0; c4 < 4; ++c4) {
-                        const float4 x = *reinterpret_cast<const float4*>(raw + a_rowoff + ((unsigned)((4 * h + c4) ^ (row & 7)) << 4));
+                        const float4 x = *reinterpret_cast<const float4*>(raw + a_rowoff + ((unsigned)((4 * half + c4) ^ (row & 7)) << 4));
                         v[4 * c4] = x.x, v[4 * c4 + 1] = x.y, v[4 * c4 + 2] = x.z, v[4 * c4 + 3] = x.w;
                     }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int k = kb_cur * TC_KC + 8 * h + j;
+                        const int k = kb_cur * TC_KC + 8 * half + j;
                         float2 a = make_float2(0.f, 0.f);
-                        if (k < M) a = (use_tma && s_row + 8 * h + j < TC_HIST_MAX) ? sh->hist[s_row + 8 * h + j] : dev_win_at(w, s_row + 8 * h + j);
+                        if (k < M) a = (use_tma && s_row + j < TC_HIST_MAX) ? sh->hist[s_row + j] : dev_win_at(w, s_row + j);
                         v[2 * j] = a.x, v[2 * j + 1] = a.y;
                     }
                 }
 #pragma unroll
                 for (int e = 0; e < 16; ++e) tf32_split(v[e], hi[e], lo[e]);
                 __syncwarp();   // tcgen05.st is warp-collective: reconverge after the per-lane source selection
-                tmem_st16(a_tmem + 16u * h, hi);
-                tmem_st16(a_tmem + 32u + 16u * h, lo);
+                tmem_st16(a_tmem0 + 64u * st, hi);
+                tmem_st16(a_tmem0 + 64u * st + 32u, lo);
             }
             const int b_hi_off = (n_cur & 1) ? TC_B_BYTES / 2 : 0;   // accumulator order: [main(0) | corr], [corr | main(1)]
+            const long long tp1 = timed ? clock64() : 0;
             mbar_arrive(smem_u32(&sh->raw_empty[r]));   // this thread's reads of the landing slot are complete (values consumed)
+            unsigned char* const bst = smem_b + (size_t)st * TC_B_BYTES;
 #pragma unroll
             for (int u = 0; u < TC_B_PER_THREAD; ++u) {
                 float2 hi, lo;
-                tf32_split(xb[u].x, hi.x, lo.x);
-                tf32_split(xb[u].y, hi.y, lo.y);
-                unsigned char* bh = bst + b_hi_off + u * 2048;
-                unsigned char* bl = bst + (TC_B_BYTES / 2 - b_hi_off) + u * 2048;
+                tf32_split(cb[u].x, hi.x, lo.x);
+                tf32_split(cb[u].y, hi.y, lo.y);
+                unsigned char* bh = bst + b_hi_off + u * 4096;
+                unsigned char* bl = bst + (TC_B_BYTES / 2 - b_hi_off) + u * 4096;
                 *reinterpret_cast<float2*>(bh + b_off_re) = make_float2(hi.x, -hi.y);   // Re(x g): x_r g_r - x_i g_i
                 *reinterpret_cast<float2*>(bh + b_off_im) = make_float2(hi.y, hi.x);    // Im(x g): x_r g_i + x_i g_r
                 *reinterpret_cast<float2*>(bl + b_off_re) = make_float2(lo.x, -lo.y);
                 *reinterpret_cast<float2*>(bl + b_off_im) = make_float2(lo.y, lo.x);
             }
+            const long long tp2 = timed ? clock64() : 0;
             tmem_st_wait();
+            const long long tp3 = timed ? clock64() : 0;
             fence_proxy_async();
             tc_fence_before();
-            mbar_arrive(smem_u32(&sh->full[grp]));
-            if (more) {
-#pragma unroll
-                for (int u = 0; u < TC_B_PER_THREAD; ++u) xb[u] = nb[u];
-            }
-            oph ^= 1u;
-            r += TC_GROUPS;
-            if (r >= TC_RAW) r -= TC_RAW, rph ^= 1u;
+            mbar_arrive(smem_u32(&sh->full[st]));
+            if (timed) p_a += tp1 - tp0, p_b += tp2 - tp1, p_stw += tp3 - tp2, p_fence += clock64() - tp3;
+            ++it;
             n_cur = n_nxt, kb_cur = kb_nxt, t_cur = t_nxt;
+        };
+        float2 xb0[TC_B_PER_THREAD], xb1[TC_B_PER_THREAD];
+        if (my_tiles > 0) issue_loads(t_cur, 0, xb0);
+        while (n_cur < my_tiles) {
+            k_block(xb0, xb1);
+            if (n_cur >= my_tiles) break;
+            k_block(xb1, xb0);
         }
-        if (dbg && lt == 0 && grp == 0) {
+        if (dbg && lt == 0) {
             atomicAdd((unsigned long long*)&dbg[5], (unsigned long long)w_acc0);                      // producers: wait for raw rows / a free stage
             atomicAdd((unsigned long long*)&dbg[6], (unsigned long long)(clock64() - t_role0));       // producers: role time
+            atomicAdd((unsigned long long*)&dbg[14], (unsigned long long)p_a);
+            atomicAdd((unsigned long long*)&dbg[15], (unsigned long long)p_b);
+            atomicAdd((unsigned long long*)&dbg[16], (unsigned long long)p_stw);
+            atomicAdd((unsigned long long*)&dbg[17], (unsigned long long)p_fence);
         }
     } else if (warp == TC_TMA_WARP) {
         // ======================================= TMA ISSUE =======================================
@@ -718,23 +724,23 @@ int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int 
     const char* de = getenv("GSDR_DIRECT_TC_DEBUG");
     long long* dbg = nullptr;
     if (de && de[0] == '1') {
-        GSDR_CUDA_OK(cudaMalloc(&dbg, 16 * sizeof(long long)));
-        GSDR_CUDA_OK(cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), stream));
+        GSDR_CUDA_OK(cudaMalloc(&dbg, 24 * sizeof(long long)));
+        GSDR_CUDA_OK(cudaMemsetAsync(dbg, 0, 24 * sizeof(long long), stream));
     }
     direct_fir_tc_kernel<F><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, use_tma, w, g, freq_dev, T, M, rate, pos0, n_out,
                                                                          row_tiles, tone_groups, out, dbg);
     GSDR_CUDA_OK(cudaGetLastError());
     if (dbg) {
-        long long h[16];
+        long long h[24];
         GSDR_CUDA_OK(cudaStreamSynchronize(stream));
         GSDR_CUDA_OK(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
         cudaFree(dbg);
         const double it = h[9] > 0 ? (double)h[9] : 1.0;
         fprintf(stderr,
                 "[direct_tc] grid %d tiles %lld use_tma %d | per stage iteration (cycles): epi wait %.0f of %.0f | mma wait-operands %.0f "
-                "wait-acc %.0f issue %.0f of %.0f | producers wait %.0f of %.0f | tma wait %.0f of %.0f | epi fold %.0f gather %.0f rotate+store %.0f\n",
+                "wait-acc %.0f issue %.0f of %.0f | producers wait %.0f of %.0f | tma wait %.0f of %.0f | epi fold %.0f gather %.0f rotate+store %.0f | prod A %.0f B %.0f st-wait %.0f fence+arrive %.0f\n",
                 grid, tiles, use_tma, h[0] / it, h[1] / it, h[2] / it, h[3] / it, h[10] / it, h[4] / it, h[5] / it, h[6] / it, h[7] / it, h[8] / it,
-                h[11] / it, h[12] / it, h[13] / it);
+                h[11] / it, h[12] / it, h[13] / it, h[14] / it, h[15] / it, h[16] / it, h[17] / it);
     }
     return 1;
 }
