@@ -66,12 +66,18 @@ def main():
     run_rx("NOISE N=2048 P=4 full spectrum (fused)", g.param(rate=200_000_000, fft_tones=2048, pf_average=4, buffer_len=1_000_000,
                                                               freq=[0], wave_type=[g.NOISE], ampl=[1.0]), 32, 16.0)
     run_rx("TONES N=1000 P=4 T=100 (generic)", pfb_param(rate=100_000_000, N=1000, P=4, T=100), 8, 8 + 8 * 100 / 1000, steps=5)
-    # cfg1 DIRECT: fp32-bound, 16*T FMA per input sample
+    # cfg1 DIRECT: 16*T real FMA per input sample.  Default = tensor-core kernel (tcgen05, 3xTF32 split GEMM) where the
+    # shape fills the GPU and decim <= 128; GSDR_DIRECT_VARIANT=fp32 forces the CUDA-core kernel for comparison.
     T = 16
-    run_rx("cfg1 DIRECT T=16 decim=100 f=4", direct_param(), 16, 8 + 8 * T / 100,
-           extra=lambda r: {"fp32_TFLOPs": r["input_MSps"] * 1e6 * 16 * T * 2 / 1e12})
-    run_rx("DIRECT T=1000 decim=1000 f=4", direct_param(T=1000, decim=1000), 2, 8 + 8.0, steps=3,
-           extra=lambda r: {"fp32_TFLOPs": r["input_MSps"] * 1e6 * 16 * 1000 * 2 / 1e12})
+    flops = lambda t: (lambda r: {"fp32_equiv_TFLOPs": r["input_MSps"] * 1e6 * 16 * t * 2 / 1e12})  # noqa: E731
+    for variant in ("tc", "fp32"):
+        os.environ["GSDR_DIRECT_VARIANT"] = variant
+        run_rx(f"cfg1 DIRECT T=16 decim=100 f=4 [{variant}]", direct_param(), 16, 8 + 8 * T / 100, extra=flops(16))
+        run_rx(f"cfg1 DIRECT, one 1e6-sample buffer per launch [{variant}]", direct_param(), 1, 8 + 8 * T / 100, steps=50, extra=flops(16))
+        run_rx(f"DIRECT T=64 decim=100 f=4 [{variant}]", direct_param(T=64), 8, 8 + 8 * 64 / 100, steps=5, extra=flops(64))
+    os.environ.pop("GSDR_DIRECT_VARIANT", None)
+    run_rx("DIRECT T=1000 decim=1000 f=4 (decim > 128: fp32 kernel)", direct_param(T=1000, decim=1000), 2, 8 + 8.0, steps=3,
+           extra=flops(1000))
     run_rx("DIRECT T=16 decim=0 (mix only)", direct_param(decim=0, f=1), 4, 8 + 8 * T, steps=5)
     # cfg3 CHIRP
     run_rx("cfg3 CHIRP lock-in ppt=2000", chirp_param(), 64, 8 + 8 / 2000)
