@@ -77,6 +77,7 @@ struct gsdr_rx {
     uint64_t launches = 0;
     size_t max_out = 0;
     const char* kernel_name = "none";
+    std::string kernel_name_buf;
 
     // carry-over (ping-pong)
     float2* hist[2] = {nullptr, nullptr};
@@ -99,6 +100,7 @@ struct gsdr_rx {
     size_t spec_bytes = 0;
     float2* d_spec_acc = nullptr;
     int spec_carried = 0;
+    bool post_decim = false;  // NOISE with decim > 0, TONES with decim > 1
     int batching = 0, T_sel = 0;
     bool fused = false;
     gsdr_buffer_helper bh{};
@@ -252,6 +254,19 @@ int init_chirp(gsdr_rx* rx, const gsdr_param* p) {
     return 0;
 }
 
+// mean of `decim` consecutive channelizer rows after the fused kernel (NOISE: every bin; TONES: the selected tones)
+int init_post_decim(gsdr_rx* rx) {
+    const size_t n = sizeof(float2) * 2 * (size_t)rx->T_sel;
+    if (cudaMalloc(&rx->d_spec_acc, n) != cudaSuccess || cudaMemset(rx->d_spec_acc, 0, n) != cudaSuccess) {
+        set_error("cudaMalloc for the post-PFB accumulator failed");
+        return -1;
+    }
+    rx->post_decim = true;
+    rx->kernel_name_buf = std::string(rx->kernel_name) + " + spectra_decimate_kernel";
+    rx->kernel_name = rx->kernel_name_buf.c_str();
+    return 0;
+}
+
 int init_direct(gsdr_rx* rx) {
     const int T = rx->T;
     if ((int)rx->freq.size() < T) {
@@ -312,7 +327,9 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
         case GSDR_TONES:
         case GSDR_NOISE: {
             long long frames = 0;
-            const bool spec_decim = rx->mode == GSDR_NOISE && rx->decim > 0;
+            // NOISE: spectral decimation (decimate_spectra); TONES: the post-PFB decimator (decimate_pfb, cpp/USRP_demodulator.cpp:520-545).
+            // Both are the mean of `decim` consecutive rows of the channelizer output; row width = T_sel.
+            const bool spec_decim = rx->post_decim;
             long long groups = 0;
             int carried = rx->spec_carried;
             for (int b = 0; b < n_buf; ++b) {
@@ -321,7 +338,7 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
                     const long long gb = ((long long)carried + rx->bh.current_batch) / rx->decim;
                     carried = (int)((long long)carried + rx->bh.current_batch - gb * rx->decim);
                     groups += gb;
-                    v = (int)(gb * rx->N);
+                    v = (int)(gb * rx->T_sel);
                 }
                 if (lens) lens[b] = v;
                 frames += rx->bh.current_batch;
@@ -330,7 +347,7 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
             }
             float2* const final_out = d_out;
             if (spec_decim) {
-                const size_t need = sizeof(float2) * (size_t)(frames > 0 ? frames : 1) * rx->N;
+                const size_t need = sizeof(float2) * (size_t)(frames > 0 ? frames : 1) * rx->T_sel;
                 if (need > rx->spec_bytes) {
                     if (rx->d_spec) cudaFree(rx->d_spec);
                     rx->d_spec = nullptr;
@@ -364,7 +381,7 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
             if (nl < 0) return -1;
             rx->launches += nl;
             if (spec_decim) {
-                const int dl = spectra_decimate_launch(rx->d_spec, frames, rx->N, rx->decim, rx->spec_carried, rx->d_spec_acc, final_out,
+                const int dl = spectra_decimate_launch(rx->d_spec, frames, rx->T_sel, rx->decim, rx->spec_carried, rx->d_spec_acc, final_out,
                                                        groups, rx->sm_count, st);
                 if (dl < 0) return -1;
                 rx->launches += dl;
@@ -559,21 +576,17 @@ gsdr_rx* gsdr_rx_create(const gsdr_param* p, int device, int diagnostic) {
                 set_error("TONES: %d wave types but only %zu frequencies", rx->T, rx->freq.size());
                 return nullptr;
             }
-            if (rx->decim > 1 && rx->diagnostic)
-                fprintf(stderr, "gsdr: TONES post-PFB decimation is not applied (broken in the reference; see DESIGN.md)\n");
             rc = init_pfb(rx.get(), false);
+            // Post-PFB decimator (decimate_pfb / accumulate_ffts, cpp/kernels.cu:754-790): the reference's kernel reads
+            // input[j * (offset % nfft)] -- not the j-th frame -- so its output is not a function worth reproducing.  Built
+            // here: what it is meant to be, out[g][t] = mean_{j<decim} X[g decim + j][bin_t], groups running across
+            // buffer boundaries (decim == 1 is the identity).
+            if (rc == 0 && rx->decim > 1) rc = init_post_decim(rx.get());
             break;
         case GSDR_NOISE:
             rc = init_pfb(rx.get(), true);
-            if (rc == 0 && rx->decim > 0) {
-                // spectral decimation (cpp/USRP_demodulator.cpp:596-624): running sum + staging row
-                if (cudaMalloc(&rx->d_spec_acc, sizeof(float2) * 2 * rx->N) != cudaSuccess ||
-                    cudaMemset(rx->d_spec_acc, 0, sizeof(float2) * 2 * rx->N) != cudaSuccess) {
-                    set_error("cudaMalloc for the spectral accumulator failed");
-                    rc = -1;
-                }
-                rx->kernel_name = "pfb_fused_wsp_2048_kernel<P> + spectra_decimate_kernel";
-            }
+            // spectral decimation (cpp/USRP_demodulator.cpp:596-624): running sum + staging row
+            if (rc == 0 && rx->decim > 0) rc = init_post_decim(rx.get());
             break;
         case GSDR_CHIRP:
             rc = init_chirp(rx.get(), p);
@@ -761,7 +774,7 @@ static int process_pfb_chunked(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* 
 
 int gsdr_rx_process(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* out) {
     if (rx && in && out && rx->fused && !rx->slots.empty() && rx->L >= 64LL * rx->N &&
-        (rx->mode == GSDR_TONES || (rx->mode == GSDR_NOISE && rx->decim <= 0))) {
+        (rx->mode == GSDR_TONES || rx->mode == GSDR_NOISE) && !rx->post_decim) {
         if (set_dev(rx)) return -1;
         // keep the ticket/slot rotation of submit() intact: the blocking path always uses slot 0 and leaves every slot idle
         for (auto& sl : rx->slots)
@@ -859,7 +872,7 @@ int gsdr_rx_reset(gsdr_rx* rx) {
         case GSDR_NOISE:
             buffer_helper_init(&rx->bh, rx->N, (int)rx->L, (int)rx->P, rx->T_sel);
             rx->spec_carried = 0;
-            if (rx->d_spec_acc) GSDR_CUDA_OK(cudaMemset(rx->d_spec_acc, 0, sizeof(float2) * 2 * rx->N));
+            if (rx->d_spec_acc) GSDR_CUDA_OK(cudaMemset(rx->d_spec_acc, 0, sizeof(float2) * 2 * rx->T_sel));
             break;
         case GSDR_CHIRP:
             rx->last_index = 0;
@@ -942,7 +955,7 @@ gsdr_rx_group* gsdr_rx_group_create(gsdr_rx** members, int n) {
     for (int i = 0; i < n; ++i) {
         gsdr_rx* m = members[i];
         if (!m || (m->mode != GSDR_TONES && m->mode != GSDR_NOISE) || !m->fused || m->device != members[0]->device ||
-            m->N != members[0]->N || m->P != members[0]->P || (m->mode == GSDR_NOISE && m->decim > 0)) {
+            m->N != members[0]->N || m->P != members[0]->P || m->post_decim) {
             set_error("gsdr_rx_group_create: member %d is not a fused TONES/NOISE stream compatible with member 0", i);
             return nullptr;
         }

@@ -281,3 +281,45 @@ np.savez(sys.argv[1], *res)
         assert len(a.files) == len(b.files) == 6
         for k in a.files:
             assert a[k].size > 0 and np.array_equal(a[k].view(np.uint32), b[k].view(np.uint32)), k
+
+
+@pytest.mark.parametrize("decim,L,T", [(4, 100_000, 50), (7, 60_000, 1000), (1, 60_000, 20), (100, 100_000, 3)])
+def test_tones_mode_post_pfb_decimation(decim, L, T):
+    """TONES with decim > 0 (decimate_pfb + accumulate_ffts, cpp/USRP_demodulator.cpp:520-545,
+    cpp/kernels.cu:754-790).  The reference's kernel indexes input[j * (offset % nfft)] instead of frame j and counts
+    floor(current_batch / decim) outputs per buffer without carrying the remainder, so parity is defined against the
+    function it is meant to compute: the mean of every `decim` consecutive frames per selected tone, groups running
+    across buffer boundaries, evaluated in fp64 on the oracle's channelizer output.  decim = 1 is the identity."""
+    p = pfb_param(T=T, L=L)
+    p.decim = decim
+    # the power sits on selected tones (bin centres, < 1 Hz off after int() truncation: the same phase in every frame,
+    # so the coherent mean does not cancel and the float32 comparison is meaningful for large `decim` too)
+    lit = list(p.freq[:min(T, 6)])
+    bufs = [tone_stream(p.rate, lit, [0.15] * len(lit), i * L, L) for i in range(5)]
+    outs = rx_run(p, bufs)
+    o = orc.PFBDemodulator(p.rate, p.fft_tones, p.pf_average, L, p.freq)
+    frames = [o.process(x).reshape(-1, T) for x in bufs]
+    carried, want_lens = 0, []
+    for f in frames:
+        gb = (carried + len(f)) // decim
+        carried = carried + len(f) - gb * decim
+        want_lens.append(gb * T)
+    assert [len(x) for x in outs] == want_lens
+    allf = np.concatenate(frames)
+    ng = len(allf) // decim
+    want = allf[: ng * decim].reshape(ng, decim, T).mean(axis=1).reshape(-1)
+    got = np.concatenate(outs)
+    assert len(got) == len(want) and len(got) > 0
+    assert orc.rel_l2(got, want) <= TOL
+    # independent of how the stream is cut into calls
+    rx = g.RX_buffer_demodulator(p)
+    d_in = g.DeviceBuffer(len(bufs) * L)
+    for i, x in enumerate(bufs):
+        d_in.upload(x, offset=i * L)
+    d_out = g.DeviceBuffer(rx.max_output_batch(len(bufs)))
+    total, lens = rx.process_device(d_in.ptr, len(bufs), d_out.ptr)
+    rx.sync()
+    batch = d_out.download(total)
+    rx.close()
+    assert list(lens) == want_lens
+    assert np.array_equal(batch.view(np.uint32), got.view(np.uint32))
