@@ -88,7 +88,11 @@ class Dist:
             backend = "nccl" if torch.cuda.is_available() else "gloo"
             if backend == "nccl":
                 torch.cuda.set_device(self.local_rank)
-            dist.init_process_group(backend)
+                # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
+                os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+                dist.init_process_group(backend, device_id=torch.device("cuda", self.local_rank))
+            else:
+                dist.init_process_group(backend)
             self.dev = torch.device("cuda", self.local_rank) if backend == "nccl" else torch.device("cpu")
 
     def barrier(self):
