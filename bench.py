@@ -308,6 +308,9 @@ def run_ours(args, dd: Dist):
             rx.wait(t)
         return d2h
 
+    numa_node = int(g.load().gsdr_device_numa_node(dd.local_rank))
+    print(f"[bench rank {dd.rank}] GPU {dd.local_rank}: NUMA node {numa_node}; pinned buffers allocated node-local when the kernel allows",
+          file=sys.stderr, flush=True)
     e2e_pass(B)  # warm-up
     dd.barrier()
     t0 = time.perf_counter()
@@ -364,7 +367,7 @@ def run_ours(args, dd: Dist):
                      "launch_ms": ms_total / args.steps},
         "e2e": {"value": e2e_val, "unit": "MS/s", "h2d_bytes_per_step": B * BUFLEN * 8, "d2h_bytes_per_step": d2h_bytes,
                 "api": "gsdr_rx_submit/gsdr_rx_wait (pinned host in/out, depth-3 pipeline)", "steps": e2e_steps,
-                "blocking_process_value": blocking_val,
+                "blocking_process_value": blocking_val, "pinned_numa_node_rank0": numa_node,
                 "sc16_ingest": {"value": sc16_val, "unit": "MS/s", "h2d_bytes_per_step": B * BUFLEN * 4,
                                 "api": "gsdr_rx_submit_sc16/gsdr_rx_wait (int16 I/Q in, conversion on the GPU)"}},
         "gpu_launches": int(l1 - l0), "clocks": clocks,

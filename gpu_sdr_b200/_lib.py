@@ -126,6 +126,7 @@ SIGNATURES = {
     "gsdr_pool_available": (C.c_int, [C.c_void_p]),
     "gsdr_pool_size": (C.c_int, [C.c_void_p]),
     "gsdr_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "gsdr_device_numa_node": (C.c_int, [C.c_int]),
     "gsdr_host_free": (None, [C.c_void_p]),
     "gsdr_dev_alloc": (C.c_void_p, [C.c_int, C.c_size_t]),
     "gsdr_dev_free": (None, [C.c_int, C.c_void_p]),

@@ -9,9 +9,69 @@
 #include <random>
 #include <thread>
 
+#include <sys/syscall.h>
+#include <unistd.h>
+
+#include <cctype>
+
 #include "common.hpp"
 
 using namespace gsdr;
+
+// ------------------------------------------------------------------------------------------------
+// NUMA-local pinned memory.  On an 8-GPU box half of the GPUs hang off the other CPU socket: a pinned
+// buffer that lives on the wrong node is DMA-ed across the socket interconnect, which all of them then
+// share.  The pool and gsdr_host_alloc therefore ask the kernel (set_mempolicy, MPOL_PREFERRED) for
+// pages on the node of the GPU that is current when the buffer is allocated; the reference pins its
+// worker threads to cores instead (cpp/USRP_server_link_threads.cpp:264,299) and allocates wherever
+// they run.  Everything degrades to a plain cudaMallocHost when sysfs or the syscall say no.
+// ------------------------------------------------------------------------------------------------
+namespace {
+int numa_node_of_device_uncached(int device) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof(bus), device) != cudaSuccess) {
+        cudaGetLastError();
+        return -1;
+    }
+    for (char* c = bus; *c; ++c) *c = (char)tolower((unsigned char)*c);
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return -1;
+    int node = -1;
+    if (fscanf(f, "%d", &node) != 1) node = -1;
+    fclose(f);
+    return node;
+}
+int numa_node_of_device(int device) {
+    static std::mutex m;
+    static int cache[64];
+    static bool known[64] = {false};
+    if (device < 0 || device >= 64) return -1;
+    std::lock_guard<std::mutex> lk(m);
+    if (!known[device]) cache[device] = numa_node_of_device_uncached(device), known[device] = true;
+    return cache[device];
+}
+// cudaMallocHost with the calling thread's memory policy pointed at the current GPU's node for the duration
+cudaError_t pinned_alloc_local(void** p, size_t bytes) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = -1, cudaGetLastError();
+    const char* e = getenv("GSDR_NUMA_LOCAL");
+    const int node = (e && e[0] == '0') ? -1 : numa_node_of_device(dev);
+    bool bound = false;
+#ifdef SYS_set_mempolicy
+    if (node >= 0 && node < 64) {
+        unsigned long mask = 1ul << node;
+        bound = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, sizeof(mask) * 8 + 1) == 0;
+    }
+#endif
+    const cudaError_t rc = cudaMallocHost(p, bytes);
+#ifdef SYS_set_mempolicy
+    if (bound) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+#endif
+    return rc;
+}
+}  // namespace
 
 // ------------------------------------------------------------------------------------------------
 // Pinned pool.  Reference: template preallocator<T>, headers/USRP_server_memory_management.hpp:
@@ -24,6 +84,7 @@ using namespace gsdr;
 struct gsdr_pool {
     size_t vector_size = 0;
     int pipe_size = 0;
+    int device = 0;  // GPU that was current at creation: pinned pages go to its NUMA node
     bool grow = true;
     std::mutex m;
     std::condition_variable cv_free, cv_grow;
@@ -36,11 +97,12 @@ struct gsdr_pool {
     // before the payload and the whole frame leaves with one send() (gsdr_packet_frame).
     gsdr_float2* alloc_one() {
         void* p = nullptr;
-        if (cudaMallocHost(&p, vector_size * sizeof(gsdr_float2) + GSDR_POOL_HEADROOM) != cudaSuccess) return nullptr;
+        if (pinned_alloc_local(&p, vector_size * sizeof(gsdr_float2) + GSDR_POOL_HEADROOM) != cudaSuccess) return nullptr;
         return reinterpret_cast<gsdr_float2*>(static_cast<char*>(p) + GSDR_POOL_HEADROOM);
     }
     static void free_one(gsdr_float2* b) { cudaFreeHost(reinterpret_cast<char*>(b) - GSDR_POOL_HEADROOM); }
     void grow_loop() {
+        cudaSetDevice(device);
         std::unique_lock<std::mutex> lk(m);
         while (!closing) {
             cv_grow.wait(lk, [&] { return closing || (grow && (double)free_list.size() < pipe_size / 10.); });
@@ -68,6 +130,7 @@ gsdr_pool* gsdr_pool_create(size_t vector_size, int pipe_size, int prefill) {
     pool->vector_size = vector_size;
     pool->pipe_size = pipe_size;
     pool->grow = prefill != 0;
+    if (cudaGetDevice(&pool->device) != cudaSuccess) pool->device = 0, cudaGetLastError();
     for (int i = 0; i < pipe_size - 1; ++i) {  // reference pre-fills pipe_size-1 buffers (:211-227)
         gsdr_float2* b = pool->alloc_one();
         if (!b) {
@@ -372,12 +435,13 @@ int gsdr_packet_frame(const gsdr_rx_packet* pkt, const void** frame, size_t* fra
 
 void* gsdr_host_alloc(size_t bytes) {
     void* p = nullptr;
-    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) {
+    if (pinned_alloc_local(&p, bytes ? bytes : 1) != cudaSuccess) {
         set_error("cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
     return p;
 }
+int gsdr_device_numa_node(int device) { return numa_node_of_device(device); }
 void gsdr_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }

@@ -206,7 +206,8 @@ void gsdr_pool_close(gsdr_pool *pool);
 int gsdr_pool_available(const gsdr_pool *pool);
 int gsdr_pool_size(const gsdr_pool *pool);
 
-void *gsdr_host_alloc(size_t bytes);   /* cudaMallocHost */
+void *gsdr_host_alloc(size_t bytes);   /* cudaMallocHost, on the NUMA node of the current GPU when the kernel allows (GSDR_NUMA_LOCAL=0: off) */
+int gsdr_device_numa_node(int device); /* /sys/bus/pci/devices/<bus id>/numa_node of the GPU, -1 when unknown */
 void gsdr_host_free(void *p);
 void *gsdr_dev_alloc(int device, size_t bytes);
 void gsdr_dev_free(int device, void *p);
