@@ -65,8 +65,8 @@ constexpr unsigned int TC_COL_CORR = 128;          // main(0) at 0, corr at 128,
 constexpr unsigned int TC_COL_A = 384;             // A stage g: hi at +64 g, lo at +64 g + 32
 constexpr int TC_L2_AHEAD = 8;                     // K blocks between the L2 prefetch of a box and its TMA load
 constexpr int TC_B_PER_THREAD = (TC_N / 2) * TC_KC / (32 * TC_LOAD_WARPS);   // 4 filter taps
-constexpr int TC_MAX_M = 128;                      // longest accumulation chain accepted (see direct_fir_tc_supported)
-constexpr int TC_HIST_MAX = 7 * TC_MAX_M;          // carried-over samples: (F - 1) * M
+constexpr int TC_SEG = 8;                          // K blocks per accumulation segment: 32 k-steps per tensor-core chain
+constexpr int TC_HIST_MAX = 7 * 128;               // carried-over samples kept in shared memory (the rest is read from global)
 static_assert((TC_EPI_WARPS + 1) % 4 == 1 && TC_GROUP_WARPS == 4, "producer warp w owns TMEM lane quarter w % 4");
 
 struct TcShared {
@@ -82,6 +82,7 @@ struct TcShared {
     double2 ph[64];          // per tone of the group: (LO phase of the tile's first row, phase step per row), integers < rate
     alignas(16) float xch[TC_EPI_WARPS][TC_XCH_FLOATS];
     alignas(16) float2 hist[TC_HIST_MAX];    // copy of the carried-over samples (rows the TMA tensor does not hold)
+    float total[TC_N * TC_ROWS];             // [column][row]: sum of a tile's finished segments (decim > 128 only)
 };
 constexpr size_t TC_SMEM_BYTES = 1024 + (size_t)TC_RAW * TC_RAW_BYTES + (size_t)TC_GROUPS * TC_B_BYTES + sizeof(TcShared);
 
@@ -265,6 +266,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
     const int ntaps = F * M;
     const int KB = (M + TC_KC - 1) / TC_KC;           // K blocks per tile
     const int ksteps_total = (M + 3) / 4;             // MMA k-steps (4 complex taps = 8 tf32) per tile
+    const int NSEG = (KB + TC_SEG - 1) / TC_SEG;      // accumulation segments per tile (1 for decim <= 128)
     const int n_tiles = n_row_tiles * n_tone_groups;
     const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const bool timed = dbg != nullptr;
@@ -328,7 +330,6 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
         const long long t_role0 = clock64();
         for (int n = 0; n < my_tiles; ++n) {
             const TcTile tl = tile_of(n);
-            const unsigned int as = n & 1, aph = (n >> 1) & 1;
             // LO phase (cpp/kernels.cu:59-75) of the tile's first output for each tone of the group, and its step per
             // output, as exact integers; row r of the tile then has phase base + r * step < 128 * rate < 2^53, formed
             // exactly by one DFMA.
@@ -345,31 +346,49 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                 }
                 sh->ph[threadIdx.x] = make_double2(base, step);
             }
-            mbar_wait_t(smem_u32(&sh->tmem_full[as]), aph, w_acc0, timed);
-            tc_fence_after();
-            const unsigned int t_main = tmem_base + ((unsigned int)(warp * 32) << 16) + as * 256u;
-            const long long te0 = timed ? clock64() : 0;
-            if (KB > 1) {
-                // main += corr, in place, and corr = 0: corr is free for the next tile long before this one has been written out
-                const unsigned int t_corr = tmem_base + ((unsigned int)(warp * 32) << 16) + TC_COL_CORR;
+            // The tensor core's accumulate truncates, so a chain is cut after TC_SEG K blocks (32 k-steps): every segment
+            // is a separate accumulation, handed over like a tile (as = segment counter & 1), and the segments of a tile
+            // are added here in fp32 (round to nearest), through a [column][row] array in shared memory.
+            unsigned int as = 0, t_main = 0;
+            for (int sgi = 0; sgi < NSEG; ++sgi) {
+                const int c = n * NSEG + sgi;
+                as = c & 1;
+                mbar_wait_t(smem_u32(&sh->tmem_full[as]), (unsigned)(c >> 1) & 1u, w_acc0, timed);
+                tc_fence_after();
+                t_main = tmem_base + ((unsigned int)(warp * 32) << 16) + as * 256u;
+                const long long te0 = timed ? clock64() : 0;
+                const bool first = sgi == 0, last = sgi == NSEG - 1;
+                if (KB > 1) {
+                    // main += corr (+ earlier segments), in place, and corr = 0: corr is free for the next segment / tile
+                    // long before this one has been written out
+                    const unsigned int t_corr = tmem_base + ((unsigned int)(warp * 32) << 16) + TC_COL_CORR;
 #pragma unroll 1
-                for (int j = 0; j < TC_N / 32; ++j) {
-                    float a[32], b[32];
-                    tmem_ld<32>(t_main + 32u * j, a);
-                    tmem_ld<32>(t_corr + 32u * j, b);
-                    tmem_ld_wait();
+                    for (int j = 0; j < TC_N / 32; ++j) {
+                        float a[32], b[32];
+                        tmem_ld<32>(t_main + 32u * j, a);
+                        tmem_ld<32>(t_corr + 32u * j, b);
+                        tmem_ld_wait();
+                        float* tot = sh->total + (32 * j) * TC_ROWS + row_in_tile;
 #pragma unroll
-                    for (int e = 0; e < 32; ++e) a[e] += b[e], b[e] = 0.f;
-                    tmem_st32(t_main + 32u * j, a);
-                    tmem_st32(t_corr + 32u * j, b);   // the next tile accumulates into corr from its second K block on
+                        for (int e = 0; e < 32; ++e) {
+                            a[e] += b[e], b[e] = 0.f;
+                            if (!first) a[e] += tot[e * TC_ROWS];
+                            if (!last) tot[e * TC_ROWS] = a[e];
+                        }
+                        if (last) tmem_st32(t_main + 32u * j, a);
+                        tmem_st32(t_corr + 32u * j, b);   // the next segment accumulates into corr from its second K block on
+                    }
+                    tmem_st_wait();
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&sh->corr_empty));
                 }
-                tmem_st_wait();
-                tc_fence_before();
-                mbar_arrive(smem_u32(&sh->corr_empty));
+                if (timed) e_fold += clock64() - te0;
+                if (!last) {   // main(as) has been read: the MMA warp may start segment c + 2 in it
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&sh->tmem_empty[as]));
+                }
             }
             const long long p = tl.row0 + row_in_tile;
-            const long long te1 = timed ? clock64() : 0;
-            e_fold += te1 - te0;
 #pragma unroll 1
             for (int c = 0; c < NCHUNK; ++c) {
                 const long long tc0 = timed ? clock64() : 0;
@@ -458,39 +477,43 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
         int it = 0;
         long long w_acc0 = 0, w_acc1 = 0, w_issue = 0;
         const long long t_role0 = clock64();
+        int c = 0;   // accumulation segment counter: accumulator stage and barrier parities follow it
         for (int n = 0; n < my_tiles; ++n) {
-            const unsigned int as = n & 1, aph = (n >> 1) & 1;
-            mbar_wait_t(smem_u32(&sh->tmem_empty[as]), aph ^ 1u, w_acc1, timed);
-            tc_fence_after();
-            const unsigned int d_main = tmem_base + as * 256u, d_corr = tmem_base + TC_COL_CORR;
-            const unsigned int d_wide = tmem_base + as * 128u;   // [main(0) | corr] or [corr | main(1)]
-            for (int kb = 0; kb < KB; ++kb, ++it) {
-                const int gst = it & 1;
-                mbar_wait_t(smem_u32(&sh->full[gst]), (unsigned)(it >> 1) & 1u, w_acc0, timed);
-                if (kb == 1) mbar_wait_t(smem_u32(&sh->corr_empty), (unsigned)(n & 1) ^ 1u, w_acc1, timed);
+            for (int sgi = 0; sgi < NSEG; ++sgi, ++c) {
+                const unsigned int as = c & 1;
+                mbar_wait_t(smem_u32(&sh->tmem_empty[as]), ((unsigned)(c >> 1) & 1u) ^ 1u, w_acc1, timed);
                 tc_fence_after();
-                if (lane == 0) {
-                    const long long ti0 = timed ? clock64() : 0;
-                    const unsigned int a_hi = tmem_base + TC_COL_A + 64u * gst;
-                    const unsigned int b0 = smem_u32(smem_b) + (unsigned)gst * TC_B_BYTES;
-                    // B tiles of the stage lie in the order of the accumulators: [B_hi | B_lo] for as = 0, [B_lo | B_hi] for as = 1
-                    const unsigned long long b_x = tc_smem_desc(b0), b_y = tc_smem_desc(b0 + TC_B_BYTES / 2);
-                    const unsigned long long b_hi = as ? b_y : b_x, b_lo = as ? b_x : b_y;
-                    const int ks_n = min(4, ksteps_total - 4 * kb);
-                    if (kb == 0) {          // first K block: every product into main, which the first MMA initialises
-                        tc_kstep<false, true>(d_main, d_main, a_hi, b_hi, b_lo, 0);
-                        for (int ks = 1; ks < ks_n; ++ks) tc_kstep<true, true>(d_main, d_main, a_hi, b_hi, b_lo, ks);
-                    } else if (ks_n == 4) { // corr was zeroed by the epilogue's fold
+                const unsigned int d_main = tmem_base + as * 256u, d_corr = tmem_base + TC_COL_CORR;
+                const unsigned int d_wide = tmem_base + as * 128u;   // [main(0) | corr] or [corr | main(1)]
+                const int kb0 = sgi * TC_SEG, kb1 = min(KB, kb0 + TC_SEG);
+                for (int kb = kb0; kb < kb1; ++kb, ++it) {
+                    const int gst = it & 1;
+                    mbar_wait_t(smem_u32(&sh->full[gst]), (unsigned)(it >> 1) & 1u, w_acc0, timed);
+                    if (kb == kb0 + 1) mbar_wait_t(smem_u32(&sh->corr_empty), (unsigned)(c & 1) ^ 1u, w_acc1, timed);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const long long ti0 = timed ? clock64() : 0;
+                        const unsigned int a_hi = tmem_base + TC_COL_A + 64u * gst;
+                        const unsigned int b0 = smem_u32(smem_b) + (unsigned)gst * TC_B_BYTES;
+                        // B tiles of the stage lie in the order of the accumulators: [B_hi | B_lo] for as = 0, [B_lo | B_hi] for as = 1
+                        const unsigned long long b_x = tc_smem_desc(b0), b_y = tc_smem_desc(b0 + TC_B_BYTES / 2);
+                        const unsigned long long b_hi = as ? b_y : b_x, b_lo = as ? b_x : b_y;
+                        const int ks_n = min(4, ksteps_total - 4 * kb);
+                        if (kb == kb0) {        // first K block of a segment: every product into main, which the first MMA initialises
+                            tc_kstep<false, true>(d_main, d_main, a_hi, b_hi, b_lo, 0);
+                            for (int ks = 1; ks < ks_n; ++ks) tc_kstep<true, true>(d_main, d_main, a_hi, b_hi, b_lo, ks);
+                        } else if (ks_n == 4) { // corr was zeroed by the epilogue's fold
 #pragma unroll
-                        for (int ks = 0; ks < 4; ++ks) tc_kstep_wide(d_wide, d_corr, a_hi, b_x, b_hi, ks);
-                    } else {
-                        for (int ks = 0; ks < ks_n; ++ks) tc_kstep_wide(d_wide, d_corr, a_hi, b_x, b_hi, ks);
+                            for (int ks = 0; ks < 4; ++ks) tc_kstep_wide(d_wide, d_corr, a_hi, b_x, b_hi, ks);
+                        } else {
+                            for (int ks = 0; ks < ks_n; ++ks) tc_kstep_wide(d_wide, d_corr, a_hi, b_x, b_hi, ks);
+                        }
+                        tc_commit(smem_u32(&sh->empty[gst]));
+                        if (kb == kb1 - 1) tc_commit(smem_u32(&sh->tmem_full[as]));
+                        if (timed) w_issue += clock64() - ti0;
                     }
-                    tc_commit(smem_u32(&sh->empty[gst]));
-                    if (kb == KB - 1) tc_commit(smem_u32(&sh->tmem_full[as]));
-                    if (timed) w_issue += clock64() - ti0;
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
         if (dbg && lane == 0) {
@@ -572,7 +595,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                 tmem_st16(a_tmem0 + 64u * st, hi);
                 tmem_st16(a_tmem0 + 64u * st + 32u, lo);
             }
-            const int b_hi_off = (n_cur & 1) ? TC_B_BYTES / 2 : 0;   // accumulator order: [main(0) | corr], [corr | main(1)]
+            const int b_hi_off = ((n_cur * NSEG + kb_cur / TC_SEG) & 1) ? TC_B_BYTES / 2 : 0;   // accumulator order of this K block's segment: [main(0) | corr], [corr | main(1)]
             const long long tp1 = timed ? clock64() : 0;
             mbar_arrive(smem_u32(&sh->raw_empty[r]));   // this thread's reads of the landing slot are complete (values consumed)
             unsigned char* const bst = smem_b + (size_t)st * TC_B_BYTES;
@@ -692,7 +715,7 @@ TcEncodeTiledFn tc_encode_fn() {
 bool tc_make_tensor_map(const Window& w, int M, CUtensorMap* map) {
     const char* e = getenv("GSDR_DIRECT_TC_TMA");   // =0: every tile through the register path (tests)
     const bool off = e && e[0] == '0';
-    if (off || M < TC_KC || (M & 1) || w.n_hist % M != 0 || w.n_hist > TC_HIST_MAX || w.n_in < M || w.n_in % M != 0) return false;
+    if (off || M < TC_KC || (M & 1) || w.n_hist % M != 0 || w.n_in < M || w.n_in % M != 0) return false;
     if (reinterpret_cast<uintptr_t>(w.in) & 15) return false;
     TcEncodeTiledFn enc = tc_encode_fn();
     if (!enc) return false;
@@ -748,10 +771,11 @@ int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int 
 }  // namespace
 
 // F in {1, 2, 4, 8} so that F * TG * 2 = 128 accumulator columns; the LO phase arithmetic needs 128 * rate < 2^53.
-// M <= 128: the tensor-core accumulation truncates (measured on B200: about 1.6e-7 relative per accumulated k-step
-// when every term has the same sign, 4e-5 at M = 1000), so one accumulation chain is kept to 32 k-steps.
+// Any decimation: the tensor-core accumulation truncates (measured on B200: about 1.6e-7 relative per accumulated k-step
+// when every term has the same sign, 4e-5 for one chain over decim = 1000), so a chain is cut after 32 k-steps (128
+// taps) and the segments are added in fp32 by the epilogue.
 bool direct_fir_tc_supported(int T, int M, int ntaps, long long n_out) {
-    if (M < 1 || M > TC_MAX_M || T < 1 || n_out < 1 || ntaps % M != 0) return false;
+    if (M < 1 || T < 1 || n_out < 1 || ntaps % M != 0) return false;
     const int f = ntaps / M;
     if (!(f == 1 || f == 2 || f == 4 || f == 8)) return false;
     const long long rb = TC_ROWS - (f - 1), tg = 64 / f;

@@ -47,18 +47,24 @@ def test_cfg1_full_size_tc():
     (70, 25, 1, 50_000, 10_000_000),        # f = 1, two tone groups of 64, four epilogue chunks
     (16, 100, 4, 1_000_000, 100_000_000),   # cfg1 shape
     (40, 13, 4, 65_000, 5_000_000),         # three tone groups, M odd
-    (2, 128, 4, 128_000, 200_000_000),      # the longest accumulation chain the path accepts
+    (2, 128, 4, 128_000, 200_000_000),      # the longest single accumulation chain (one segment)
     (3, 1, 2, 4_096, 1_000_000),            # decim = 1
 ])
 def test_tc_vs_oracle(T, decim, f, L, rate):
     run_case(direct_param(rate=rate, T=T, decim=decim, f=f, L=L), 3)
 
 
-@pytest.mark.parametrize("T,decim,f,L,rate", [(1, 1000, 4, 100_000, 100_000_000), (2, 5000, 4, 100_000, 200_000_000)])
-def test_long_decimation_stays_on_fp32(T, decim, f, L, rate):
-    """decim > 128 would need accumulation chains long enough for the tensor cores' truncating accumulate to show
-    (4e-5 at decim = 1000): those shapes run the fp32 kernel even when the tensor-core path is forced."""
-    run_case(direct_param(rate=rate, T=T, decim=decim, f=f, L=L), 2, expect_tc=False)
+@pytest.mark.parametrize("T,decim,f,L,rate", [
+    (1, 1000, 4, 100_000, 100_000_000),     # one tone, 250 k-steps: 8 accumulation segments (one chain: 4e-5, measured)
+    (2, 5000, 4, 100_000, 200_000_000),     # 313 K blocks per tile = 40 segments, the last one short; 20 outputs
+    (20, 136, 2, 68_000, 10_000_000),       # 9 K blocks: a full segment and a one-block segment
+    (16, 256, 4, 1_024_000, 100_000_000),   # two full segments, 32 row tiles
+    (3, 1000, 8, 200_000, 50_000_000),      # f = 8: seven history rows of 1000 samples (beyond the shared-memory copy)
+])
+def test_long_decimation_accumulates_in_segments(T, decim, f, L, rate):
+    """decim > 128: the tensor core's truncating accumulate would show in one long chain (about 1.6e-7 per k-step when
+    all terms have one sign), so a chain is cut every 32 k-steps and the epilogue adds the segments in fp32."""
+    run_case(direct_param(rate=rate, T=T, decim=decim, f=f, L=L), 3)
 
 
 def test_unsupported_block_count_falls_back():

@@ -75,9 +75,8 @@ def main():
         run_rx(f"cfg1 DIRECT T=16 decim=100 f=4 [{variant}]", direct_param(), 16, 8 + 8 * T / 100, extra=flops(16))
         run_rx(f"cfg1 DIRECT, one 1e6-sample buffer per launch [{variant}]", direct_param(), 1, 8 + 8 * T / 100, steps=50, extra=flops(16))
         run_rx(f"DIRECT T=64 decim=100 f=4 [{variant}]", direct_param(T=64), 8, 8 + 8 * 64 / 100, steps=5, extra=flops(64))
+        run_rx(f"DIRECT T=1000 decim=1000 f=4 [{variant}]", direct_param(T=1000, decim=1000), 2, 8 + 8.0, steps=3, extra=flops(1000))
     os.environ.pop("GSDR_DIRECT_VARIANT", None)
-    run_rx("DIRECT T=1000 decim=1000 f=4 (decim > 128: fp32 kernel)", direct_param(T=1000, decim=1000), 2, 8 + 8.0, steps=3,
-           extra=flops(1000))
     run_rx("DIRECT T=16 decim=0 (mix only)", direct_param(decim=0, f=1), 4, 8 + 8 * T, steps=5)
     # cfg3 CHIRP
     run_rx("cfg3 CHIRP lock-in ppt=2000", chirp_param(), 64, 8 + 8 / 2000)
