@@ -223,37 +223,52 @@ direct_fir_tiled_kernel(const Window w, const float2* __restrict__ g, const int*
 }
 
 // decim == 0: pure mixing, out[n*T + ch] = x[n] e^{-j theta_ch n} (cpp/USRP_demodulator.cpp:442-457).
-constexpr int MIX_S = 32;  // samples per block
+// A block takes MIX_S consecutive samples and all tones.  Per tone, once per block: tf = freq mod R (positive residue) and
+// the integer phase of the block's first sample, base = (tf * n0) mod R, in 64-bit integers.  Sample i of the block then
+// has phase base + i*tf < 1025 R < 2^53, formed exactly by one DFMA, and the 32-bit phase word round(phase * 2^32 / R)
+// mod 2^32 is the low mantissa word of a second DFMA with the constant 1.5 * 2^52: no remainder, no division and no
+// int <-> double conversion per output.  Warps walk samples, lanes walk tones: stores are tone-fastest, coalesced.
+constexpr int MIX_S_MAX = 1024;  // samples per block: about 8192 outputs (32 per thread), between 32 and 1024 samples
 __global__ void __launch_bounds__(256)
 direct_mix_kernel(const float2* __restrict__ in, long long n, const int* __restrict__ freq, int T, int rate, long long pos0,
-                  float2* __restrict__ out) {
-    __shared__ float2 xs[MIX_S];
-    __shared__ long long base_ph[256];
+                  int MIX_S, float2* __restrict__ out) {
+    __shared__ float2 xs[MIX_S_MAX];
+    __shared__ double2 bs[256];   // (base phase, phase step per sample) of the tones of the current group of 256
     const long long s0 = (long long)blockIdx.x * MIX_S;
-    if (threadIdx.x < MIX_S) xs[threadIdx.x] = (s0 + threadIdx.x < n) ? in[s0 + threadIdx.x] : make_float2(0.f, 0.f);
-    const double inv_R = 1.0 / (double)rate;
+    for (int i = threadIdx.x; i < MIX_S; i += blockDim.x) xs[i] = (s0 + i < n) ? in[s0 + i] : make_float2(0.f, 0.f);
+    const double word_per_phase = 4294967296.0 / (double)rate;
     const long long nb = (pos0 + s0) % rate;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_here = (int)min((long long)MIX_S, n - s0);
     for (int c0 = 0; c0 < T; c0 += 256) {
         __syncthreads();
         const int ch = c0 + threadIdx.x;
         if (ch < T) {
-            long long ph = direct_phase_signed(freq[ch], (unsigned long long)nb, rate);
-            if (ph < 0) ph += rate;
-            base_ph[threadIdx.x] = ph;
+            long long tf = (long long)freq[ch] % rate;
+            if (tf < 0) tf += rate;   // same residue class as the reference's signed remainder (cpp/kernels.cu:59-75)
+            const unsigned long long base = ((unsigned long long)tf * (unsigned long long)nb) % (unsigned long long)rate;
+            bs[threadIdx.x] = make_double2((double)base, (double)tf);
         }
         __syncthreads();
         const int tones_here = min(256, T - c0);
-        for (int e = threadIdx.x; e < tones_here * MIX_S; e += 256) {
-            const int i = e / tones_here, cl = e - i * tones_here;  // tone fastest: coalesced stores
-            if (s0 + i >= n) continue;
-            long long tf = freq[c0 + cl] % rate;
-            if (tf < 0) tf += rate;
-            // (base + tf*i) mod R without a 64-bit division: quotient from a double product, then one fix-up
-            long long ph = base_ph[cl] + tf * i;  // < 33 R
-            ph -= (long long)((double)ph * inv_R) * rate;
-            if (ph < 0) ph += rate;
-            if (ph >= rate) ph -= rate;
-            out[(s0 + i) * T + c0 + cl] = dev_cmul(xs[i], lo_phasor(ph, inv_R));
+        // few tones: a warp takes 32 / tp2 samples at once (tp2 = tones rounded up to a power of two), so that all lanes work
+        int sh = 5;
+        while (sh > 0 && (1 << (sh - 1)) >= tones_here) --sh;
+        const int tp2 = 1 << sh, spw = 32 >> sh;
+        for (int i0 = warp * spw; i0 < n_here; i0 += 8 * spw) {
+            const int i = i0 + (lane >> sh);
+            if (i >= n_here) continue;
+            const float2 x = xs[i];
+            const double di = (double)i;
+            float2* row = out + (s0 + i) * T + c0;
+            for (int cl = lane & (tp2 - 1); cl < tones_here; cl += tp2) {
+                const double2 b = bs[cl];
+                const double ph = fma(di, b.y, b.x);
+                const unsigned int word = (unsigned int)__double2loint(fma(ph, word_per_phase, 6755399441055744.0));
+                float sn, cs;
+                sincos_phase32(word, sn, cs);
+                row[cl] = dev_cmul(x, make_float2(cs, -sn));
+            }
         }
     }
 }
@@ -326,7 +341,9 @@ int direct_fir_launch(const Window& w, const float2* g, const int* freq_dev, int
 int direct_mix_launch(const float2* in, long long n, const int* freq_dev, int T, int rate, long long pos0, float2* out,
                       cudaStream_t stream) {
     if (n <= 0) return 0;
-    direct_mix_kernel<<<(unsigned)((n + MIX_S - 1) / MIX_S), 256, 0, stream>>>(in, n, freq_dev, T, rate, pos0, out);
+    int S = 8192 / (T > 0 ? T : 1);
+    S = S < 32 ? 32 : (S > MIX_S_MAX ? MIX_S_MAX : S & ~31);
+    direct_mix_kernel<<<(unsigned)((n + S - 1) / S), 256, 0, stream>>>(in, n, freq_dev, T, rate, pos0, S, out);
     GSDR_CUDA_OK(cudaGetLastError());
     return 1;
 }
