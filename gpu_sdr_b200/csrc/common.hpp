@@ -111,8 +111,9 @@ int direct_fir_launch(const Window& w, const float2* g /* [T][ntaps] */, const i
 // tcgen05 / TMEM version of direct_fir_launch (direct_tc_kernels.cu): 3xTF32 split GEMM, pf_average in {1,2,4,8}
 bool direct_fir_tc_supported(int T, int M, int ntaps, long long n_out);
 bool direct_fir_tc_preferred(int T, int M, int ntaps, long long n_out);
+// rotate = 0: no LO rotation of the outputs (freq_dev unused) -- the form the generic-size polyphase channelizer takes
 int direct_fir_tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int M, int ntaps, int rate, long long pos0,
-                         long long n_out, float2* out, int sm_count, cudaStream_t stream);
+                         long long n_out, float2* out, int sm_count, cudaStream_t stream, int rotate = 1);
 int direct_mix_launch(const float2* in, long long n, const int* freq_dev, int T, int rate, long long pos0, float2* out,
                       cudaStream_t stream);
 int direct_phase_probe_launch(long long* out, unsigned int n, int tone_freq, int rate, unsigned long long index_counter,

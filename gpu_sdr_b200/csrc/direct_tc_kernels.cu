@@ -246,9 +246,10 @@ struct TcTile {
 // F = FIR blocks (pf_average); TG = 64 / F tones per group; outputs per tile = 128 - (F - 1)
 template <int F>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma, const Window w, const float2* __restrict__ g,
-                     const int* __restrict__ freq, int T, int M, int rate, long long pos0, long long n_out, int n_row_tiles,
-                     int n_tone_groups, float2* __restrict__ out, long long* __restrict__ dbg) {
+direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma, const long long hist_rows, const int rotate,
+                     const Window w, const float2* __restrict__ g, const int* __restrict__ freq, int T, int M, int rate,
+                     long long pos0, long long n_out, int n_row_tiles, int n_tone_groups, float2* __restrict__ out,
+                     long long* __restrict__ dbg) {
     constexpr int TG = 64 / F;
     constexpr int RB = TC_ROWS - (F - 1);
     constexpr int TCW = TG < 16 ? TG : 16;     // tones per epilogue chunk
@@ -291,8 +292,8 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    // the carried-over samples: the first window rows of the stream, which the TMA tensor (the `in` segment) lacks
-    const long long hist_rows = w.n_hist / M;
+    // the carried-over samples: the first `hist_rows` window rows hold samples of the previous call; the TMA tensor
+    // starts at the first row that lies entirely in the `in` segment
 
     if ((int)blockIdx.x < n_tone_groups)   // only the CTAs that own a tile of the first row tile meet history rows
         for (int i = threadIdx.x; i < TC_HIST_MAX && i < w.n_hist; i += TC_THREADS) sh->hist[i] = w.hist[i];
@@ -333,7 +334,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
             // LO phase (cpp/kernels.cu:59-75) of the tile's first output for each tone of the group, and its step per
             // output, as exact integers; row r of the tile then has phase base + r * step < 128 * rate < 2^53, formed
             // exactly by one DFMA.
-            if (threadIdx.x < TG) {
+            if (rotate && threadIdx.x < TG) {
                 const int ch = tl.ch0 + (int)threadIdx.x;
                 double base = 0.0, step = 0.0;
                 if (ch < T) {
@@ -439,12 +440,15 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                     float2 o[TCW];
 #pragma unroll
                     for (int t = 0; t < TCW; ++t) {
-                        const double2 bs = sh->ph[c * TCW + t];
-                        const double r = fma(row_d, bs.y, bs.x);
-                        const unsigned int word = (unsigned int)__double2loint(fma(r, word_per_phase, 6755399441055744.0));
-                        float sn, cs;
-                        sincos_phase32(word, sn, cs);
-                        o[t] = dev_cmul(make_float2(y[2 * t], y[2 * t + 1]), make_float2(cs, -sn));
+                        o[t] = make_float2(y[2 * t], y[2 * t + 1]);
+                        if (rotate) {   // the channelizer form (pfb as GEMM) has no LO: whole turns per row
+                            const double2 bs = sh->ph[c * TCW + t];
+                            const double r = fma(row_d, bs.y, bs.x);
+                            const unsigned int word = (unsigned int)__double2loint(fma(r, word_per_phase, 6755399441055744.0));
+                            float sn, cs;
+                            sincos_phase32(word, sn, cs);
+                            o[t] = dev_cmul(o[t], make_float2(cs, -sn));
+                        }
                     }
                     float2* dst = out + p * T + tl.ch0 + c * TCW;
                     const int n_valid = T - (tl.ch0 + c * TCW);   // tones of this chunk that exist
@@ -585,7 +589,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                     for (int j = 0; j < 8; ++j) {
                         const int k = kb_cur * TC_KC + 8 * half + j;
                         float2 a = make_float2(0.f, 0.f);
-                        if (k < M) a = (use_tma && s_row + j < TC_HIST_MAX) ? sh->hist[s_row + j] : dev_win_at(w, s_row + j);
+                        if (k < M) a = (use_tma && s_row + j < w.n_hist && s_row + j < TC_HIST_MAX) ? sh->hist[s_row + j] : dev_win_at(w, s_row + j);
                         v[2 * j] = a.x, v[2 * j + 1] = a.y;
                     }
                 }
@@ -710,27 +714,31 @@ TcEncodeTiledFn tc_encode_fn() {
     return fn;
 }
 
-// The `in` segment as a 2-D tensor [rows][2 M floats] (row pitch M * 8 bytes), box = 128 rows x 32 floats, 128-byte
-// swizzle: exactly the K-major operand tile of one K block.  Needs a 16-byte-aligned base and pitch.
-bool tc_make_tensor_map(const Window& w, int M, CUtensorMap* map) {
+// The part of the `in` segment that starts on a window-row boundary as a 2-D tensor [rows][2 M floats] (row pitch M * 8
+// bytes), box = 128 rows x 32 floats, 128-byte swizzle: exactly the K-major operand tile of one K block.  Needs a
+// 16-byte-aligned base and pitch.  *hist_rows = window rows that hold carried-over samples (ceil(n_hist / M)).
+bool tc_make_tensor_map(const Window& w, int M, CUtensorMap* map, long long* hist_rows) {
+    const long long hr = (w.n_hist + M - 1) / M, off0 = hr * M - w.n_hist;
+    *hist_rows = hr;
     const char* e = getenv("GSDR_DIRECT_TC_TMA");   // =0: every tile through the register path (tests)
     const bool off = e && e[0] == '0';
-    if (off || M < TC_KC || (M & 1) || w.n_hist % M != 0 || w.n_in < M || w.n_in % M != 0) return false;
-    if (reinterpret_cast<uintptr_t>(w.in) & 15) return false;
+    if (off || M < TC_KC || (M & 1) || w.n_in - off0 < M) return false;
+    const float2* base = w.in + off0;
+    if (reinterpret_cast<uintptr_t>(base) & 15) return false;
     TcEncodeTiledFn enc = tc_encode_fn();
     if (!enc) return false;
-    const cuuint64_t dims[2] = {(cuuint64_t)(2 * M), (cuuint64_t)(w.n_in / M)};
+    const cuuint64_t dims[2] = {(cuuint64_t)(2 * M), (cuuint64_t)((w.n_in - off0) / M)};
     const cuuint64_t strides[1] = {(cuuint64_t)M * 8};
     const cuuint32_t box[2] = {2 * TC_KC, TC_ROWS};
     const cuuint32_t estr[2] = {1, 1};
-    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(w.in), dims, strides, box, estr,
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(base), dims, strides, box, estr,
                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 template <int F>
 int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int M, int rate, long long pos0, long long n_out,
-              float2* out, int sm_count, cudaStream_t stream) {
+              float2* out, int sm_count, cudaStream_t stream, int rotate) {
     constexpr int TG = 64 / F, RB = TC_ROWS - (F - 1);
     const int row_tiles = (int)((n_out + RB - 1) / RB), tone_groups = (T + TG - 1) / TG;
     static bool attr_set = false;
@@ -740,7 +748,8 @@ int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int 
     }
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
-    const int use_tma = tc_make_tensor_map(w, M, &map) ? 1 : 0;
+    long long hist_rows = 0;
+    const int use_tma = tc_make_tensor_map(w, M, &map, &hist_rows) ? 1 : 0;
     const long long tiles = (long long)row_tiles * tone_groups;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
     // GSDR_DIRECT_TC_DEBUG=1: per-role wait / run cycles of this launch on stderr (synchronises; schedule tuning only)
@@ -750,8 +759,8 @@ int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int 
         GSDR_CUDA_OK(cudaMalloc(&dbg, 24 * sizeof(long long)));
         GSDR_CUDA_OK(cudaMemsetAsync(dbg, 0, 24 * sizeof(long long), stream));
     }
-    direct_fir_tc_kernel<F><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, use_tma, w, g, freq_dev, T, M, rate, pos0, n_out,
-                                                                         row_tiles, tone_groups, out, dbg);
+    direct_fir_tc_kernel<F><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, use_tma, hist_rows, rotate, w, g, freq_dev, T, M, rate,
+                                                                         pos0, n_out, row_tiles, tone_groups, out, dbg);
     GSDR_CUDA_OK(cudaGetLastError());
     if (dbg) {
         long long h[24];
@@ -794,17 +803,17 @@ bool direct_fir_tc_preferred(int T, int M, int ntaps, long long n_out) {
 }
 
 int direct_fir_tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int M, int ntaps, int rate, long long pos0,
-                         long long n_out, float2* out, int sm_count, cudaStream_t stream) {
+                         long long n_out, float2* out, int sm_count, cudaStream_t stream, int rotate) {
     if (n_out <= 0) return 0;
     if (!direct_fir_tc_supported(T, M, ntaps, n_out)) {
         set_error("direct_fir_tc_launch: unsupported shape (T=%d M=%d ntaps=%d)", T, M, ntaps);
         return -1;
     }
     switch (ntaps / M) {
-        case 1: return tc_launch<1>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream);
-        case 2: return tc_launch<2>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream);
-        case 4: return tc_launch<4>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream);
-        default: return tc_launch<8>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream);
+        case 1: return tc_launch<1>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate);
+        case 2: return tc_launch<2>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate);
+        case 4: return tc_launch<4>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate);
+        default: return tc_launch<8>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate);
     }
 }
 

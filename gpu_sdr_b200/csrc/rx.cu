@@ -101,6 +101,7 @@ struct gsdr_rx {
     float2* d_spec_acc = nullptr;
     int spec_carried = 0;
     bool post_decim = false;  // NOISE with decim > 0, TONES with decim > 1
+    bool pfb_tc = false;      // channelizer size without a fused kernel: the filter bank as a GEMM on the tensor cores
     int batching = 0, T_sel = 0;
     bool fused = false;
     gsdr_buffer_helper bh{};
@@ -211,6 +212,29 @@ int init_pfb(gsdr_rx* rx, bool all_bins) {
     } else {
         auto tw = generic_twiddles(N);
         if (dev_upload(&rx->d_tw, tw.data(), tw.size())) return -1;
+        // Any channel count the fused kernel does not cover (the pyUSRP client sets fft_tones to its decimation factor,
+        // pyUSRP/USRP_noise.py:509-521): the channelizer IS a bank of decimating complex FIRs,
+        //     out[b][u] = sum_{i<P} sum_{k<N} x[(b+i)N + k] * ( w[iN+k] e^{-2 pi j k bin_u / N} ),
+        // i.e. DIRECT with decim = N, pf_average = P, per-tone taps g_u[m] = w[m] e^{-2 pi j (m bin_u mod N)/N} and no LO
+        // rotation (whole turns per frame) -- direct_fir_tc_kernel runs it as a 3xTF32 GEMM on the tensor cores instead of
+        // an O(N T) DFT on the CUDA cores.  GSDR_PFB_VARIANT=generic keeps the CUDA-core pair (cross-checks).
+        const char* e = getenv("GSDR_PFB_VARIANT");
+        const size_t n_g = (size_t)rx->T_sel * N * P;
+        if (!(e && !strcmp(e, "generic")) && n_g <= (size_t)32 << 20 && direct_fir_tc_supported(rx->T_sel, N, N * P, 1)) {
+            std::vector<float2> g(n_g);
+            const double two_pi = 6.283185307179586476925286766559;
+            for (int u = 0; u < rx->T_sel; ++u) {
+                const long long bin = all_bins ? u : rx->bins_host[u];
+                for (int m = 0; m < N * P; ++m) {
+                    const double a = -two_pi * (double)((bin * m) % N) / (double)N;
+                    const double h = rx->taps_host[m];
+                    g[(size_t)u * N * P + m] = make_float2((float)(h * std::cos(a)), (float)(h * std::sin(a)));
+                }
+            }
+            if (dev_upload(&rx->d_g, g.data(), g.size())) return -1;
+            rx->pfb_tc = true;
+            rx->kernel_name = "direct_fir_tc_kernel (filter bank as GEMM)";
+        }
     }
     rx->hist_cap = (long long)N * P + 16;
     rx->max_out = (size_t)rx->T_sel * rx->batching;
@@ -365,7 +389,7 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
                 return -1;
             }
             PfbJob job{w, rx->d_taps, rx->d_bins, d_out, 0, (int)frames, rx->N, (int)rx->P, rx->T_sel, rx->d_xperm};
-            if (!rx->fused) {
+            if (!rx->fused && !rx->pfb_tc) {
                 const size_t need = pfb_workspace_bytes(rx->N, (int)rx->P, (int)frames);
                 if (need > rx->work_bytes) {
                     if (rx->d_work) cudaFree(rx->d_work);
@@ -377,7 +401,9 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
                     rx->work_bytes = need;
                 }
             }
-            const int nl = pfb_launch(&job, 1, nullptr, rx->d_work, rx->d_tw, rx->sm_count, st);
+            const int nl = rx->pfb_tc ? direct_fir_tc_launch(w, rx->d_g, nullptr, rx->T_sel, rx->N, rx->N * (int)rx->P, 1, 0, frames, d_out,
+                                                             rx->sm_count, st, /*rotate=*/0)
+                                      : pfb_launch(&job, 1, nullptr, rx->d_work, rx->d_tw, rx->sm_count, st);
             if (nl < 0) return -1;
             rx->launches += nl;
             if (spec_decim) {

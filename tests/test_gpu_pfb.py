@@ -61,6 +61,15 @@ def test_cfg2_full_size_eight_buffers():
 def test_generic_path_vs_oracle(N, P, T, L, rate):
     p = pfb_param(rate=rate, N=N, P=P, T=T, L=L)
     bufs = [tone_stream(rate, p.freq, p.ampl, i * L, L) for i in range(3)]
+    # pf_average in {1,2,4,8}: the filter bank runs as a GEMM on the tensor cores; otherwise the CUDA-core FIR + DFT pair
+    check_against_oracle(p, bufs, "direct_fir_tc_kernel" if P in (1, 2, 4, 8) else "generic")
+
+
+@pytest.mark.parametrize("N,P,T,L,rate", [(64, 4, 8, 20_000, 1_000_000), (1000, 2, 100, 60_000, 100_000_000)])
+def test_generic_cuda_core_pair_still_matches(N, P, T, L, rate, monkeypatch):
+    monkeypatch.setenv("GSDR_PFB_VARIANT", "generic")
+    p = pfb_param(rate=rate, N=N, P=P, T=T, L=L)
+    bufs = [tone_stream(rate, p.freq, p.ampl, i * L, L) for i in range(3)]
     check_against_oracle(p, bufs, "generic")
 
 
