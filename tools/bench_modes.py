@@ -65,7 +65,16 @@ def main():
     run_rx("TONES N=2048 P=2 T=100 (fused)", pfb_param(P=2, T=100), 64, 8 + 8 * 100 / 2048)
     run_rx("NOISE N=2048 P=4 full spectrum (fused)", g.param(rate=200_000_000, fft_tones=2048, pf_average=4, buffer_len=1_000_000,
                                                               freq=[0], wave_type=[g.NOISE], ampl=[1.0]), 32, 16.0)
-    run_rx("TONES N=1000 P=4 T=100 (generic)", pfb_param(rate=100_000_000, N=1000, P=4, T=100), 8, 8 + 8 * 100 / 1000, steps=5)
+    # channel counts without a fused kernel (the pyUSRP client sets fft_tones = its decimation factor): the filter bank as a
+    # GEMM on the tensor cores (default) against the CUDA-core FIR + DFT pair (GSDR_PFB_VARIANT=generic)
+    for variant in ("tc", "generic"):
+        if variant == "generic":
+            os.environ["GSDR_PFB_VARIANT"] = "generic"
+        run_rx(f"TONES N=100 P=4 T=16 [{variant}]", pfb_param(rate=100_000_000, N=100, P=4, T=16), 8, 8 + 8 * 16 / 100, steps=5,
+               extra=lambda r: {"fp32_equiv_TFLOPs": r["input_MSps"] * 1e6 * 8 * 4 * 16 / 1e12})
+        run_rx(f"TONES N=1000 P=4 T=100 [{variant}]", pfb_param(rate=100_000_000, N=1000, P=4, T=100), 8, 8 + 8 * 100 / 1000, steps=5,
+               extra=lambda r: {"fp32_equiv_TFLOPs": r["input_MSps"] * 1e6 * 8 * 4 * 100 / 1e12})
+    os.environ.pop("GSDR_PFB_VARIANT", None)
     # cfg1 DIRECT: 16*T real FMA per input sample.  Default = tensor-core kernel (tcgen05, 3xTF32 split GEMM) where the
     # shape fills the GPU and decim <= 128; GSDR_DIRECT_VARIANT=fp32 forces the CUDA-core kernel for comparison.
     T = 16
