@@ -65,7 +65,7 @@ constexpr unsigned int TC_COL_CORR = 128;          // main(0) at 0, corr at 128,
 constexpr unsigned int TC_COL_A = 384;             // A stage g: hi at +64 g, lo at +64 g + 32
 constexpr int TC_L2_AHEAD = 8;                     // K blocks between the L2 prefetch of a box and its TMA load
 constexpr int TC_B_PER_THREAD = (TC_N / 2) * TC_KC / (32 * TC_LOAD_WARPS);   // 4 filter taps
-constexpr int TC_SEG = 8;                          // K blocks per accumulation segment: 32 k-steps per tensor-core chain
+constexpr int TC_SEG_MAX = 8;                      // K blocks per accumulation segment: at most 32 k-steps per tensor-core chain
 constexpr int TC_HIST_MAX = 7 * 128;               // carried-over samples kept in shared memory (the rest is read from global)
 static_assert((TC_EPI_WARPS + 1) % 4 == 1 && TC_GROUP_WARPS == 4, "producer warp w owns TMEM lane quarter w % 4");
 
@@ -248,7 +248,7 @@ template <int F>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma, const long long hist_rows, const int rotate,
                      const Window w, const float2* __restrict__ g, const int* __restrict__ freq, int T, int M, int rate,
-                     long long pos0, long long n_out, int n_row_tiles, int n_tone_groups, float2* __restrict__ out,
+                     long long pos0, long long n_out, int n_row_tiles, int n_tone_groups, const int TC_SEG, float2* __restrict__ out,
                      long long* __restrict__ dbg) {
     constexpr int TG = 64 / F;
     constexpr int RB = TC_ROWS - (F - 1);
@@ -347,7 +347,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                 }
                 sh->ph[threadIdx.x] = make_double2(base, step);
             }
-            // The tensor core's accumulate truncates, so a chain is cut after TC_SEG K blocks (32 k-steps): every segment
+            // The tensor core's accumulate truncates, so a chain is cut after TC_SEG K blocks (at most 32 k-steps): every segment
             // is a separate accumulation, handed over like a tile (as = segment counter & 1), and the segments of a tile
             // are added here in fp32 (round to nearest), through a [column][row] array in shared memory.
             unsigned int as = 0, t_main = 0;
@@ -759,8 +759,15 @@ int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int 
         GSDR_CUDA_OK(cudaMalloc(&dbg, 24 * sizeof(long long)));
         GSDR_CUDA_OK(cudaMemsetAsync(dbg, 0, 24 * sizeof(long long), stream));
     }
+    // GSDR_DIRECT_TC_SEG = 1..8: K blocks (of 16 taps) per accumulation chain.  Shorter chains cost folds and the 12-MMA first
+    // K block of every segment, and buy accuracy: the chain's truncating accumulate is the kernel's largest error term.
+    int seg = TC_SEG_MAX;
+    if (const char* se = getenv("GSDR_DIRECT_TC_SEG")) {
+        const int v = atoi(se);
+        if (v >= 1 && v <= TC_SEG_MAX) seg = v;
+    }
     direct_fir_tc_kernel<F><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, use_tma, hist_rows, rotate, w, g, freq_dev, T, M, rate,
-                                                                         pos0, n_out, row_tiles, tone_groups, out, dbg);
+                                                                         pos0, n_out, row_tiles, tone_groups, seg, out, dbg);
     GSDR_CUDA_OK(cudaGetLastError());
     if (dbg) {
         long long h[24];
