@@ -1,4 +1,4 @@
-// DIRECT-mode demodulator on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
+// DIRECT-mode demodulator (and generic-size channelizer) on the 5th-generation tensor cores (tcgen05 + TMEM), sm_100a only.
 //
 // Same function as direct_fir_tiled_kernel (direct_kernels.cu), i.e. the reference's
 // direct_demodulator_integer + T x FIR::run_fir + cublasCgeam (cpp/kernels.cu:45-86, cpp/fir.cu:44-88,
@@ -15,6 +15,14 @@
 // operands are split x = hi + lo (hi = x rounded to TF32, lo = x - hi, exact) and three MMAs are issued per k-step:
 // hi*hi into the `main` TMEM accumulator, lo*hi + hi*lo into a second one (`corr`: kept apart so that the small
 // terms do not add truncating accumulation steps to the long chain); the dropped lo*lo term is 2^-22 relative.
+//
+// The tensor core's accumulate truncates (about 1.6e-7 relative per accumulated k-step when all terms have one sign), so
+// a chain is cut after at most 32 k-steps (8 K blocks of 16 taps): each such SEGMENT is a separate accumulation and the
+// epilogue adds the segments of a tile in fp32 -- any decimation runs here, not only decim <= 128.
+//
+// The same kernel with rotate = 0 is the polyphase channelizer for every channel count that has no fused FFT kernel: a
+// PFB followed by a DFT of which T bins are kept is DIRECT with decim = N, F = P and taps w[m] e^{-2 pi j m bin / N}
+// (rx.cu, init_pfb).
 //
 // What bounds the kernel is shared-memory bandwidth (128 B/clk/SM), which the operand fetch of tcgen05.mma shares
 // with TMA writes and LDS/STS.  So the A operand (the samples) is fed from TENSOR MEMORY, written there by the
