@@ -450,11 +450,17 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     args.steps = max(args.steps, 1)
+    # stdout carries exactly ONE JSON line: whatever a library prints to file descriptor 1 (NCCL's version banner does,
+    # whatever NCCL_DEBUG_FILE says) is sent to stderr, and the result goes to the saved descriptor.
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     dd = Dist(args.gpus)
     try:
         res = run_reference(args, dd) if args.impl == "reference" else run_ours(args, dd)
         if dd.rank == 0 and res is not None:
-            print(json.dumps(res), flush=True)
+            sys.stdout.flush()
+            os.write(json_fd, (json.dumps(res) + "\n").encode())
     finally:
         dd.close()
 
