@@ -735,7 +735,16 @@ int gsdr_rx_pipeline_depth(const gsdr_rx* rx) { return rx ? (int)(rx->slots.empt
 // 3.9 MB down); this makes the unchanged blocking drop-in call run at the speed of the slower PCIe direction.
 // Results are identical to the one-launch path: same frames, same kernel, same carry-over.
 static int process_pfb_chunked(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* out) {
-    constexpr int kChunks = 4;
+    // Upload chunks per call.  More chunks shorten the tail (the last chunk's kernel + download) but cost ~6 API calls each,
+    // and on this pool's hosts those dominate: measured per 1e6-sample buffer (8 MB up, 3.9 MB down) 1 chunk 259 us, 2 chunks
+    // 228 us, 4 chunks 242 us, 8 chunks 272 us, 16 chunks 316 us.  GSDR_PROCESS_CHUNKS overrides.  (Storing the tones straight
+    // into the mapped pinned output buffer instead of copying them was tried: same times -- the call is bound by the upload
+    // plus the cross-stream hand-offs, not by the number of API calls.)
+    static const int kChunks = [] {
+        const char* e = getenv("GSDR_PROCESS_CHUNKS");
+        const int v = e ? atoi(e) : 0;
+        return (v >= 1 && v <= 32) ? v : 2;
+    }();
     const long long L = rx->L, N = rx->N, P = rx->P;
     Slot& s = rx->slots[0];
     if (s.used) GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));
