@@ -252,11 +252,11 @@ struct TcTile {
 };
 
 // F = FIR blocks (pf_average); TG = 64 / F tones per group; outputs per tile = 128 - (F - 1)
-template <int F>
+template <int F, bool rotate>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma, const long long hist_rows, const int rotate,
+direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma, const long long hist_rows,
                      const Window w, const float2* __restrict__ g, const int* __restrict__ freq, int T, int M, int rate,
-                     long long pos0, long long n_out, int n_row_tiles, int n_tone_groups, const int TC_SEG, float2* __restrict__ out,
+                     long long pos0, long long n_out, int n_row_tiles, int n_tone_groups, const int seg_shift, float2* __restrict__ out,
                      long long* __restrict__ dbg) {
     constexpr int TG = 64 / F;
     constexpr int RB = TC_ROWS - (F - 1);
@@ -275,7 +275,8 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
     const int ntaps = F * M;
     const int KB = (M + TC_KC - 1) / TC_KC;           // K blocks per tile
     const int ksteps_total = (M + 3) / 4;             // MMA k-steps (4 complex taps = 8 tf32) per tile
-    const int NSEG = (KB + TC_SEG - 1) / TC_SEG;      // accumulation segments per tile (1 for decim <= 128)
+    const int TC_SEG = 1 << seg_shift;                // K blocks per accumulation segment (1, 2, 4 or 8)
+    const int NSEG = (KB + TC_SEG - 1) >> seg_shift;  // accumulation segments per tile (1 for decim <= 128 at the default 8)
     const int n_tiles = n_row_tiles * n_tone_groups;
     const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const bool timed = dbg != nullptr;
@@ -497,7 +498,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                 tc_fence_after();
                 const unsigned int d_main = tmem_base + as * 256u, d_corr = tmem_base + TC_COL_CORR;
                 const unsigned int d_wide = tmem_base + as * 128u;   // [main(0) | corr] or [corr | main(1)]
-                const int kb0 = sgi * TC_SEG, kb1 = min(KB, kb0 + TC_SEG);
+                const int kb0 = sgi << seg_shift, kb1 = min(KB, kb0 + TC_SEG);
                 for (int kb = kb0; kb < kb1; ++kb, ++it) {
                     const int gst = it & 1;
                     mbar_wait_t(smem_u32(&sh->full[gst]), (unsigned)(it >> 1) & 1u, w_acc0, timed);
@@ -607,7 +608,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                 tmem_st16(a_tmem0 + 64u * st, hi);
                 tmem_st16(a_tmem0 + 64u * st + 32u, lo);
             }
-            const int b_hi_off = ((n_cur * NSEG + kb_cur / TC_SEG) & 1) ? TC_B_BYTES / 2 : 0;   // accumulator order of this K block's segment: [main(0) | corr], [corr | main(1)]
+            const int b_hi_off = ((n_cur * NSEG + (kb_cur >> seg_shift)) & 1) ? TC_B_BYTES / 2 : 0;   // accumulator order of this K block's segment: [main(0) | corr], [corr | main(1)]
             const long long tp1 = timed ? clock64() : 0;
             mbar_arrive(smem_u32(&sh->raw_empty[r]));   // this thread's reads of the landing slot are complete (values consumed)
             unsigned char* const bst = smem_b + (size_t)st * TC_B_BYTES;
@@ -751,7 +752,8 @@ int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int 
     const int row_tiles = (int)((n_out + RB - 1) / RB), tone_groups = (T + TG - 1) / TG;
     static bool attr_set = false;
     if (!attr_set) {
-        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_tc_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_tc_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
+        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_tc_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
         attr_set = true;
     }
     CUtensorMap map;
@@ -767,15 +769,19 @@ int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int 
         GSDR_CUDA_OK(cudaMalloc(&dbg, 24 * sizeof(long long)));
         GSDR_CUDA_OK(cudaMemsetAsync(dbg, 0, 24 * sizeof(long long), stream));
     }
-    // GSDR_DIRECT_TC_SEG = 1..8: K blocks (of 16 taps) per accumulation chain.  Shorter chains cost folds and the 12-MMA first
+    // GSDR_DIRECT_TC_SEG = 1, 2, 4 or 8: K blocks (of 16 taps) per accumulation chain.  Shorter chains cost folds and the 12-MMA first
     // K block of every segment, and buy accuracy: the chain's truncating accumulate is the kernel's largest error term.
-    int seg = TC_SEG_MAX;
+    int seg_shift = 3;   // 8 K blocks = TC_SEG_MAX
     if (const char* se = getenv("GSDR_DIRECT_TC_SEG")) {
         const int v = atoi(se);
-        if (v >= 1 && v <= TC_SEG_MAX) seg = v;
+        if (v == 1 || v == 2 || v == 4 || v == 8) seg_shift = v == 1 ? 0 : v == 2 ? 1 : v == 4 ? 2 : 3;
     }
-    direct_fir_tc_kernel<F><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, use_tma, hist_rows, rotate, w, g, freq_dev, T, M, rate,
-                                                                         pos0, n_out, row_tiles, tone_groups, seg, out, dbg);
+    if (rotate)
+        direct_fir_tc_kernel<F, true><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, use_tma, hist_rows, w, g, freq_dev, T, M, rate, pos0,
+                                                                                   n_out, row_tiles, tone_groups, seg_shift, out, dbg);
+    else
+        direct_fir_tc_kernel<F, false><<<grid, TC_THREADS, TC_SMEM_BYTES, stream>>>(map, use_tma, hist_rows, w, g, freq_dev, T, M, rate, pos0,
+                                                                                    n_out, row_tiles, tone_groups, seg_shift, out, dbg);
     GSDR_CUDA_OK(cudaGetLastError());
     if (dbg) {
         long long h[24];
