@@ -69,6 +69,11 @@ struct PfbJob {          // one stream's share of a launch
     int n_frames;
     int N, P, T;
     const unsigned char* xperm = nullptr;  // [2048] in-row position of each bin (pfb_gather_coloring); nullptr => k2
+    // Carry-over of a single-stream launch: the last tail_n samples of the window go to tail_dst (the other half of the
+    // history ping-pong).  The warp-specialised fused kernel does this copy itself (its last CTA has the short remainder
+    // tile), which saves the separate window_tail_kernel launch; every other path copies after its kernels.
+    float2* tail_dst = nullptr;
+    long long tail_n = 0;
 };
 // Returns the number of kernel launches issued (>0) or -1.  `workspace` is device scratch of at
 // least pfb_workspace_bytes() for the generic path (may be null for the fused path).

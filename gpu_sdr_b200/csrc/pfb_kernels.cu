@@ -522,6 +522,12 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
             mbar_init(xempty0 + 8 * i, WS_FRONT / 32);
         }
     }
+    // carry-over of a single-stream launch (what move_buffer does in the reference, cpp/kernels.cu:444-470): the CTA with
+    // the last, shorter tile copies the window's tail into the other history buffer -- input only, nothing here reads it
+    if (n_jobs == 1 && single.tail_dst != nullptr && blockIdx.x == gridDim.x - 1) {
+        const long long first = single.win.n_hist + single.win.n_in - single.tail_n;
+        for (long long i = t; i < single.tail_n; i += WS_THREADS) single.tail_dst[i] = win_at(single.win, first + i);
+    }
     __syncthreads();
     // frame number n (per CTA) -> team n & 1, that team's frame c = n >> 1, tile c % WP_XB, use c / WP_XB of the tile
 
@@ -1085,22 +1091,32 @@ int pfb_launch(const PfbJob* jobs, int n_jobs, void* scratch, void* workspace, c
     bool fused = true;
     for (int j = 0; j < n_jobs; ++j)
         fused = fused && pfb_fused_supported(jobs[j].N, jobs[j].P, jobs[j].T, jobs[j].win) && jobs[j].P == jobs[0].P;
+    // carry-over requested through the job (single stream): done by the warp-specialised kernel itself, else copied here
+    auto tail_after = [&](int nl, bool kernel_did_it) {
+        if (nl < 0 || n_jobs != 1 || !jobs[0].tail_dst || jobs[0].tail_n <= 0 || kernel_did_it) return nl;
+        const int tl = window_tail_copy(jobs[0].win, jobs[0].tail_n, jobs[0].tail_dst, stream);
+        return tl < 0 ? -1 : nl + tl;
+    };
     if (fused && pfb_variant() == 1) {
         const float2* tws = tw + FTW1 + FTW2;
+        int nl;
         switch (jobs[0].P) {
-            case 1: return launch_ws<1>(jobs, n_jobs, scratch, tws, sm_count, stream);
-            case 2: return launch_ws<2>(jobs, n_jobs, scratch, tws, sm_count, stream);
-            case 3: return launch_ws<3>(jobs, n_jobs, scratch, tws, sm_count, stream);
-            default: return launch_ws<4>(jobs, n_jobs, scratch, tws, sm_count, stream);
+            case 1: nl = launch_ws<1>(jobs, n_jobs, scratch, tws, sm_count, stream); break;
+            case 2: nl = launch_ws<2>(jobs, n_jobs, scratch, tws, sm_count, stream); break;
+            case 3: nl = launch_ws<3>(jobs, n_jobs, scratch, tws, sm_count, stream); break;
+            default: nl = launch_ws<4>(jobs, n_jobs, scratch, tws, sm_count, stream); break;
         }
+        return tail_after(nl, nl > 0);   // nl == 0: no frames, no launch
     }
     if (fused) {
+        int nl;
         switch (jobs[0].P) {
-            case 1: return launch_fused<1>(jobs, n_jobs, scratch, tw, sm_count, stream);
-            case 2: return launch_fused<2>(jobs, n_jobs, scratch, tw, sm_count, stream);
-            case 3: return launch_fused<3>(jobs, n_jobs, scratch, tw, sm_count, stream);
-            default: return launch_fused<4>(jobs, n_jobs, scratch, tw, sm_count, stream);
+            case 1: nl = launch_fused<1>(jobs, n_jobs, scratch, tw, sm_count, stream); break;
+            case 2: nl = launch_fused<2>(jobs, n_jobs, scratch, tw, sm_count, stream); break;
+            case 3: nl = launch_fused<3>(jobs, n_jobs, scratch, tw, sm_count, stream); break;
+            default: nl = launch_fused<4>(jobs, n_jobs, scratch, tw, sm_count, stream); break;
         }
+        return tail_after(nl, false);
     }
     int launches = 0;
     for (int j = 0; j < n_jobs; ++j) {
@@ -1120,7 +1136,7 @@ int pfb_launch(const PfbJob* jobs, int n_jobs, void* scratch, void* workspace, c
         GSDR_CUDA_OK(cudaGetLastError());
         launches += 2;
     }
-    return launches;
+    return tail_after(launches, false);
 }
 
 // acc: device buffer of 2*N float2 (running sum + staging).  Returns launches or -1.

@@ -389,6 +389,10 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
                 return -1;
             }
             PfbJob job{w, rx->d_taps, rx->d_bins, d_out, 0, (int)frames, rx->N, (int)rx->P, rx->T_sel, rx->d_xperm};
+            if (!rx->pfb_tc) {   // the channelizer launch carries the carry-over copy (fused kernel: inside the kernel)
+                job.tail_dst = rx->hist[rx->hist_cur ^ 1];
+                job.tail_n = tail;
+            }
             if (!rx->fused && !rx->pfb_tc) {
                 const size_t need = pfb_workspace_bytes(rx->N, (int)rx->P, (int)frames);
                 if (need > rx->work_bytes) {
@@ -413,9 +417,11 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
                 rx->launches += dl;
                 rx->spec_carried = carried;
             }
-            const int tl = window_tail_copy(w, tail, rx->hist[rx->hist_cur ^ 1], st);
-            if (tl < 0) return -1;
-            rx->launches += tl;
+            if (rx->pfb_tc) {
+                const int tl = window_tail_copy(w, tail, rx->hist[rx->hist_cur ^ 1], st);
+                if (tl < 0) return -1;
+                rx->launches += tl;
+            }
             rx->hist_cur ^= 1;
             rx->n_hist = tail;
             break;
