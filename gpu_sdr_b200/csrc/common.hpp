@@ -74,6 +74,10 @@ struct PfbJob {          // one stream's share of a launch
     // tile), which saves the separate window_tail_kernel launch; every other path copies after its kernels.
     float2* tail_dst = nullptr;
     long long tail_n = 0;
+    // Launch hint (host side only): lower bound on the frames per tile.  Set when the window lives in pinned HOST memory
+    // (zero-copy blocking call): reads over PCIe are not kept in L2, so the P-1 halo rows at every tile start are paid in
+    // full and few long tiles beat one short tile per SM.
+    int min_tile = 0;
 };
 // Returns the number of kernel launches issued (>0) or -1.  `workspace` is device scratch of at
 // least pfb_workspace_bytes() for the generic path (may be null for the fused path).

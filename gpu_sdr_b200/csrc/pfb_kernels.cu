@@ -1034,6 +1034,15 @@ static int launch_ws(const PfbJob* jobs, int n_jobs, void* scratch, const float2
     if (total_frames == 0) return 0;
     int frames_per_tile = (int)((total_frames + sm_count - 1) / sm_count);
     if (frames_per_tile < 1) frames_per_tile = 1;
+    {   // experiment hook: a lower bound on the tile length (fewer, longer tiles: less halo re-read per frame)
+        static int min_tile = -1;
+        if (min_tile < 0) {
+            const char* e = getenv("GSDR_PFB_MIN_TILE");
+            min_tile = e ? atoi(e) : 0;
+        }
+        if (min_tile > frames_per_tile) frames_per_tile = min_tile;
+        if (min_tile == 0 && n_jobs == 1 && jobs[0].min_tile > frames_per_tile) frames_per_tile = jobs[0].min_tile;
+    }
     std::vector<int> tile_begin(n_jobs + 1, 0);
     // Tiles never span two streams, so with several jobs the per-job round-up can push the tile count
     // just past one wave (152 tiles on 148 SMs doubles the makespan): grow the tile until one wave holds it.

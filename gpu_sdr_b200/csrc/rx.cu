@@ -14,6 +14,7 @@
 #include <cmath>
 #include <memory>
 #include <mutex>
+#include <unordered_map>
 
 #include "common.hpp"
 
@@ -104,6 +105,8 @@ struct gsdr_rx {
     bool pfb_tc = false;      // channelizer size without a fused kernel: the filter bank as a GEMM on the tensor cores
     int batching = 0, T_sel = 0;
     bool fused = false;
+    std::unordered_map<const void*, void*> alias_cache;  // GSDR_PROCESS_PTRCACHE=1: host buffer -> device alias (nullptr = pageable)
+    bool host_window = false;  // this call's input window is pinned host memory read in place (zero-copy blocking call)
     gsdr_buffer_helper bh{};
 
     // CHIRP
@@ -392,6 +395,10 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
             if (!rx->pfb_tc) {   // the channelizer launch carries the carry-over copy (fused kernel: inside the kernel)
                 job.tail_dst = rx->hist[rx->hist_cur ^ 1];
                 job.tail_n = tail;
+            }
+            if (rx->host_window) {  // about eight CTAs keep the PCIe read pipe full; at most 64 frames each (halo 3/64)
+                const long long per8 = (frames + 7) / 8;
+                job.min_tile = (int)(per8 < 64 ? per8 : 64);
             }
             if (!rx->fused && !rx->pfb_tc) {
                 const size_t need = pfb_workspace_bytes(rx->N, (int)rx->P, (int)frames);
@@ -813,6 +820,35 @@ static int process_pfb_chunked(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* 
     return len;
 }
 
+// Device-side alias of a pinned (page-locked, mapped) host pointer, or nullptr when the memory is pageable / not mapped.
+static void* mapped_alias(const void* host) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
+// Blocking call, fused filter bank, zero-copy form (the default when both buffers are pinned and mapped; GSDR_PROCESS_ZEROCOPY=0
+// turns it off): ONE kernel launch whose loads read the caller's pinned input buffer over PCIe and whose stores write the
+// tones into the caller's pinned output buffer, so both PCIe directions run concurrently under a single launch and no
+// copy-engine call or cross-stream hand-off is made.  Same kernel, same frames, same carry-over as every other entry point
+// (outputs bit-identical).  Measured per 1e6-sample buffer on B200 (tools/process_latency.py, profiles/r1_process_latency.jsonl):
+// chunked copies 229 us; zero-copy with one 4-frame tile per SM 328 us (reads from host memory are not kept in L2, so the
+// three halo rows of every tile cross PCIe again: 1.75x the bytes); with 8 / 16 / 32 / 64 / 128-frame tiles 261 / 227 / 205 /
+// 195 / 257 us (128: four CTAs no longer keep the read pipe full).  All of them sit on ~43 GB/s of PCIe reads.
+static int process_pfb_zerocopy(gsdr_rx* rx, const float2* in_alias, float2* out_alias) {
+    int len = 0;
+    rx->host_window = true;
+    const long long total = enqueue_compute(rx, in_alias, 1, out_alias, &len);
+    rx->host_window = false;
+    if (total < 0) return -1;
+    rx->tickets++;
+    GSDR_CUDA_OK(cudaStreamSynchronize(rx->s_comp));
+    return len;
+}
+
 int gsdr_rx_process(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* out) {
     if (rx && in && out && rx->fused && !rx->slots.empty() && rx->L >= 64LL * rx->N &&
         (rx->mode == GSDR_TONES || rx->mode == GSDR_NOISE) && !rx->post_decim) {
@@ -820,6 +856,25 @@ int gsdr_rx_process(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* out) {
         // keep the ticket/slot rotation of submit() intact: the blocking path always uses slot 0 and leaves every slot idle
         for (auto& sl : rx->slots)
             if (sl.used) GSDR_CUDA_OK(cudaEventSynchronize(sl.out_done));
+        const char* zc = getenv("GSDR_PROCESS_ZEROCOPY");  // read per call (a few ns) so one process can compare both forms
+        if (!(zc && zc[0] == '0')) {
+            // GSDR_PROCESS_PTRCACHE=1: remember the answer per buffer address (pool buffers come back every few calls).  Opt-in:
+            // it assumes what the reference's pool guarantees -- a buffer handed to process() stays pinned while this
+            // demodulator lives -- and a cudaHostUnregister behind our back would leave a stale alias.
+            const char* pc = getenv("GSDR_PROCESS_PTRCACHE");
+            const bool use_cache = pc && pc[0] == '1';
+            auto alias_of = [&](const void* h) -> void* {
+                if (!use_cache) return mapped_alias(h);
+                auto it = rx->alias_cache.find(h);
+                if (it != rx->alias_cache.end()) return it->second;
+                void* a = mapped_alias(h);
+                if (rx->alias_cache.size() < 4096) rx->alias_cache.emplace(h, a);
+                return a;
+            };
+            void* ia = alias_of(in);
+            void* oa = alias_of(out);
+            if (ia && oa) return process_pfb_zerocopy(rx, static_cast<const float2*>(ia), static_cast<float2*>(oa));
+        }
         return process_pfb_chunked(rx, in, out);
     }
     int len = 0;

@@ -230,3 +230,47 @@ def test_packet_frame_in_place_is_one_contiguous_wire_frame():
     assert np.reshape(data, (4000 // 8, 8)).T.shape == (8, 500)
     pool.trash(buf)
     pool.close()
+
+
+@pytest.mark.parametrize("L,T,mode", [(1_000_000, 1000, "tones"), (200_000, 17, "tones"), (131_073, 40, "tones"), (200_000, 0, "noise")])
+def test_blocking_process_zero_copy_equals_copied(L, T, mode, monkeypatch):
+    """Blocking process() on pinned buffers runs ONE kernel that reads the caller's input and writes the caller's output in
+    place over PCIe (gsdr_rx_process, zero-copy form); with GSDR_PROCESS_ZEROCOPY=0, or pageable buffers, the same call
+    uploads / launches / downloads in chunks.  Same kernel and frames: outputs and valid lengths must be bit-identical,
+    carry-over included (5 consecutive buffers), and the input must not be modified."""
+    if mode == "noise":
+        p = g.param(mode="RX", rate=200_000_000, fft_tones=2048, pf_average=4, buffer_len=L, decim=0, freq=[0], wave_type=[g.NOISE], ampl=[1.0])
+    else:
+        p = pfb_param(N=2048, P=4, T=T, L=L)
+    rng = np.random.default_rng(21)
+    bufs = [(0.1 * (rng.standard_normal(L) + 1j * rng.standard_normal(L))).astype(np.complex64) for _ in range(5)]
+
+    def run(pinned_in):
+        rx = g.RX_buffer_demodulator(p)
+        pool_in = g.preallocator(L, 4)           # pool buffers: interior pointers of a pinned allocation (headroom in front)
+        out = g.pinned_empty(rx.max_output())
+        res, launches = [], []
+        for x in bufs:
+            hin = pool_in.get() if pinned_in else x.copy()
+            hin[:] = x
+            l0 = rx.launch_count()
+            n = rx.process(hin, out)
+            launches.append(rx.launch_count() - l0)
+            assert np.array_equal(hin, x)
+            res.append(out[:n].copy())
+            if pinned_in:
+                pool_in.trash(hin)
+        rx.close()
+        pool_in.close()
+        g.pinned_free(out)
+        return res, launches
+
+    zc, zc_launches = run(True)
+    assert zc_launches == [1] * 5, zc_launches      # one launch per buffer, carry-over copy included
+    pageable, _ = run(False)                        # pageable input: falls back to the copied form
+    monkeypatch.setenv("GSDR_PROCESS_ZEROCOPY", "0")
+    copied, copied_launches = run(True)
+    assert max(copied_launches) >= 2
+    for a, b, c in zip(zc, copied, pageable):
+        assert len(a) == len(b) == len(c) and len(a) > 0
+        assert np.array_equal(a, b) and np.array_equal(a, c)
