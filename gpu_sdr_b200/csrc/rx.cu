@@ -396,9 +396,14 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
                 job.tail_dst = rx->hist[rx->hist_cur ^ 1];
                 job.tail_n = tail;
             }
-            if (rx->host_window) {  // about eight CTAs keep the PCIe read pipe full; at most 64 frames each (halo 3/64)
-                const long long per8 = (frames + 7) / 8;
-                job.min_tile = (int)(per8 < 64 ? per8 : 64);
+            if (rx->host_window) {
+                // Tile length when the window is read over PCIe: the largest power of two that still leaves six CTAs, at most
+                // 128 frames.  Measured (tools/process_latency.py, B200, us per buffer): 488 frames (buffer_len 1e6): 4 (one
+                // tile per SM) 328, 8: 261, 16: 227, 32: 205, 48: 199, 61: 206-208, 64: 195, 80: 199, 96: 216, 128: 257;
+                // 2929 frames (6e6): 64: 1044, 128: 1018, 256: 1018; 97 frames (2e5): 13: 73, 16: 65, 32: 84.
+                long long tile = 1;
+                while (tile * 2 * 6 <= frames && tile < 128) tile *= 2;
+                job.min_tile = (int)tile;
             }
             if (!rx->fused && !rx->pfb_tc) {
                 const size_t need = pfb_workspace_bytes(rx->N, (int)rx->P, (int)frames);
