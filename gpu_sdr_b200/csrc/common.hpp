@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -16,6 +17,25 @@ namespace gsdr {
 // thread-local error string behind gsdr_last_error()
 void set_error(const char* fmt, ...);
 const char* get_error();
+
+// "Done once per device": cudaFuncSetAttribute applies to the current device only, so a process that runs demodulators on
+// several GPUs has to raise a kernel's dynamic shared-memory limit on each of them; worker threads of different instances
+// may get here concurrently (a repeated set is harmless, a missing one fails the launch).
+class DeviceOnce {
+    std::atomic<unsigned long long> mask_{0};
+
+  public:
+    // device to prepare, or -1 when the current device already is (devices >= 64 are prepared on every call)
+    int pending() const {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess) return 0;
+        if (d < 0 || d >= 64) return d < 0 ? 0 : d;
+        return ((mask_.load(std::memory_order_acquire) >> d) & 1ull) ? -1 : d;
+    }
+    void done(int d) {
+        if (d >= 0 && d < 64) mask_.fetch_or(1ull << d, std::memory_order_release);
+    }
+};
 
 #define GSDR_CUDA_OK(expr)                                                                 \
     do {                                                                                   \

@@ -298,12 +298,12 @@ int direct_fir_launch(const Window& w, const float2* g, const int* freq_dev, int
         const int PB2 = small ? 64 : 128;
         const size_t smem = ((size_t)(PB2 + f - 1) * (D_KC + 1) + (size_t)f * D_KC * D_GST + 2) * sizeof(float2);
         dim3 grid((unsigned)((n_out + PB2 - 1) / PB2), (unsigned)tone_groups);
-        static bool attr_set = false;
-        if (!attr_set) {
+        static DeviceOnce attr_once;
+        if (const int dev = attr_once.pending(); dev >= 0) {
             const int cap = (int)(((size_t)(128 + D_FMAX - 1) * (D_KC + 1) + (size_t)D_FMAX * D_KC * D_GST + 2) * sizeof(float2));
             GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_tiled_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
             GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap));
-            attr_set = true;
+            attr_once.done(dev);
         }
         if (small)
             direct_fir_tiled_kernel<2><<<grid, 64, smem, stream>>>(w, g, freq_dev, T, M, f, rate, pos0, n_out, out);

@@ -750,11 +750,11 @@ int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int 
               float2* out, int sm_count, cudaStream_t stream, int rotate) {
     constexpr int TG = 64 / F, RB = TC_ROWS - (F - 1);
     const int row_tiles = (int)((n_out + RB - 1) / RB), tone_groups = (T + TG - 1) / TG;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (const int dev = attr_once.pending(); dev >= 0) {
         GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_tc_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
         GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_tc_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC_SMEM_BYTES));
-        attr_set = true;
+        attr_once.done(dev);
     }
     CUtensorMap map;
     memset(&map, 0, sizeof(map));

@@ -978,11 +978,11 @@ size_t pfb_workspace_bytes(int N, int P, int max_frames) {
 
 template <int P>
 static int launch_fused(const PfbJob* jobs, int n_jobs, void* scratch, const float2* tw, int sm_count, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static DeviceOnce attr_once;
+    if (const int dev = attr_once.pending(); dev >= 0) {
         GSDR_CUDA_OK(cudaFuncSetAttribute(pfb_fused_2048_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)sizeof(FusedSmem)));
-        attr_set = true;
+        attr_once.done(dev);
     }
     long long total_iters = 0;
     for (int j = 0; j < n_jobs; ++j) total_iters += (jobs[j].n_frames + FTEAMS - 1) / FTEAMS;
@@ -1022,12 +1022,12 @@ static int launch_fused(const PfbJob* jobs, int n_jobs, void* scratch, const flo
 
 template <int P>
 static int launch_ws(const PfbJob* jobs, int n_jobs, void* scratch, const float2* tw, int sm_count, cudaStream_t stream) {
-    static bool attr_set = false;
+    static DeviceOnce attr_once;
     constexpr size_t smem_bytes = sizeof(WpSmem);
     auto kernel = pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST>;
-    if (!attr_set) {
+    if (const int dev = attr_once.pending(); dev >= 0) {
         GSDR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        attr_set = true;
+        attr_once.done(dev);
     }
     long long total_frames = 0;
     for (int j = 0; j < n_jobs; ++j) total_frames += jobs[j].n_frames;
