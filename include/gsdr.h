@@ -81,7 +81,12 @@ void gsdr_rx_destroy(gsdr_rx *rx);
 /* Blocking drop-in for RX_buffer_demodulator::process: `in` = buffer_len float2 in host memory
  * (pinned for full speed; not modified), `out` = host buffer of at least gsdr_rx_max_output()
  * float2.  Returns the number of valid float2 written (all channels, sample-major
- * out[t*channels + c]) or <0 on error. */
+ * out[t*channels + c]) or <0 on error.  On return `in` has been fully consumed (the caller may
+ * recycle it at once, cpp/USRP_server_link_threads.cpp:669) and out[0..ret) is complete.
+ * With the fused channelizer (TONES / NOISE, 2048 channels) and both buffers pinned (pool
+ * buffers, gsdr_host_alloc, cudaMallocHost), the call is ONE kernel launch that reads `in` and
+ * writes `out` in place over PCIe; otherwise the data is copied up and down in chunks.  Same
+ * results either way (GSDR_PROCESS_ZEROCOPY=0 forces the copied form). */
 int gsdr_rx_process(gsdr_rx *rx, const gsdr_float2 *in, gsdr_float2 *out);
 
 /* Pipelined variant: submit returns immediately after enqueuing H2D | kernel | D2H on the
