@@ -342,3 +342,54 @@ def rel_l2(a, b) -> float:
     b = np.asarray(b, dtype=np.complex128).reshape(-1)
     den = np.linalg.norm(b)
     return float(np.linalg.norm(a - b) / den) if den > 0 else float(np.linalg.norm(a - b))
+
+
+# ---- client-side noise spectra: the specification a GPU version will be checked against ------------
+def welch_psd_real(x, fs, nperseg):
+    """One-sided power spectral density of a real series by Welch's method exactly as the client asks SciPy for it
+    (pyUSRP/USRP_noise.py:698-699: `signal.welch(x, nperseg=welch, fs=sampling_rate, detrend='linear', scaling='density')`),
+    written out: periodic Hann window, 50 % overlap (`noverlap = nperseg // 2`), no padding (a trailing partial segment is
+    dropped), a least-squares straight line removed from every segment before windowing, |rfft|^2 / (fs * sum(w^2)), doubled
+    except at DC and (nperseg even) at Nyquist, mean over segments.  fp64.  Returns (freqs, psd)."""
+    x = np.asarray(x, dtype=np.float64)
+    nperseg = int(min(nperseg, x.size))
+    step = nperseg - nperseg // 2
+    n = np.arange(nperseg, dtype=np.float64)
+    w = 0.5 - 0.5 * np.cos(2.0 * np.pi * n / nperseg)
+    nseg = (x.size - nperseg) // step + 1
+    t = n - n.mean()
+    tt = float(np.dot(t, t))
+    acc = np.zeros(nperseg // 2 + 1, dtype=np.float64)
+    for s in range(nseg):
+        seg = x[s * step:s * step + nperseg]
+        m = seg.mean()
+        slope = float(np.dot(t, seg - m)) / tt if tt > 0 else 0.0
+        X = np.fft.rfft((seg - m - slope * t) * w)
+        acc += X.real ** 2 + X.imag ** 2
+    psd = acc / nseg / (fs * float(np.dot(w, w)))
+    if nperseg % 2:
+        psd[1:] *= 2.0
+    else:
+        psd[1:-1] *= 2.0
+    return np.fft.rfftfreq(nperseg, 1.0 / fs), psd
+
+
+def spec_from_samples(samples, sampling_rate=1.0, welch=None, dbc=False, rotate=True, clip_samples=False):
+    """pyUSRP/USRP_noise.py:655-703 restated: rotate the IQ plane so the mean is real and positive, optionally scale to the
+    carrier (dBc) and remove it, clip `clip_samples` at both ends, then the Welch PSD of the real and of the imaginary part with
+    `nperseg = int(L / welch)` (L = the unclipped length; `welch=None` -> one segment of L).  Returns
+    (freqs, 10 log10 PSD(real part), 10 log10 PSD(imaginary part)) -- the order the reference returns, not the one its docstring says."""
+    z = np.asarray(samples, dtype=np.complex128)
+    L = z.size
+    nperseg = L if welch is None else int(L / welch)
+    lo, hi = (0, L) if not clip_samples else (int(clip_samples), int(L - clip_samples))
+    if rotate:
+        m = z.mean()
+        z = z * (abs(m) / m)
+    if dbc:
+        z = z / z.mean()
+        z = z - z.mean()
+    f, re = welch_psd_real(z[lo:hi].real, sampling_rate, nperseg)
+    _, im = welch_psd_real(z[lo:hi].imag, sampling_rate, nperseg)
+    with np.errstate(divide="ignore"):
+        return f, 10.0 * np.log10(re), 10.0 * np.log10(im)

@@ -131,3 +131,33 @@ def test_cpu_port_matches_oracle():
     for i in range(2):
         x = tone_stream(1_000_000, [12345, -4321], [0.5, 0.5], i * 20_000, 20_000)
         assert orc.rel_l2(cd.process(x), od.process(x)) <= TOL
+
+
+# ---- client noise spectra: the oracle is pinned on SciPy, which is what the reference calls ---------
+@pytest.mark.parametrize("L,welch,clip,dbc", [(10_000, 10, False, False), (10_007, 7, 100, False), (4_096, None, False, True),
+                                              (50_000, 33, 1_000, True), (999, 3, 10, False)])
+def test_spec_from_samples_matches_scipy_welch(L, welch, clip, dbc):
+    """oracle.spec_from_samples writes out what pyUSRP/USRP_noise.py:655-703 asks scipy.signal.welch for (linear detrend, Hann,
+    50 % overlap, density scaling, one-sided); pin the restatement on SciPy itself, odd and even segment lengths included."""
+    from scipy import signal
+    rng = np.random.default_rng(L)
+    n = np.arange(L)
+    z = (1.0 + 0.3j) * np.exp(1j * 0.2) + 1e-3 * np.exp(2j * np.pi * 0.0137 * n) + 1e-4 * (rng.standard_normal(L) + 1j * rng.standard_normal(L))
+    z = z + 1e-6 * n  # a drift for the detrend to remove
+    fs = 1e6 / 100
+    f, re_db, im_db = orc.spec_from_samples(z, sampling_rate=fs, welch=welch, dbc=dbc, rotate=True, clip_samples=clip)
+    # the reference's own lines, verbatim in behaviour
+    s = z * (np.abs(np.mean(z)) / np.mean(z))
+    if dbc:
+        s = s / np.mean(s)
+        s = s - np.mean(s)
+    nperseg = L if welch is None else int(L / welch)
+    lo, hi = (0, L) if not clip else (int(clip), int(L - clip))
+    fr, pr = signal.welch(s[lo:hi].real, nperseg=nperseg, fs=fs, detrend='linear', scaling='density')
+    fi, pi = signal.welch(s[lo:hi].imag, nperseg=nperseg, fs=fs, detrend='linear', scaling='density')
+    assert np.allclose(f, fr, rtol=1e-12, atol=0)
+    floor = max(pr.max(), pi.max()) * 1e-20   # bins that are pure rounding noise after the detrend are not compared in dB
+    k = (pr > floor) & (pi > floor)
+    assert k.sum() > 0.9 * k.size
+    assert np.allclose(10 ** (re_db[k] / 10), pr[k], rtol=1e-7)
+    assert np.allclose(10 ** (im_db[k] / 10), pi[k], rtol=1e-7)
