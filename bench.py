@@ -4,25 +4,33 @@
 Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`, one rank per
 GPU under torchrun for N>1, ONE JSON line on rank 0.
 
-Workload = BASELINE.json configs[1]: 2048-channel, 4-tap PFB, 1000 selected tones, pf_average=4,
-one 200 MS/s IQ stream per GPU, transport buffers of 1e6 complex samples.  A "step" is one pass of
-the hot path over one batch of BUFFERS consecutive transport buffers of that stream:
+Workload = BASELINE.json configs[4] built from configs[1]: 64 concurrent 200 MS/s IQ streams, each
+channelized by the 2048-channel, 4-tap PFB into 1000 selected tones (pf_average=4), transport buffers
+of 1e6 complex samples, sharded by stream over the N GPUs (64/N streams per GPU, stream s -> rank
+s mod N, no data-path collective).  One step = N transport buffers per stream, so every GPU
+processes 64e6 input samples per step at every N ("weak": per-GPU work is fixed).
 
-  value    inputs already resident in HBM (two alternating 512 MB batches, i.e. larger than the
-           126 MB L2, so no step can be served from cache); CUDA events on the launching stream.
-  e2e      the same batch through the reference-facing call (pinned HOST buffers in, pinned host
-           buffers out; H2D and D2H inside the timed region), pipelined submit/wait.
+  value    inputs already resident in HBM (two alternating 512 MB batches per GPU, i.e. larger than
+           the 126 MB L2, so no step can be served from cache); ONE group launch per step; CUDA
+           events on the launching stream.
+  e2e      the same streams through the host-fed call (gsdr_rx_group_submit / _wait): pinned HOST
+           buffers in, pinned host buffers out, one packet period (one buffer of every stream) per
+           call, H2D and D2H inside the timed region.  Reported with the plain-cudaMemcpyAsync
+           ceiling of the platform measured at the same N (`e2e.pcie`).
   roofline algorithmic bytes (8 + 8*T/N per input sample) / event-timed launch duration vs the
            measured HBM copy peak in MEASURED_PEAKS.json.
+  modes    (N=1) every other BASELINE configuration, device-resident, with its own roofline
+           fraction: cfg2 single stream, single-buffer launches, cfg1 DIRECT, cfg3 CHIRP, TX chirp,
+           cfg4 full duplex.
   cpu_baseline  the NumPy/SciPy port of the same chain (oracle/cpu_port.py) on the host cores, on a
            bounded sample, rank 0 at N=1 only.
 
-`--impl reference` times the reference's own RX_buffer_demodulator::process (unmodified sources
-compiled for sm_100a into oracle/_ref/libgsdr_ref.so) on the same workload through host buffers;
-the reference has no CPU DSP implementation, so its arm runs on the GPU as it does in production.
-Multi-GPU: streams are independent (one demodulator instance each), so ranks shard by stream with
-no data-path collective ("weak" scaling); torch.distributed is used for the barrier and the
-max-over-ranks time only.
+`--impl reference` runs the reference's own RX_buffer_demodulator (unmodified sources compiled for
+sm_100a into oracle/_ref/libgsdr_ref.so) on the same workload, one instance per stream and one
+process per GPU: `value` is its kernels alone (CUDA events on its stream around process(), its two
+copies timed separately and subtracted), `e2e` its blocking process() from one worker thread per
+stream (its threading model) with pinned host buffers.  The reference has no CPU DSP path, so its
+arm runs on the GPU as it does in production.
 """
 from __future__ import annotations
 
@@ -43,12 +51,15 @@ sys.path.insert(0, ROOT)
 
 RATE, NFFT, PTAPS, NTONES, BUFLEN = 200_000_000, 2048, 4, 1000, 1_000_000
 BYTES_PER_SAMPLE = 8.0 + 8.0 * NTONES / NFFT  # 11.90625 B per input sample
+TOTAL_STREAMS = 64                            # BASELINE.json configs[4]
 SEED = 1337
+METRIC = "demodulated input MS/s (1000-tone PFB, whole job)"
 
 
-def workload_param():
+def workload_param(stream: int = 0):
+    """cfg2 parameters; every stream has its own 1000-tone list (seeded by the global stream number)."""
     import gpu_sdr_b200 as g
-    rng = np.random.default_rng(SEED)
+    rng = np.random.default_rng(SEED + 7919 * stream)
     ks = rng.choice(np.arange(-NFFT // 2 + 1, NFFT // 2), size=NTONES, replace=False)
     freq = [int(k * (RATE / NFFT)) for k in ks]
     return g.param(mode="RX", rate=RATE, fft_tones=NFFT, pf_average=PTAPS, buffer_len=BUFLEN, decim=0, freq=freq,
@@ -59,22 +70,38 @@ def synth_buffers(p, n_distinct, seed):
     """n_distinct transport buffers of tones + noise on the sc16 grid (float32 exact)."""
     rng = np.random.default_rng(seed)
     f = np.array(p.freq[:32], dtype=np.int64)  # 32 of the tones carry power; the rest see noise
+    L = int(p.buffer_len)
     out = []
     for b in range(n_distinct):
-        n = np.arange(b * BUFLEN, (b + 1) * BUFLEN, dtype=np.int64)
-        x = np.zeros(BUFLEN, dtype=np.complex64)
+        n = np.arange(b * L, (b + 1) * L, dtype=np.int64)
+        x = np.zeros(L, dtype=np.complex64)
         for fi in f:
-            ph = ((fi * n) % RATE).astype(np.float32) * np.float32(2 * np.pi / RATE)
+            ph = ((fi * n) % p.rate).astype(np.float32) * np.float32(2 * np.pi / p.rate)
             x += (np.cos(ph) + 1j * np.sin(ph)).astype(np.complex64) * np.float32(1.0 / 64)
-        x += (rng.standard_normal(BUFLEN, dtype=np.float32) + 1j * rng.standard_normal(BUFLEN, dtype=np.float32)) * np.float32(1e-3)
+        x += (rng.standard_normal(L, dtype=np.float32) + 1j * rng.standard_normal(L, dtype=np.float32)) * np.float32(1e-3)
         x = (np.round(x.real * 32768) + 1j * np.round(x.imag * 32768)).astype(np.complex64) / np.float32(32768)
         out.append(x.astype(np.complex64))
     return out
 
 
+def layout(world: int, streams_total: int = TOTAL_STREAMS):
+    """(streams per GPU, buffers per stream per step): per-GPU work per step is streams_total x 1e6 samples at every N."""
+    s = max(1, streams_total // world)
+    return s, max(1, streams_total // s)
+
+
+def shared_config(world, S, B):
+    """`config` is identical in our arm and the reference arm: it names the workload, nothing else."""
+    return {"workload": f"cfg5 (BASELINE configs[4] on configs[1] parameters): {S * world} concurrent 200 MS/s IQ streams x 1000-tone PFB "
+                        f"(N={NFFT} channels, P={PTAPS} taps, pf_average={PTAPS}), sharded by stream over {world} GPU(s) = {S} streams per GPU; "
+                        f"one step = {B} transport buffer(s) of 1e6 samples per stream = {S * B}e6 input samples per GPU",
+            "streams_total": S * world, "streams_per_gpu": S, "buffers_per_stream_per_step": B, "buffer_len": BUFLEN,
+            "l2": "inputs larger than L2: two alternating 512 MB batches per GPU"}
+
+
 # ---- distributed plumbing ------------------------------------------------------------------------
 class Dist:
-    def __init__(self, n_gpus):
+    def __init__(self, n_gpus, force_gloo=False):
         self.world = int(os.environ.get("WORLD_SIZE", "1"))
         self.rank = int(os.environ.get("RANK", "0"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -85,7 +112,7 @@ class Dist:
             import torch.distributed as dist
             self.torch, self.dist = torch, dist
             os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-            backend = "nccl" if torch.cuda.is_available() else "gloo"
+            backend = "nccl" if (torch.cuda.is_available() and not force_gloo) else "gloo"
             if backend == "nccl":
                 torch.cuda.set_device(self.local_rank)
                 # stdout carries exactly one JSON line: NCCL's own banner / debug output goes to stderr
@@ -99,19 +126,21 @@ class Dist:
         if self.dist:
             self.dist.barrier()
 
-    def max(self, v: float) -> float:
+    def _reduce(self, v: float, op) -> float:
         if not self.dist:
             return v
         t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        self.dist.all_reduce(t, op=op)
         return float(t.item())
 
+    def max(self, v: float) -> float:
+        return self._reduce(v, self.dist.ReduceOp.MAX) if self.dist else v
+
+    def min(self, v: float) -> float:
+        return self._reduce(v, self.dist.ReduceOp.MIN) if self.dist else v
+
     def sum(self, v: float) -> float:
-        if not self.dist:
-            return v
-        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
-        self.dist.all_reduce(t, op=self.dist.ReduceOp.SUM)
-        return float(t.item())
+        return self._reduce(v, self.dist.ReduceOp.SUM) if self.dist else v
 
     def close(self):
         if self.dist:
@@ -178,8 +207,7 @@ def measured_peak():
 def ncu_traffic():
     """dram bytes per launch of the fused kernel from the committed ncu summary, if any."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "pfb_traffic.json")))
-        return d
+        return json.load(open(os.path.join(ROOT, "profiles", "pfb_traffic.json")))
     except Exception:
         return None
 
@@ -198,8 +226,186 @@ def cpu_baseline(p, budget_s=12.0):
         if (el >= budget_s and n >= 8) or n >= 4000:
             break
     return {"value": n * BUFLEN / el / 1e6, "unit": "MS/s", "cores": cpu_port.cores(), "kind": "port",
-            "sample": f"{n} transport buffers of 1e6 samples ({el:.1f} s) through oracle/cpu_port.PFBPort "
+            "sample": f"{n} transport buffers of 1e6 samples of one stream ({el:.1f} s) through oracle/cpu_port.PFBPort "
                       f"(complex64 NumPy + scipy.fft workers={cpu_port.cores()})"}
+
+
+# ---- per-mode device-resident figures (N=1) --------------------------------------------------------
+def _noise(n, seed=1):
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal(n, dtype=np.float32) * 0.1 + 1j * rng.standard_normal(n, dtype=np.float32) * 0.1).astype(np.complex64)
+
+
+def _rx_mode(g, dev, peak, name, p, n_buf, bytes_per_sample, steps, bytes_note=None):
+    """Device-resident rate of one RX configuration: n_buf consecutive buffers per launch, two alternating input batches."""
+    rx = g.RX_buffer_demodulator(p, device=dev)
+    L = int(p.buffer_len)
+    base = _noise(L)
+    n_alt = 2 if n_buf * L * 8 > 200e6 else max(2, int(300e6 // (n_buf * L * 8)) + 1)   # rotate through > L2 worth of inputs
+    ins = []
+    for h in range(n_alt):
+        d = g.DeviceBuffer(n_buf * L, device=dev)
+        for b in range(n_buf):
+            d.upload(np.roll(base, 7 * (b + h)), offset=b * L)
+        ins.append(d)
+    out = g.DeviceBuffer(rx.max_output_batch(n_buf), device=dev)
+    for i in range(3):
+        rx.process_device(ins[i % n_alt].ptr, n_buf, out.ptr)
+    rx.sync()
+    l0 = rx.launch_count()
+    rx.timer_start()
+    for i in range(steps):
+        rx.process_device(ins[i % n_alt].ptr, n_buf, out.ptr)
+    ms = rx.timer_stop() / steps
+    gbs = n_buf * L * bytes_per_sample / (ms * 1e-3) / 1e9
+    res = {"mode": name, "kernel": rx.kernel_name(), "value": n_buf * L / (ms * 1e-3) / 1e6, "unit": "MS/s", "buffers_per_launch": n_buf,
+           "ms_per_step": ms, "steps": steps, "launches_per_step": (rx.launch_count() - l0) / steps,
+           "bytes_per_sample": bytes_per_sample, "achieved_GBps": gbs, "frac": gbs / peak}
+    if bytes_note:
+        res["bytes_note"] = bytes_note
+    rx.close()
+    for d in ins:
+        d.free()
+    out.free()
+    return res
+
+
+def direct_param(g, rate=100_000_000, T=16, decim=100, f=4, L=BUFLEN):
+    """cfg1 (same builder as tests/common.py: T distinct integer tones in (-rate/2, rate/2), a quarter of them negative)."""
+    rng = np.random.default_rng(SEED + 1)
+    freq = []
+    while len(freq) < T:
+        v = int(rng.integers(-rate // 2 + 1, rate // 2))
+        if len(freq) < max(T // 4, 1):
+            v = -abs(v) - 1
+        if v not in freq:
+            freq.append(v)
+    return g.param(mode="RX", rate=rate, decim=decim, pf_average=f, buffer_len=L, freq=freq, wave_type=[g.DIRECT] * T, ampl=[1.0 / T] * T,
+                   data_mem_mult=max(int(np.ceil(T / max(decim, 1))), 1))
+
+
+def chirp_param(g, mode="RX", ampl=0.5):
+    """cfg3 (get_VNA workload): 100 MHz span, 1e5 points, 1 s, decim 1 -> 2000 samples per point."""
+    return g.param(mode=mode, rate=RATE, decim=1, buffer_len=BUFLEN, freq=[-50_000_000], chirp_f=[50_000_000], swipe_s=[100_000],
+                   chirp_t=[1.0], wave_type=[g.CHIRP], ampl=[ampl])
+
+
+def run_modes(g, dev, peak):
+    modes = []
+    p2 = workload_param(0)
+    modes.append(_rx_mode(g, dev, peak, "cfg2: one stream, 64 buffers per launch (the round-1 headline)", p2, 64, BYTES_PER_SAMPLE, 20))
+    modes.append(_rx_mode(g, dev, peak, "cfg2: one stream, ONE 1e6-sample buffer per launch (real-time shape), back to back", p2, 1,
+                          BYTES_PER_SAMPLE, 200))
+    pd = direct_param(g)
+    bd = 8 + 8 * 16 / 100
+    modes.append(_rx_mode(g, dev, peak, "cfg1: DIRECT T=16 decim=100 pf_average=4, rate 1e8, 64 buffers per launch", pd, 64, bd, 10))
+    modes.append(_rx_mode(g, dev, peak, "cfg1: DIRECT, ONE 1e6-sample buffer per launch, back to back", pd, 1, bd, 100))
+    pc = chirp_param(g)
+    ppt = 2000
+    bc = 8 * (1 - (ppt // 10) / ppt) + 8 / ppt
+    modes.append(_rx_mode(g, dev, peak, "cfg3: CHIRP lock-in, 1e5 points over 100 MHz, ppt=2000, 64 buffers per launch", pc, 64, bc, 20,
+                          bytes_note="the lock-in profile is zero for the first ppt/10 samples of every point (make_flat_window), which the "
+                                     "kernel neither reads nor demodulates: 0.9 x 8 B read + 8/ppt B written per input sample"))
+    # TX chirp synthesis
+    pt = chirp_param(g, mode="TX")
+    tx = g.TX_buffer_generator(pt, device=dev)
+    n_buf = 64
+    d = g.DeviceBuffer(n_buf * BUFLEN, device=dev)
+    for _ in range(3):
+        tx.get_device(d.ptr, n_buf)
+    tx.sync()
+    tx.timer_start()
+    for _ in range(20):
+        tx.get_device(d.ptr, n_buf)
+    ms = tx.timer_stop() / 20
+    n = n_buf * BUFLEN
+    modes.append({"mode": "TX CHIRP synthesis, 64 buffers per launch", "kernel": "chirp_gen_kernel", "value": n / (ms * 1e-3) / 1e6,
+                  "unit": "MS/s (output)", "ms_per_step": ms, "steps": 20, "bytes_per_sample": 8.0, "achieved_GBps": n * 8 / (ms * 1e-3) / 1e9,
+                  "frac": n * 8 / (ms * 1e-3) / 1e9 / peak})
+    tx.close()
+    d.free()
+    modes.append(full_duplex_mode(g, dev, peak))
+    return modes
+
+
+def full_duplex_mode(g, dev, peak):
+    """cfg4: 1000-tone TX buffer synthesis + RX at 200 MS/s on two front-ends (A, B) of one GPU, full size.
+    TX: TX_buffer_generator TONES, T=1000, rate 2e8 (one period of 2e8 samples + buffer_len wrap, built once; get() is
+    pointer arithmetic, cpp/USRP_buffer_generator.cpp:60-99,226-229).  RX: each front-end channelizes the looped-back TX
+    waveform into its 1000 tones (--sw_loop identity): device-resident as one group launch over both front-ends, and
+    end to end with two worker threads calling tx.get() + the blocking rx.process() like TXRX::tx_single_link /
+    rx_single_link (cpp/USRP_server_link_threads.cpp:542-702)."""
+    res = {"mode": "cfg4: full duplex, TX TONES T=1000 synthesis + RX PFB on two front-ends at 200 MS/s"}
+    ps = [workload_param(1000 + fe) for fe in range(2)]
+    t0 = time.perf_counter()
+    txs = []
+    for p in ps:
+        q = g.param(mode="TX", rate=p.rate, buffer_len=p.buffer_len, freq=p.freq, ampl=p.ampl, wave_type=p.wave_type)
+        txs.append(g.TX_buffer_generator(q, device=dev))
+    res["tx_init_s_per_front_end"] = (time.perf_counter() - t0) / 2
+    res["tx_kernel"] = "tones_synth_kernel (integer-phase GEMM over 2e8 samples x 1000 tones)"
+    res["tx_tone_samples_per_s"] = RATE * NTONES / res["tx_init_s_per_front_end"]
+    rxs = [g.RX_buffer_demodulator(p, device=dev) for p in ps]
+    grp = g.RxGroup(rxs)
+    nb = 32
+    ins = [[g.DeviceBuffer(nb * BUFLEN, device=dev) for _ in range(2)] for _ in range(2)]
+    for fe in range(2):
+        for h in range(2):
+            txs[fe].get_device(ins[fe][h].ptr, nb)   # consecutive TX buffers, as a loop-back cable would deliver them
+        txs[fe].sync()
+    outs = [g.DeviceBuffer(rx.max_output_batch(nb), device=dev) for rx in rxs]
+    for i in range(3):
+        grp.process_device([ins[0][i & 1].ptr, ins[1][i & 1].ptr], nb, [o.ptr for o in outs])
+    grp.sync()
+    grp.timer_start()
+    steps = 20
+    for i in range(steps):
+        grp.process_device([ins[0][i & 1].ptr, ins[1][i & 1].ptr], nb, [o.ptr for o in outs])
+    ms = grp.timer_stop() / steps
+    n = 2 * nb * BUFLEN
+    gbs = n * BYTES_PER_SAMPLE / (ms * 1e-3) / 1e9
+    res.update({"kernel": rxs[0].kernel_name(), "value": n / (ms * 1e-3) / 1e6, "unit": "MS/s (RX input, both front-ends)",
+                "ms_per_step": ms, "steps": steps, "bytes_per_sample": BYTES_PER_SAMPLE, "achieved_GBps": gbs, "frac": gbs / peak})
+    # known answer of the loop: tones on bin centres with amplitude 1/T -> every selected bin is ~1/T in every frame
+    tot, lens = grp.process_device([ins[0][0].ptr, ins[1][0].ptr], 1, [o.ptr for o in outs])
+    grp.sync()
+    y = outs[0].download(int(lens[0][0]))
+    res["loopback_bin_amplitude_times_T"] = float(np.median(np.abs(y))) * NTONES
+    grp.close()
+    for fe in range(2):
+        for h in range(2):
+            ins[fe][h].free()
+    for o in outs:
+        o.free()
+    # end to end: worker thread per front-end, tx.get() -> blocking rx.process() on pinned buffers
+    for rx in rxs:
+        rx.reset()
+    houts = [g.pinned_empty(rx.max_output()) for rx in rxs]
+    n_pk = 64
+
+    def worker(fe, n_packets):
+        for _ in range(n_packets):
+            buf = txs[fe].get()
+            rxs[fe].process(buf, houts[fe])
+
+    for fe in range(2):
+        worker(fe, 4)
+    th = [threading.Thread(target=worker, args=(fe, n_pk)) for fe in range(2)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    res["e2e"] = {"value": 2 * n_pk * BUFLEN / dt / 1e6, "unit": "MS/s", "api": "TX_buffer_generator::get + RX_buffer_demodulator::process, "
+                  "one thread per front-end", "required_MSps": 2 * RATE / 1e6}
+    for o in houts:
+        g.pinned_free(o)
+    for rx in rxs:
+        rx.close()
+    for tx in txs:
+        tx.close()
+    return res
 
 
 # ---- our arm -------------------------------------------------------------------------------------
@@ -210,16 +416,17 @@ def run_ours(args, dd: Dist):
     if ndev <= 0:
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path (" + g._lib.last_error() + ")")
     dev = dd.local_rank % ndev
-    p = workload_param()
-    B = args.buffers
-    n_streams_total = args.streams * dd.world
-    my_streams = shard_streams(n_streams_total, dd.rank, dd.world)
-    S = len(my_streams)
-
-    rxs = [g.RX_buffer_demodulator(p, device=dev) for _ in my_streams]
+    S, B = layout(dd.world, args.streams_total)
+    if args.buffers:
+        B = args.buffers
+    my_streams = shard_streams(S * dd.world, dd.rank, dd.world)
+    assert len(my_streams) == S
+    params = [workload_param(s) for s in my_streams]
+    rxs = [g.RX_buffer_demodulator(p, device=dev) for p in params]
     kernel_name = rxs[0].kernel_name()
+    group = g.RxGroup(rxs)
     # device-resident input: two alternating batches per stream built from 4 distinct buffers
-    distinct = synth_buffers(p, 4, SEED)
+    distinct = synth_buffers(params[0], 4, SEED)
     ins = []
     for s in range(S):
         pair = []
@@ -229,23 +436,16 @@ def run_ours(args, dd: Dist):
                 d.upload(distinct[(b + half + s) % 4], offset=b * BUFLEN)
             pair.append(d)
         ins.append(pair)
-    outs = [g.DeviceBuffer(rxs[0].max_output_batch(B), device=dev) for _ in range(S)]
-    group = g.RxGroup(rxs) if S > 1 else None
+    outs = [g.DeviceBuffer(rx.max_output_batch(B), device=dev) for rx in rxs]
+    in_ptrs = [[ins[s][h].ptr for s in range(S)] for h in range(2)]
+    out_ptrs = [o.ptr for o in outs]
 
     def step(i):
-        if group:
-            group.process_device([ins[s][i & 1].ptr for s in range(S)], B, [o.ptr for o in outs])
-        else:
-            rxs[0].process_device(ins[0][i & 1].ptr, B, outs[0].ptr)
-
-    timer = group if group else rxs[0]
-
-    def launches():
-        return (group.launch_count() if group else 0) + sum(r.launch_count() for r in rxs)
+        group.process_device(in_ptrs[i & 1], B, out_ptrs)
 
     for i in range(args.warmup):
         step(i)
-    timer.sync()
+    group.sync()
     sampler = ClockSampler(dev)
     time.sleep(0.25)
     # The sampler's start-up leaves the GPU idle for a quarter of a second and the clocks fall back: with a small K the
@@ -254,27 +454,26 @@ def run_ours(args, dd: Dist):
     ramp_steps = max(0, 128 - args.warmup)
     for i in range(ramp_steps):
         step(i)
-    timer.sync()
+    group.sync()
     dd.barrier()
-    timer.sync()
-    l0 = launches()
+    group.sync()
+    l0 = group.launch_count()
     t_begin = time.time()
-    timer.timer_start()
+    group.timer_start()
     for i in range(args.steps):
         step(args.warmup + i)
-    ms_total = timer.timer_stop()
+    ms_total = group.timer_stop()
     dd.barrier()
-    timer.sync()
-    t_end = time.time()
-    l1 = launches()
+    group.sync()
+    l1 = group.launch_count()
     # keep the same load running until the clock sampler has seen it for ~1.2 s (100 ms period)
     extra_i = 0
     while time.time() - t_begin < 1.2 and not args.profile:
         step(extra_i)
         extra_i += 1
         if extra_i % 16 == 0:
-            timer.sync()
-    timer.sync()
+            group.sync()
+    group.sync()
     clocks = sampler.stop(t_begin, time.time())
     clocks["window"] = "timed region + same load continued to 1.2 s"
 
@@ -283,166 +482,249 @@ def run_ours(args, dd: Dist):
     value = samples_step / (ms_step * 1e-3) / 1e6
     peak, peak_src = measured_peak()
     achieved = (S * B * BUFLEN * BYTES_PER_SAMPLE) / ((ms_total / args.steps) * 1e-3) / 1e9  # this rank's GB/s
+    achieved_min = dd.min(achieved)
     traffic = ncu_traffic()
+    for s in range(S):
+        for d in ins[s]:
+            d.free()
+    for o in outs:
+        o.free()
 
+    base = {"metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": dd.world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": shared_config(dd.world, S, B), "kernel": kernel_name, "clock_ramp_steps": ramp_steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "frac_min_over_ranks": achieved_min / peak,
+                         "traffic": (traffic or {}).get("dram_bytes_per_launch"), "traffic_note": (traffic or {}).get("note"),
+                         "peak_source": peak_src, "bytes_per_sample": BYTES_PER_SAMPLE, "samples_per_launch": S * B * BUFLEN,
+                         "launch_ms": ms_total / args.steps, "kernel": kernel_name},
+            "gpu_launches": int(l1 - l0), "clocks": clocks}
     if args.profile:  # launch-list / ncu runs: device-resident leg only
+        base["profile_run"] = True
+        group.close()
         for r in rxs:
             r.close()
-        return {"metric": "demodulated input MS/s (1000-tone PFB, whole job)", "value": value, "unit": "MS/s", "n_gpus": dd.world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "profile_run": True,
-                "roofline": {"achieved": achieved, "peak": peak, "frac": achieved / peak}, "gpu_launches": int(l1 - l0)}
+        return base
 
-    # ---- e2e: host buffers through the public pipelined call, same batch size ----------------------
-    rx = rxs[0]
-    rx.reset()
-    depth = 4
-    hin = [g.pinned_empty(BUFLEN) for _ in range(depth)]
-    hout = [g.pinned_empty(rx.max_output()) for _ in range(depth)]
-    for k in range(depth):
-        hin[k][:] = distinct[k % 4]
-    e2e_steps = max(2, min(args.steps, 10))
+    # ---- e2e: host buffers through the host-fed group call, one packet period (one buffer per stream) per call -------------
+    for r in rxs:
+        r.reset()
+    ring = 3
+    numa_node = int(lib.gsdr_device_numa_node(dev))
+    print(f"[bench rank {dd.rank}] GPU {dev}: NUMA node {numa_node}; pinned buffers allocated node-local when the kernel allows",
+          file=sys.stderr, flush=True)
+    hin = [[g.pinned_empty(BUFLEN) for _ in range(S)] for _ in range(ring)]
+    hout = [[g.pinned_empty(rx.max_output()) for rx in rxs] for _ in range(ring)]
+    for k in range(ring):
+        for s in range(S):
+            hin[k][s][:] = distinct[(k + s) % 4]
+    ptrs = [group.pointer_arrays(hin[k], hout[k]) for k in range(ring)]
+    e2e_steps = max(2, min(args.steps, 20))
 
-    def e2e_pass(n_buf):
+    def e2e_pass(n_periods, arrays, sc16=False):
         tickets, d2h = [], 0
-        for b in range(n_buf):
-            k = b % depth
-            if len(tickets) >= depth - 1:
-                rx.wait(tickets.pop(0))
-            t, n = rx.submit(hin[k], hout[k])
-            d2h += n * 8
+        for b in range(n_periods):
+            if len(tickets) >= ring - 1:
+                group.wait(tickets.pop(0))
+            t, lens = group.submit(*arrays[b % ring], sc16=sc16)
+            d2h += 8 * sum(lens)
             tickets.append(t)
         for t in tickets:
-            rx.wait(t)
+            group.wait(t)
         return d2h
 
-    numa_node = int(g.load().gsdr_device_numa_node(dd.local_rank))
-    print(f"[bench rank {dd.rank}] GPU {dd.local_rank}: NUMA node {numa_node}; pinned buffers allocated node-local when the kernel allows",
-          file=sys.stderr, flush=True)
-    e2e_pass(B)  # warm-up
-    dd.barrier()
-    t0 = time.perf_counter()
+    def timed_e2e(arrays, sc16=False):
+        e2e_pass(B, arrays, sc16)  # warm-up
+        dd.barrier()
+        t0 = time.perf_counter()
+        d2h = 0
+        for _ in range(e2e_steps):
+            d2h = e2e_pass(B, arrays, sc16)
+        sec = dd.max((time.perf_counter() - t0) / e2e_steps)
+        return dd.sum(float(S * B * BUFLEN)) / sec / 1e6, d2h, sec
+
+    forms = {}
     d2h_bytes = 0
-    for _ in range(e2e_steps):
-        d2h_bytes = e2e_pass(B)
-    e2e_s = dd.max((time.perf_counter() - t0) / e2e_steps)
-    e2e_val = dd.sum(float(B * BUFLEN)) / e2e_s / 1e6
+    for form, on in (("copied", 0), ("zero_copy", 1)):
+        lib.gsdr_rx_group_set_zero_copy(group._h, on)
+        for r in rxs:
+            r.reset()
+        v, d2h_bytes, sec = timed_e2e(ptrs)
+        forms[form] = {"value": v, "unit": "MS/s", "s_per_step": sec, "took_zero_copy_form": bool(group.zero_copy())}
+    default_form = "zero_copy" if args.e2e_form == "zero_copy" else "copied"
+    lib.gsdr_rx_group_set_zero_copy(group._h, 1 if default_form == "zero_copy" else 0)
+    e2e_val = forms[default_form]["value"]
     # sc16 ingest: the wire format crosses PCIe, conversion on the GPU.  Reported beside the
     # fc32 figure, never instead of it: the reference's interface is fc32.
-    rx.reset()
-    hraw = [g.pinned_empty(BUFLEN // 2).view(np.int16) for _ in range(depth)]
-    for k in range(depth):
-        v = distinct[k % 4].view(np.float32) * np.float32(32767.0)
-        hraw[k][:] = np.clip(np.round(v), -32768, 32767).astype(np.int16)
+    for r in rxs:
+        r.reset()
+    hraw = [[g.pinned_empty(BUFLEN // 2).view(np.int16) for _ in range(S)] for _ in range(ring)]
+    for k in range(ring):
+        for s in range(S):
+            v = hin[k][s].view(np.float32) * np.float32(32767.0)
+            hraw[k][s][:] = np.clip(np.round(v), -32768, 32767).astype(np.int16)
+    ptrs16 = [group.pointer_arrays(hraw[k], hout[k]) for k in range(ring)]
+    sc16_val, _, _ = timed_e2e(ptrs16, sc16=True)
+    # the unchanged blocking drop-in call, RX_buffer_demodulator::process: (a) one stream alone, (b) every stream of this GPU
+    # from its own worker thread at once (the reference's threading model, cpp/USRP_server_link_threads.cpp:605-702)
+    for r in rxs:
+        r.reset()
+    n_blk = 32
+    for b in range(4):
+        rxs[0].process(hin[b % ring][0], hout[b % ring][0])
+    t0 = time.perf_counter()
+    for b in range(n_blk):
+        rxs[0].process(hin[b % ring][0], hout[b % ring][0])
+    blocking_one = n_blk * BUFLEN / (time.perf_counter() - t0) / 1e6
 
-    def e2e_pass_sc16(n_buf):
-        tickets = []
-        for b in range(n_buf):
-            k = b % depth
-            if len(tickets) >= depth - 1:
-                rx.wait(tickets.pop(0))
-            t, _ = rx.submit_sc16(hraw[k], hout[k])
-            tickets.append(t)
-        for t in tickets:
-            rx.wait(t)
+    def blk_worker(s, n):
+        for b in range(n):
+            rxs[s].process(hin[b % ring][s], hout[b % ring][s])
 
-    e2e_pass_sc16(B)
+    n_thr = max(4, 2 * B)
     dd.barrier()
+    th = [threading.Thread(target=blk_worker, args=(s, n_thr)) for s in range(S)]
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_pass_sc16(B)
-    sc16_s = dd.max((time.perf_counter() - t0) / e2e_steps)
-    sc16_val = dd.sum(float(B * BUFLEN)) / sc16_s / 1e6
-    # blocking drop-in call (submit+wait per buffer), for the record
-    rx.reset()
-    t0 = time.perf_counter()
-    for b in range(B):
-        rx.process(hin[b % depth], hout[b % depth])
-    blocking_val = B * BUFLEN / (time.perf_counter() - t0) / 1e6
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    blk_sec = dd.max(time.perf_counter() - t0)
+    blocking_threads = dd.sum(float(S * n_thr * BUFLEN)) / blk_sec / 1e6
+    # what plain cudaMemcpyAsync gives on this platform at this N (every rank at once): the ceiling of any host-fed figure
+    gbs = (C.c_double * 4)()
+    dd.barrier()
+    rc = lib.gsdr_pcie_copy_ceiling(dev, BUFLEN * 8, NTONES * 488 * 8, 64, gbs)
+    dd.barrier()
+    pcie = None
+    if rc == 0:
+        h2d_need = BUFLEN * 8.0
+        d2h_need = d2h_bytes / max(1, S * B)   # bytes down per buffer
+        # time per buffer if both directions ran at their concurrent ceilings
+        t_buf = max(h2d_need / (gbs[2] * 1e9), d2h_need / (gbs[3] * 1e9)) if gbs[2] > 0 and gbs[3] > 0 else float("inf")
+        ceil_rank = BUFLEN / t_buf / 1e6
+        ceil_total = dd.sum(ceil_rank)
+        pcie = {"h2d_alone_GBps": gbs[0], "d2h_alone_GBps": gbs[1], "h2d_duplex_GBps": gbs[2], "d2h_duplex_GBps": gbs[3],
+                "rank": 0, "min_over_ranks_h2d_duplex_GBps": dd.min(gbs[2]), "min_over_ranks_d2h_duplex_GBps": dd.min(gbs[3]),
+                "how": "gsdr_pcie_copy_ceiling: one cudaMemcpyAsync per 8 MB buffer up and per 3.9 MB buffer down, pinned host memory, "
+                       "two streams, every rank at once",
+                "e2e_ceiling_MSps": ceil_total, "e2e_frac_of_ceiling": e2e_val / ceil_total if ceil_total > 0 else None}
+    else:
+        dd.min(0.0), dd.min(0.0), dd.sum(0.0)
 
-    res = {
-        "metric": "demodulated input MS/s (1000-tone PFB, whole job)", "value": value, "unit": "MS/s",
-        "n_gpus": dd.world, "steps": args.steps, "warmup": args.warmup, "clock_ramp_steps": ramp_steps, "ms_per_step": ms_step,
-        "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"cfg2 TONES PFB: N={NFFT} channels, P={PTAPS} taps, T={NTONES} tones, pf_average={PTAPS}, "
-                               f"{args.streams} x 200 MS/s stream per GPU, {B} transport buffers of 1e6 samples per step",
-                   "streams_per_gpu": args.streams, "buffers_per_step": B, "buffer_len": BUFLEN,
-                   "l2": "inputs larger than L2: two alternating 512 MB device batches per stream",
-                   "kernel": kernel_name},
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                     "bytes_per_sample": BYTES_PER_SAMPLE, "samples_per_launch": S * B * BUFLEN,
-                     "launch_ms": ms_total / args.steps},
-        "e2e": {"value": e2e_val, "unit": "MS/s", "h2d_bytes_per_step": B * BUFLEN * 8, "d2h_bytes_per_step": d2h_bytes,
-                "api": "gsdr_rx_submit/gsdr_rx_wait (pinned host in/out, depth-3 pipeline)", "steps": e2e_steps,
-                "blocking_process_value": blocking_val, "pinned_numa_node_rank0": numa_node,
-                "sc16_ingest": {"value": sc16_val, "unit": "MS/s", "h2d_bytes_per_step": B * BUFLEN * 4,
-                                "api": "gsdr_rx_submit_sc16/gsdr_rx_wait (int16 I/Q in, conversion on the GPU)"}},
-        "gpu_launches": int(l1 - l0), "clocks": clocks,
-    }
-    if dd.rank == 0 and dd.world == 1 and not args.no_cpu:
-        res["cpu_baseline"] = cpu_baseline(p)
+    res = dict(base)
+    res["e2e"] = {"value": e2e_val, "unit": "MS/s", "h2d_bytes_per_step": S * B * BUFLEN * 8, "d2h_bytes_per_step": d2h_bytes,
+                  "api": f"gsdr_rx_group_submit/gsdr_rx_group_wait: {S} pinned host buffers in and {S} out per call (one packet period), "
+                         f"depth-3 pipeline, {default_form} form", "steps": e2e_steps, "forms": forms, "default_form": default_form,
+                  "real_time_need_MSps": S * dd.world * RATE / 1e6, "pcie": pcie,
+                  "blocking_process_value": blocking_one,
+                  "blocking_process_all_streams_threads": {"value": blocking_threads, "unit": "MS/s", "threads_per_gpu": S,
+                                                           "api": "gsdr_rx_process (RX_buffer_demodulator::process), one worker thread per stream"},
+                  "pinned_numa_node_rank0": numa_node,
+                  "sc16_ingest": {"value": sc16_val, "unit": "MS/s", "h2d_bytes_per_step": S * B * BUFLEN * 4,
+                                  "api": "gsdr_rx_group_submit_sc16 (int16 I/Q in, conversion on the GPU)"}}
+    group.close()
     for r in rxs:
         r.close()
+    for k in range(ring):
+        for a in hin[k] + hout[k]:
+            g.pinned_free(a)
+        for a in hraw[k]:
+            g.pinned_free(a.view(np.complex64))
+    if dd.rank == 0 and dd.world == 1 and not args.no_modes:
+        res["modes"] = run_modes(g, dev, peak)
+    if dd.rank == 0 and dd.world == 1 and not args.no_cpu:
+        res["cpu_baseline"] = cpu_baseline(params[0])
     return res
 
 
 # ---- reference arm -------------------------------------------------------------------------------
 def run_reference(args, dd: Dist):
-    if dd.rank != 0:
-        return None
     import importlib.util  # test infrastructure: the reference's own object code behind tests/common.py
     spec = importlib.util.spec_from_file_location("gsdr_tests_common", os.path.join(ROOT, "tests", "common.py"))
     tc = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(tc)
     RefRX, ref_lib = tc.RefRX, tc.ref_lib
-    p = workload_param()
-    B = args.buffers
+    S, B = layout(dd.world, args.streams_total)
+    if args.buffers:
+        B = args.buffers
+    my_streams = shard_streams(S * dd.world, dd.rank, dd.world)
+    params = [workload_param(s) for s in my_streams]
     lib = ref_lib()
-    cpu = cpu_baseline(p, budget_s=8.0)
-    if lib is None or lib.gsdr_ref_device_count() <= 0:
-        # reference object library not built / no GPU: the oracle port is the only runnable restatement
-        return {"impl": "reference", "metric": "demodulated input MS/s (1000-tone PFB, whole job)", "value": cpu["value"],
-                "unit": "MS/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True,
-                "ms_per_step": B * BUFLEN / (cpu["value"] * 1e6) * 1e3, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic", "config": {"workload": "cfg2 TONES PFB (CPU port; oracle/_ref unavailable)"},
-                "cpu_baseline": cpu, "e2e": {"value": cpu["value"], "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    ref = RefRX(p)
-    distinct = synth_buffers(p, 4, SEED)
-    hin = []
-    for k in range(4):
-        ptr = lib.gsdr_ref_host_alloc(BUFLEN * 8)
-        a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(2 * BUFLEN,)).view(np.complex64)
-        a[:] = distinct[k]
-        hin.append((ptr, a))
-    cap = NTONES * lib.gsdr_ref_rx_batching(ref.h)
-    optr = lib.gsdr_ref_host_alloc(cap * 8)
-    last = C.c_int(0)
-    steps = max(1, min(args.steps, 10))
+    have = lib is not None and lib.gsdr_ref_device_count() > 0
+    if not (dd.min(1.0 if have else 0.0) > 0):
+        # reference object library not built / no GPU: the oracle port is the only runnable restatement (rank 0, one stream)
+        if dd.rank != 0:
+            return None
+        cpu = cpu_baseline(params[0], budget_s=8.0)
+        return {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "MS/s", "n_gpus": dd.world, "steps": args.steps,
+                "warmup": args.warmup, "higher_is_better": True, "ms_per_step": S * B * BUFLEN / (cpu["value"] * 1e6) * 1e3,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": shared_config(dd.world, S, B),
+                "impl_detail": "oracle/_ref unavailable: CPU port of the chain (oracle/cpu_port.py)", "cpu_baseline": cpu,
+                "e2e": {"value": cpu["value"], "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    refs = [RefRX(p) for p in params]
+    distinct = synth_buffers(params[0], 4, SEED)
+    ring = 2
+    hin, keep = [], []
+    for s in range(S):
+        for k in range(ring):
+            ptr = lib.gsdr_ref_host_alloc(BUFLEN * 8)
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_float)), shape=(2 * BUFLEN,)).view(np.complex64)
+            a[:] = distinct[(k + s) % 4]
+            hin.append(ptr)
+            keep.append(a)
+    cap = NTONES * lib.gsdr_ref_rx_batching(refs[0].h)
+    houts = [lib.gsdr_ref_host_alloc(cap * 8) for _ in range(S)]
+    hs = (C.c_void_p * S)(*[r.h for r in refs])
+    ins_arr = (C.c_void_p * (S * ring))(*hin)
+    outs_arr = (C.c_void_p * S)(*houts)
 
-    def one_step():
-        tot = 0.0
-        for b in range(B):
-            tot += lib.gsdr_ref_rx_process_timed(ref.h, hin[b % 4][0], optr, 1, C.byref(last))
-        return tot
-
-    for _ in range(max(1, min(args.warmup, 3))):
-        one_step()
-    t = [one_step() for _ in range(steps)]
-    sec = sum(t) / len(t)
-    val = B * BUFLEN / sec / 1e6
-    ref.close()
-    return {"impl": "reference", "metric": "demodulated input MS/s (1000-tone PFB, whole job)", "value": val, "unit": "MS/s",
-            "n_gpus": 1, "steps": steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"cfg2 TONES PFB: N={NFFT}, P={PTAPS}, T={NTONES}, one 200 MS/s stream, {B} transport buffers "
-                                   "of 1e6 samples per step through RX_buffer_demodulator::process (pinned host in/out)",
-                       "reference": "unmodified cpp/kernels.cu + cpp/USRP_demodulator.cpp compiled for sm_100a "
-                                    "(oracle/_ref/libgsdr_ref.so); the reference has no CPU DSP path, so this arm runs "
-                                    "its CUDA path on the same B200"},
-            "cpu_baseline": cpu,
-            "e2e": {"value": val, "unit": "MS/s", "h2d_bytes_per_step": B * BUFLEN * 8, "d2h_bytes_per_step": B * cap * 8},
-            "gpu_launches": 0}
+    # e2e: the reference's threading model, one worker thread per front-end calling the blocking process()
+    for _ in range(args.warmup):
+        lib.gsdr_ref_rx_multi_process_timed(hs, S, ins_arr, ring, outs_arr, B)
+    dd.barrier()
+    t = [lib.gsdr_ref_rx_multi_process_timed(hs, S, ins_arr, ring, outs_arr, B) for _ in range(args.steps)]
+    e2e_sec = dd.max(sum(t) / len(t))
+    e2e_val = dd.sum(float(S * B * BUFLEN)) / e2e_sec / 1e6
+    # kernels alone: CUDA events on each instance's stream around process(), its two copies timed alone and subtracted;
+    # streams one after the other, so the figure is the GPU time of the reference's launches for one step
+    tot_ms, cop_ms = C.c_double(0), C.c_double(0)
+    kern_ms_steps = []
+    n_kernel_steps = args.warmup + args.steps
+    for it in range(n_kernel_steps):
+        k_ms = 0.0
+        for s in range(S):
+            sub = (C.c_void_p * ring)(*hin[s * ring:(s + 1) * ring])
+            rc = lib.gsdr_ref_rx_process_split_timed(refs[s].h, sub, ring, houts[s], B, BUFLEN * 8, cap * 8, C.byref(tot_ms), C.byref(cop_ms))
+            if rc != 0:
+                raise SystemExit("reference split timing failed")
+            k_ms += max(tot_ms.value - cop_ms.value, 0.0)
+        if it >= args.warmup:
+            kern_ms_steps.append(k_ms)
+    ms_step = dd.max(sum(kern_ms_steps) / len(kern_ms_steps))
+    val = dd.sum(float(S * B * BUFLEN)) / (ms_step * 1e-3) / 1e6
+    for r in refs:
+        r.close()
+    if dd.rank != 0:
+        return None
+    cpu = cpu_baseline(params[0], budget_s=8.0) if (dd.world == 1 and not args.no_cpu) else None
+    res = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MS/s", "n_gpus": dd.world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": shared_config(dd.world, S, B),
+           "impl_detail": {"reference": "unmodified cpp/kernels.cu + cpp/USRP_demodulator.cpp compiled for sm_100a (oracle/_ref/libgsdr_ref.so), one "
+                                        "RX_buffer_demodulator per stream, one process per GPU; the reference has no CPU DSP path, so this arm runs "
+                                        "its CUDA path on the same B200(s)",
+                           "value": "kernels only: CUDA events on the instance's stream around RX_buffer_demodulator::process minus its two copies "
+                                    "(timed alone on the same stream), summed over the GPU's streams (cpp/USRP_demodulator.cpp:486-565: "
+                                    "polyphase_filter + cufftExecC2C + move_buffer + tone_select)",
+                           "e2e": "blocking process() with pinned host buffers from one worker thread per stream "
+                                  "(cpp/USRP_server_link_threads.cpp:605-702)"},
+           "e2e": {"value": e2e_val, "unit": "MS/s", "h2d_bytes_per_step": S * B * BUFLEN * 8, "d2h_bytes_per_step": S * B * cap * 8,
+                   "api": "RX_buffer_demodulator::process, one thread per stream", "steps": args.steps},
+           "gpu_launches": 0}
+    if cpu:
+        res["cpu_baseline"] = cpu
+    return res
 
 
 def main():
@@ -451,19 +733,26 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--buffers", type=int, default=64, help="transport buffers per step (batch)")
-    ap.add_argument("--streams", type=int, default=1, help="IQ streams per GPU")
+    ap.add_argument("--streams-total", type=int, default=TOTAL_STREAMS, help="IQ streams of the whole job (cfg5: 64)")
+    ap.add_argument("--buffers", type=int, default=0, help="transport buffers per stream per step (default: number of GPUs)")
+    ap.add_argument("--e2e-form", default="zero_copy", choices=["zero_copy", "copied"], help="form of the host-fed call behind e2e.value")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-modes", action="store_true", help="skip the per-configuration `modes` legs (N=1)")
     ap.add_argument("--profile", action="store_true", help="device-resident leg only (for ncu launch lists / captures)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     args.steps = max(args.steps, 1)
+    if args.impl == "reference" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # the reference never selects a device (it runs on the current one): give every rank its own GPU before CUDA starts
+        lr = int(os.environ.get("LOCAL_RANK", "0"))
+        vis = [v for v in os.environ.get("CUDA_VISIBLE_DEVICES", "").split(",") if v.strip()]
+        os.environ["CUDA_VISIBLE_DEVICES"] = vis[lr % len(vis)] if vis else str(lr)
     # stdout carries exactly ONE JSON line: whatever a library prints to file descriptor 1 (NCCL's version banner does,
     # whatever NCCL_DEBUG_FILE says) is sent to stderr, and the result goes to the saved descriptor.
     sys.stdout.flush()
     json_fd = os.dup(1)
     os.dup2(2, 1)
-    dd = Dist(args.gpus)
+    dd = Dist(args.gpus, force_gloo=(args.impl == "reference"))
     try:
         res = run_reference(args, dd) if args.impl == "reference" else run_ours(args, dd)
         if dd.rank == 0 and res is not None:

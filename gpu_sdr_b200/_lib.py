@@ -92,6 +92,15 @@ SIGNATURES = {
     "gsdr_rx_group_destroy": (None, [C.c_void_p]),
     "gsdr_rx_group_process_device": (C.c_int64, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p),
                                                  C.POINTER(C.c_int)]),
+    "gsdr_rx_group_submit": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    "gsdr_rx_group_submit_sc16": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    "gsdr_rx_group_wait": (C.c_int, [C.c_void_p, C.c_int]),
+    "gsdr_rx_group_input_consumed": (C.c_int, [C.c_void_p, C.c_int]),
+    "gsdr_rx_group_process": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int)]),
+    "gsdr_rx_group_pipeline_depth": (C.c_int, [C.c_void_p]),
+    "gsdr_rx_group_members": (C.c_int, [C.c_void_p]),
+    "gsdr_rx_group_zero_copy": (C.c_int, [C.c_void_p]),
+    "gsdr_rx_group_set_zero_copy": (C.c_int, [C.c_void_p, C.c_int]),
     "gsdr_rx_group_sync": (C.c_int, [C.c_void_p]),
     "gsdr_rx_group_timer_start": (C.c_int, [C.c_void_p]),
     "gsdr_rx_group_timer_stop": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
@@ -125,6 +134,7 @@ SIGNATURES = {
     "gsdr_pool_close": (None, [C.c_void_p]),
     "gsdr_pool_available": (C.c_int, [C.c_void_p]),
     "gsdr_pool_size": (C.c_int, [C.c_void_p]),
+    "gsdr_pcie_copy_ceiling": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
     "gsdr_host_alloc": (C.c_void_p, [C.c_size_t]),
     "gsdr_device_numa_node": (C.c_int, [C.c_int]),
     "gsdr_host_free": (None, [C.c_void_p]),

@@ -57,6 +57,15 @@ class DeviceOnce {
         }                                                                                  \
     } while (0)
 
+// ---- host runtime helpers (host.cu) -----------------------------------------------------------
+// Device-side alias of [host, host+bytes) when it is pinned and mapped (a kernel may read / write it in place), else nullptr.
+// Library allocations are answered from a registry; foreign pointers are asked of the driver (cached only on request).
+void* host_alias_of(const void* host, size_t bytes);
+void host_registry_add(const void* p, size_t bytes);
+void host_registry_remove(const void* p);
+// cudaSetDevice only when the calling thread's current device differs (cudaGetDevice is a thread-local read)
+int ensure_device(int device);
+
 // ---- host logic that defines results (hostlogic.cpp) ----------------------------------------
 void make_sinc_window(int length, float fc, float* out);
 void make_flat_window(int length, int side, float* out);
@@ -99,6 +108,16 @@ struct PfbJob {          // one stream's share of a launch
     // full and few long tiles beat one short tile per SM.
     int min_tile = 0;
 };
+// One tile of a multi-stream launch of the warp-specialised fused kernel: frames [fa, fb) of job `job`, relative to the job's
+// first_frame.  The host cuts the concatenated frame sequence of all jobs into equal shares, one per CTA, and splits a share
+// where it crosses a stream boundary, so every CTA carries the same number of frames whatever the number of streams
+// (uniform per-job tiles leave up to a quarter of the SMs idle at 64 streams).  flags bit 0: this is the job's last tile --
+// its CTA also copies the job's carry-over tail (PfbJob::tail_dst).
+struct PfbTile {
+    int job, fa, fb, flags;
+};
+// Device scratch a multi-stream launch needs for its job table, tile list and per-CTA tile ranges.
+size_t pfb_table_bytes(int n_jobs, int sm_count);
 // Returns the number of kernel launches issued (>0) or -1.  `workspace` is device scratch of at
 // least pfb_workspace_bytes() for the generic path (may be null for the fused path).
 bool pfb_fused_supported(int N, int P, int T, const Window& w);
@@ -140,9 +159,11 @@ int direct_fir_launch(const Window& w, const float2* g /* [T][ntaps] */, const i
 // tcgen05 / TMEM version of direct_fir_launch (direct_tc_kernels.cu): 3xTF32 split GEMM, pf_average in {1,2,4,8}
 bool direct_fir_tc_supported(int T, int M, int ntaps, long long n_out);
 bool direct_fir_tc_preferred(int T, int M, int ntaps, long long n_out);
-// rotate = 0: no LO rotation of the outputs (freq_dev unused) -- the form the generic-size polyphase channelizer takes
+// rotate = 0: no LO rotation of the outputs (freq_dev unused) -- the form the generic-size polyphase channelizer takes.
+// allow_tma = false: the window rows come through plain loads instead of TMA boxes (GSDR_DIRECT_TC_TMA=0 at create; windows
+// in pinned host memory unless GSDR_DIRECT_TC_HOST_TMA=1).
 int direct_fir_tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int M, int ntaps, int rate, long long pos0,
-                         long long n_out, float2* out, int sm_count, cudaStream_t stream, int rotate = 1);
+                         long long n_out, float2* out, int sm_count, cudaStream_t stream, int rotate = 1, bool allow_tma = true);
 int direct_mix_launch(const float2* in, long long n, const int* freq_dev, int T, int rate, long long pos0, float2* out,
                       cudaStream_t stream);
 int direct_phase_probe_launch(long long* out, unsigned int n, int tone_freq, int rate, unsigned long long index_counter,

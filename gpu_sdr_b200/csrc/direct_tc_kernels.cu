@@ -726,12 +726,10 @@ TcEncodeTiledFn tc_encode_fn() {
 // The part of the `in` segment that starts on a window-row boundary as a 2-D tensor [rows][2 M floats] (row pitch M * 8
 // bytes), box = 128 rows x 32 floats, 128-byte swizzle: exactly the K-major operand tile of one K block.  Needs a
 // 16-byte-aligned base and pitch.  *hist_rows = window rows that hold carried-over samples (ceil(n_hist / M)).
-bool tc_make_tensor_map(const Window& w, int M, CUtensorMap* map, long long* hist_rows) {
+bool tc_make_tensor_map(const Window& w, int M, CUtensorMap* map, long long* hist_rows, bool allow_tma) {
     const long long hr = (w.n_hist + M - 1) / M, off0 = hr * M - w.n_hist;
     *hist_rows = hr;
-    const char* e = getenv("GSDR_DIRECT_TC_TMA");   // =0: every tile through the register path (tests)
-    const bool off = e && e[0] == '0';
-    if (off || M < TC_KC || (M & 1) || w.n_in - off0 < M) return false;
+    if (!allow_tma || M < TC_KC || (M & 1) || w.n_in - off0 < M) return false;
     const float2* base = w.in + off0;
     if (reinterpret_cast<uintptr_t>(base) & 15) return false;
     TcEncodeTiledFn enc = tc_encode_fn();
@@ -747,7 +745,7 @@ bool tc_make_tensor_map(const Window& w, int M, CUtensorMap* map, long long* his
 
 template <int F>
 int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int M, int rate, long long pos0, long long n_out,
-              float2* out, int sm_count, cudaStream_t stream, int rotate) {
+              float2* out, int sm_count, cudaStream_t stream, int rotate, bool allow_tma) {
     constexpr int TG = 64 / F, RB = TC_ROWS - (F - 1);
     const int row_tiles = (int)((n_out + RB - 1) / RB), tone_groups = (T + TG - 1) / TG;
     static DeviceOnce attr_once;
@@ -759,7 +757,7 @@ int tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int 
     CUtensorMap map;
     memset(&map, 0, sizeof(map));
     long long hist_rows = 0;
-    const int use_tma = tc_make_tensor_map(w, M, &map, &hist_rows) ? 1 : 0;
+    const int use_tma = tc_make_tensor_map(w, M, &map, &hist_rows, allow_tma) ? 1 : 0;
     const long long tiles = (long long)row_tiles * tone_groups;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
     // GSDR_DIRECT_TC_DEBUG=1: per-role wait / run cycles of this launch on stderr (synchronises; schedule tuning only)
@@ -824,17 +822,17 @@ bool direct_fir_tc_preferred(int T, int M, int ntaps, long long n_out) {
 }
 
 int direct_fir_tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int M, int ntaps, int rate, long long pos0,
-                         long long n_out, float2* out, int sm_count, cudaStream_t stream, int rotate) {
+                         long long n_out, float2* out, int sm_count, cudaStream_t stream, int rotate, bool allow_tma) {
     if (n_out <= 0) return 0;
     if (!direct_fir_tc_supported(T, M, ntaps, n_out)) {
         set_error("direct_fir_tc_launch: unsupported shape (T=%d M=%d ntaps=%d)", T, M, ntaps);
         return -1;
     }
     switch (ntaps / M) {
-        case 1: return tc_launch<1>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate);
-        case 2: return tc_launch<2>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate);
-        case 4: return tc_launch<4>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate);
-        default: return tc_launch<8>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate);
+        case 1: return tc_launch<1>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate, allow_tma);
+        case 2: return tc_launch<2>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate, allow_tma);
+        case 4: return tc_launch<4>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate, allow_tma);
+        default: return tc_launch<8>(w, g, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate, allow_tma);
     }
 }
 

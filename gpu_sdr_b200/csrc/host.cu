@@ -6,8 +6,11 @@
 #include <deque>
 #include <memory>
 #include <mutex>
+#include <map>
 #include <random>
+#include <shared_mutex>
 #include <thread>
+#include <unordered_map>
 
 #include <sys/syscall.h>
 #include <unistd.h>
@@ -52,25 +55,111 @@ int numa_node_of_device(int device) {
     if (!known[device]) cache[device] = numa_node_of_device_uncached(device), known[device] = true;
     return cache[device];
 }
-// cudaMallocHost with the calling thread's memory policy pointed at the current GPU's node for the duration
+// cudaMallocHost with the calling thread's memory policy pointed at the current GPU's node for the duration.  The caller's
+// own policy (numactl --membind / --interleave, or a set_mempolicy of the application -- the caller may be the reference
+// server's link thread) is read first and put back exactly as it was.
 cudaError_t pinned_alloc_local(void** p, size_t bytes) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) dev = -1, cudaGetLastError();
-    const char* e = getenv("GSDR_NUMA_LOCAL");
-    const int node = (e && e[0] == '0') ? -1 : numa_node_of_device(dev);
+    static const bool numa_off = [] {
+        const char* e = getenv("GSDR_NUMA_LOCAL");
+        return e && e[0] == '0';
+    }();
+    const int node = numa_off ? -1 : numa_node_of_device(dev);
     bool bound = false;
-#ifdef SYS_set_mempolicy
-    if (node >= 0 && node < 64) {
+    int old_mode = 0;
+    unsigned long old_mask[16] = {0};   // 1024 nodes
+#if defined(SYS_set_mempolicy) && defined(SYS_get_mempolicy)
+    if (node >= 0 && node < 64 &&
+        syscall(SYS_get_mempolicy, &old_mode, old_mask, sizeof(old_mask) * 8, nullptr, 0) == 0) {
         unsigned long mask = 1ul << node;
         bound = syscall(SYS_set_mempolicy, 1 /* MPOL_PREFERRED */, &mask, sizeof(mask) * 8 + 1) == 0;
     }
 #endif
     const cudaError_t rc = cudaMallocHost(p, bytes);
-#ifdef SYS_set_mempolicy
-    if (bound) syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+#if defined(SYS_set_mempolicy) && defined(SYS_get_mempolicy)
+    if (bound) {
+        bool any = false;
+        for (unsigned long m : old_mask) any = any || m != 0;
+        if (syscall(SYS_set_mempolicy, old_mode, any ? old_mask : nullptr, any ? sizeof(old_mask) * 8 : 0) != 0)
+            syscall(SYS_set_mempolicy, 0 /* MPOL_DEFAULT */, nullptr, 0);
+    }
 #endif
     return rc;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Which host pointers can a kernel read / write in place?  Every pinned block this library hands out (pool buffers,
+// gsdr_host_alloc, the TX period buffer) is entered here with its device-side alias, so the zero-copy entry points
+// answer "is this buffer pinned and mapped" with one ordered-map lookup and no CUDA call -- that is the reference's flow
+// (buffers come from the preallocator) and the bench's.  Pointers the library did not allocate are asked of the driver
+// (cudaPointerGetAttributes, ~1 us) on every call: remembering the answer would be wrong the day such a buffer is freed and
+// its address reused by pageable memory.  GSDR_PROCESS_PTRCACHE=1 remembers it anyway, for callers that guarantee a buffer
+// keeps its nature while the library is in use.
+// ------------------------------------------------------------------------------------------------
+struct HostRange {
+    size_t bytes;
+    intptr_t delta;   // device alias = host address + delta (0 under unified addressing)
+};
+std::shared_mutex g_reg_mutex;
+std::map<uintptr_t, HostRange> g_ranges;                 // keyed by base address
+std::unordered_map<uintptr_t, void*> g_foreign;          // pointer -> alias (nullptr: pageable / not mapped)
+}  // namespace
+
+namespace gsdr {
+void host_registry_add(const void* p, size_t bytes) {
+    if (!p || !bytes) return;
+    void* d = nullptr;
+    if (cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0) != cudaSuccess) {
+        cudaGetLastError();
+        return;
+    }
+    std::unique_lock<std::shared_mutex> lk(g_reg_mutex);
+    g_ranges[reinterpret_cast<uintptr_t>(p)] = HostRange{bytes, (intptr_t)(reinterpret_cast<uintptr_t>(d) - reinterpret_cast<uintptr_t>(p))};
+}
+void host_registry_remove(const void* p) {
+    if (!p) return;
+    std::unique_lock<std::shared_mutex> lk(g_reg_mutex);
+    g_ranges.erase(reinterpret_cast<uintptr_t>(p));
+    g_foreign.clear();   // addresses may be reused by memory of another kind
+}
+void* host_alias_of(const void* host, size_t bytes) {
+    static const bool cache_on = [] {
+        const char* e = getenv("GSDR_PROCESS_PTRCACHE");
+        return e && e[0] == '1';
+    }();
+    const uintptr_t a = reinterpret_cast<uintptr_t>(host);
+    {
+        std::shared_lock<std::shared_mutex> lk(g_reg_mutex);
+        auto it = g_ranges.upper_bound(a);
+        if (it != g_ranges.begin()) {
+            --it;
+            if (a >= it->first && a + bytes <= it->first + it->second.bytes) return reinterpret_cast<void*>(a + it->second.delta);
+        }
+        if (cache_on) {
+            auto f = g_foreign.find(a);
+            if (f != g_foreign.end()) return f->second;
+        }
+    }
+    cudaPointerAttributes at{};
+    void* alias = nullptr;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) cudaGetLastError();
+    else if (at.type == cudaMemoryTypeHost) alias = at.devicePointer;
+    if (cache_on) {
+        std::unique_lock<std::shared_mutex> lk(g_reg_mutex);
+        if (g_foreign.size() < 65536) g_foreign[a] = alias;
+    }
+    return alias;
+}
+int ensure_device(int device) {
+    int cur = -1;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur == device) return 0;
+    GSDR_CUDA_OK(cudaSetDevice(device));
+    return 0;
+}
+}  // namespace gsdr
+
+namespace {
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -92,15 +181,23 @@ struct gsdr_pool {
     std::vector<gsdr_float2*> all;
     std::thread grower;
     bool closing = false;
+    int waiters = 0;   // threads inside gsdr_pool_get: close() does not free the pool under them
+    std::condition_variable cv_idle;
 
     // Every buffer has GSDR_POOL_HEADROOM bytes in front of it, so the data-socket header can be written directly
     // before the payload and the whole frame leaves with one send() (gsdr_packet_frame).
     gsdr_float2* alloc_one() {
         void* p = nullptr;
-        if (pinned_alloc_local(&p, vector_size * sizeof(gsdr_float2) + GSDR_POOL_HEADROOM) != cudaSuccess) return nullptr;
+        const size_t bytes = vector_size * sizeof(gsdr_float2) + GSDR_POOL_HEADROOM;
+        if (pinned_alloc_local(&p, bytes) != cudaSuccess) return nullptr;
+        host_registry_add(p, bytes);
         return reinterpret_cast<gsdr_float2*>(static_cast<char*>(p) + GSDR_POOL_HEADROOM);
     }
-    static void free_one(gsdr_float2* b) { cudaFreeHost(reinterpret_cast<char*>(b) - GSDR_POOL_HEADROOM); }
+    static void free_one(gsdr_float2* b) {
+        void* p = reinterpret_cast<char*>(b) - GSDR_POOL_HEADROOM;
+        host_registry_remove(p);
+        cudaFreeHost(p);
+    }
     void grow_loop() {
         cudaSetDevice(device);
         std::unique_lock<std::mutex> lk(m);
@@ -149,11 +246,16 @@ gsdr_pool* gsdr_pool_create(size_t vector_size, int pipe_size, int prefill) {
 gsdr_float2* gsdr_pool_get(gsdr_pool* pool) {
     if (!pool) return nullptr;
     std::unique_lock<std::mutex> lk(pool->m);
+    if (pool->closing) return nullptr;
+    ++pool->waiters;
     if ((double)pool->free_list.size() - 1 < pool->pipe_size / 10.) pool->cv_grow.notify_one();
     pool->cv_free.wait(lk, [&] { return pool->closing || !pool->free_list.empty(); });
-    if (pool->free_list.empty()) return nullptr;
-    gsdr_float2* b = pool->free_list.front();
-    pool->free_list.pop_front();
+    gsdr_float2* b = nullptr;
+    if (!pool->closing && !pool->free_list.empty()) {
+        b = pool->free_list.front();
+        pool->free_list.pop_front();
+    }
+    if (--pool->waiters == 0 && pool->closing) pool->cv_idle.notify_all();
     return b;
 }
 
@@ -175,6 +277,10 @@ void gsdr_pool_close(gsdr_pool* pool) {
     pool->cv_grow.notify_all();
     pool->cv_free.notify_all();
     if (pool->grower.joinable()) pool->grower.join();
+    {   // getters woken by `closing` still hold or re-acquire the mutex: let them leave before the pool goes away
+        std::unique_lock<std::mutex> lk(pool->m);
+        pool->cv_idle.wait(lk, [&] { return pool->waiters == 0; });
+    }
     for (auto* b : pool->all) gsdr_pool::free_one(b);
     delete pool;
 }
@@ -274,7 +380,10 @@ int gsdr_replay_next(gsdr_replay* r, gsdr_rx_packet* pkt) {
         return -1;
     }
     gsdr_float2* src = buf;
-    if (gsdr_tx_get(r->tx, &src)) return -1;  // TONES re-points src; CHIRP fills buf
+    if (gsdr_tx_get(r->tx, &src)) {  // TONES re-points src; CHIRP fills buf
+        gsdr_pool_trash(r->pool, buf);
+        return -1;
+    }
     if (src != buf) std::memcpy(buf, src, sizeof(gsdr_float2) * r->L);
     if (r->sigma > 0.f) {
         const gsdr_float2* nz = r->noise.data() + (r->packets * 7919ull) % gsdr_replay::kBankExtra;
@@ -433,17 +542,83 @@ int gsdr_packet_frame(const gsdr_rx_packet* pkt, const void** frame, size_t* fra
     return 0;
 }
 
+// What plain cudaMemcpyAsync between pinned host memory and `device` delivers on this platform: the ceiling every host-fed
+// figure is measured against.  One cudaMemcpyAsync per buffer (h2d_bytes up / d2h_bytes down, `reps` buffers each way), three
+// passes: upload alone, download alone, both directions at once on two streams.  out_gbs = {h2d, d2h, duplex h2d, duplex d2h}
+// in 1e9 bytes/s.  Ranks of a multi-GPU job call it between barriers, so the numbers include what the host shares out.
+int gsdr_pcie_copy_ceiling(int device, size_t h2d_bytes, size_t d2h_bytes, int reps, double* out_gbs) {
+    if (!out_gbs || reps < 1 || (h2d_bytes == 0 && d2h_bytes == 0)) {
+        set_error("gsdr_pcie_copy_ceiling: bad argument");
+        return -1;
+    }
+    GSDR_CUDA_OK(cudaSetDevice(device));
+    constexpr int kBufs = 4;
+    void *h_in[kBufs] = {nullptr}, *h_out[kBufs] = {nullptr}, *d_in = nullptr, *d_out = nullptr;
+    cudaStream_t s_up = nullptr, s_dn = nullptr;
+    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    int rc = -1;
+    do {
+        bool ok = cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking) == cudaSuccess &&
+                  cudaStreamCreateWithFlags(&s_dn, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreate(&e[i]) == cudaSuccess;
+        ok = ok && cudaMalloc(&d_in, h2d_bytes ? h2d_bytes : 1) == cudaSuccess && cudaMalloc(&d_out, d2h_bytes ? d2h_bytes : 1) == cudaSuccess;
+        for (int i = 0; i < kBufs && ok; ++i) {
+            ok = pinned_alloc_local(&h_in[i], h2d_bytes ? h2d_bytes : 1) == cudaSuccess &&
+                 pinned_alloc_local(&h_out[i], d2h_bytes ? d2h_bytes : 1) == cudaSuccess;
+            if (ok) memset(h_in[i], 1, h2d_bytes ? h2d_bytes : 1), memset(h_out[i], 0, d2h_bytes ? d2h_bytes : 1);
+        }
+        if (!ok) break;
+        auto pass = [&](bool up, bool dn, double* up_gbs, double* dn_gbs) -> bool {
+            for (int w = 0; w < 2; ++w) {   // w == 0: warm-up
+                const int n = w ? reps : 2;
+                if (cudaStreamSynchronize(s_up) != cudaSuccess || cudaStreamSynchronize(s_dn) != cudaSuccess) return false;
+                if (up) cudaEventRecord(e[0], s_up);
+                if (dn) cudaEventRecord(e[2], s_dn);
+                for (int i = 0; i < n; ++i) {
+                    if (up && h2d_bytes) cudaMemcpyAsync(d_in, h_in[i % kBufs], h2d_bytes, cudaMemcpyHostToDevice, s_up);
+                    if (dn && d2h_bytes) cudaMemcpyAsync(h_out[i % kBufs], d_out, d2h_bytes, cudaMemcpyDeviceToHost, s_dn);
+                }
+                if (up) cudaEventRecord(e[1], s_up);
+                if (dn) cudaEventRecord(e[3], s_dn);
+                if (cudaStreamSynchronize(s_up) != cudaSuccess || cudaStreamSynchronize(s_dn) != cudaSuccess) return false;
+            }
+            float ms = 0.f;
+            if (up && up_gbs) *up_gbs = cudaEventElapsedTime(&ms, e[0], e[1]) == cudaSuccess && ms > 0 ? (double)h2d_bytes * reps / (ms * 1e6) : 0.0;
+            if (dn && dn_gbs) *dn_gbs = cudaEventElapsedTime(&ms, e[2], e[3]) == cudaSuccess && ms > 0 ? (double)d2h_bytes * reps / (ms * 1e6) : 0.0;
+            return true;
+        };
+        out_gbs[0] = out_gbs[1] = out_gbs[2] = out_gbs[3] = 0.0;
+        if (!pass(true, false, &out_gbs[0], nullptr) || !pass(false, true, nullptr, &out_gbs[1]) || !pass(true, true, &out_gbs[2], &out_gbs[3])) break;
+        rc = 0;
+    } while (false);
+    if (rc) set_error("gsdr_pcie_copy_ceiling: %s", cudaGetErrorString(cudaGetLastError()));
+    for (int i = 0; i < kBufs; ++i) {
+        if (h_in[i]) cudaFreeHost(h_in[i]);
+        if (h_out[i]) cudaFreeHost(h_out[i]);
+    }
+    if (d_in) cudaFree(d_in);
+    if (d_out) cudaFree(d_out);
+    for (auto ev : e)
+        if (ev) cudaEventDestroy(ev);
+    if (s_up) cudaStreamDestroy(s_up);
+    if (s_dn) cudaStreamDestroy(s_dn);
+    return rc;
+}
+
 void* gsdr_host_alloc(size_t bytes) {
     void* p = nullptr;
     if (pinned_alloc_local(&p, bytes ? bytes : 1) != cudaSuccess) {
         set_error("cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }
+    host_registry_add(p, bytes ? bytes : 1);
     return p;
 }
 int gsdr_device_numa_node(int device) { return numa_node_of_device(device); }
 void gsdr_host_free(void* p) {
-    if (p) cudaFreeHost(p);
+    if (!p) return;
+    host_registry_remove(p);
+    cudaFreeHost(p);
 }
 void* gsdr_dev_alloc(int device, size_t bytes) {
     void* p = nullptr;

@@ -383,7 +383,9 @@ __device__ __forceinline__ void bar_arrive(int id, int count) {
 }
 constexpr int WS_PC = WS_FRONT + WS_TEAM;        // participants of a full/empty barrier
 
-// tile -> (job, frame range); identical in every warp role so the frame counters stay in step
+// tile -> (job, frame range); identical in every warp role so the frame counters stay in step.
+// Two forms: arithmetic (one stream, or the lock-step kernel's uniform tiles) and an explicit table built by the host for
+// multi-stream launches (PfbTile: balanced over the CTAs, tiles never span two streams).
 struct WsTile {
     int job;
     long long fa, fb;  // window frame indices [fa, fb)
@@ -403,6 +405,15 @@ __device__ __forceinline__ WsTile ws_locate(int tile, const PfbJob& single, cons
     r.fa = (long long)job.first_frame + (long long)tile_in_job * frames_per_tile;
     const long long end = (long long)job.first_frame + job.n_frames;
     r.fb = r.fa + frames_per_tile < end ? r.fa + frames_per_tile : end;
+    return r;
+}
+__device__ __forceinline__ WsTile ws_locate_table(const PfbTile* tiles, int ti, const PfbJob* table, PfbJob& job) {
+    const PfbTile tt = tiles[ti];
+    job = table[tt.job];
+    WsTile r;
+    r.job = tt.job;
+    r.fa = (long long)job.first_frame + tt.fa;
+    r.fb = (long long)job.first_frame + tt.fb;
     return r;
 }
 
@@ -507,7 +518,8 @@ __device__ __forceinline__ void for_each_index(std::integer_sequence<int, I...>,
 template <int P, int LA, bool HOIST>
 __global__ void __launch_bounds__(WP_THREADS, 1)
 pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, const int* __restrict__ tile_begin, int n_jobs,
-                          int frames_per_tile, int total_tiles, const float2* __restrict__ tw_global) {
+                          int frames_per_tile, int total_tiles, const float2* __restrict__ tw_global,
+                          const PfbTile* __restrict__ tiles, const int* __restrict__ cta_begin) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WpSmem& sm = *reinterpret_cast<WpSmem*>(smem_raw);
     const int t = threadIdx.x;
@@ -522,9 +534,25 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
             mbar_init(xempty0 + 8 * i, WS_FRONT / 32);
         }
     }
-    // carry-over of a single-stream launch (what move_buffer does in the reference, cpp/kernels.cu:444-470): the CTA with
-    // the last, shorter tile copies the window's tail into the other history buffer -- input only, nothing here reads it
-    if (n_jobs == 1 && single.tail_dst != nullptr && blockIdx.x == gridDim.x - 1) {
+    // This CTA's tiles: [t_lo, t_hi) step t_step.  Table form (multi-stream): a contiguous run of the host-built tile list;
+    // arithmetic form: tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int t_lo = tiles ? cta_begin[blockIdx.x] : (int)blockIdx.x;
+    const int t_hi = tiles ? cta_begin[blockIdx.x + 1] : total_tiles;
+    const int t_step = tiles ? 1 : (int)gridDim.x;
+    // carry-over (what move_buffer does in the reference, cpp/kernels.cu:444-470): the CTA that owns a stream's last tile
+    // copies the window's tail into the other history buffer -- input only, nothing in this launch reads it
+    if (tiles) {
+        for (int ti = t_lo; ti < t_hi; ++ti) {
+            const PfbTile tt = tiles[ti];
+            if (tt.flags & 1) {
+                const PfbJob jb = table[tt.job];
+                if (jb.tail_dst != nullptr) {
+                    const long long first = jb.win.n_hist + jb.win.n_in - jb.tail_n;
+                    for (long long i = t; i < jb.tail_n; i += WS_THREADS) jb.tail_dst[i] = win_at(jb.win, first + i);
+                }
+            }
+        }
+    } else if (n_jobs == 1 && single.tail_dst != nullptr && blockIdx.x == gridDim.x - 1) {
         const long long first = single.win.n_hist + single.win.n_in - single.tail_n;
         for (long long i = t; i < single.tail_n; i += WS_THREADS) single.tail_dst[i] = win_at(single.win, first + i);
     }
@@ -559,8 +587,9 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
         int nv = 0;               // how many of the NU output slots exist (u < T)
         const unsigned int x_base = (unsigned int)__cvta_generic_to_shared(&sm.x[0][0][0]);
         int loaded_job = -1;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const WsTile tl = ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
+        for (int tile = t_lo; tile < t_hi; tile += t_step) {
+            const WsTile tl = tiles ? ws_locate_table(tiles, tile, table, job)
+                                    : ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
             if (tl.job != loaded_job) {
 #pragma unroll
                 for (int i = 0; i < P; ++i)
@@ -760,8 +789,9 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
         const unsigned int xw0 = (unsigned int)__cvta_generic_to_shared(&sm.x[q][0][0]) + (unsigned int)(k1 * 256 * sizeof(float2));
         unsigned int xo[4];  // byte offset inside row (k1, k3) of this thread's bin k1 + 8 k2 + 128 k3, one byte per k3
         int loaded_job = -1;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const WsTile tl = ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
+        for (int tile = t_lo; tile < t_hi; tile += t_step) {
+            const WsTile tl = tiles ? ws_locate_table(tiles, tile, table, job)
+                                    : ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
             if (tl.job != loaded_job) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -1043,42 +1073,85 @@ static int launch_ws(const PfbJob* jobs, int n_jobs, void* scratch, const float2
         if (min_tile > frames_per_tile) frames_per_tile = min_tile;
         if (min_tile == 0 && n_jobs == 1 && jobs[0].min_tile > frames_per_tile) frames_per_tile = jobs[0].min_tile;
     }
-    std::vector<int> tile_begin(n_jobs + 1, 0);
-    // Tiles never span two streams, so with several jobs the per-job round-up can push the tile count
-    // just past one wave (152 tiles on 148 SMs doubles the makespan): grow the tile until one wave holds it.
-    for (;; ++frames_per_tile) {
-        for (int j = 0; j < n_jobs; ++j)
-            tile_begin[j + 1] = tile_begin[j] + (jobs[j].n_frames + frames_per_tile - 1) / frames_per_tile;
-        if (tile_begin[n_jobs] <= sm_count || n_jobs > sm_count) break;
-    }
-    const int total_tiles = tile_begin[n_jobs];
-    int grid = total_tiles < sm_count ? total_tiles : sm_count;
-    {   // test hook: a smaller grid makes every CTA walk several tiles (the path a launch of more than sm_count
-        // streams takes); results must not change
+    int grid_cap = 0;
+    {   // test hook: a smaller grid makes every CTA walk several tiles; results must not change
         static int cap = -1;
         if (cap < 0) {
             const char* e = getenv("GSDR_PFB_MAX_GRID");
             cap = e ? atoi(e) : 0;
         }
-        if (cap > 0 && grid > cap) grid = cap;
+        grid_cap = cap;
     }
-    const PfbJob* table = nullptr;
-    const int* tb = nullptr;
     if (n_jobs > 1) {
+        // ---- multi-stream launch: balanced explicit tile list ------------------------------------------------------------
         if (!scratch) {
             set_error("pfb_launch: multi-stream launch needs a job table buffer");
             return -1;
         }
+        int grid = (int)(total_frames < sm_count ? total_frames : sm_count);
+        // windows in pinned HOST memory (zero-copy group submit): reads over PCIe are not kept in L2, so the P-1 halo rows of
+        // every tile cross the link again -- fewer, longer tiles (PfbJob::min_tile frames), never fewer than six CTAs
+        int want_tile = 0;
+        for (int j = 0; j < n_jobs; ++j) want_tile = jobs[j].min_tile > want_tile ? jobs[j].min_tile : want_tile;
+        if (want_tile > 0) {
+            long long g2 = total_frames / want_tile;
+            g2 = g2 < 6 ? 6 : g2;
+            if (g2 < grid) grid = (int)g2;
+        }
+        if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
+        std::vector<PfbTile> tiles;
+        std::vector<int> cta_begin(grid + 1, 0);
+        tiles.reserve((size_t)grid + n_jobs);
+        int j = 0;
+        long long job_lo = 0;   // global index of job j's first frame
+        while (j < n_jobs && jobs[j].n_frames == 0) ++j;
+        for (int c = 0; c < grid; ++c) {
+            cta_begin[c] = (int)tiles.size();
+            long long lo = total_frames * c / grid;
+            const long long hi = total_frames * (c + 1) / grid;
+            while (lo < hi) {
+                while (lo >= job_lo + jobs[j].n_frames) job_lo += jobs[j].n_frames, ++j;
+                const long long job_hi = job_lo + jobs[j].n_frames;
+                const long long e = hi < job_hi ? hi : job_hi;
+                tiles.push_back(PfbTile{j, (int)(lo - job_lo), (int)(e - job_lo), e == job_hi ? 1 : 0});
+                lo = e;
+            }
+        }
+        cta_begin[grid] = (int)tiles.size();
+        // streams without frames in this launch still carry their tail: give them an empty tile on the last CTA
+        for (int k = 0; k < n_jobs; ++k)
+            if (jobs[k].n_frames == 0 && jobs[k].tail_dst && jobs[k].tail_n > 0) tiles.push_back(PfbTile{k, 0, 0, 1}), cta_begin[grid] = (int)tiles.size();
+        const size_t off_tiles = (sizeof(PfbJob) * n_jobs + 15) & ~size_t(15);
+        const size_t off_cta = off_tiles + sizeof(PfbTile) * tiles.size();
+        const size_t bytes = off_cta + sizeof(int) * cta_begin.size();
+        if (bytes > pfb_table_bytes(n_jobs, sm_count)) {
+            set_error("pfb_launch: internal: tile table larger than its buffer");
+            return -1;
+        }
+        std::vector<unsigned char> blob(bytes);
+        memcpy(blob.data(), jobs, sizeof(PfbJob) * n_jobs);
+        memcpy(blob.data() + off_tiles, tiles.data(), sizeof(PfbTile) * tiles.size());
+        memcpy(blob.data() + off_cta, cta_begin.data(), sizeof(int) * cta_begin.size());
         unsigned char* base = static_cast<unsigned char*>(scratch);
-        GSDR_CUDA_OK(cudaMemcpyAsync(base, jobs, sizeof(PfbJob) * n_jobs, cudaMemcpyHostToDevice, stream));
-        const size_t off = (sizeof(PfbJob) * n_jobs + 15) & ~size_t(15);
-        GSDR_CUDA_OK(cudaMemcpyAsync(base + off, tile_begin.data(), sizeof(int) * (n_jobs + 1), cudaMemcpyHostToDevice, stream));
-        table = reinterpret_cast<const PfbJob*>(base);
-        tb = reinterpret_cast<const int*>(base + off);
+        // < 64 KB from pageable memory: the driver embeds the bytes in the command stream, the call does not wait for the GPU
+        GSDR_CUDA_OK(cudaMemcpyAsync(base, blob.data(), bytes, cudaMemcpyHostToDevice, stream));
+        kernel<<<grid, WS_THREADS, smem_bytes, stream>>>(jobs[0], reinterpret_cast<const PfbJob*>(base), nullptr, n_jobs, 0, (int)tiles.size(), tw,
+                                                         reinterpret_cast<const PfbTile*>(base + off_tiles),
+                                                         reinterpret_cast<const int*>(base + off_cta));
+        GSDR_CUDA_OK(cudaGetLastError());
+        return 1;
     }
-    kernel<<<grid, WS_THREADS, smem_bytes, stream>>>(jobs[0], table, tb, n_jobs, frames_per_tile, total_tiles, tw);
+    const int total_tiles = (int)((total_frames + frames_per_tile - 1) / frames_per_tile);
+    int grid = total_tiles < sm_count ? total_tiles : sm_count;
+    if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
+    kernel<<<grid, WS_THREADS, smem_bytes, stream>>>(jobs[0], nullptr, nullptr, 1, frames_per_tile, total_tiles, tw, nullptr, nullptr);
     GSDR_CUDA_OK(cudaGetLastError());
     return 1;
+}
+
+size_t pfb_table_bytes(int n_jobs, int sm_count) {
+    return ((sizeof(PfbJob) * (size_t)n_jobs + 15) & ~size_t(15)) + sizeof(PfbTile) * ((size_t)sm_count + 2 * (size_t)n_jobs + 8) +
+           sizeof(int) * ((size_t)sm_count + 2) + 256;
 }
 
 // 0 = lock-step kernel (kept as an independent second implementation for cross-checks),

@@ -105,8 +105,9 @@ struct gsdr_rx {
     bool pfb_tc = false;      // channelizer size without a fused kernel: the filter bank as a GEMM on the tensor cores
     int batching = 0, T_sel = 0;
     bool fused = false;
-    std::unordered_map<const void*, void*> alias_cache;  // GSDR_PROCESS_PTRCACHE=1: host buffer -> device alias (nullptr = pageable)
+    bool zc_enabled = true;    // GSDR_PROCESS_ZEROCOPY (read once, at create): blocking process() on pinned buffers is one launch
     bool host_window = false;  // this call's input window is pinned host memory read in place (zero-copy blocking call)
+    bool tc_tma = true, tc_host_tma = false;  // GSDR_DIRECT_TC_TMA=0 / GSDR_DIRECT_TC_HOST_TMA=1, read at create
     gsdr_buffer_helper bh{};
 
     // CHIRP
@@ -129,9 +130,24 @@ struct gsdr_rx {
 
 namespace {
 
-int set_dev(const gsdr_rx* rx) {
-    GSDR_CUDA_OK(cudaSetDevice(rx->device));
-    return 0;
+int set_dev(const gsdr_rx* rx) { return ensure_device(rx->device); }
+bool tc_tma_allowed(const gsdr_rx* rx) { return rx->tc_tma && (!rx->host_window || rx->tc_host_tma); }
+
+// Stream state that a call advances.  enqueue_compute works on the live fields and puts this snapshot back when anything
+// fails after the helpers have moved, so a failed call (cudaMalloc, a launch) leaves the demodulator where it was.
+struct RxState {
+    gsdr_buffer_helper bh;
+    gsdr_vna_helper vh;
+    int spec_carried, hist_cur;
+    long long n_hist, index_counter;
+    unsigned long long last_index;
+};
+RxState save_state(const gsdr_rx* rx) {
+    return RxState{rx->bh, rx->vh, rx->spec_carried, rx->hist_cur, rx->n_hist, rx->index_counter, rx->last_index};
+}
+void restore_state(gsdr_rx* rx, const RxState& st) {
+    rx->bh = st.bh, rx->vh = st.vh, rx->spec_carried = st.spec_carried, rx->hist_cur = st.hist_cur;
+    rx->n_hist = st.n_hist, rx->index_counter = st.index_counter, rx->last_index = st.last_index;
 }
 
 template <class Tp>
@@ -345,7 +361,14 @@ int init_direct(gsdr_rx* rx) {
 
 // Enqueue the compute for n_buf consecutive buffers at d_in on s_comp.  Fills lens (per buffer) and
 // returns the total valid float2 count.
+long long enqueue_compute_impl(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_out, int* lens);
 long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_out, int* lens) {
+    const RxState before = save_state(rx);
+    const long long total = enqueue_compute_impl(rx, d_in, n_buf, d_out, lens);
+    if (total < 0) restore_state(rx, before);
+    return total;
+}
+long long enqueue_compute_impl(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_out, int* lens) {
     cudaStream_t st = rx->s_comp;
     const long long L = rx->L;
     Window w{rx->hist[rx->hist_cur], d_in, rx->n_hist, L * n_buf};
@@ -418,7 +441,7 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
                 }
             }
             const int nl = rx->pfb_tc ? direct_fir_tc_launch(w, rx->d_g, nullptr, rx->T_sel, rx->N, rx->N * (int)rx->P, 1, 0, frames, d_out,
-                                                             rx->sm_count, st, /*rotate=*/0)
+                                                             rx->sm_count, st, /*rotate=*/0, tc_tma_allowed(rx))
                                       : pfb_launch(&job, 1, nullptr, rx->d_work, rx->d_tw, rx->sm_count, st);
             if (nl < 0) return -1;
             rx->launches += nl;
@@ -500,7 +523,7 @@ long long enqueue_compute(gsdr_rx* rx, const float2* d_in, int n_buf, float2* d_
                 long long pos0 = (rx->index_counter - w.n_hist) % rx->rate;
                 if (pos0 < 0) pos0 += rx->rate;
                 const int nl = rx->direct_tc ? direct_fir_tc_launch(w, rx->d_g, rx->d_freq, rx->T, (int)M, rx->ntaps, rx->rate, pos0,
-                                                                    n_out, d_out, rx->sm_count, st)
+                                                                    n_out, d_out, rx->sm_count, st, /*rotate=*/1, tc_tma_allowed(rx))
                                              : direct_fir_launch(w, rx->d_g, rx->d_freq, rx->T, (int)M, rx->ntaps, rx->rate, pos0, n_out,
                                                                  d_out, st);
                 if (nl < 0) return -1;
@@ -599,6 +622,14 @@ gsdr_rx* gsdr_rx_create(const gsdr_param* p, int device, int diagnostic) {
     rx->device = device;
     rx->mode = mode;
     rx->diagnostic = diagnostic != 0;
+    {   // process-wide switches are read here, once, never on the per-buffer path
+        const char* zc = getenv("GSDR_PROCESS_ZEROCOPY");
+        rx->zc_enabled = !(zc && zc[0] == '0');
+        const char* tm = getenv("GSDR_DIRECT_TC_TMA");        // =0: every tile through the register path (tests)
+        rx->tc_tma = !(tm && tm[0] == '0');
+        const char* ht = getenv("GSDR_DIRECT_TC_HOST_TMA");   // =1: TMA boxes fetched from pinned host memory
+        rx->tc_host_tma = ht && ht[0] == '1';
+    }
     rx->rate = p->rate;
     rx->N = p->fft_tones;
     rx->L = (long long)p->buffer_len;
@@ -752,7 +783,14 @@ int gsdr_rx_pipeline_depth(const gsdr_rx* rx) { return rx ? (int)(rx->slots.empt
 // reference's process_pfb (cpp/USRP_demodulator.cpp:486-565) and a naive port serialise the three (8 MB up, kernels,
 // 3.9 MB down); this makes the unchanged blocking drop-in call run at the speed of the slower PCIe direction.
 // Results are identical to the one-launch path: same frames, same kernel, same carry-over.
+static int process_pfb_chunked_impl(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* out);
 static int process_pfb_chunked(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* out) {
+    const RxState before = save_state(rx);
+    const int len = process_pfb_chunked_impl(rx, in, out);
+    if (len < 0) restore_state(rx, before);
+    return len;
+}
+static int process_pfb_chunked_impl(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* out) {
     // Upload chunks per call.  More chunks shorten the tail (the last chunk's kernel + download) but cost ~6 API calls each,
     // and on this pool's hosts those dominate: measured per 1e6-sample buffer (8 MB up, 3.9 MB down) 1 chunk 259 us, 2 chunks
     // 228 us, 4 chunks 242 us, 8 chunks 272 us, 16 chunks 316 us.  GSDR_PROCESS_CHUNKS overrides.  (Storing the tones straight
@@ -765,7 +803,6 @@ static int process_pfb_chunked(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* 
     }();
     const long long L = rx->L, N = rx->N, P = rx->P;
     Slot& s = rx->slots[0];
-    if (s.used) GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));
     if (rx->ev_chunk_in.empty()) {
         rx->ev_chunk_in.resize(kChunks);
         rx->ev_chunk_comp.resize(kChunks);
@@ -818,32 +855,21 @@ static int process_pfb_chunked(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* 
     GSDR_CUDA_OK(cudaEventRecord(s.in_done, rx->s_in));
     GSDR_CUDA_OK(cudaEventRecord(s.comp_done, rx->s_comp));
     GSDR_CUDA_OK(cudaEventRecord(s.out_done, rx->s_out));
-    s.used = true;
     rx->tickets++;
     GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));
     GSDR_CUDA_OK(cudaEventSynchronize(s.comp_done));  // carry-over written, input fully consumed
     return len;
 }
 
-// Device-side alias of a pinned (page-locked, mapped) host pointer, or nullptr when the memory is pageable / not mapped.
-static void* mapped_alias(const void* host) {
-    cudaPointerAttributes a{};
-    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) {
-        cudaGetLastError();
-        return nullptr;
-    }
-    return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
-}
-
-// Blocking call, fused filter bank, zero-copy form (the default when both buffers are pinned and mapped; GSDR_PROCESS_ZEROCOPY=0
-// turns it off): ONE kernel launch whose loads read the caller's pinned input buffer over PCIe and whose stores write the
-// tones into the caller's pinned output buffer, so both PCIe directions run concurrently under a single launch and no
-// copy-engine call or cross-stream hand-off is made.  Same kernel, same frames, same carry-over as every other entry point
-// (outputs bit-identical).  Measured per 1e6-sample buffer on B200 (tools/process_latency.py, profiles/r1_process_latency.jsonl):
-// chunked copies 229 us; zero-copy with one 4-frame tile per SM 328 us (reads from host memory are not kept in L2, so the
-// three halo rows of every tile cross PCIe again: 1.75x the bytes); with 8 / 16 / 32 / 64 / 128-frame tiles 261 / 227 / 205 /
-// 195 / 257 us (128: four CTAs no longer keep the read pipe full).  All of them sit on ~43 GB/s of PCIe reads.
-static int process_pfb_zerocopy(gsdr_rx* rx, const float2* in_alias, float2* out_alias) {
+// Blocking call, zero-copy form (the default when both buffers are pinned and mapped; GSDR_PROCESS_ZEROCOPY=0 at create turns
+// it off): the kernels' loads read the caller's pinned input buffer over PCIe and their stores write the result into the
+// caller's pinned output buffer, so both PCIe directions run concurrently under the launch itself and no copy-engine call or
+// cross-stream hand-off is made.  Same kernels, same frames, same carry-over as every other entry point (outputs
+// bit-identical).  Fused channelizer, measured per 1e6-sample buffer on B200 (tools/process_latency.py,
+// profiles/r1_process_latency.jsonl): chunked copies 229 us; zero-copy with one 4-frame tile per SM 328 us (reads from host
+// memory are not kept in L2, so the three halo rows of every tile cross PCIe again: 1.75x the bytes); with 8 / 16 / 32 / 64 /
+// 128-frame tiles 261 / 227 / 205 / 195 / 257 us (128: four CTAs no longer keep the read pipe full).
+static int process_zerocopy(gsdr_rx* rx, const float2* in_alias, float2* out_alias) {
     int len = 0;
     rx->host_window = true;
     const long long total = enqueue_compute(rx, in_alias, 1, out_alias, &len);
@@ -855,33 +881,32 @@ static int process_pfb_zerocopy(gsdr_rx* rx, const float2* in_alias, float2* out
 }
 
 int gsdr_rx_process(gsdr_rx* rx, const gsdr_float2* in, gsdr_float2* out) {
-    if (rx && in && out && rx->fused && !rx->slots.empty() && rx->L >= 64LL * rx->N &&
-        (rx->mode == GSDR_TONES || rx->mode == GSDR_NOISE) && !rx->post_decim) {
-        if (set_dev(rx)) return -1;
-        // keep the ticket/slot rotation of submit() intact: the blocking path always uses slot 0 and leaves every slot idle
-        for (auto& sl : rx->slots)
-            if (sl.used) GSDR_CUDA_OK(cudaEventSynchronize(sl.out_done));
-        const char* zc = getenv("GSDR_PROCESS_ZEROCOPY");  // read per call (a few ns) so one process can compare both forms
-        if (!(zc && zc[0] == '0')) {
-            // GSDR_PROCESS_PTRCACHE=1: remember the answer per buffer address (pool buffers come back every few calls).  Opt-in:
-            // it assumes what the reference's pool guarantees -- a buffer handed to process() stays pinned while this
-            // demodulator lives -- and a cudaHostUnregister behind our back would leave a stale alias.
-            const char* pc = getenv("GSDR_PROCESS_PTRCACHE");
-            const bool use_cache = pc && pc[0] == '1';
-            auto alias_of = [&](const void* h) -> void* {
-                if (!use_cache) return mapped_alias(h);
-                auto it = rx->alias_cache.find(h);
-                if (it != rx->alias_cache.end()) return it->second;
-                void* a = mapped_alias(h);
-                if (rx->alias_cache.size() < 4096) rx->alias_cache.emplace(h, a);
-                return a;
-            };
-            void* ia = alias_of(in);
-            void* oa = alias_of(out);
-            if (ia && oa) return process_pfb_zerocopy(rx, static_cast<const float2*>(ia), static_cast<float2*>(oa));
-        }
-        return process_pfb_chunked(rx, in, out);
+    if (!rx || !in || !out) {
+        set_error("gsdr_rx_process: null argument");
+        return -1;
     }
+    if (rx->mode == GSDR_NODSP || rx->slots.empty()) {
+        int len = 0;
+        const int ticket = gsdr_rx_submit(rx, in, out, &len);
+        return ticket < 0 ? -1 : len;
+    }
+    if (set_dev(rx)) return -1;
+    // keep the ticket/slot rotation of submit() intact: the blocking paths leave every slot idle
+    for (auto& sl : rx->slots)
+        if (sl.used) {
+            GSDR_CUDA_OK(cudaEventSynchronize(sl.out_done));
+            sl.used = false;
+        }
+    const bool pfb = (rx->mode == GSDR_TONES || rx->mode == GSDR_NOISE);
+    const bool pfb_fused_call = pfb && rx->fused && rx->L >= 64LL * rx->N && !rx->post_decim;
+    // one-launch form: the fused channelizer (measured faster than the copied form), DIRECT and CHIRP (one pass over the input,
+    // so reading it over PCIe costs what the upload would, and the kernels, the download and ~10 API calls overlap with it)
+    if (rx->zc_enabled && (pfb_fused_call || rx->mode == GSDR_DIRECT || rx->mode == GSDR_CHIRP)) {
+        void* ia = host_alias_of(in, sizeof(float2) * (size_t)rx->L);
+        void* oa = ia ? host_alias_of(out, sizeof(float2) * (rx->max_out ? rx->max_out : 1)) : nullptr;
+        if (ia && oa) return process_zerocopy(rx, static_cast<const float2*>(ia), static_cast<float2*>(oa));
+    }
+    if (pfb_fused_call) return process_pfb_chunked(rx, in, out);
     int len = 0;
     const int ticket = gsdr_rx_submit(rx, in, out, &len);
     if (ticket < 0) return -1;
@@ -1038,15 +1063,150 @@ int gsdr_rx_get_bins(const gsdr_rx* rx, int32_t* bins, size_t cap) {
 }
 
 // ---- multi-stream group: one persistent launch over every member's frames ----------------------
+// cfg5 as the reference would run it is one RX_buffer_demodulator per front-end, each fed by its own link thread calling
+// the blocking process() (cpp/USRP_server_link_threads.cpp:605-702, call at :666).  With S streams on a GPU that is S
+// uploads, S x 4 kernel launches and S downloads per packet period, each launch a fraction of a wave.  A group takes one
+// buffer of every member stream per call and issues ONE channelizer launch whose tile list spans all of them:
+//   device-resident  gsdr_rx_group_process_device   (inputs already in HBM)
+//   host-fed         gsdr_rx_group_submit / _wait   (pinned host buffers in and out, pipelined, fc32 or sc16)
+// Host-fed, copied form: one cudaMemcpyAsync per stream buffer on the copy-in stream into a contiguous staging area, the
+// launch on the compute stream, one cudaMemcpyAsync per stream on the copy-out stream; three slots, so the upload of period
+// k+1, the launch of period k and the download of period k-1 overlap.  Zero-copy form (every buffer pinned and mapped): the
+// launch reads the S host buffers and writes the S host outputs in place -- one table upload and one launch per period.
+namespace {
+struct GroupSlot {
+    float2* d_in = nullptr;    // [S][L]           (copied form)
+    float2* d_out = nullptr;   // [sum max_out_i]  (copied form)
+    short2* d_raw = nullptr;   // [S][L] sc16 staging, allocated on first use
+    cudaEvent_t in_done = nullptr, comp_done = nullptr, out_done = nullptr;
+    bool used = false;
+};
+// up to 64 raw sc16 buffers per conversion launch (kernel parameter block)
+struct Sc16Batch {
+    const short2* src[64];
+    float2* dst[64];
+};
+__global__ void __launch_bounds__(256) sc16_to_fc32_batch_kernel(const Sc16Batch b, long long n) {
+    const short2* __restrict__ in = b.src[blockIdx.y];
+    float2* __restrict__ out = b.dst[blockIdx.y];
+    const long long n4 = n >> 2;
+    const bool vec = ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (vec) {
+        for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+            const int4 v = __ldg(reinterpret_cast<const int4*>(in) + i);
+            const int w[4] = {v.x, v.y, v.z, v.w};
+            float4 o[2];
+            float* of = reinterpret_cast<float*>(o);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                of[2 * k] = (float)(short)(w[k] & 0xffff) * kSc16Scale;
+                of[2 * k + 1] = (float)(short)(w[k] >> 16) * kSc16Scale;
+            }
+            reinterpret_cast<float4*>(out)[2 * i] = o[0];
+            reinterpret_cast<float4*>(out)[2 * i + 1] = o[1];
+        }
+    }
+    for (long long i = (vec ? (n4 << 2) : 0) + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const short2 v = in[i];
+        out[i] = make_float2((float)v.x * kSc16Scale, (float)v.y * kSc16Scale);
+    }
+}
+}  // namespace
+
 struct gsdr_rx_group {
     std::vector<gsdr_rx*> members;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr, s_in = nullptr, s_out = nullptr;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     void* d_table = nullptr;
     void* d_tail = nullptr;
     uint64_t launches = 0;
     int device = 0;
+    // host-fed path
+    std::vector<GroupSlot> slots;
+    std::vector<size_t> out_off;   // member i's outputs start at d_out + out_off[i]
+    size_t out_total = 0;
+    long long L = 0;
+    uint64_t tickets = 0;
+    bool zc_enabled = true;        // GSDR_GROUP_ZEROCOPY (read at create)
+    bool last_zero_copy = false;
 };
+
+namespace {
+void group_free(gsdr_rx_group* g) {
+    cudaSetDevice(g->device);
+    for (auto& s : g->slots) {
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.d_raw) cudaFree(s.d_raw);
+        if (s.in_done) cudaEventDestroy(s.in_done);
+        if (s.comp_done) cudaEventDestroy(s.comp_done);
+        if (s.out_done) cudaEventDestroy(s.out_done);
+    }
+    if (g->d_table) cudaFree(g->d_table);
+    if (g->d_tail) cudaFree(g->d_tail);
+    if (g->t0) cudaEventDestroy(g->t0);
+    if (g->t1) cudaEventDestroy(g->t1);
+    if (g->stream) cudaStreamDestroy(g->stream);
+    if (g->s_in) cudaStreamDestroy(g->s_in);
+    if (g->s_out) cudaStreamDestroy(g->s_out);
+}
+
+// One channelizer launch over n_buffers consecutive buffers of every member (in[i] / out[i]: device pointers or device
+// aliases of pinned host buffers).  Member state is advanced on copies and committed only after every launch succeeded.
+int64_t group_enqueue(gsdr_rx_group* g, const float2* const* in, int n_buffers, float2* const* out, int* valid_lens, bool host_window) {
+    const int n = (int)g->members.size();
+    std::vector<PfbJob> jobs(n);
+    std::vector<long long> tails(n);
+    std::vector<gsdr_buffer_helper> bhs(n);
+    int64_t total = 0;
+    long long frames_all = 0;
+    for (int i = 0; i < n; ++i) {
+        gsdr_rx* rx = g->members[i];
+        bhs[i] = rx->bh;
+        Window w{rx->hist[rx->hist_cur], in[i], rx->n_hist, rx->L * n_buffers};
+        long long frames = 0;
+        for (int b = 0; b < n_buffers; ++b) {
+            const int v = rx->T_sel * bhs[i].current_batch;
+            if (valid_lens) valid_lens[(size_t)i * n_buffers + b] = v;
+            frames += bhs[i].current_batch;
+            total += v;
+            buffer_helper_update(&bhs[i]);
+        }
+        tails[i] = bhs[i].new_0;
+        if (w.n_hist + w.n_in - frames * rx->N != tails[i]) {
+            set_error("internal: PFB carry-over mismatch in group member %d", i);
+            return -1;
+        }
+        frames_all += frames;
+        jobs[i] = PfbJob{w, rx->d_taps, rx->d_bins, out[i], 0, (int)frames, rx->N, (int)rx->P, rx->T_sel, rx->d_xperm};
+        jobs[i].tail_dst = rx->hist[rx->hist_cur ^ 1];   // the launch carries every member's carry-over copy
+        jobs[i].tail_n = tails[i];
+        if (host_window) jobs[i].min_tile = 64;          // reads over PCIe: long tiles (see gsdr_rx_process, zero-copy form)
+    }
+    int nl = pfb_launch(jobs.data(), n, g->d_table, nullptr, g->members[0]->d_tw, g->members[0]->sm_count, g->stream);
+    if (nl < 0) return -1;
+    if (n == 1 || frames_all == 0) {
+        // a single member goes through the one-stream launch, which does its tail itself (pfb_launch); no frames at all
+        // (buffers shorter than a frame): nothing was launched, only the carry-over grows
+        if (frames_all == 0) {
+            std::vector<Window> wins(n);
+            std::vector<float2*> dsts(n);
+            for (int i = 0; i < n; ++i) wins[i] = jobs[i].win, dsts[i] = jobs[i].tail_dst;
+            const int tl = window_tail_copy_multi(wins.data(), tails.data(), dsts.data(), n, g->d_tail, g->stream);
+            if (tl < 0) return -1;
+            nl += tl;
+        }
+    }
+    g->launches += nl;
+    for (int i = 0; i < n; ++i) {
+        gsdr_rx* rx = g->members[i];
+        rx->bh = bhs[i];
+        rx->hist_cur ^= 1;
+        rx->n_hist = tails[i];
+    }
+    return total;
+}
+}  // namespace
 
 gsdr_rx_group* gsdr_rx_group_create(gsdr_rx** members, int n) {
     if (!members || n <= 0) {
@@ -1056,32 +1216,53 @@ gsdr_rx_group* gsdr_rx_group_create(gsdr_rx** members, int n) {
     for (int i = 0; i < n; ++i) {
         gsdr_rx* m = members[i];
         if (!m || (m->mode != GSDR_TONES && m->mode != GSDR_NOISE) || !m->fused || m->device != members[0]->device ||
-            m->N != members[0]->N || m->P != members[0]->P || m->post_decim) {
+            m->N != members[0]->N || m->P != members[0]->P || m->post_decim || m->L != members[0]->L) {
             set_error("gsdr_rx_group_create: member %d is not a fused TONES/NOISE stream compatible with member 0", i);
             return nullptr;
         }
+        for (int k = 0; k < i; ++k)
+            if (members[k] == m) {
+                set_error("gsdr_rx_group_create: member %d appears twice", i);
+                return nullptr;
+            }
     }
-    std::unique_ptr<gsdr_rx_group> g(new gsdr_rx_group());
+    gsdr_rx_group* g = new gsdr_rx_group();
     g->members.assign(members, members + n);
     g->device = members[0]->device;
-    cudaSetDevice(g->device);
-    GSDR_CUDA_OK_NULL(cudaStreamCreateWithFlags(&g->stream, cudaStreamNonBlocking));
-    GSDR_CUDA_OK_NULL(cudaEventCreate(&g->t0));
-    GSDR_CUDA_OK_NULL(cudaEventCreate(&g->t1));
-    GSDR_CUDA_OK_NULL(cudaMalloc(&g->d_table, (sizeof(PfbJob) + 64) * (size_t)n + 256));
-    GSDR_CUDA_OK_NULL(cudaMalloc(&g->d_tail, window_tail_multi_scratch_bytes(n)));
-    return g.release();
+    g->L = members[0]->L;
+    {
+        const char* zc = getenv("GSDR_GROUP_ZEROCOPY");
+        g->zc_enabled = !(zc && zc[0] == '0');
+    }
+    g->out_off.resize(n);
+    for (int i = 0; i < n; ++i) {
+        g->out_off[i] = g->out_total;
+        g->out_total += (members[i]->max_out + 1) & ~size_t(1);   // 16-byte aligned starts
+    }
+    int lo = 0, hi = 0;
+    bool ok = cudaSetDevice(g->device) == cudaSuccess && cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&g->stream, cudaStreamNonBlocking, lo) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&g->s_in, cudaStreamNonBlocking, lo) == cudaSuccess &&
+              cudaStreamCreateWithPriority(&g->s_out, cudaStreamNonBlocking, lo) == cudaSuccess &&
+              cudaEventCreate(&g->t0) == cudaSuccess && cudaEventCreate(&g->t1) == cudaSuccess &&
+              cudaMalloc(&g->d_table, pfb_table_bytes(n, members[0]->sm_count)) == cudaSuccess &&
+              cudaMalloc(&g->d_tail, window_tail_multi_scratch_bytes(n)) == cudaSuccess;
+    if (!ok) {
+        set_error("gsdr_rx_group_create: CUDA resource allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
+        group_free(g);
+        delete g;
+        return nullptr;
+    }
+    return g;
 }
 
 void gsdr_rx_group_destroy(gsdr_rx_group* g) {
     if (!g) return;
     cudaSetDevice(g->device);
+    if (g->s_in) cudaStreamSynchronize(g->s_in);
     if (g->stream) cudaStreamSynchronize(g->stream);
-    if (g->d_table) cudaFree(g->d_table);
-    if (g->d_tail) cudaFree(g->d_tail);
-    if (g->t0) cudaEventDestroy(g->t0);
-    if (g->t1) cudaEventDestroy(g->t1);
-    if (g->stream) cudaStreamDestroy(g->stream);
+    if (g->s_out) cudaStreamSynchronize(g->s_out);
+    group_free(g);
     delete g;
 }
 
@@ -1091,60 +1272,168 @@ int64_t gsdr_rx_group_process_device(gsdr_rx_group* g, const gsdr_float2* const*
         set_error("gsdr_rx_group_process_device: bad argument");
         return -1;
     }
-    GSDR_CUDA_OK(cudaSetDevice(g->device));
-    const int n = (int)g->members.size();
-    std::vector<PfbJob> jobs(n);
-    std::vector<long long> tails(n);
-    int64_t total = 0;
-    for (int i = 0; i < n; ++i) {
-        gsdr_rx* rx = g->members[i];
-        Window w{rx->hist[rx->hist_cur], reinterpret_cast<const float2*>(in_dev[i]), rx->n_hist, rx->L * n_buffers};
-        long long frames = 0;
-        for (int b = 0; b < n_buffers; ++b) {
-            const int v = rx->T_sel * rx->bh.current_batch;
-            if (valid_lens) valid_lens[(size_t)i * n_buffers + b] = v;
-            frames += rx->bh.current_batch;
-            total += v;
-            buffer_helper_update(&rx->bh);
+    if (ensure_device(g->device)) return -1;
+    return group_enqueue(g, reinterpret_cast<const float2* const*>(in_dev), n_buffers, reinterpret_cast<float2* const*>(out_dev), valid_lens,
+                         false);
+}
+
+// kDepth pipeline slots, allocated on the first host-fed call (a device-resident-only group never pays for them)
+static int group_slots_ready(gsdr_rx_group* g, bool need_staging, bool need_raw) {
+    if (g->slots.empty()) {
+        g->slots.resize(kDepth);
+        for (auto& s : g->slots) {
+            GSDR_CUDA_OK(cudaEventCreateWithFlags(&s.in_done, cudaEventDisableTiming));
+            GSDR_CUDA_OK(cudaEventCreateWithFlags(&s.comp_done, cudaEventDisableTiming));
+            GSDR_CUDA_OK(cudaEventCreateWithFlags(&s.out_done, cudaEventDisableTiming));
         }
-        tails[i] = rx->bh.new_0;
-        jobs[i] = PfbJob{w, rx->d_taps, rx->d_bins, reinterpret_cast<float2*>(out_dev[i]), 0, (int)frames, rx->N, (int)rx->P, rx->T_sel, rx->d_xperm};
     }
-    const int nl = pfb_launch(jobs.data(), n, g->d_table, nullptr, g->members[0]->d_tw, g->members[0]->sm_count, g->stream);
-    if (nl < 0) return -1;
-    g->launches += nl;
-    std::vector<Window> wins(n);
-    std::vector<float2*> dsts(n);
-    for (int i = 0; i < n; ++i) {
-        wins[i] = jobs[i].win;
-        dsts[i] = g->members[i]->hist[g->members[i]->hist_cur ^ 1];
+    const size_t S = g->members.size();
+    for (auto& s : g->slots) {
+        if ((need_staging || need_raw) && !s.d_in) GSDR_CUDA_OK(cudaMalloc(&s.d_in, sizeof(float2) * S * (size_t)g->L));
+        if (need_staging && !s.d_out) GSDR_CUDA_OK(cudaMalloc(&s.d_out, sizeof(float2) * (g->out_total ? g->out_total : 1)));
+        if (need_raw && !s.d_raw) GSDR_CUDA_OK(cudaMalloc(&s.d_raw, sizeof(short2) * S * (size_t)g->L));
     }
-    const int tl = window_tail_copy_multi(wins.data(), tails.data(), dsts.data(), n, g->d_tail, g->stream);
-    if (tl < 0) return -1;
-    g->launches += tl;
-    for (int i = 0; i < n; ++i) {
-        gsdr_rx* rx = g->members[i];
-        rx->hist_cur ^= 1;
-        rx->n_hist = tails[i];
+    return 0;
+}
+
+static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool sc16, gsdr_float2* const* out_host, int* valid_lens) {
+    if (!g || !in_host || !out_host) {
+        set_error("gsdr_rx_group_submit: null argument");
+        return -1;
     }
-    return total;
+    if (ensure_device(g->device)) return -1;
+    const int S = (int)g->members.size();
+    const size_t in_bytes = (sc16 ? sizeof(short2) : sizeof(float2)) * (size_t)g->L;
+    // zero-copy when every buffer of the period is pinned and mapped
+    std::vector<const void*> ia(S);
+    std::vector<float2*> oa(S);
+    bool zero_copy = g->zc_enabled;
+    for (int i = 0; i < S && zero_copy; ++i) {
+        if (!in_host[i] || !out_host[i]) {
+            set_error("gsdr_rx_group_submit: null buffer for member %d", i);
+            return -1;
+        }
+        ia[i] = host_alias_of(in_host[i], in_bytes);
+        oa[i] = static_cast<float2*>(host_alias_of(out_host[i], sizeof(float2) * g->members[i]->max_out));
+        zero_copy = ia[i] && oa[i];
+    }
+    if (group_slots_ready(g, !zero_copy, sc16)) return -1;
+    const int ticket = (int)(g->tickets % 0x40000000u);
+    GroupSlot& s = g->slots[(size_t)ticket % g->slots.size()];
+    if (s.used) GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));   // the slot's previous period is fully done
+    std::vector<const float2*> kin(S);
+    std::vector<float2*> kout(S);
+    if (!zero_copy) {
+        // ---- copied form: one cudaMemcpyAsync per stream buffer ----------------------------------------------------------
+        for (int i = 0; i < S; ++i) {
+            if (!in_host[i] || !out_host[i]) {
+                set_error("gsdr_rx_group_submit: null buffer for member %d", i);
+                return -1;
+            }
+            void* dst = sc16 ? static_cast<void*>(s.d_raw + (size_t)i * g->L) : static_cast<void*>(s.d_in + (size_t)i * g->L);
+            GSDR_CUDA_OK(cudaMemcpyAsync(dst, in_host[i], in_bytes, cudaMemcpyHostToDevice, g->s_in));
+            kin[i] = s.d_in + (size_t)i * g->L;
+            kout[i] = s.d_out + g->out_off[i];
+        }
+        GSDR_CUDA_OK(cudaEventRecord(s.in_done, g->s_in));
+        GSDR_CUDA_OK(cudaStreamWaitEvent(g->stream, s.in_done, 0));
+    } else {
+        for (int i = 0; i < S; ++i) {
+            kin[i] = sc16 ? s.d_in + (size_t)i * g->L : static_cast<const float2*>(ia[i]);
+            kout[i] = oa[i];
+        }
+    }
+    if (sc16) {   // wire format -> fc32, one launch per 64 streams (reads the host buffers in place in the zero-copy form)
+        long long blocks = ((g->L >> 2) + 255) / 256;
+        blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
+        for (int i0 = 0; i0 < S; i0 += 64) {
+            Sc16Batch b{};
+            const int nb = S - i0 < 64 ? S - i0 : 64;
+            for (int k = 0; k < nb; ++k) {
+                b.src[k] = zero_copy ? static_cast<const short2*>(ia[i0 + k]) : s.d_raw + (size_t)(i0 + k) * g->L;
+                b.dst[k] = s.d_in + (size_t)(i0 + k) * g->L;
+            }
+            sc16_to_fc32_batch_kernel<<<dim3((unsigned)blocks, (unsigned)nb), 256, 0, g->stream>>>(b, g->L);
+            GSDR_CUDA_OK(cudaGetLastError());
+            g->launches++;
+        }
+        if (zero_copy) GSDR_CUDA_OK(cudaEventRecord(s.in_done, g->stream));   // the conversion has read the host buffers
+    }
+    std::vector<int> lens(S);
+    const int64_t total = group_enqueue(g, kin.data(), 1, kout.data(), lens.data(), zero_copy && !sc16);
+    if (total < 0) return -1;
+    GSDR_CUDA_OK(cudaEventRecord(s.comp_done, g->stream));
+    if (!zero_copy) {
+        GSDR_CUDA_OK(cudaStreamWaitEvent(g->s_out, s.comp_done, 0));
+        for (int i = 0; i < S; ++i)
+            if (lens[i] > 0)
+                GSDR_CUDA_OK(cudaMemcpyAsync(out_host[i], kout[i], sizeof(float2) * (size_t)lens[i], cudaMemcpyDeviceToHost, g->s_out));
+        GSDR_CUDA_OK(cudaEventRecord(s.out_done, g->s_out));
+    } else {
+        if (!sc16) GSDR_CUDA_OK(cudaEventRecord(s.in_done, g->stream));   // the launch itself consumes the inputs
+        GSDR_CUDA_OK(cudaEventRecord(s.out_done, g->stream));
+    }
+    s.used = true;
+    g->last_zero_copy = zero_copy;
+    g->tickets++;
+    if (valid_lens)
+        for (int i = 0; i < S; ++i) valid_lens[i] = lens[i];
+    return ticket;
+}
+
+int gsdr_rx_group_submit(gsdr_rx_group* g, const gsdr_float2* const* in_host, gsdr_float2* const* out_host, int* valid_lens) {
+    return group_submit_any(g, reinterpret_cast<const void* const*>(in_host), false, out_host, valid_lens);
+}
+int gsdr_rx_group_submit_sc16(gsdr_rx_group* g, const int16_t* const* in_iq, gsdr_float2* const* out_host, int* valid_lens) {
+    return group_submit_any(g, reinterpret_cast<const void* const*>(in_iq), true, out_host, valid_lens);
+}
+int gsdr_rx_group_wait(gsdr_rx_group* g, int ticket) {
+    if (!g) return -1;
+    if (g->slots.empty()) return 0;
+    if (ensure_device(g->device)) return -1;
+    GroupSlot& s = g->slots[(uint64_t)ticket % g->slots.size()];
+    if (!s.used) return 0;
+    GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));
+    return 0;
+}
+int gsdr_rx_group_input_consumed(gsdr_rx_group* g, int ticket) {
+    if (!g) return -1;
+    if (g->slots.empty()) return 1;
+    GroupSlot& s = g->slots[(uint64_t)ticket % g->slots.size()];
+    if (!s.used) return 1;
+    return cudaEventQuery(s.in_done) == cudaSuccess ? 1 : 0;
+}
+int gsdr_rx_group_process(gsdr_rx_group* g, const gsdr_float2* const* in_host, gsdr_float2* const* out_host, int* valid_lens) {
+    const int t = gsdr_rx_group_submit(g, in_host, out_host, valid_lens);
+    if (t < 0) return -1;
+    return gsdr_rx_group_wait(g, t);
+}
+int gsdr_rx_group_pipeline_depth(const gsdr_rx_group* g) { return g ? kDepth : 0; }
+int gsdr_rx_group_members(const gsdr_rx_group* g) { return g ? (int)g->members.size() : 0; }
+int gsdr_rx_group_zero_copy(const gsdr_rx_group* g) { return g && g->last_zero_copy ? 1 : 0; }
+int gsdr_rx_group_set_zero_copy(gsdr_rx_group* g, int on) {
+    if (!g) return -1;
+    g->zc_enabled = on != 0;
+    return 0;
 }
 
 int gsdr_rx_group_sync(gsdr_rx_group* g) {
     if (!g) return -1;
-    GSDR_CUDA_OK(cudaSetDevice(g->device));
+    if (ensure_device(g->device)) return -1;
+    GSDR_CUDA_OK(cudaStreamSynchronize(g->s_in));
     GSDR_CUDA_OK(cudaStreamSynchronize(g->stream));
+    GSDR_CUDA_OK(cudaStreamSynchronize(g->s_out));
     return 0;
 }
 int gsdr_rx_group_timer_start(gsdr_rx_group* g) {
     if (!g) return -1;
-    GSDR_CUDA_OK(cudaSetDevice(g->device));
+    if (ensure_device(g->device)) return -1;
     GSDR_CUDA_OK(cudaEventRecord(g->t0, g->stream));
     return 0;
 }
 int gsdr_rx_group_timer_stop(gsdr_rx_group* g, float* ms) {
     if (!g) return -1;
-    GSDR_CUDA_OK(cudaSetDevice(g->device));
+    if (ensure_device(g->device)) return -1;
     GSDR_CUDA_OK(cudaEventRecord(g->t1, g->stream));
     GSDR_CUDA_OK(cudaEventSynchronize(g->t1));
     float v = 0.f;

@@ -38,7 +38,10 @@ namespace {
 
 void tx_free(gsdr_tx* tx) {
     cudaSetDevice(tx->device);
-    if (tx->h_base) cudaFreeHost(tx->h_base);
+    if (tx->h_base) {
+        host_registry_remove(tx->h_base);
+        cudaFreeHost(tx->h_base);
+    }
     if (tx->d_base) cudaFree(tx->d_base);
     if (tx->d_buf) cudaFree(tx->d_buf);
     if (tx->t0) cudaEventDestroy(tx->t0);
@@ -65,6 +68,8 @@ int init_tones(gsdr_tx* tx, const gsdr_param* p) {
         const long long f = p->freq[i];
         const long long k = f > 0 ? f : R + f;
         if (k >= 0 && k < R) slots[(int)k] = p->ampl[i];
+        else if (f == 0)   // the reference writes spectrum slot R, one past its buffer (cpp/kernels.cu:626-631): a DC tone is silent
+            fprintf(stderr, "gsdr_tx: warning: TX tone %zu has freq == 0 Hz; like the reference it contributes nothing to the buffer\n", i);
     }
     std::vector<int> bins;
     std::vector<float> ampl;
@@ -98,6 +103,7 @@ int init_tones(gsdr_tx* tx, const gsdr_param* p) {
     GSDR_CUDA_OK(cudaMemcpyAsync(tx->d_base + tx->period_len, tx->d_base, sizeof(float2) * tx->L, cudaMemcpyDeviceToDevice,
                                  tx->stream));
     GSDR_CUDA_OK(cudaMallocHost(&tx->h_base, sizeof(float2) * total));
+    host_registry_add(tx->h_base, sizeof(float2) * total);   // get() hands out pointers into it: RX may read them in place
     GSDR_CUDA_OK(cudaMemcpyAsync(tx->h_base, tx->d_base, sizeof(float2) * total, cudaMemcpyDeviceToHost, tx->stream));
     GSDR_CUDA_OK(cudaStreamSynchronize(tx->stream));
     cudaFree(d_bins);

@@ -199,6 +199,41 @@ class RxGroup:
         tot = check(self.lib.gsdr_rx_group_process_device(self._h, ins, n_buffers, outs, lens), "gsdr_rx_group_process_device")
         return int(tot), np.array(lens, dtype=np.int64).reshape(n, n_buffers)
 
+    # -- host-fed, one packet period per call (cfg5: many streams per GPU) -------------------------
+    def pointer_arrays(self, ins, outs):
+        """Pre-built ctypes pointer arrays for submit(): build once per ring position, reuse every period."""
+        n = len(self.members)
+        if len(ins) != n or len(outs) != n:
+            raise ValueError("one input and one output buffer per member")
+        for m, o in zip(self.members, outs):
+            if o.size < m.max_output():
+                raise ValueError("output buffer shorter than the member's max_output()")
+        ia = (C.c_void_p * n)(*[a.ctypes.data for a in ins])
+        oa = (C.c_void_p * n)(*[_ptr(a).value for a in outs])
+        return ia, oa
+
+    def submit(self, ins, outs=None, sc16=False):
+        """ins/outs: lists of per-member buffers, or the pair returned by pointer_arrays().  -> (ticket, valid lengths)"""
+        ia, oa = (ins, outs) if isinstance(ins, C.Array) else self.pointer_arrays(ins, outs)
+        lens = (C.c_int * len(self.members))()
+        fn = self.lib.gsdr_rx_group_submit_sc16 if sc16 else self.lib.gsdr_rx_group_submit
+        t = check(fn(self._h, ia, oa, lens), "gsdr_rx_group_submit")
+        return t, list(lens)
+
+    def wait(self, ticket: int) -> None:
+        check(self.lib.gsdr_rx_group_wait(self._h, int(ticket)), "gsdr_rx_group_wait")
+
+    def process(self, ins, outs=None, sc16=False):
+        t, lens = self.submit(ins, outs, sc16=sc16)
+        self.wait(t)
+        return lens
+
+    def input_consumed(self, ticket: int) -> bool:
+        return bool(check(self.lib.gsdr_rx_group_input_consumed(self._h, int(ticket)), "gsdr_rx_group_input_consumed"))
+
+    def zero_copy(self) -> bool:
+        return bool(self.lib.gsdr_rx_group_zero_copy(self._h))
+
     def sync(self):
         check(self.lib.gsdr_rx_group_sync(self._h), "gsdr_rx_group_sync")
 

@@ -83,10 +83,13 @@ void gsdr_rx_destroy(gsdr_rx *rx);
  * float2.  Returns the number of valid float2 written (all channels, sample-major
  * out[t*channels + c]) or <0 on error.  On return `in` has been fully consumed (the caller may
  * recycle it at once, cpp/USRP_server_link_threads.cpp:669) and out[0..ret) is complete.
- * With the fused channelizer (TONES / NOISE, 2048 channels) and both buffers pinned (pool
- * buffers, gsdr_host_alloc, cudaMallocHost), the call is ONE kernel launch that reads `in` and
- * writes `out` in place over PCIe; otherwise the data is copied up and down in chunks.  Same
- * results either way (GSDR_PROCESS_ZEROCOPY=0 forces the copied form). */
+ * With both buffers pinned and mapped (pool buffers, gsdr_host_alloc, cudaMallocHost) the fused
+ * channelizer (TONES / NOISE, 2048 channels), DIRECT and CHIRP run as kernel launches that read `in`
+ * and write `out` in place over PCIe; otherwise the data is copied up and down.  Same results either
+ * way (GSDR_PROCESS_ZEROCOPY=0 when the instance is created forces the copied form).
+ * Buffers allocated by this library (gsdr_pool, gsdr_host_alloc) are recognised without a driver
+ * call; any other pointer is asked of the driver on every call (GSDR_PROCESS_PTRCACHE=1 remembers
+ * the answer per address, for callers whose buffers keep their nature while the library is in use). */
 int gsdr_rx_process(gsdr_rx *rx, const gsdr_float2 *in, gsdr_float2 *out);
 
 /* Pipelined variant: submit returns immediately after enqueuing H2D | kernel | D2H on the
@@ -132,17 +135,41 @@ int gsdr_rx_timer_stop(gsdr_rx *rx, float *elapsed_ms); /* synchronises */
 int gsdr_rx_get_taps(const gsdr_rx *rx, float *taps, size_t cap);   /* returns tap count */
 int gsdr_rx_get_bins(const gsdr_rx *rx, int32_t *bins, size_t cap); /* returns bin count */
 int gsdr_rx_chirp_param(const gsdr_rx *rx, struct gsdr_chirp_param *out);  /* CHIRP instances only */
-/* Which kernel variant serves this instance: e.g. "pfb_fused_r2<2048,4>" or "pfb_generic". */
+/* Which kernel serves this instance: e.g. "pfb_fused_wsp_2048_kernel<4>", "direct_fir_tc_kernel". */
 const char *gsdr_rx_kernel_name(const gsdr_rx *rx);
 
-/* A group launches ONE persistent kernel over all member streams' frames (TONES members only):
- * the multi-stream path for many concurrent IQ streams per GPU.  Same semantics as calling
- * gsdr_rx_process_device on each member. in_dev[i]/out_dev[i] are per-member device pointers. */
+/* A group launches ONE persistent kernel over all member streams' frames (TONES / NOISE members on the fused
+ * 2048-channel kernel, same buffer_len): the multi-stream path for many concurrent IQ streams per GPU.  It stands where
+ * the reference runs one RX_buffer_demodulator per front-end, each fed by its own link thread through the blocking
+ * process() (cpp/USRP_server_link_threads.cpp:605-702, call at :666).  Results and state are exactly those of calling
+ * gsdr_rx_process / gsdr_rx_process_device on each member.  Members stay owned by the caller and must outlive the group;
+ * while a group is in use its members must not be driven through their own entry points.
+ *
+ * Device-resident: in_dev[i] / out_dev[i] are per-member device pointers, n_buffers consecutive buffers each. */
 typedef struct gsdr_rx_group gsdr_rx_group;
 gsdr_rx_group *gsdr_rx_group_create(gsdr_rx **members, int n_members);
 void gsdr_rx_group_destroy(gsdr_rx_group *g);
 int64_t gsdr_rx_group_process_device(gsdr_rx_group *g, const gsdr_float2 *const *in_dev, int n_buffers,
                                      gsdr_float2 *const *out_dev, int *valid_lens /* [member][buffer] */);
+/* Host-fed, one packet period per call: in_host[i] = member i's next transport buffer (buffer_len float2, or
+ * buffer_len interleaved int16 I/Q pairs for _sc16) and out_host[i] its output buffer (>= gsdr_rx_max_output(member i)
+ * float2), both in host memory; valid_lens[i] receives member i's valid float2 count (known at submit time from the
+ * integer helpers).  submit returns a ticket after enqueuing the period; up to gsdr_rx_group_pipeline_depth() tickets
+ * may be outstanding; wait blocks until every out_host[i] of that ticket is complete; input buffers may be recycled once
+ * gsdr_rx_group_input_consumed(ticket) returns 1 (always true after wait).
+ * Pinned, mapped buffers (gsdr_pool / gsdr_host_alloc / cudaMallocHost): ONE launch per period reads the S input
+ * buffers and writes the S outputs in place over PCIe (GSDR_GROUP_ZEROCOPY=0 at create selects the copied form).
+ * Otherwise: one cudaMemcpyAsync per stream buffer up, one launch, one cudaMemcpyAsync per stream down, on three
+ * streams so that consecutive periods overlap.  gsdr_rx_group_process = submit + wait. */
+int gsdr_rx_group_submit(gsdr_rx_group *g, const gsdr_float2 *const *in_host, gsdr_float2 *const *out_host, int *valid_lens);
+int gsdr_rx_group_submit_sc16(gsdr_rx_group *g, const int16_t *const *in_iq, gsdr_float2 *const *out_host, int *valid_lens);
+int gsdr_rx_group_wait(gsdr_rx_group *g, int ticket);
+int gsdr_rx_group_input_consumed(gsdr_rx_group *g, int ticket);
+int gsdr_rx_group_process(gsdr_rx_group *g, const gsdr_float2 *const *in_host, gsdr_float2 *const *out_host, int *valid_lens);
+int gsdr_rx_group_pipeline_depth(const gsdr_rx_group *g);
+int gsdr_rx_group_members(const gsdr_rx_group *g);
+int gsdr_rx_group_zero_copy(const gsdr_rx_group *g);   /* 1 when the last submit took the zero-copy form */
+int gsdr_rx_group_set_zero_copy(gsdr_rx_group *g, int on);   /* allow (default) / forbid the zero-copy form from the next submit on */
 int gsdr_rx_group_sync(gsdr_rx_group *g);
 int gsdr_rx_group_timer_start(gsdr_rx_group *g);
 int gsdr_rx_group_timer_stop(gsdr_rx_group *g, float *elapsed_ms);
@@ -211,6 +238,10 @@ void gsdr_pool_close(gsdr_pool *pool);
 int gsdr_pool_available(const gsdr_pool *pool);
 int gsdr_pool_size(const gsdr_pool *pool);
 
+/* Plain cudaMemcpyAsync ceiling between pinned host memory and `device` (one call per buffer): out_gbs[4] =
+ * {h2d alone, d2h alone, h2d while both run, d2h while both run} in 1e9 bytes/s.  bench.py reports end-to-end figures
+ * against it. */
+int gsdr_pcie_copy_ceiling(int device, size_t h2d_bytes, size_t d2h_bytes, int reps, double *out_gbs);
 void *gsdr_host_alloc(size_t bytes);   /* cudaMallocHost, on the NUMA node of the current GPU when the kernel allows (GSDR_NUMA_LOCAL=0: off) */
 int gsdr_device_numa_node(int device); /* /sys/bus/pci/devices/<bus id>/numa_node of the GPU, -1 when unknown */
 void gsdr_host_free(void *p);

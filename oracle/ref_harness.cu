@@ -16,6 +16,8 @@
 
 #include <chrono>
 #include <new>
+#include <thread>
+#include <vector>
 #include "../include/gsdr.h"
 
 // ---- non-DSP symbols normally provided by USRP_server_settings.cpp / USRP_server_diagnostic.cpp
@@ -99,6 +101,71 @@ double gsdr_ref_rx_process_timed(void* h, gsdr_float2* in, gsdr_float2* out, int
     auto t1 = std::chrono::steady_clock::now();
     if (last_len) *last_len = len;
     return std::chrono::duration<double>(t1 - t0).count();
+}
+// The reference's threading model for several front-ends: one worker thread per RX_buffer_demodulator, each calling the
+// blocking process() on its own packets (TXRX::rx_single_link, cpp/USRP_server_link_threads.cpp:605-702).  n instances,
+// thread i makes k calls cycling through its `ring` input buffers ins[i*ring .. i*ring+ring).  Wall-clock seconds.
+double gsdr_ref_rx_multi_process_timed(void** hs, int n, gsdr_float2** ins, int ring, gsdr_float2** outs, int k) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceSynchronize();
+    std::vector<std::thread> th;
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < n; i++)
+        th.emplace_back([=] {
+            cudaSetDevice(dev);
+            ref_rx* r = (ref_rx*)hs[i];
+            for (int c = 0; c < k; c++) {
+                float2* in = (float2*)ins[(size_t)i * ring + (c % ring)];
+                float2* out = (float2*)outs[i];
+                r->d->process(&in, &out);
+            }
+        });
+    for (auto& t : th) t.join();
+    cudaDeviceSynchronize();
+    auto t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+// Device time of k process() calls split into "everything the call enqueues on its stream" and "its two copies": CUDA events
+// on the instance's own stream around the unmodified process() (which ends with cudaStreamSynchronize, so the stream is idle
+// at both events), then the same two cudaMemcpyAsync (in_bytes up, out_bytes down, same pinned host buffers) alone on that
+// stream.  kernels = total - copies: the reference's launch sequence (cpp/USRP_demodulator.cpp:486-565 for TONES) without
+// H2D / D2H, as SURVEY.md section 8(d) asks.
+int gsdr_ref_rx_process_split_timed(void* h, gsdr_float2** ins, int ring, gsdr_float2* out, int k, size_t in_bytes, size_t out_bytes,
+                                    double* total_ms, double* copy_ms) {
+    ref_rx* r = (ref_rx*)h;
+    cudaStream_t st = r->d->internal_stream;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    void *d_a = nullptr, *d_b = nullptr;
+    if (cudaMalloc(&d_a, in_bytes ? in_bytes : 1) != cudaSuccess || cudaMalloc(&d_b, out_bytes ? out_bytes : 1) != cudaSuccess) return -1;
+    double tot = 0.0, cop = 0.0;
+    float ms = 0.f;
+    for (int c = 0; c < k; c++) {
+        float2* in = (float2*)ins[c % ring];
+        float2* o = (float2*)out;
+        cudaEventRecord(e0, st);
+        r->d->process(&in, &o);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        tot += ms;
+        cudaEventRecord(e0, st);
+        cudaMemcpyAsync(d_a, in, in_bytes, cudaMemcpyHostToDevice, st);
+        cudaMemcpyAsync(o, d_b, out_bytes, cudaMemcpyDeviceToHost, st);
+        cudaEventRecord(e1, st);
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+        cop += ms;
+    }
+    cudaFree(d_a);
+    cudaFree(d_b);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (total_ms) *total_ms = tot;
+    if (copy_ms) *copy_ms = cop;
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
 }
 void gsdr_ref_rx_close(void* h) {
     ref_rx* r = (ref_rx*)h;

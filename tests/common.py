@@ -110,6 +110,12 @@ def ref_lib():
         lib.gsdr_ref_rx_process.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         lib.gsdr_ref_rx_process_timed.restype = C.c_double
         lib.gsdr_ref_rx_process_timed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        lib.gsdr_ref_rx_multi_process_timed.restype = C.c_double
+        lib.gsdr_ref_rx_multi_process_timed.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p), C.c_int,
+                                                        C.POINTER(C.c_void_p), C.c_int]
+        lib.gsdr_ref_rx_process_split_timed.restype = C.c_int
+        lib.gsdr_ref_rx_process_split_timed.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_void_p, C.c_int, C.c_size_t,
+                                                        C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         lib.gsdr_ref_rx_close.argtypes = [C.c_void_p]
         lib.gsdr_ref_rx_bins.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         lib.gsdr_ref_rx_batching.argtypes = [C.c_void_p]

@@ -1,0 +1,139 @@
+"""Host-fed multi-stream group (gsdr_rx_group_submit / _wait): cfg5 as the reference would run it -- one
+RX_buffer_demodulator per front-end, each fed through the blocking process() (cpp/USRP_server_link_threads.cpp:605-702) --
+as ONE launch per packet period.  Every form (copied, zero-copy, sc16) must reproduce the per-stream calls bit for bit,
+valid lengths and carry-over included."""
+import numpy as np
+import pytest
+
+from common import g, pfb_param, tone_stream
+
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("gpu_required")]
+
+SPECS = ((1000, 1), (37, 2), (513, 3), (1, 4), (2047, 5))   # (tones, seed): different tone lists and output widths
+
+
+def _streams(L, n_periods, specs=SPECS):
+    ps = [pfb_param(N=2048, P=4, T=t, L=L, seed=s) for t, s in specs]
+    bufs = [[tone_stream(p.rate, p.freq[:12], p.ampl[:12], b * L, L, seed=100 + i) for b in range(n_periods)] for i, p in enumerate(ps)]
+    return ps, bufs
+
+
+def _per_stream(ps, bufs, sc16=False):
+    want = []
+    for p, bs in zip(ps, bufs):
+        rx = g.RX_buffer_demodulator(p)
+        out = g.pinned_empty(rx.max_output())
+        res = []
+        for x in bs:
+            n = rx.process_sc16(x, out) if sc16 else rx.process(x, out)
+            res.append(out[:n].copy())
+        rx.close()
+        g.pinned_free(out)
+        want.append(res)
+    return want
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+@pytest.mark.parametrize("L", [150_000, 131_073])
+def test_group_submit_wait_matches_per_stream_process(pinned, L):
+    n_periods = 7
+    ps, bufs = _streams(L, n_periods)
+    want = _per_stream(ps, bufs)
+    rxs = [g.RX_buffer_demodulator(p) for p in ps]
+    grp = g.RxGroup(rxs)
+    depth = 3
+    alloc = g.pinned_empty if pinned else (lambda n: np.empty(n, dtype=np.complex64))
+    hin = [[alloc(L) for _ in ps] for _ in range(depth)]
+    hout = [[alloc(rx.max_output()) for rx in rxs] for _ in range(n_periods)]   # one output set per period: compared at the end
+    pending, lens_all = [], []
+    l0 = grp.launch_count()
+    for b in range(n_periods):
+        k = b % depth
+        if len(pending) >= depth - 1:
+            grp.wait(pending.pop(0))
+        for i in range(len(ps)):
+            hin[k][i][:] = bufs[i][b]
+        t, lens = grp.submit(hin[k], hout[b])
+        pending.append(t)
+        lens_all.append(lens)
+    for t in pending:
+        grp.wait(t)
+    assert grp.zero_copy() == pinned
+    assert grp.launch_count() - l0 == n_periods          # ONE launch per packet period, carry-over copies included
+    for i in range(len(ps)):
+        for b in range(n_periods):
+            n = lens_all[b][i]
+            assert n == len(want[i][b]) and n > 0
+            assert np.array_equal(hout[b][i][:n].view(np.uint32), want[i][b].view(np.uint32)), (i, b)
+    grp.close()
+    for rx in rxs:
+        rx.close()
+
+
+@pytest.mark.parametrize("pinned", [False, True])
+def test_group_submit_sc16_matches_per_stream(pinned):
+    L, n_periods = 120_000, 5
+    ps, bufs = _streams(L, n_periods, SPECS[:3])
+    raw = [[np.clip(np.round(x.view(np.float32) * 32767.0), -32768, 32767).astype(np.int16) for x in bs] for bs in bufs]
+    want = _per_stream(ps, raw, sc16=True)
+    rxs = [g.RX_buffer_demodulator(p) for p in ps]
+    grp = g.RxGroup(rxs)
+    if pinned:
+        hin = [g.pinned_empty(L // 2).view(np.int16) for _ in ps]
+        hout = [g.pinned_empty(rx.max_output()) for rx in rxs]
+    else:
+        hin = [np.empty(2 * L, dtype=np.int16) for _ in ps]
+        hout = [np.empty(rx.max_output(), dtype=np.complex64) for rx in rxs]
+    for b in range(n_periods):
+        for i in range(len(ps)):
+            hin[i][:] = raw[i][b]
+        lens = grp.process(hin, hout, sc16=True)
+        for i in range(len(ps)):
+            assert lens[i] == len(want[i][b])
+            assert np.array_equal(hout[i][:lens[i]].view(np.uint32), want[i][b].view(np.uint32)), (i, b)
+    assert grp.zero_copy() == pinned
+    grp.close()
+    for rx in rxs:
+        rx.close()
+
+
+def test_group_of_64_streams_device_resident_balanced_tiles():
+    """64 streams in one launch: the tile list is balanced over the 148 CTAs (tiles split at stream boundaries); outputs
+    equal the per-stream results."""
+    L, nb, S = 100_000, 2, 64
+    ps = [pfb_param(N=2048, P=4, T=1000, L=L, seed=50 + s) for s in range(S)]
+    rng = np.random.default_rng(5)
+    x = [(0.1 * (rng.standard_normal(nb * L) + 1j * rng.standard_normal(nb * L))).astype(np.complex64) for _ in range(4)]
+    rxs = [g.RX_buffer_demodulator(p) for p in ps]
+    grp = g.RxGroup(rxs)
+    ins, outs = [], []
+    for s in range(S):
+        d = g.DeviceBuffer(nb * L)
+        d.upload(x[s % 4])
+        ins.append(d)
+        outs.append(g.DeviceBuffer(rxs[s].max_output_batch(nb)))
+    tot, lens = grp.process_device([d.ptr for d in ins], nb, [o.ptr for o in outs])
+    grp.sync()
+    got = [o.download(int(l.sum())) for o, l in zip(outs, lens)]
+    grp.close()
+    for s in (0, 1, 31, 63):
+        rx = g.RX_buffer_demodulator(ps[s])
+        d_out = g.DeviceBuffer(rx.max_output_batch(nb))
+        t1, _ = rx.process_device(ins[s].ptr, nb, d_out.ptr)
+        rx.sync()
+        assert t1 == len(got[s])
+        assert np.array_equal(d_out.download(t1).view(np.uint32), got[s].view(np.uint32)), s
+        rx.close()
+    for rx in rxs:
+        rx.close()
+
+
+def test_group_rejects_incompatible_members():
+    a = g.RX_buffer_demodulator(pfb_param(N=2048, P=4, T=10, L=100_000))
+    b = g.RX_buffer_demodulator(pfb_param(N=2048, P=4, T=10, L=120_000))
+    with pytest.raises(g.GsdrError):
+        g.RxGroup([a, b])
+    with pytest.raises(g.GsdrError):
+        g.RxGroup([a, a])
+    a.close()
+    b.close()
