@@ -133,9 +133,13 @@ direct_fir_tiled_kernel(const Window w, const float2* __restrict__ g, const int*
     const int ch0 = blockIdx.y * D_TC;
     const int ntaps = f * M;
 
-    c2 acc[D_TC];
+    // Blocked summation: every (tap chunk, FIR block) pair -- at most D_KC taps -- is its own fp32 chain `acc`, folded into
+    // `tot` when it ends.  One chain over all f*M taps (400 at cfg1) leaves 3 - 4e-7 relative L2 against fp64; the reference's
+    // cuBLAS Cgemm per block of M taps plus f axpy (cpp/fir.cu:48-57) 1.2e-7; chains of <= 32 taps sit below that
+    // (tools/direct_accum_emulation.py).
+    c2 acc[D_TC], tot[D_TC];
 #pragma unroll
-    for (int b = 0; b < D_TC; ++b) acc[b] = c2_pack(0.f, 0.f);
+    for (int b = 0; b < D_TC; ++b) tot[b] = c2_pack(0.f, 0.f);
 
     // equal chunks (M = 100 -> 4 x 25 rather than 32 + 32 + 32 + 4: every chunk pays the same staging round trip)
     const int n_chunks = (M + D_KC - 1) / D_KC;
@@ -189,6 +193,8 @@ direct_fir_tiled_kernel(const Window w, const float2* __restrict__ g, const int*
         for (int i = 0; i < f; ++i) {
             const float2* xr = xs + (tid + i) * (D_KC + 1);
             const float4* gr = reinterpret_cast<const float4*>(gs + i * D_KC * D_GST);
+#pragma unroll
+            for (int b = 0; b < D_TC; ++b) acc[b] = c2_pack(0.f, 0.f);
 #pragma unroll 4
             for (int kk = 0; kk < kc; ++kk) {
                 const float2 xv = xr[kk];
@@ -202,6 +208,8 @@ direct_fir_tiled_kernel(const Window w, const float2* __restrict__ g, const int*
                     acc[2 * b2 + 1] = c2_fma_s(jx, gg.w, acc[2 * b2 + 1]);
                 }
             }
+#pragma unroll
+            for (int b = 0; b < D_TC; ++b) tot[b] = c2_add(tot[b], acc[b]);
         }
     }
     // rotate by the LO phase of the output's first tap (integer phase, cpp/kernels.cu:59-75) and store sample-major
@@ -216,7 +224,7 @@ direct_fir_tiled_kernel(const Window w, const float2* __restrict__ g, const int*
             if (ch < T) {
                 long long ph = direct_phase_signed(freq[ch], (unsigned long long)n0, rate);
                 if (ph < 0) ph += rate;  // same residue class; the reference keeps the sign
-                out[p * T + ch] = dev_cmul(c2_to(acc[b]), lo_phasor(ph, inv_R));
+                out[p * T + ch] = dev_cmul(c2_to(tot[b]), lo_phasor(ph, inv_R));
             }
         }
     }
@@ -318,10 +326,10 @@ int direct_fir_launch(const Window& w, const float2* g, const int* freq_dev, int
     size_t smem = ((size_t)(PB - 1) * M + ntaps) * sizeof(float2);
     const bool staged = smem <= 96 * 1024;
     if (!staged) smem = 0;
-    static size_t configured = 0;
-    if (smem > configured) {
-        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    static DeviceOnce fallback_once;   // per device (the attribute is): the largest staging area this launcher ever asks for
+    if (const int dev = fallback_once.pending(); dev >= 0) {
+        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        fallback_once.done(dev);
     }
     // Split a block's (output group, tone group) units over gridDim.y only when there are too few output
     // blocks to fill the GPU: every y-slice re-stages the same input span.

@@ -651,17 +651,24 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
             const Window win = job.win;
             const long long fast_lo = (win.n_hist + FN - 1) / FN;    // first row fully inside `in`
             const long long fast_hi = (win.n_hist + win.n_in) / FN;  // first row not fully present
-            // The span body is instantiated twice: kFast when every row it touches lies fully inside the
-            // `in` segment (plain coalesced 8-byte loads, no per-row range logic), general otherwise.
-            auto run_tile = [&](auto fast_tag, const long long fa, const long long fb) {
-                constexpr bool kFast = decltype(fast_tag)::value;
+            const long long hist_full = win.n_hist / FN;             // rows [0, hist_full) lie fully inside the carried-over history
+            // The span body is instantiated three times: kMode 1 when every row it touches lies fully inside the `in` segment
+            // (plain coalesced 8-byte loads, no per-row range logic); kMode 2 for the tile at the head of a stream's window,
+            // whose first rows are carried-over history -- a CTA-uniform choice of the base pointer per row, only the one
+            // row that straddles history and new samples is read element by element (a multi-stream launch has such a tile
+            // per stream: splitting it into a general and a fast span restarted the FIR pipeline twice per stream);
+            // kMode 0 otherwise (ragged window end).
+            auto run_tile = [&](auto mode_tag, const long long fa, const long long fb) {
+                constexpr int kMode = decltype(mode_tag)::value;
+                constexpr bool kFast = kMode == 1;
                 const long long last_row = fb + P - 1;      // rows this span needs: [fa, last_row)
                 const long long n_steps = last_row - fa;    // one step per input row
                 auto load_row8 = [&](long long row, c2 (&dst)[8]) {
-                    if (kFast) {
+                    if (kFast || (kMode == 2 && (row >= fast_lo || row < hist_full))) {
                         // volatile: the loads stay where the pipeline puts them (after the FIR that frees their
                         // landing registers) instead of being hoisted into extra registers by the scheduler
-                        const c2* p = reinterpret_cast<const c2*>(win.in + (row * FN - win.n_hist) + l);
+                        const float2* base = (kFast || row >= fast_lo) ? win.in + (row * FN - win.n_hist) : win.hist + row * FN;
+                        const c2* p = reinterpret_cast<const c2*>(base + l);
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             asm volatile("ld.global.L1::no_allocate.b64 %0, [%1];" : "=l"(dst[j]) : "l"(p + 256 * j) : "memory");
@@ -672,7 +679,7 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
                 };
                 // warp 0 pulls a whole row (128 lines of 128 bytes) towards L2 several frames ahead
                 auto prefetch_row = [&](long long row) {
-                    if (kFast && l < 32 && row < last_row) {
+                    if ((kFast || (kMode == 2 && row >= fast_lo)) && l < 32 && row < last_row) {
                         const float2* p = win.in + (row * FN - win.n_hist) + 16 * l;
 #pragma unroll
                         for (int jj = 0; jj < 4; ++jj) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 512 * jj));
@@ -762,15 +769,15 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
                 // tail
                 for (; s < n_steps; s += U) guarded_group(s);
             };
-            // frames whose P rows all lie inside `in` take the fast body; the few that touch the carried-over
-            // history (head of a window) or its ragged end take the general one
-            long long f0 = tl.fa > fast_lo ? tl.fa : fast_lo;
+            // frames whose P rows all lie inside `in` take the fast body; a tile that starts in the carried-over history takes
+            // the mixed one; frames past the last complete row (never produced by buffer_helper, kept for safety) the general
             long long f1 = tl.fb < fast_hi - P + 1 ? tl.fb : fast_hi - P + 1;
-            if (f0 > tl.fb) f0 = tl.fb;
-            if (f1 < f0) f1 = f0;
-            if (tl.fa < f0) run_tile(std::false_type{}, tl.fa, f0);
-            if (f0 < f1) run_tile(std::true_type{}, f0, f1);
-            if (f1 < tl.fb) run_tile(std::false_type{}, f1, tl.fb);
+            if (f1 < tl.fa) f1 = tl.fa;
+            if (tl.fa < f1) {
+                if (tl.fa >= fast_lo) run_tile(std::integral_constant<int, 1>{}, tl.fa, f1);
+                else run_tile(std::integral_constant<int, 2>{}, tl.fa, f1);
+            }
+            if (f1 < tl.fb) run_tile(std::integral_constant<int, 0>{}, f1, tl.fb);
             // drain: what the polls have not stored yet
             for (; g < f; ++g) gather(g, true);
         }
@@ -1054,9 +1061,14 @@ template <int P>
 static int launch_ws(const PfbJob* jobs, int n_jobs, void* scratch, const float2* tw, int sm_count, cudaStream_t stream) {
     static DeviceOnce attr_once;
     constexpr size_t smem_bytes = sizeof(WpSmem);
-    auto kernel = pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST>;
+    // Windows in pinned host memory (zero-copy calls) are latency-bound on PCIe reads: two input rows in flight per producer
+    // thread instead of one (LA = 2) doubles the bytes a CTA keeps outstanding.
+    bool host_window = false;
+    for (int j = 0; j < n_jobs; ++j) host_window = host_window || jobs[j].min_tile > 0;
+    auto kernel = host_window ? pfb_fused_wsp_2048_kernel<P, 2, WP_HOIST> : pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST>;
     if (const int dev = attr_once.pending(); dev >= 0) {
-        GSDR_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        GSDR_CUDA_OK(cudaFuncSetAttribute(pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        GSDR_CUDA_OK(cudaFuncSetAttribute(pfb_fused_wsp_2048_kernel<P, 2, WP_HOIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         attr_once.done(dev);
     }
     long long total_frames = 0;

@@ -1335,15 +1335,15 @@ static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool s
             kin[i] = s.d_in + (size_t)i * g->L;
             kout[i] = s.d_out + g->out_off[i];
         }
-        GSDR_CUDA_OK(cudaEventRecord(s.in_done, g->s_in));
-        GSDR_CUDA_OK(cudaStreamWaitEvent(g->stream, s.in_done, 0));
     } else {
         for (int i = 0; i < S; ++i) {
             kin[i] = sc16 ? s.d_in + (size_t)i * g->L : static_cast<const float2*>(ia[i]);
             kout[i] = oa[i];
         }
     }
-    if (sc16) {   // wire format -> fc32, one launch per 64 streams (reads the host buffers in place in the zero-copy form)
+    if (sc16) {
+        // wire format -> fc32 on the copy-in stream, one launch per 64 streams (reading the host buffers in place in the
+        // zero-copy form): the conversion of period k+1 overlaps the channelizer launch and the output traffic of period k
         long long blocks = ((g->L >> 2) + 255) / 256;
         blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
         for (int i0 = 0; i0 < S; i0 += 64) {
@@ -1353,11 +1353,14 @@ static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool s
                 b.src[k] = zero_copy ? static_cast<const short2*>(ia[i0 + k]) : s.d_raw + (size_t)(i0 + k) * g->L;
                 b.dst[k] = s.d_in + (size_t)(i0 + k) * g->L;
             }
-            sc16_to_fc32_batch_kernel<<<dim3((unsigned)blocks, (unsigned)nb), 256, 0, g->stream>>>(b, g->L);
+            sc16_to_fc32_batch_kernel<<<dim3((unsigned)blocks, (unsigned)nb), 256, 0, g->s_in>>>(b, g->L);
             GSDR_CUDA_OK(cudaGetLastError());
             g->launches++;
         }
-        if (zero_copy) GSDR_CUDA_OK(cudaEventRecord(s.in_done, g->stream));   // the conversion has read the host buffers
+    }
+    if (!zero_copy || sc16) {
+        GSDR_CUDA_OK(cudaEventRecord(s.in_done, g->s_in));   // the inputs are on the device: the host buffers are free
+        GSDR_CUDA_OK(cudaStreamWaitEvent(g->stream, s.in_done, 0));
     }
     std::vector<int> lens(S);
     const int64_t total = group_enqueue(g, kin.data(), 1, kout.data(), lens.data(), zero_copy && !sc16);
