@@ -164,6 +164,20 @@ bool direct_fir_tc_preferred(int T, int M, int ntaps, long long n_out);
 // in pinned host memory unless GSDR_DIRECT_TC_HOST_TMA=1).
 int direct_fir_tc_launch(const Window& w, const float2* g, const int* freq_dev, int T, int M, int ntaps, int rate, long long pos0,
                          long long n_out, float2* out, int sm_count, cudaStream_t stream, int rotate = 1, bool allow_tma = true);
+// exact integer version (direct_i8_kernels.cu): kind::i8 MMAs on 24-bit fixed-point operands cut into three signed digits,
+// int32 accumulators, 64-bit combine -- no accumulation error at all.  The filter bank is prepared once per demodulator.
+struct DirectI8Bank {
+    void* d_bank = nullptr;        // digit planes of the filter bank, rows of 128 bytes (see direct_i8_bank_create)
+    float* d_inv_sb = nullptr;     // [tone groups * TG] 1 / (fixed-point scale of the tone's taps)
+    int KQ = 0, tone_groups = 0;   // quads of K blocks per tile, tone groups
+    alignas(64) unsigned char tmap_b[128];   // CUtensorMap of the bank
+};
+bool direct_fir_i8_supported(int T, int M, int ntaps, long long n_out);
+bool direct_fir_i8_preferred(int T, int M, int ntaps, long long n_out);
+int direct_i8_bank_create(const double* g /* [T][ntaps] (re, im) */, int T, int M, int ntaps, DirectI8Bank* bank);
+void direct_i8_bank_destroy(DirectI8Bank* bank);
+int direct_fir_i8_launch(const DirectI8Bank& bank, const Window& w, const int* freq_dev, int T, int M, int ntaps, int rate, long long pos0,
+                         long long n_out, float2* out, int sm_count, cudaStream_t stream, int rotate = 1, bool allow_tma = true);
 int direct_mix_launch(const float2* in, long long n, const int* freq_dev, int T, int rate, long long pos0, float2* out,
                       cudaStream_t stream);
 int direct_phase_probe_launch(long long* out, unsigned int n, int tone_freq, int rate, unsigned long long index_counter,

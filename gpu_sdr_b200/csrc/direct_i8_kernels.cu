@@ -1,0 +1,679 @@
+// DIRECT-mode demodulator (and generic-size channelizer) as an EXACT integer GEMM on the 5th-generation tensor cores
+// (tcgen05.mma kind::i8, int32 accumulators in TMEM), sm_100a only.
+//
+// Same function as direct_fir_tc_kernel (direct_tc_kernels.cu) and direct_fir_tiled_kernel (direct_kernels.cu), i.e. the
+// reference's direct_demodulator_integer + T x FIR::run_fir + cublasCgeam (cpp/kernels.cu:45-86, cpp/fir.cu:44-88,
+// cpp/USRP_demodulator.cpp:400-464):
+//     y[p,t] = rot(p,t) * sum_{i<F} Z_i[p+i, t],      Z_i[r, t] = sum_{k<M} w[r M + k] g_t[i M + k]
+// with the window cut into rows of M samples (A [rows x 2M], the samples as they lie in memory) and the per-tone complex
+// filters as the real matrix B [2M x F*TG*2] = (g_r, g_i ; -g_i, g_r).
+//
+// Why integers.  The TF32 path (three split products, fp32 accumulators) is bound in accuracy by the tensor core's
+// truncating accumulate: 5.1e-7 relative L2 against fp64 on cfg1, where the reference's cuBLAS chain has 1.2e-7
+// (tools/direct_tc_emulation.py reproduces both).  Here both operands are put on a 24-bit fixed-point grid and cut into
+// three signed 8-bit digits,
+//     round(x * sA) = a1 2^16 + a2 2^8 + a3,     round(g * sB) = b1 2^16 + b2 2^8 + b3,     a_i, b_j in [-128, 127],
+// and the six digit products of weight >= 2^16 are accumulated by kind::i8 MMAs in int32 -- exactly, whatever the chain
+// length -- in three accumulators (weights 2^32, 2^24, 2^16).  The epilogue combines them in 64-bit integers, adds the F
+// row-shifted blocks (the reference's overlap-add, cpp/fir.cu:55-69) still in integers, and converts ONCE to float.  What
+// is left is the quantisation of the operands (2^-24 of the tile's largest sample, of each tone's largest tap) and two fp32
+// roundings of the result.  Six int8 MMAs of K = 32 per 16-tap K block cost half the tensor time of the TF32 scheme's
+// twelve, and the operands are 3 bytes per real instead of 8.
+//
+//   sB  per tone, fixed when the demodulator is created (the bank is built on the host from the double-precision taps and
+//       lies in HBM as ready-made K-major tiles: the producers never touch the filters, TMA brings them);
+//   sA  per tile (128 window rows), from the largest |sample| of the tile: the epilogue warps scan the rows of tile n+2
+//       (plain coalesced loads, which also pull them into L2 for the TMA boxes that follow) while the MMAs of tile n+1 run.
+//
+// Warp roles (one persistent CTA per SM, static scheduler over (row tile, tone group)):
+//   warps 0-3   epilogue: tcgen05.ld of the three accumulators, 64-bit combine, row shift-and-add, int -> float, LO rotation
+//               from the integer phase (cpp/kernels.cu:59-75), sample-major store; then the |x| scan of tile n+2
+//   warp  4     TMEM allocation + single-thread tcgen05.mma issue: per K block two N=256 and two N=128 MMAs
+//   warps 5-12  operand producers: thread = one window row (TMEM lane) and one half of its K block: 4 x LDS.128 from the TMA
+//               landing slot, scale, round, digits, tcgen05.st -- the A operand only ever exists in tensor memory
+//   warp  13    TMA issue: one box (128 rows x 32 floats, SWIZZLE_128B) per K block for A, three boxes (128 x 128 bytes)
+//               per four K blocks for the digit planes of B
+#include <cuda.h>
+
+#include <cmath>
+#include <cstdlib>
+
+#include "devmath.cuh"
+#include "direct_common.cuh"
+
+namespace gsdr {
+namespace {
+
+constexpr int I8_ROWS = 128;                 // window rows per tile = UMMA M
+constexpr int I8_N = 128;                    // accumulator columns = F * TG * 2
+constexpr int I8_KC = 16;                    // complex taps per K block: 32 reals = one kind::i8 MMA (K = 32)
+constexpr int I8_RAW = 4;                    // TMA landing slots for A
+constexpr int I8_AST = 4;                    // A operand stages in TMEM
+constexpr int I8_BST = 2;                    // B operand stages in shared memory (each: 3 digit planes x 4 K blocks)
+constexpr int I8_EPI_WARPS = 4;
+constexpr int I8_PROD_WARPS = 8;
+constexpr int I8_THREADS = 32 * (I8_EPI_WARPS + 1 + I8_PROD_WARPS + 1);
+constexpr int I8_TMA_WARP = I8_EPI_WARPS + 1 + I8_PROD_WARPS;
+constexpr int I8_RAW_BYTES = I8_ROWS * 128;  // one landing slot: 128 rows x 128 bytes
+constexpr int I8_B_PLANE = I8_N * 128;       // one digit plane: 128 columns (rows of the K-major tile) x 128 bytes (4 K blocks)
+constexpr int I8_B_STAGE = 3 * I8_B_PLANE;
+constexpr unsigned int I8_COL_A = 384;       // accumulators: weight 2^32 at column 0, 2^24 at 128, 2^16 at 256; A stage s at 384 + 24 s
+constexpr int I8_TMEM_COLS = 512;
+constexpr int I8_XCH = 7 * 7 * 16;           // per epilogue warp: (F-1) lanes x (F-1) blocks x chunk columns, F <= 8
+constexpr int I8_HIST_MAX = 7 * 128;
+constexpr float I8_FULL_SCALE = 8355000.0f;  // |digits| <= 127 * (2^16 + 2^8 + 1) = 8355711
+static_assert((I8_EPI_WARPS + 1) % 4 == 1, "producer warp w owns TMEM lane quarter w % 4");
+
+struct I8Shared {
+    unsigned long long raw_full[I8_RAW], raw_empty[I8_RAW];   // TMA <-> producers: window rows of a K block
+    unsigned long long a_full[I8_AST], a_empty[I8_AST];       // producers <-> MMA: A digits in TMEM
+    unsigned long long b_full[I8_BST], b_empty[I8_BST];       // TMA <-> MMA: digit planes of B
+    unsigned long long tmem_full, tmem_empty;                 // MMA <-> epilogue: the accumulators
+    unsigned long long scale_full[4];                         // epilogue (scan) -> producers: largest |sample| of a tile
+    unsigned int tmem_base;
+    unsigned int amax_bits[4];
+    double2 ph[64];          // per tone of the group: (LO phase of the tile's first row, phase step per row), integers < rate
+    float inv_sb[64];        // per tone of the group: 1 / sB
+    alignas(16) long long xch[I8_EPI_WARPS][I8_XCH];
+    alignas(16) float2 hist[I8_HIST_MAX];
+};
+constexpr size_t I8_SMEM_BYTES = 1024 + (size_t)I8_RAW * I8_RAW_BYTES + (size_t)I8_BST * I8_B_STAGE + sizeof(I8Shared);
+
+// ---- PTX wrappers -----------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned int addr, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned int addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+// Bounded wait: a protocol error traps (the launch fails) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(unsigned int addr, unsigned int parity) {
+    long long t0 = 0;
+    for (unsigned int spins = 0;; ++spins) {
+        unsigned int done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (spins == 64) t0 = clock64();
+        if (spins > 64 && (spins & 255u) == 0 && clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned int addr, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(unsigned int dst, const CUtensorMap* map, int c0, int c1, unsigned int mbar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+        "l"(reinterpret_cast<unsigned long long>(map)), "r"(c0), "r"(c1), "r"(mbar)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned int mbar_addr) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mbar_addr) : "memory");
+}
+// cute::UMMA::InstrDescriptor: D = s32 (2 @4), A = B = signed int8 (1 @7, 1 @10), K-major both, N>>3 @17, M>>4 @24
+constexpr unsigned int i8_idesc(int n) { return (2u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(I8_ROWS >> 4) << 24); }
+constexpr unsigned int I8_IDESC = i8_idesc(I8_N);
+constexpr unsigned int I8_IDESC_WIDE = i8_idesc(2 * I8_N);
+// D[tmem] (+)= A[tmem] * B[smem]: A = 128 lanes x 8 columns (32 int8 per lane)
+__device__ __forceinline__ void mma_i8_ts(unsigned int d_tmem, unsigned int a_tmem, unsigned long long b_desc, unsigned int idesc,
+                                          unsigned int accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30) = 1, SBO>>4 [32,46) = 64, version [46,48) = 1,
+// layout [61,64) = 2 (SWIZZLE_128B)).
+__device__ __forceinline__ unsigned long long i8_smem_desc(unsigned int saddr) {
+    const unsigned int lo = ((saddr & 0x3FFFFu) >> 4) | (1u << 16);
+    const unsigned int hi = 64u | (1u << 14) | (2u << 29);
+    return ((unsigned long long)hi << 32) | lo;
+}
+__device__ __forceinline__ void tmem_ld16(unsigned int taddr, int* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st4(unsigned int taddr, unsigned int a, unsigned int b, unsigned int c, unsigned int d) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory"); }
+
+struct I8Tile {
+    long long row0;   // first window row of the tile
+    int ch0;          // first tone of the group
+    int tg;           // tone group index
+};
+
+// F = FIR blocks (pf_average); TG = 64 / F tones per group; outputs per tile = 128 - (F - 1)
+template <int F, bool rotate>
+__global__ void __launch_bounds__(I8_THREADS, 1)
+direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const int use_tma,
+                     const long long hist_rows, const Window w, const float* __restrict__ inv_sb, const int* __restrict__ freq, int T,
+                     int M, int rate, long long pos0, long long n_out, int n_row_tiles, int n_tone_groups, int KQ,
+                     const unsigned int a_order, float2* __restrict__ out) {
+    constexpr int TG = 64 / F;
+    constexpr int RB = I8_ROWS - (F - 1);
+    constexpr int NUNIT = TG / 8;              // epilogue units of 8 tones (16 accumulator columns) per tile
+    static_assert(TG % 8 == 0 && (F - 1) * (F - 1) * 16 <= I8_XCH, "exchange buffer");
+
+    extern __shared__ unsigned char i8_smem_raw[];
+    unsigned char* smem = i8_smem_raw + ((1024u - (smem_u32(i8_smem_raw) & 1023u)) & 1023u);
+    unsigned char* smem_b = smem + (size_t)I8_RAW * I8_RAW_BYTES;
+    I8Shared* sh = reinterpret_cast<I8Shared*>(smem_b + (size_t)I8_BST * I8_B_STAGE);
+    const unsigned int smem_base = smem_u32(smem);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int KB = (M + I8_KC - 1) / I8_KC;           // K blocks per tile
+    const int n_tiles = n_row_tiles * n_tone_groups;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < I8_RAW; ++s) {
+            mbar_init(smem_u32(&sh->raw_full[s]), 1);
+            mbar_init(smem_u32(&sh->raw_empty[s]), 32 * I8_PROD_WARPS);
+        }
+        for (int s = 0; s < I8_AST; ++s) {
+            mbar_init(smem_u32(&sh->a_full[s]), 32 * I8_PROD_WARPS);
+            mbar_init(smem_u32(&sh->a_empty[s]), 1);
+        }
+        for (int s = 0; s < I8_BST; ++s) {
+            mbar_init(smem_u32(&sh->b_full[s]), 1);
+            mbar_init(smem_u32(&sh->b_empty[s]), 1);
+        }
+        mbar_init(smem_u32(&sh->tmem_full), 1);
+        mbar_init(smem_u32(&sh->tmem_empty), 32 * I8_EPI_WARPS);
+        for (int s = 0; s < 4; ++s) mbar_init(smem_u32(&sh->scale_full[s]), I8_EPI_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == I8_EPI_WARPS) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                     "r"(I8_TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if ((int)blockIdx.x < n_tone_groups)   // only the CTAs that own a tile of the first row tile meet history rows
+        for (int i = threadIdx.x; i < I8_HIST_MAX && i < w.n_hist; i += I8_THREADS) sh->hist[i] = w.hist[i];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned int tmem_base = sh->tmem_base;
+
+    auto tile_of = [&](int n) {
+        const int id = (int)blockIdx.x + n * (int)gridDim.x;
+        I8Tile t;
+        t.row0 = (long long)(id / n_tone_groups) * RB;
+        t.tg = id % n_tone_groups;
+        t.ch0 = t.tg * TG;
+        return t;
+    };
+
+    if (warp < I8_EPI_WARPS) {
+        // ======================================= EPILOGUE (+ scan) =======================================
+        const int et = (int)threadIdx.x;                      // 0..127
+        const int row_in_tile = warp * 32 + lane;
+        const double row_d = (double)row_in_tile;
+        const double word_per_phase = 4294967296.0 / (double)rate;
+        long long* xw = sh->xch[warp];
+        const long long* xn = sh->xch[(warp + 1) & 3];
+        const unsigned int lane_base = tmem_base + ((unsigned int)(warp * 32) << 16);
+        // Largest |sample| of tile n -> amax_bits[n & 3], then scale_full[n & 3].  The tile's rows are one contiguous run of the
+        // window (the rows do not overlap and the pitch is M), so the scan is a coalesced sweep.
+        auto scan_tile = [&](int n) {
+            const int slot = n & 3;
+            if (et == 0) sh->amax_bits[slot] = 0u;
+            epi_bar();
+            const I8Tile tl = tile_of(n);
+            const long long s0 = tl.row0 * (long long)M, s1 = s0 + (long long)I8_ROWS * M;
+            float m = 0.f;
+            for (long long s = s0 + et; s < s1; s += 32 * I8_EPI_WARPS) {
+                const float2 v = dev_win_at(w, s);
+                m = fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y)));
+            }
+            const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));   // non-negative floats order like integers
+            if (lane == 0) {
+                atomicMax(&sh->amax_bits[slot], wm);
+                mbar_arrive(smem_u32(&sh->scale_full[slot]));   // release: the atomic is visible to whoever acquires the phase
+            }
+        };
+        if (my_tiles > 0) scan_tile(0);
+        if (my_tiles > 1) scan_tile(1);
+        for (int n = 0; n < my_tiles; ++n) {
+            const I8Tile tl = tile_of(n);
+            if (et < TG) {
+                const int ch = tl.ch0 + et;
+                double base = 0.0, step = 0.0;
+                float isb = 0.f;
+                if (ch < T) {
+                    isb = inv_sb[ch];
+                    if (rotate) {
+                        long long tf = (long long)freq[ch] % rate;
+                        if (tf < 0) tf += rate;   // same residue class as the reference's signed remainder
+                        long long n0 = (pos0 + tl.row0 * (long long)M) % rate;
+                        if (n0 < 0) n0 += rate;
+                        base = (double)(((unsigned long long)tf * (unsigned long long)n0) % (unsigned long long)rate);
+                        step = (double)(((unsigned long long)tf * (unsigned long long)(M % rate)) % (unsigned long long)rate);
+                    }
+                }
+                sh->ph[et] = make_double2(base, step);
+                sh->inv_sb[et] = isb;
+            }
+            // all four scan arrivals of this tile happened long ago (two tiles back): plain acquire
+            mbar_wait(smem_u32(&sh->scale_full[n & 3]), (unsigned)(n >> 2) & 1u);
+            const float amax = __uint_as_float(sh->amax_bits[n & 3]);
+            const float inv_sa = amax * (1.0f / I8_FULL_SCALE);
+            mbar_wait(smem_u32(&sh->tmem_full), (unsigned)n & 1u);
+            tc_fence_after();
+            const long long p = tl.row0 + row_in_tile;
+#pragma unroll 1
+            for (int u = 0; u < NUNIT; ++u) {
+                // exact 64-bit value of every (row, column) = D1 2^16 + D2 2^8 + D3 (in units of 2^16 / (sA sB)), blocks added with
+                // their row shift: S[j] = sum_i Z_i[row + i][column j of block i]; one unit = 8 tones = 16 accumulator columns
+                long long S[16];
+#pragma unroll
+                for (int i = 0; i < F; ++i) {
+                    const unsigned int col = (unsigned)((i * TG + u * 8) * 2);
+                    int d1[16], d2[16], d3[16];
+                    tmem_ld16(lane_base + col, d1);
+                    tmem_ld16(lane_base + 128u + col, d2);
+                    tmem_ld16(lane_base + 256u + col, d3);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const long long v = ((long long)d1[j] << 16) + ((long long)d2[j] << 8) + (long long)d3[j];
+                        if (i == 0) {
+                            S[j] = v;
+                        } else {
+                            if (lane < F - 1) xw[(lane * (F - 1) + (i - 1)) * 16 + j] = v;
+                            const long long o = __shfl_down_sync(0xffffffffu, v, i);
+                            if (lane + i < 32) S[j] += o;
+                        }
+                    }
+                }
+                // every accumulator column of the tile is in registers: the MMA warp may start the next tile
+                if (u == NUNIT - 1) {
+                    tc_fence_before();
+                    mbar_arrive(smem_u32(&sh->tmem_empty));
+                }
+                epi_bar();   // exchange buffers written; sh->ph / sh->inv_sb published
+                if (F > 1) {
+#pragma unroll
+                    for (int i = 1; i < F; ++i) {
+                        if (lane + i >= 32) {   // rows of the next warp (meaningless for the last warp: those outputs belong to the next tile)
+                            const long long* src = xn + ((lane + i - 32) * (F - 1) + (i - 1)) * 16;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) S[j] += src[j];
+                        }
+                    }
+                }
+                if (row_in_tile < RB && p < n_out) {
+                    float2 o[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        const float sc = inv_sa * sh->inv_sb[u * 8 + t] * 65536.0f;   // S is in units of 2^-16 of a digit-1 product
+                        o[t] = make_float2(__ll2float_rn(S[2 * t]) * sc, __ll2float_rn(S[2 * t + 1]) * sc);
+                        if (rotate) {   // the channelizer form (pfb as GEMM) has no LO: whole turns per row
+                            const double2 bs = sh->ph[u * 8 + t];
+                            const double r = fma(row_d, bs.y, bs.x);
+                            const unsigned int word = (unsigned int)__double2loint(fma(r, word_per_phase, 6755399441055744.0));
+                            float sn, cs;
+                            sincos_phase32(word, sn, cs);
+                            o[t] = dev_cmul(o[t], make_float2(cs, -sn));
+                        }
+                    }
+                    float2* dst = out + p * T + tl.ch0 + u * 8;
+                    const int n_valid = T - (tl.ch0 + u * 8);   // tones of this unit that exist
+                    if (n_valid >= 8 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+#pragma unroll
+                        for (int t = 0; t < 8; t += 2) *reinterpret_cast<float4*>(dst + t) = make_float4(o[t].x, o[t].y, o[t + 1].x, o[t + 1].y);
+                    } else {
+#pragma unroll
+                        for (int t = 0; t < 8; ++t)
+                            if (t < n_valid) dst[t] = o[t];
+                    }
+                }
+                epi_bar();   // the exchange buffer (and sh->ph after the last unit) may be rewritten
+            }
+            if (n + 2 < my_tiles) scan_tile(n + 2);
+        }
+    } else if (warp == I8_EPI_WARPS) {
+        // ======================================= MMA ISSUE =======================================
+        int it = 0, bc = 0;   // K blocks issued (A stage = it & 3), B stages consumed (stage = bc & 1)
+        const unsigned int d1 = tmem_base, d2 = tmem_base + 128u, d3 = tmem_base + 256u;
+        for (int n = 0; n < my_tiles; ++n) {
+            mbar_wait(smem_u32(&sh->tmem_empty), ((unsigned)n & 1u) ^ 1u);
+            tc_fence_after();
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int st = it & (I8_AST - 1), bs = bc & (I8_BST - 1);
+                if ((kb & 3) == 0) mbar_wait(smem_u32(&sh->b_full[bs]), (unsigned)(bc >> 1) & 1u);
+                mbar_wait(smem_u32(&sh->a_full[st]), (unsigned)(it >> 2) & 1u);
+                tc_fence_after();
+                if (lane == 0) {
+                    const unsigned int a1 = tmem_base + I8_COL_A + 24u * st, a2 = a1 + 8u, a3 = a1 + 16u;
+                    const unsigned int b0 = smem_u32(smem_b) + (unsigned)bs * I8_B_STAGE;
+                    const unsigned long long adv = (unsigned long long)(2 * (kb & 3));   // 32 bytes >> 4 per K block inside the 128-byte row
+                    const unsigned long long B1 = i8_smem_desc(b0) + adv, B3 = i8_smem_desc(b0 + 2 * I8_B_PLANE) + adv;
+                    const unsigned int acc = kb > 0 ? 1u : 0u;
+                    mma_i8_ts(d3, a1, B3, I8_IDESC, acc);          // 2^16: a1 b3
+                    mma_i8_ts(d1, a1, B1, I8_IDESC_WIDE, acc);     // 2^32: a1 b1 | 2^24: a1 b2      ([B1 | B2] -> [D1 | D2])
+                    mma_i8_ts(d2, a2, B1, I8_IDESC_WIDE, 1u);      // 2^24: a2 b1 | 2^16: a2 b2      ([B1 | B2] -> [D2 | D3])
+                    mma_i8_ts(d3, a3, B1, I8_IDESC, 1u);           // 2^16: a3 b1
+                    tc_commit(smem_u32(&sh->a_empty[st]));
+                    if ((kb & 3) == 3 || kb == KB - 1) tc_commit(smem_u32(&sh->b_empty[bs]));
+                    if (kb == KB - 1) tc_commit(smem_u32(&sh->tmem_full));
+                }
+                __syncwarp();
+                if ((kb & 3) == 3 || kb == KB - 1) ++bc;
+            }
+        }
+    } else if (warp < I8_TMA_WARP) {
+        // ======================================= OPERAND PRODUCERS =======================================
+        const int half = (warp - (I8_EPI_WARPS + 1)) / 4;    // which 16 reals of the 32-real K block
+        const int q = warp & 3;                              // TMEM lane quarter this warp may access
+        const int row = 32 * q + lane;                       // window row of the tile == TMEM lane
+        const unsigned int a_rowoff = (unsigned)(row >> 3) * 1024u + (unsigned)(row & 7) * 128u;
+        const unsigned int a_tmem0 = tmem_base + ((unsigned int)(32 * q) << 16) + I8_COL_A + 4u * half;
+        // byte order of the four K elements inside a 32-bit TMEM column: a_order = 0 -> K ascending with byte significance
+        const unsigned int sel_pair = a_order ? 0x0004u : 0x0040u;   // (x.b0, y.b0) -> low half-word
+        const unsigned int sel_quad = a_order ? 0x1054u : 0x5410u;
+        int it = 0;
+        for (int n = 0; n < my_tiles; ++n) {
+            const I8Tile tl = tile_of(n);
+            mbar_wait(smem_u32(&sh->scale_full[n & 3]), (unsigned)(n >> 2) & 1u);
+            const float amax = __uint_as_float(sh->amax_bits[n & 3]);
+            const float sa = amax > 0.f ? I8_FULL_SCALE / amax : 0.f;
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int st = it & (I8_AST - 1), r = it & (I8_RAW - 1);
+                mbar_wait(smem_u32(&sh->a_empty[st]), ((unsigned)(it >> 2) & 1u) ^ 1u);   // the MMAs of this stage's previous use are done
+                mbar_wait(smem_u32(&sh->raw_full[r]), (unsigned)(it >> 2) & 1u);
+                tc_fence_after();
+                const unsigned char* raw = smem + (size_t)r * I8_RAW_BYTES;
+                const bool from_smem = use_tma && tl.row0 + row >= hist_rows;   // else: history row, or no TMA at all
+                const long long s_row = (tl.row0 + row) * (long long)M + kb * I8_KC + 8 * half;
+                float v[16];
+                if (from_smem) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        const float4 x = *reinterpret_cast<const float4*>(raw + a_rowoff + ((unsigned)((4 * half + c4) ^ (row & 7)) << 4));
+                        v[4 * c4] = x.x, v[4 * c4 + 1] = x.y, v[4 * c4 + 2] = x.z, v[4 * c4 + 3] = x.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int k = kb * I8_KC + 8 * half + j;
+                        float2 a = make_float2(0.f, 0.f);
+                        if (k < M) a = (use_tma && s_row + j < w.n_hist && s_row + j < I8_HIST_MAX) ? sh->hist[s_row + j] : dev_win_at(w, s_row + j);
+                        v[2 * j] = a.x, v[2 * j + 1] = a.y;
+                    }
+                }
+                mbar_arrive(smem_u32(&sh->raw_empty[r]));   // this thread's reads of the landing slot are complete (values in registers)
+                // fixed point, three signed digits: q = d1 2^16 + d2 2^8 + d3 with d = low byte taken as signed and the carry moved up
+                unsigned int w1[4], w2[4], w3[4];
+#pragma unroll
+                for (int g4 = 0; g4 < 4; ++g4) {
+                    int q0[4], q1[4], q2[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        q0[e] = __float2int_rn(v[4 * g4 + e] * sa);
+                        q1[e] = (q0[e] + 128) >> 8;
+                        q2[e] = (q1[e] + 128) >> 8;
+                    }
+                    w3[g4] = __byte_perm(__byte_perm(q0[0], q0[1], sel_pair), __byte_perm(q0[2], q0[3], sel_pair), sel_quad);
+                    w2[g4] = __byte_perm(__byte_perm(q1[0], q1[1], sel_pair), __byte_perm(q1[2], q1[3], sel_pair), sel_quad);
+                    w1[g4] = __byte_perm(__byte_perm(q2[0], q2[1], sel_pair), __byte_perm(q2[2], q2[3], sel_pair), sel_quad);
+                }
+                __syncwarp();   // tcgen05.st is warp-collective: reconverge after the per-lane source selection
+                const unsigned int ta = a_tmem0 + 24u * st;
+                tmem_st4(ta, w1[0], w1[1], w1[2], w1[3]);
+                tmem_st4(ta + 8u, w2[0], w2[1], w2[2], w2[3]);
+                tmem_st4(ta + 16u, w3[0], w3[1], w3[2], w3[3]);
+                tmem_st_wait();
+                tc_fence_before();
+                mbar_arrive(smem_u32(&sh->a_full[st]));
+            }
+        }
+    } else if (warp == I8_TMA_WARP) {
+        // ======================================= TMA ISSUE =======================================
+        if (lane == 0) {
+            int it = 0, bc = 0;
+            for (int n = 0; n < my_tiles; ++n) {
+                const I8Tile tl = tile_of(n);
+                for (int kb = 0; kb < KB; ++kb, ++it) {
+                    if ((kb & 3) == 0) {   // the three digit planes of the next four K blocks of this tone group
+                        const int bs = bc & (I8_BST - 1);
+                        mbar_wait(smem_u32(&sh->b_empty[bs]), ((unsigned)(bc >> 1) & 1u) ^ 1u);
+                        const unsigned int bar = smem_u32(&sh->b_full[bs]);
+                        mbar_arrive_expect_tx(bar, I8_B_STAGE);
+                        const int row_b = ((tl.tg * KQ + (kb >> 2)) * 3) * I8_N;
+                        const unsigned int dst = smem_u32(smem_b) + (unsigned)bs * I8_B_STAGE;
+                        for (int pl = 0; pl < 3; ++pl) tma_load_2d(dst + (unsigned)pl * I8_B_PLANE, &tmap_b, 0, row_b + pl * I8_N, bar);
+                        ++bc;
+                    }
+                    const int s = it & (I8_RAW - 1);
+                    mbar_wait(smem_u32(&sh->raw_empty[s]), ((unsigned)(it >> 2) & 1u) ^ 1u);
+                    const unsigned int bar = smem_u32(&sh->raw_full[s]);
+                    if (use_tma) {
+                        mbar_arrive_expect_tx(bar, I8_RAW_BYTES);
+                        tma_load_2d(smem_base + (unsigned)s * I8_RAW_BYTES, &tmap_a, kb * 2 * I8_KC, (int)(tl.row0 - hist_rows), bar);
+                    } else {
+                        mbar_arrive(bar);
+                    }
+                }
+            }
+        }
+    }
+
+    // teardown: every MMA has completed before the last tmem_full arrival, every tcgen05.ld before this barrier
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (warp == I8_EPI_WARPS) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(I8_TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*I8EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+I8EncodeTiledFn i8_encode_fn() {
+    static I8EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<I8EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// The part of the `in` segment that starts on a window-row boundary as a 2-D tensor [rows][2 M floats] (row pitch M * 8
+// bytes), box = 128 rows x 32 floats, 128-byte swizzle.  *hist_rows = window rows that hold carried-over samples.
+bool i8_make_tensor_map_a(const Window& w, int M, CUtensorMap* map, long long* hist_rows, bool allow_tma) {
+    const long long hr = (w.n_hist + M - 1) / M, off0 = hr * M - w.n_hist;
+    *hist_rows = hr;
+    if (!allow_tma || M < I8_KC || (M & 1) || w.n_in - off0 < M) return false;
+    const float2* base = w.in + off0;
+    if (reinterpret_cast<uintptr_t>(base) & 15) return false;
+    I8EncodeTiledFn enc = i8_encode_fn();
+    if (!enc) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)(2 * M), (cuuint64_t)((w.n_in - off0) / M)};
+    const cuuint64_t strides[1] = {(cuuint64_t)M * 8};
+    const cuuint32_t box[2] = {2 * I8_KC, I8_ROWS};
+    const cuuint32_t estr[2] = {1, 1};
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float2*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int F>
+int i8_launch(const DirectI8Bank& bank, const Window& w, const int* freq_dev, int T, int M, int rate, long long pos0, long long n_out,
+              float2* out, int sm_count, cudaStream_t stream, int rotate, bool allow_tma) {
+    constexpr int TG = 64 / F, RB = I8_ROWS - (F - 1);
+    const int row_tiles = (int)((n_out + RB - 1) / RB), tone_groups = (T + TG - 1) / TG;
+    static DeviceOnce attr_once;
+    if (const int dev = attr_once.pending(); dev >= 0) {
+        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_i8_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM_BYTES));
+        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_i8_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM_BYTES));
+        attr_once.done(dev);
+    }
+    CUtensorMap map_a;
+    memset(&map_a, 0, sizeof(map_a));
+    long long hist_rows = 0;
+    const int use_tma = i8_make_tensor_map_a(w, M, &map_a, &hist_rows, allow_tma) ? 1 : 0;
+    CUtensorMap map_b;
+    static_assert(sizeof(map_b) == sizeof(bank.tmap_b), "tensor map storage");
+    memcpy(&map_b, bank.tmap_b, sizeof(map_b));
+    const long long tiles = (long long)row_tiles * tone_groups;
+    const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+    static const unsigned int a_order = [] {
+        const char* e = getenv("GSDR_I8_AORDER");
+        return (e && e[0] == '1') ? 1u : 0u;
+    }();
+    if (rotate)
+        direct_fir_i8_kernel<F, true><<<grid, I8_THREADS, I8_SMEM_BYTES, stream>>>(map_a, map_b, use_tma, hist_rows, w, bank.d_inv_sb, freq_dev, T, M,
+                                                                                   rate, pos0, n_out, row_tiles, tone_groups, bank.KQ, a_order, out);
+    else
+        direct_fir_i8_kernel<F, false><<<grid, I8_THREADS, I8_SMEM_BYTES, stream>>>(map_a, map_b, use_tma, hist_rows, w, bank.d_inv_sb, freq_dev, T, M,
+                                                                                    rate, pos0, n_out, row_tiles, tone_groups, bank.KQ, a_order, out);
+    GSDR_CUDA_OK(cudaGetLastError());
+    return 1;
+}
+
+}  // namespace
+
+// F in {1, 2, 4, 8} so that F * TG * 2 = 128 accumulator columns; the LO phase arithmetic needs 128 * rate < 2^53; the int32
+// accumulators hold three digit products of at most 2^14 per real tap: 3 * 2 M * 2^14 < 2^31.
+bool direct_fir_i8_supported(int T, int M, int ntaps, long long n_out) {
+    if (M < 1 || T < 1 || n_out < 1 || ntaps % M != 0 || M > 16384) return false;
+    const int f = ntaps / M;
+    if (!(f == 1 || f == 2 || f == 4 || f == 8)) return false;
+    const long long rb = I8_ROWS - (f - 1), tg = 64 / f;
+    const long long tiles = ((n_out + rb - 1) / rb) * ((T + tg - 1) / tg);
+    const long long kq = ((M + I8_KC - 1) / I8_KC + 3) / 4;
+    const long long bank_bytes = ((T + tg - 1) / tg) * kq * I8_B_STAGE;
+    return tiles < (1ll << 30) && bank_bytes <= (512ll << 20);
+}
+
+// Worth it when there are enough (row tile, tone group) tiles to occupy a good part of the GPU.
+bool direct_fir_i8_preferred(int T, int M, int ntaps, long long n_out) {
+    if (!direct_fir_i8_supported(T, M, ntaps, n_out)) return false;
+    const int f = ntaps / M;
+    const long long rb = I8_ROWS - (f - 1), tg = 64 / f;
+    const long long tiles = ((n_out + rb - 1) / rb) * ((T + tg - 1) / tg);
+    return tiles >= 64;
+}
+
+// The filter bank as digit planes.  g = T x ntaps complex taps in double (re, im interleaved).  Layout in HBM: rows of 128
+// bytes; row ((tg KQ + kq) 3 + plane) 128 + n holds, for accumulator column n = (block i, tone t, re/im) of tone group tg, the
+// digits of plane `plane` (0: 2^16, 1: 2^8, 2: 2^0) for K blocks 4 kq .. 4 kq + 3 (32 bytes each: reals 2k, 2k+1 of taps
+// 16 kb + k).  TMA (SWIZZLE_128B) turns 128 such rows into one K-major operand tile.
+int direct_i8_bank_create(const double* g, int T, int M, int ntaps, DirectI8Bank* bank) {
+    memset(bank, 0, sizeof(*bank));
+    if (!direct_fir_i8_supported(T, M, ntaps, 1)) {
+        set_error("direct_i8_bank_create: unsupported shape (T=%d M=%d ntaps=%d)", T, M, ntaps);
+        return -1;
+    }
+    const int F = ntaps / M, TG = 64 / F, tone_groups = (T + TG - 1) / TG;
+    const int KB = (M + I8_KC - 1) / I8_KC, KQ = (KB + 3) / 4;
+    const size_t rows = (size_t)tone_groups * KQ * 3 * I8_N;
+    std::vector<signed char> host(rows * 128, 0);
+    std::vector<float> inv_sb((size_t)tone_groups * TG, 0.f);
+    for (int t = 0; t < T; ++t) {
+        double mx = 0.0;
+        for (int m = 0; m < 2 * ntaps; ++m) mx = std::fmax(mx, std::fabs(g[(size_t)t * 2 * ntaps + m]));
+        const double sb = mx > 0.0 ? (double)I8_FULL_SCALE / mx : 0.0;
+        inv_sb[t] = mx > 0.0 ? (float)(1.0 / sb) : 0.f;
+        const int tg = t / TG, tt = t % TG;
+        for (int i = 0; i < F; ++i)
+            for (int k = 0; k < M; ++k) {
+                const double gr = g[((size_t)t * ntaps + (size_t)i * M + k) * 2], gi = g[((size_t)t * ntaps + (size_t)i * M + k) * 2 + 1];
+                // column Re: (x_r, x_i) . (g_r, -g_i); column Im: (x_r, x_i) . (g_i, g_r)
+                const double col_re[2] = {gr, -gi}, col_im[2] = {gi, gr};
+                const int kb = k / I8_KC, kk = k % I8_KC, kq = kb / 4, kj = kb % 4;
+                for (int c = 0; c < 2; ++c) {
+                    const int ncol = (i * TG + tt) * 2 + c;
+                    for (int e = 0; e < 2; ++e) {
+                        const long long q0 = llrint((c == 0 ? col_re[e] : col_im[e]) * sb);
+                        const long long q1 = (q0 + 128) >> 8, q2 = (q1 + 128) >> 8;
+                        const signed char dg[3] = {(signed char)(q2 & 0xff), (signed char)(q1 & 0xff), (signed char)(q0 & 0xff)};
+                        for (int pl = 0; pl < 3; ++pl) {
+                            const size_t row = ((size_t)(tg * KQ + kq) * 3 + pl) * I8_N + ncol;
+                            host[row * 128 + kj * 32 + 2 * kk + e] = dg[pl];
+                        }
+                    }
+                }
+            }
+    }
+    void* d = nullptr;
+    float* d_inv = nullptr;
+    GSDR_CUDA_OK(cudaMalloc(&d, host.size()));
+    if (cudaMemcpy(d, host.data(), host.size(), cudaMemcpyHostToDevice) != cudaSuccess || cudaMalloc(&d_inv, sizeof(float) * inv_sb.size()) != cudaSuccess ||
+        cudaMemcpy(d_inv, inv_sb.data(), sizeof(float) * inv_sb.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
+        set_error("direct_i8_bank_create: %s", cudaGetErrorString(cudaGetLastError()));
+        cudaFree(d);
+        if (d_inv) cudaFree(d_inv);
+        return -1;
+    }
+    I8EncodeTiledFn enc = i8_encode_fn();
+    CUtensorMap map;
+    const cuuint64_t dims[2] = {128, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {128};
+    const cuuint32_t box[2] = {128, I8_N};
+    const cuuint32_t estr[2] = {1, 1};
+    if (!enc || enc(&map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        set_error("direct_i8_bank_create: cuTensorMapEncodeTiled failed for the filter bank");
+        cudaFree(d);
+        cudaFree(d_inv);
+        return -1;
+    }
+    static_assert(sizeof(map) == sizeof(bank->tmap_b), "tensor map storage");
+    memcpy(bank->tmap_b, &map, sizeof(map));
+    bank->d_bank = d;
+    bank->d_inv_sb = d_inv;
+    bank->KQ = KQ;
+    bank->tone_groups = tone_groups;
+    return 0;
+}
+
+void direct_i8_bank_destroy(DirectI8Bank* bank) {
+    if (bank->d_bank) cudaFree(bank->d_bank);
+    if (bank->d_inv_sb) cudaFree(bank->d_inv_sb);
+    memset(bank, 0, sizeof(*bank));
+}
+
+int direct_fir_i8_launch(const DirectI8Bank& bank, const Window& w, const int* freq_dev, int T, int M, int ntaps, int rate, long long pos0,
+                         long long n_out, float2* out, int sm_count, cudaStream_t stream, int rotate, bool allow_tma) {
+    if (n_out <= 0) return 0;
+    if (!bank.d_bank || !direct_fir_i8_supported(T, M, ntaps, n_out)) {
+        set_error("direct_fir_i8_launch: unsupported shape (T=%d M=%d ntaps=%d) or missing bank", T, M, ntaps);
+        return -1;
+    }
+    switch (ntaps / M) {
+        case 1: return i8_launch<1>(bank, w, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate, allow_tma);
+        case 2: return i8_launch<2>(bank, w, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate, allow_tma);
+        case 4: return i8_launch<4>(bank, w, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate, allow_tma);
+        default: return i8_launch<8>(bank, w, freq_dev, T, M, rate, pos0, n_out, out, sm_count, stream, rotate, allow_tma);
+    }
+}
+
+}  // namespace gsdr

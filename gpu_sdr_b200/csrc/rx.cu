@@ -126,6 +126,9 @@ struct gsdr_rx {
     int ntaps = 0;
     long long index_counter = 0;
     bool direct_tc = false;
+    // exact integer tensor-core path (direct_i8_kernels.cu), DIRECT and the generic-size channelizer
+    bool direct_i8 = false, pfb_i8 = false;
+    DirectI8Bank i8bank;
 };
 
 namespace {
@@ -237,22 +240,33 @@ int init_pfb(gsdr_rx* rx, bool all_bins) {
         // i.e. DIRECT with decim = N, pf_average = P, per-tone taps g_u[m] = w[m] e^{-2 pi j (m bin_u mod N)/N} and no LO
         // rotation (whole turns per frame) -- direct_fir_tc_kernel runs it as a 3xTF32 GEMM on the tensor cores instead of
         // an O(N T) DFT on the CUDA cores.  GSDR_PFB_VARIANT=generic keeps the CUDA-core pair (cross-checks).
+        // GSDR_PFB_VARIANT: i8 (default: exact integer MMAs) | tc (3xTF32) | generic (CUDA-core FIR + DFT pair, cross-checks)
         const char* e = getenv("GSDR_PFB_VARIANT");
+        const bool want_generic = e && !strcmp(e, "generic"), want_tc = e && !strcmp(e, "tc");
         const size_t n_g = (size_t)rx->T_sel * N * P;
-        if (!(e && !strcmp(e, "generic")) && n_g <= (size_t)32 << 20 && direct_fir_tc_supported(rx->T_sel, N, N * P, 1)) {
-            std::vector<float2> g(n_g);
+        if (!want_generic && n_g <= (size_t)32 << 20 && direct_fir_tc_supported(rx->T_sel, N, N * P, 1)) {
+            std::vector<double> gd(2 * n_g);
             const double two_pi = 6.283185307179586476925286766559;
             for (int u = 0; u < rx->T_sel; ++u) {
                 const long long bin = all_bins ? u : rx->bins_host[u];
                 for (int m = 0; m < N * P; ++m) {
                     const double a = -two_pi * (double)((bin * m) % N) / (double)N;
                     const double h = rx->taps_host[m];
-                    g[(size_t)u * N * P + m] = make_float2((float)(h * std::cos(a)), (float)(h * std::sin(a)));
+                    gd[2 * ((size_t)u * N * P + m)] = h * std::cos(a);
+                    gd[2 * ((size_t)u * N * P + m) + 1] = h * std::sin(a);
                 }
             }
-            if (dev_upload(&rx->d_g, g.data(), g.size())) return -1;
-            rx->pfb_tc = true;
-            rx->kernel_name = "direct_fir_tc_kernel (filter bank as GEMM)";
+            if (!want_tc && direct_fir_i8_supported(rx->T_sel, N, N * P, 1)) {
+                if (direct_i8_bank_create(gd.data(), rx->T_sel, N, N * P, &rx->i8bank)) return -1;
+                rx->pfb_tc = rx->pfb_i8 = true;   // pfb_tc: "the channelizer runs as a decimating filter bank GEMM"
+                rx->kernel_name = "direct_fir_i8_kernel (filter bank as GEMM)";
+            } else {
+                std::vector<float2> g(n_g);
+                for (size_t k = 0; k < n_g; ++k) g[k] = make_float2((float)gd[2 * k], (float)gd[2 * k + 1]);
+                if (dev_upload(&rx->d_g, g.data(), g.size())) return -1;
+                rx->pfb_tc = true;
+                rx->kernel_name = "direct_fir_tc_kernel (filter bank as GEMM)";
+            }
         }
     }
     rx->hist_cap = (long long)N * P + 16;
@@ -334,6 +348,7 @@ int init_direct(gsdr_rx* rx) {
         rx->taps_host.resize(rx->ntaps);
         make_sinc_window(rx->ntaps, (float)(0.75 / (M * 2)), rx->taps_host.data());  // cpp/USRP_demodulator.cpp:99
         // g[ch][m] = h[m] * exp(-2 pi j ((tf*m) mod R)/R): per-tone complex FIR, built in double
+        std::vector<double> gd(2 * (size_t)T * rx->ntaps);
         std::vector<float2> g((size_t)T * rx->ntaps);
         const double two_pi = 6.283185307179586476925286766559;
         for (int ch = 0; ch < T; ++ch)
@@ -341,19 +356,27 @@ int init_direct(gsdr_rx* rx) {
                 long long ph = ((long long)rx->freq[ch] * (long long)(m % rx->rate)) % rx->rate;
                 const double a = -two_pi * (double)ph / (double)rx->rate;
                 const double h = rx->taps_host[m];
-                g[(size_t)ch * rx->ntaps + m] = make_float2((float)(h * std::cos(a)), (float)(h * std::sin(a)));
+                const size_t k = (size_t)ch * rx->ntaps + m;
+                gd[2 * k] = h * std::cos(a), gd[2 * k + 1] = h * std::sin(a);
+                g[k] = make_float2((float)gd[2 * k], (float)gd[2 * k + 1]);
             }
         if (dev_upload(&rx->d_g, g.data(), g.size())) return -1;
         rx->hist_cap = (f - 1) * M + 16;
         rx->n_hist = (f - 1) * M;  // FIR history starts as zeros (cpp/fir.cu:23-26)
         rx->max_out = (size_t)(rx->L / M) * T;
         rx->kernel_name = (rx->P >= 1 && rx->P <= 8) ? "direct_fir_tiled_kernel" : "direct_fir_kernel";
-        // tensor-core path (direct_tc_kernels.cu): default when the shape fills the GPU; GSDR_DIRECT_VARIANT=tc|fp32 forces
+        // Tensor-core paths: the exact integer GEMM (direct_i8_kernels.cu) is the default when the shape fills the GPU;
+        // GSDR_DIRECT_VARIANT = i8 | tc (3xTF32, direct_tc_kernels.cu) | fp32 (CUDA cores) forces one.
         const long long n_out1 = rx->L / M;
         const char* e = getenv("GSDR_DIRECT_VARIANT");
-        rx->direct_tc = direct_fir_tc_preferred(T, (int)M, rx->ntaps, n_out1);
-        if (e && !strcmp(e, "tc")) rx->direct_tc = direct_fir_tc_supported(T, (int)M, rx->ntaps, n_out1);
-        if (e && !strcmp(e, "fp32")) rx->direct_tc = false;
+        rx->direct_i8 = direct_fir_i8_preferred(T, (int)M, rx->ntaps, n_out1);
+        if (e && !strcmp(e, "i8")) rx->direct_i8 = direct_fir_i8_supported(T, (int)M, rx->ntaps, n_out1);
+        if (e && !strcmp(e, "tc")) rx->direct_i8 = false, rx->direct_tc = direct_fir_tc_supported(T, (int)M, rx->ntaps, n_out1);
+        if (e && !strcmp(e, "fp32")) rx->direct_i8 = rx->direct_tc = false;
+        if (rx->direct_i8) {
+            if (direct_i8_bank_create(gd.data(), T, (int)M, rx->ntaps, &rx->i8bank)) return -1;
+            rx->kernel_name = "direct_fir_i8_kernel";
+        }
         if (rx->direct_tc) rx->kernel_name = "direct_fir_tc_kernel";
     }
     return 0;
@@ -440,9 +463,11 @@ long long enqueue_compute_impl(gsdr_rx* rx, const float2* d_in, int n_buf, float
                     rx->work_bytes = need;
                 }
             }
-            const int nl = rx->pfb_tc ? direct_fir_tc_launch(w, rx->d_g, nullptr, rx->T_sel, rx->N, rx->N * (int)rx->P, 1, 0, frames, d_out,
-                                                             rx->sm_count, st, /*rotate=*/0, tc_tma_allowed(rx))
-                                      : pfb_launch(&job, 1, nullptr, rx->d_work, rx->d_tw, rx->sm_count, st);
+            const int nl = rx->pfb_i8   ? direct_fir_i8_launch(rx->i8bank, w, nullptr, rx->T_sel, rx->N, rx->N * (int)rx->P, 1, 0, frames, d_out,
+                                                               rx->sm_count, st, /*rotate=*/0, tc_tma_allowed(rx))
+                           : rx->pfb_tc ? direct_fir_tc_launch(w, rx->d_g, nullptr, rx->T_sel, rx->N, rx->N * (int)rx->P, 1, 0, frames, d_out,
+                                                               rx->sm_count, st, /*rotate=*/0, tc_tma_allowed(rx))
+                                        : pfb_launch(&job, 1, nullptr, rx->d_work, rx->d_tw, rx->sm_count, st);
             if (nl < 0) return -1;
             rx->launches += nl;
             if (spec_decim) {
@@ -522,7 +547,9 @@ long long enqueue_compute_impl(gsdr_rx* rx, const float2* d_in, int n_buf, float
                 const long long n_out = (L / M) * n_buf;
                 long long pos0 = (rx->index_counter - w.n_hist) % rx->rate;
                 if (pos0 < 0) pos0 += rx->rate;
-                const int nl = rx->direct_tc ? direct_fir_tc_launch(w, rx->d_g, rx->d_freq, rx->T, (int)M, rx->ntaps, rx->rate, pos0,
+                const int nl = rx->direct_i8 ? direct_fir_i8_launch(rx->i8bank, w, rx->d_freq, rx->T, (int)M, rx->ntaps, rx->rate, pos0,
+                                                                    n_out, d_out, rx->sm_count, st, /*rotate=*/1, tc_tma_allowed(rx))
+                               : rx->direct_tc ? direct_fir_tc_launch(w, rx->d_g, rx->d_freq, rx->T, (int)M, rx->ntaps, rx->rate, pos0,
                                                                     n_out, d_out, rx->sm_count, st, /*rotate=*/1, tc_tma_allowed(rx))
                                              : direct_fir_launch(w, rx->d_g, rx->d_freq, rx->T, (int)M, rx->ntaps, rx->rate, pos0, n_out,
                                                                  d_out, st);
@@ -571,6 +598,7 @@ void free_all(gsdr_rx* rx) {
     if (rx->d_profile) cudaFree(rx->d_profile);
     if (rx->d_partial) cudaFree(rx->d_partial);
     if (rx->d_g) cudaFree(rx->d_g);
+    direct_i8_bank_destroy(&rx->i8bank);
     if (rx->d_freq) cudaFree(rx->d_freq);
     if (rx->t0) cudaEventDestroy(rx->t0);
     if (rx->t1) cudaEventDestroy(rx->t1);

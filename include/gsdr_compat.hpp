@@ -17,17 +17,22 @@
 #pragma once
 #include <cstddef>
 #include <cstdio>
+#include <condition_variable>
 #include <cstdlib>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "gsdr.h"
 
+// GSDR_COMPAT_REFERENCE_SETTINGS: the including translation unit has the reference's own headers/USRP_server_settings.hpp
+// (float2 from CUDA, w_type, ant_mode, param, RX_wrapper, the queue typedefs) -- the way the reference's server is built
+// against this library (tests/cpp/reference_shim/).  Otherwise the same types are defined here, field for field.
+#ifndef GSDR_COMPAT_REFERENCE_SETTINGS
 #if !defined(__VECTOR_TYPES_H__) && !defined(GSDR_COMPAT_HAVE_FLOAT2)
 #define GSDR_COMPAT_HAVE_FLOAT2
 struct float2 { float x, y; };
 #endif
-static_assert(sizeof(float2) == sizeof(gsdr_float2), "float2 layout");
 
 enum w_type { TONES, CHIRP, NOISE, RAMP, NODSP, SWONLY, DIRECT };
 enum ant_mode { TX, RX, OFF };
@@ -69,6 +74,8 @@ struct RX_wrapper {
     int errors;
     int channels;
 };
+#endif  // GSDR_COMPAT_REFERENCE_SETTINGS
+static_assert(sizeof(float2) == sizeof(gsdr_float2), "float2 layout");
 
 namespace gsdr_compat {
 struct flat_param {  // keeps the int32 copy of wave_type alive next to the POD block
@@ -96,6 +103,35 @@ struct flat_param {  // keeps the int32 copy of wave_type alive next to the POD 
     std::exit(-1);
 }
 }  // namespace gsdr_compat
+
+// headers/USRP_server_memory_management.hpp:9-19 (the link threads wait on it before joining)
+class threading_condition {
+  public:
+    threading_condition() : ready(false) {}
+    void wait() {
+        std::unique_lock<std::mutex> lock(ready_mutex);
+        while (!ready) ready_cond.wait(lock);
+    }
+    void release() {
+        {
+            std::unique_lock<std::mutex> lock(ready_mutex);
+            ready = true;
+        }
+        ready_cond.notify_all();
+    }
+    void rearm() {
+        {
+            std::unique_lock<std::mutex> lock(ready_mutex);
+            ready = false;
+        }
+        ready_cond.notify_all();
+    }
+
+  private:
+    std::condition_variable ready_cond;
+    std::mutex ready_mutex;
+    bool ready;
+};
 
 template <typename vector_type>
 class preallocator {

@@ -1,0 +1,1 @@
+#include "gsdr_more_stubs.hpp"

@@ -62,7 +62,7 @@ def test_generic_path_vs_oracle(N, P, T, L, rate):
     p = pfb_param(rate=rate, N=N, P=P, T=T, L=L)
     bufs = [tone_stream(rate, p.freq, p.ampl, i * L, L) for i in range(3)]
     # pf_average in {1,2,4,8}: the filter bank runs as a GEMM on the tensor cores; otherwise the CUDA-core FIR + DFT pair
-    check_against_oracle(p, bufs, "direct_fir_tc_kernel" if P in (1, 2, 4, 8) else "generic")
+    check_against_oracle(p, bufs, "direct_fir_i8_kernel" if P in (1, 2, 4, 8) else "generic")
 
 
 @pytest.mark.parametrize("N,P,T,L,rate", [(64, 4, 8, 20_000, 1_000_000), (1000, 2, 100, 60_000, 100_000_000)])
