@@ -11,7 +11,14 @@ NVFLAGS := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC,-O2,-ffp-contract=o
 CU_SRCS := pfb_kernels chirp_kernels direct_kernels direct_tc_kernels direct_i8_kernels tones_kernels rx tx host
 OBJS    := $(addprefix $(OBJDIR)/,$(addsuffix .o,$(CU_SRCS))) $(OBJDIR)/hostlogic.o
 
-all: $(OUT)
+FEEDER := tests/cpp/bin/realtime_feeder
+
+all: $(OUT) $(FEEDER)
+
+# C++ real-time feeder (tests/cpp/realtime_feeder.cpp): plain g++, links the C-ABI only
+$(FEEDER): tests/cpp/realtime_feeder.cpp include/gsdr.h $(OUT)
+	@mkdir -p tests/cpp/bin
+	g++ -O2 -std=c++17 -Wall -I include $< -o $@ $(OUT) -pthread -Wl,-rpath,'$$ORIGIN/../../../gpu_sdr_b200'
 
 $(OBJDIR)/%.o: $(SRC)/%.cu $(SRC)/common.hpp $(SRC)/devmath.cuh $(SRC)/direct_common.cuh $(SRC)/packed_f32x2.cuh include/gsdr.h
 	@mkdir -p $(OBJDIR)

@@ -107,6 +107,9 @@ struct PfbJob {          // one stream's share of a launch
     // (zero-copy blocking call): reads over PCIe are not kept in L2, so the P-1 halo rows at every tile start are paid in
     // full and few long tiles beat one short tile per SM.
     int min_tile = 0;
+    // sc16 ingest fused into the warp-specialised kernel: win.in then points at interleaved int16 I/Q pairs (n_in samples of
+    // 4 bytes) and the producers convert on the fly, (float)v * (1/32767); the history is fc32 as always.
+    int in_sc16 = 0;
 };
 // One tile of a multi-stream launch of the warp-specialised fused kernel: frames [fa, fb) of job `job`, relative to the job's
 // first_frame.  The host cuts the concatenated frame sequence of all jobs into equal shares, one per CTA, and splits a share
@@ -121,6 +124,7 @@ size_t pfb_table_bytes(int n_jobs, int sm_count);
 // Returns the number of kernel launches issued (>0) or -1.  `workspace` is device scratch of at
 // least pfb_workspace_bytes() for the generic path (may be null for the fused path).
 bool pfb_fused_supported(int N, int P, int T, const Window& w);
+bool pfb_fused_sc16_available();   // the default (warp-specialised) kernel reads sc16 windows; the lock-step cross-check kernel does not
 const char* pfb_kernel_name(int N, int P, int T);
 size_t pfb_workspace_bytes(int N, int P, int max_frames);
 int pfb_launch(const PfbJob* jobs_host, int n_jobs, void* jobs_dev_scratch, void* workspace, const float2* twiddle_dev,
@@ -170,13 +174,15 @@ struct DirectI8Bank {
     void* d_bank = nullptr;        // digit planes of the filter bank, rows of 128 bytes (see direct_i8_bank_create)
     float* d_inv_sb = nullptr;     // [tone groups * TG] 1 / (fixed-point scale of the tone's taps)
     int KQ = 0, tone_groups = 0;   // quads of K blocks per tile, tone groups
+    float* d_row_amax = nullptr;   // scratch: largest |sample| per row tile (launches with more than two tone groups)
+    size_t row_amax_cap = 0;
     alignas(64) unsigned char tmap_b[128];   // CUtensorMap of the bank
 };
 bool direct_fir_i8_supported(int T, int M, int ntaps, long long n_out);
 bool direct_fir_i8_preferred(int T, int M, int ntaps, long long n_out);
 int direct_i8_bank_create(const double* g /* [T][ntaps] (re, im) */, int T, int M, int ntaps, DirectI8Bank* bank);
 void direct_i8_bank_destroy(DirectI8Bank* bank);
-int direct_fir_i8_launch(const DirectI8Bank& bank, const Window& w, const int* freq_dev, int T, int M, int ntaps, int rate, long long pos0,
+int direct_fir_i8_launch(DirectI8Bank& bank, const Window& w, const int* freq_dev, int T, int M, int ntaps, int rate, long long pos0,
                          long long n_out, float2* out, int sm_count, cudaStream_t stream, int rotate = 1, bool allow_tma = true);
 int direct_mix_launch(const float2* in, long long n, const int* freq_dev, int T, int rate, long long pos0, float2* out,
                       cudaStream_t stream);

@@ -59,7 +59,7 @@ constexpr int I8_B_PLANE = I8_N * 128;       // one digit plane: 128 columns (ro
 constexpr int I8_B_STAGE = 3 * I8_B_PLANE;
 constexpr unsigned int I8_COL_A = 384;       // accumulators: weight 2^32 at column 0, 2^24 at 128, 2^16 at 256; A stage s at 384 + 24 s
 constexpr int I8_TMEM_COLS = 512;
-constexpr int I8_XCH = 7 * 7 * 16;           // per epilogue warp: (F-1) lanes x (F-1) blocks x chunk columns, F <= 8
+constexpr int I8_XCH = 7 * 7 * 3 * 16;       // per epilogue warp: (F-1) lanes x (F-1) blocks x 3 accumulators x 16 columns, F <= 8
 constexpr int I8_HIST_MAX = 7 * 128;
 constexpr float I8_FULL_SCALE = 8355000.0f;  // |digits| <= 127 * (2^16 + 2^8 + 1) = 8355711
 static_assert((I8_EPI_WARPS + 1) % 4 == 1, "producer warp w owns TMEM lane quarter w % 4");
@@ -74,7 +74,7 @@ struct I8Shared {
     unsigned int amax_bits[4];
     double2 ph[64];          // per tone of the group: (LO phase of the tile's first row, phase step per row), integers < rate
     float inv_sb[64];        // per tone of the group: 1 / sB
-    alignas(16) long long xch[I8_EPI_WARPS][I8_XCH];
+    alignas(16) int xch[I8_EPI_WARPS][I8_XCH];
     alignas(16) float2 hist[I8_HIST_MAX];
 };
 constexpr size_t I8_SMEM_BYTES = 1024 + (size_t)I8_RAW * I8_RAW_BYTES + (size_t)I8_BST * I8_B_STAGE + sizeof(I8Shared);
@@ -101,6 +101,16 @@ __device__ __forceinline__ void mbar_wait(unsigned int addr, unsigned int parity
         if (spins == 64) t0 = clock64();
         if (spins > 64 && (spins & 255u) == 0 && clock64() - t0 > 4000000000LL) __trap();
     }
+}
+// schedule tuning (GSDR_DIRECT_I8_DEBUG=1): cycles spent in a wait, accumulated per role
+__device__ __forceinline__ void mbar_wait_t(unsigned int addr, unsigned int parity, long long& acc, bool on) {
+    if (!on) {
+        mbar_wait(addr, parity);
+        return;
+    }
+    const long long t0 = clock64();
+    mbar_wait(addr, parity);
+    acc += clock64() - t0;
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned int addr, unsigned int bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
@@ -154,6 +164,16 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory"); }
 
+// round_to_nearest_float(s1 2^16 + s2 2^8 + s3): the exact 64-bit sum, cut into a high part (arithmetic shift by 21: an int32
+// here, |sum| < 2^52) and a 21-bit low part, both converted exactly; the one rounding is the FFMA's.
+__device__ __forceinline__ float i8_combine(int s1, int s2, int s3) {
+    const long long v = ((long long)s1 << 16) + ((long long)s2 << 8) + (long long)s3;
+    const int hi = (int)(v >> 21);
+    const int lo = (int)((unsigned int)v & 0x1FFFFFu);
+    const float flo = __int_as_float(0x4B000000 | lo) - 8388608.0f;   // exact: lo < 2^21
+    return fmaf((float)hi, 2097152.0f, flo);
+}
+
 struct I8Tile {
     long long row0;   // first window row of the tile
     int ch0;          // first tone of the group
@@ -166,11 +186,11 @@ __global__ void __launch_bounds__(I8_THREADS, 1)
 direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const int use_tma,
                      const long long hist_rows, const Window w, const float* __restrict__ inv_sb, const int* __restrict__ freq, int T,
                      int M, int rate, long long pos0, long long n_out, int n_row_tiles, int n_tone_groups, int KQ,
-                     const unsigned int a_order, float2* __restrict__ out) {
+                     const unsigned int a_order, const float* __restrict__ amax_rows, float2* __restrict__ out, long long* __restrict__ dbg) {
     constexpr int TG = 64 / F;
     constexpr int RB = I8_ROWS - (F - 1);
     constexpr int NUNIT = TG / 8;              // epilogue units of 8 tones (16 accumulator columns) per tile
-    static_assert(TG % 8 == 0 && (F - 1) * (F - 1) * 16 <= I8_XCH, "exchange buffer");
+    static_assert(TG % 8 == 0 && (F - 1) * (F - 1) * 3 * 16 <= I8_XCH, "exchange buffer");
 
     extern __shared__ unsigned char i8_smem_raw[];
     unsigned char* smem = i8_smem_raw + ((1024u - (smem_u32(i8_smem_raw) & 1023u)) & 1023u);
@@ -182,6 +202,9 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     const int KB = (M + I8_KC - 1) / I8_KC;           // K blocks per tile
     const int n_tiles = n_row_tiles * n_tone_groups;
     const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const bool timed = dbg != nullptr;
+    long long wt0 = 0, wt1 = 0, wt2 = 0;
+    const long long t_role0 = clock64();
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < I8_RAW; ++s) {
@@ -229,21 +252,69 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const int row_in_tile = warp * 32 + lane;
         const double row_d = (double)row_in_tile;
         const double word_per_phase = 4294967296.0 / (double)rate;
-        long long* xw = sh->xch[warp];
-        const long long* xn = sh->xch[(warp + 1) & 3];
+        int* xw = sh->xch[warp];
+        const int* xn = sh->xch[(warp + 1) & 3];
         const unsigned int lane_base = tmem_base + ((unsigned int)(warp * 32) << 16);
         // Largest |sample| of tile n -> amax_bits[n & 3], then scale_full[n & 3].  The tile's rows are one contiguous run of the
         // window (the rows do not overlap and the pitch is M), so the scan is a coalesced sweep.
         auto scan_tile = [&](int n) {
             const int slot = n & 3;
+            const I8Tile tl = tile_of(n);
+            if (amax_rows != nullptr) {   // many tone groups share a row tile: a pre-pass has scanned every row tile once
+                if (et == 0) sh->amax_bits[slot] = __float_as_uint(amax_rows[tl.row0 / RB]);
+                __syncwarp();
+                epi_bar();
+                if (lane == 0) mbar_arrive(smem_u32(&sh->scale_full[slot]));
+                return;
+            }
             if (et == 0) sh->amax_bits[slot] = 0u;
             epi_bar();
-            const I8Tile tl = tile_of(n);
             const long long s0 = tl.row0 * (long long)M, s1 = s0 + (long long)I8_ROWS * M;
             float m = 0.f;
-            for (long long s = s0 + et; s < s1; s += 32 * I8_EPI_WARPS) {
-                const float2 v = dev_win_at(w, s);
-                m = fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y)));
+            if (s0 >= w.n_hist && s1 <= w.n_hist + w.n_in) {
+                // whole tile inside the new samples: batches of independent loads (one load per iteration would pay a
+                // memory latency per load: 100 of them per tile at M = 100)
+                const float2* p = w.in + (s0 - w.n_hist);
+                const int n_s = I8_ROWS * M;
+                if (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (n_s & 1) == 0) {
+                    const float4* p4 = reinterpret_cast<const float4*>(p);
+                    const int n4 = n_s >> 1;
+                    // the tile after this one: pull its lines towards L2 now, so that its own scan (one tile period from now)
+                    // and the TMA boxes that follow find them there
+                    {
+                        const long long step = (long long)gridDim.x / n_tone_groups * RB * M;   // samples between this CTA's consecutive row tiles (approx.)
+                        const char* q = reinterpret_cast<const char*>(p + step);
+                        const char* q_end = reinterpret_cast<const char*>(w.in + w.n_in);
+                        for (int i = et * 128; i < n_s * 8; i += 128 * 128)
+                            if (q + i + 128 <= q_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + i));
+                    }
+                    for (int i = et; i < n4; i += 128 * 16) {
+                        float4 v[16];
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) {
+                            const int idx = i + u * 128;
+                            v[u] = idx < n4 ? __ldg(p4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 16; ++u) m = fmaxf(fmaxf(m, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
+                    }
+                } else {
+                    for (int i = et; i < n_s; i += 128 * 10) {
+                        float2 v[10];
+#pragma unroll
+                        for (int u = 0; u < 10; ++u) {
+                            const int idx = i + u * 128;
+                            v[u] = idx < n_s ? __ldg(p + idx) : make_float2(0.f, 0.f);
+                        }
+#pragma unroll
+                        for (int u = 0; u < 10; ++u) m = fmaxf(m, fmaxf(fabsf(v[u].x), fabsf(v[u].y)));
+                    }
+                }
+            } else {
+                for (long long s = s0 + et; s < s1; s += 32 * I8_EPI_WARPS) {
+                    const float2 v = dev_win_at(w, s);
+                    m = fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y)));
+                }
             }
             const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));   // non-negative floats order like integers
             if (lane == 0) {
@@ -277,31 +348,38 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             mbar_wait(smem_u32(&sh->scale_full[n & 3]), (unsigned)(n >> 2) & 1u);
             const float amax = __uint_as_float(sh->amax_bits[n & 3]);
             const float inv_sa = amax * (1.0f / I8_FULL_SCALE);
-            mbar_wait(smem_u32(&sh->tmem_full), (unsigned)n & 1u);
+            mbar_wait_t(smem_u32(&sh->tmem_full), (unsigned)n & 1u, wt0, timed);
             tc_fence_after();
             const long long p = tl.row0 + row_in_tile;
 #pragma unroll 1
             for (int u = 0; u < NUNIT; ++u) {
-                // exact 64-bit value of every (row, column) = D1 2^16 + D2 2^8 + D3 (in units of 2^16 / (sA sB)), blocks added with
-                // their row shift: S[j] = sum_i Z_i[row + i][column j of block i]; one unit = 8 tones = 16 accumulator columns
-                long long S[16];
+                // One unit = 8 tones = 16 accumulator columns.  The F blocks are added with their row shift (the reference's
+                // overlap-add, cpp/fir.cu:55-69) per accumulator, in int32 -- |D| <= 3 * 2 M * 2^14, times F, stays below 2^31 --
+                // so the 64-bit combine D1 2^16 + D2 2^8 + D3 runs once per output and not once per block.
+                int S[3][16];
 #pragma unroll
-                for (int i = 0; i < F; ++i) {
-                    const unsigned int col = (unsigned)((i * TG + u * 8) * 2);
-                    int d1[16], d2[16], d3[16];
-                    tmem_ld16(lane_base + col, d1);
-                    tmem_ld16(lane_base + 128u + col, d2);
-                    tmem_ld16(lane_base + 256u + col, d3);
-                    tmem_ld_wait();
+                for (int a = 0; a < 3; ++a) {   // one accumulator at a time: 16 sums + 16 fresh values live
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        const long long v = ((long long)d1[j] << 16) + ((long long)d2[j] << 8) + (long long)d3[j];
+                    for (int i = 0; i < F; ++i) {
+                        const unsigned int col = 128u * a + (unsigned)((i * TG + u * 8) * 2);
+                        int d[16];
+                        tmem_ld16(lane_base + col, d);
+                        tmem_ld_wait();
                         if (i == 0) {
-                            S[j] = v;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) S[a][j] = d[j];
                         } else {
-                            if (lane < F - 1) xw[(lane * (F - 1) + (i - 1)) * 16 + j] = v;
-                            const long long o = __shfl_down_sync(0xffffffffu, v, i);
-                            if (lane + i < 32) S[j] += o;
+                            if (lane < F - 1) {   // rows the previous warp needs: its lanes 32 - i .. 31 read them after the barrier
+                                int4* dst = reinterpret_cast<int4*>(xw + (((lane * (F - 1) + (i - 1)) * 3) + a) * 16);
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_int4(d[4 * j4], d[4 * j4 + 1], d[4 * j4 + 2], d[4 * j4 + 3]);
+                            }
+                            const bool here = lane + i < 32;
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                const int o = __shfl_down_sync(0xffffffffu, d[j], i);
+                                if (here) S[a][j] += o;
+                            }
                         }
                     }
                 }
@@ -315,9 +393,14 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
                     for (int i = 1; i < F; ++i) {
                         if (lane + i >= 32) {   // rows of the next warp (meaningless for the last warp: those outputs belong to the next tile)
-                            const long long* src = xn + ((lane + i - 32) * (F - 1) + (i - 1)) * 16;
+                            const int4* src = reinterpret_cast<const int4*>(xn + (((lane + i - 32) * (F - 1) + (i - 1)) * 3) * 16);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) S[j] += src[j];
+                            for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; ++j4) {
+                                    const int4 v = src[4 * a + j4];
+                                    S[a][4 * j4] += v.x, S[a][4 * j4 + 1] += v.y, S[a][4 * j4 + 2] += v.z, S[a][4 * j4 + 3] += v.w;
+                                }
                         }
                     }
                 }
@@ -325,8 +408,8 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     float2 o[8];
 #pragma unroll
                     for (int t = 0; t < 8; ++t) {
-                        const float sc = inv_sa * sh->inv_sb[u * 8 + t] * 65536.0f;   // S is in units of 2^-16 of a digit-1 product
-                        o[t] = make_float2(__ll2float_rn(S[2 * t]) * sc, __ll2float_rn(S[2 * t + 1]) * sc);
+                        const float sc = inv_sa * sh->inv_sb[u * 8 + t] * 65536.0f;   // the sum is in units of 2^-16 of a digit-1 product
+                        o[t] = make_float2(i8_combine(S[0][2 * t], S[1][2 * t], S[2][2 * t]) * sc, i8_combine(S[0][2 * t + 1], S[1][2 * t + 1], S[2][2 * t + 1]) * sc);
                         if (rotate) {   // the channelizer form (pfb as GEMM) has no LO: whole turns per row
                             const double2 bs = sh->ph[u * 8 + t];
                             const double r = fma(row_d, bs.y, bs.x);
@@ -349,19 +432,29 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 }
                 epi_bar();   // the exchange buffer (and sh->ph after the last unit) may be rewritten
             }
-            if (n + 2 < my_tiles) scan_tile(n + 2);
+            if (n + 2 < my_tiles) {
+                const long long ts = timed ? clock64() : 0;
+                scan_tile(n + 2);
+                if (timed) wt1 += clock64() - ts;
+            }
+        }
+        if (dbg && threadIdx.x == 0) {
+            atomicAdd((unsigned long long*)&dbg[0], (unsigned long long)wt0);                     // epilogue: wait for accumulators
+            atomicAdd((unsigned long long*)&dbg[1], (unsigned long long)wt1);                     // epilogue: scan
+            atomicAdd((unsigned long long*)&dbg[2], (unsigned long long)(clock64() - t_role0));   // epilogue: role time
+            atomicAdd((unsigned long long*)&dbg[15], (unsigned long long)my_tiles);
         }
     } else if (warp == I8_EPI_WARPS) {
         // ======================================= MMA ISSUE =======================================
         int it = 0, bc = 0;   // K blocks issued (A stage = it & 3), B stages consumed (stage = bc & 1)
         const unsigned int d1 = tmem_base, d2 = tmem_base + 128u, d3 = tmem_base + 256u;
         for (int n = 0; n < my_tiles; ++n) {
-            mbar_wait(smem_u32(&sh->tmem_empty), ((unsigned)n & 1u) ^ 1u);
+            mbar_wait_t(smem_u32(&sh->tmem_empty), ((unsigned)n & 1u) ^ 1u, wt0, timed);
             tc_fence_after();
             for (int kb = 0; kb < KB; ++kb, ++it) {
                 const int st = it & (I8_AST - 1), bs = bc & (I8_BST - 1);
-                if ((kb & 3) == 0) mbar_wait(smem_u32(&sh->b_full[bs]), (unsigned)(bc >> 1) & 1u);
-                mbar_wait(smem_u32(&sh->a_full[st]), (unsigned)(it >> 2) & 1u);
+                if ((kb & 3) == 0) mbar_wait_t(smem_u32(&sh->b_full[bs]), (unsigned)(bc >> 1) & 1u, wt1, timed);
+                mbar_wait_t(smem_u32(&sh->a_full[st]), (unsigned)(it >> 2) & 1u, wt2, timed);
                 tc_fence_after();
                 if (lane == 0) {
                     const unsigned int a1 = tmem_base + I8_COL_A + 24u * st, a2 = a1 + 8u, a3 = a1 + 16u;
@@ -381,6 +474,12 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 if ((kb & 3) == 3 || kb == KB - 1) ++bc;
             }
         }
+        if (dbg && lane == 0) {
+            atomicAdd((unsigned long long*)&dbg[3], (unsigned long long)wt0);                     // MMA: wait for free accumulators
+            atomicAdd((unsigned long long*)&dbg[4], (unsigned long long)wt1);                     // MMA: wait for B planes
+            atomicAdd((unsigned long long*)&dbg[5], (unsigned long long)wt2);                     // MMA: wait for A digits
+            atomicAdd((unsigned long long*)&dbg[6], (unsigned long long)(clock64() - t_role0));   // MMA: role time
+        }
     } else if (warp < I8_TMA_WARP) {
         // ======================================= OPERAND PRODUCERS =======================================
         const int half = (warp - (I8_EPI_WARPS + 1)) / 4;    // which 16 reals of the 32-real K block
@@ -394,13 +493,13 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         int it = 0;
         for (int n = 0; n < my_tiles; ++n) {
             const I8Tile tl = tile_of(n);
-            mbar_wait(smem_u32(&sh->scale_full[n & 3]), (unsigned)(n >> 2) & 1u);
+            mbar_wait_t(smem_u32(&sh->scale_full[n & 3]), (unsigned)(n >> 2) & 1u, wt0, timed);
             const float amax = __uint_as_float(sh->amax_bits[n & 3]);
             const float sa = amax > 0.f ? I8_FULL_SCALE / amax : 0.f;
             for (int kb = 0; kb < KB; ++kb, ++it) {
                 const int st = it & (I8_AST - 1), r = it & (I8_RAW - 1);
-                mbar_wait(smem_u32(&sh->a_empty[st]), ((unsigned)(it >> 2) & 1u) ^ 1u);   // the MMAs of this stage's previous use are done
-                mbar_wait(smem_u32(&sh->raw_full[r]), (unsigned)(it >> 2) & 1u);
+                mbar_wait_t(smem_u32(&sh->a_empty[st]), ((unsigned)(it >> 2) & 1u) ^ 1u, wt1, timed);   // the MMAs of this stage's previous use are done
+                mbar_wait_t(smem_u32(&sh->raw_full[r]), (unsigned)(it >> 2) & 1u, wt2, timed);
                 tc_fence_after();
                 const unsigned char* raw = smem + (size_t)r * I8_RAW_BYTES;
                 const bool from_smem = use_tma && tl.row0 + row >= hist_rows;   // else: history row, or no TMA at all
@@ -447,6 +546,12 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 mbar_arrive(smem_u32(&sh->a_full[st]));
             }
         }
+        if (dbg && (int)threadIdx.x == 32 * (I8_EPI_WARPS + 1)) {
+            atomicAdd((unsigned long long*)&dbg[7], (unsigned long long)wt0);                     // producers: wait for the tile's scale
+            atomicAdd((unsigned long long*)&dbg[8], (unsigned long long)wt1);                     // producers: wait for a free A stage
+            atomicAdd((unsigned long long*)&dbg[9], (unsigned long long)wt2);                     // producers: wait for the TMA rows
+            atomicAdd((unsigned long long*)&dbg[10], (unsigned long long)(clock64() - t_role0));  // producers: role time
+        }
     } else if (warp == I8_TMA_WARP) {
         // ======================================= TMA ISSUE =======================================
         if (lane == 0) {
@@ -456,7 +561,7 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     if ((kb & 3) == 0) {   // the three digit planes of the next four K blocks of this tone group
                         const int bs = bc & (I8_BST - 1);
-                        mbar_wait(smem_u32(&sh->b_empty[bs]), ((unsigned)(bc >> 1) & 1u) ^ 1u);
+                        mbar_wait_t(smem_u32(&sh->b_empty[bs]), ((unsigned)(bc >> 1) & 1u) ^ 1u, wt0, timed);
                         const unsigned int bar = smem_u32(&sh->b_full[bs]);
                         mbar_arrive_expect_tx(bar, I8_B_STAGE);
                         const int row_b = ((tl.tg * KQ + (kb >> 2)) * 3) * I8_N;
@@ -465,7 +570,7 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         ++bc;
                     }
                     const int s = it & (I8_RAW - 1);
-                    mbar_wait(smem_u32(&sh->raw_empty[s]), ((unsigned)(it >> 2) & 1u) ^ 1u);
+                    mbar_wait_t(smem_u32(&sh->raw_empty[s]), ((unsigned)(it >> 2) & 1u) ^ 1u, wt1, timed);
                     const unsigned int bar = smem_u32(&sh->raw_full[s]);
                     if (use_tma) {
                         mbar_arrive_expect_tx(bar, I8_RAW_BYTES);
@@ -474,6 +579,11 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         mbar_arrive(bar);
                     }
                 }
+            }
+            if (dbg) {
+                atomicAdd((unsigned long long*)&dbg[11], (unsigned long long)wt0);                     // TMA: wait for a free B stage
+                atomicAdd((unsigned long long*)&dbg[12], (unsigned long long)wt1);                     // TMA: wait for a free landing slot
+                atomicAdd((unsigned long long*)&dbg[13], (unsigned long long)(clock64() - t_role0));   // TMA: role time
             }
         }
     }
@@ -485,6 +595,27 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     if (warp == I8_EPI_WARPS) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(I8_TMEM_COLS) : "memory");
     }
+}
+
+// Largest |sample| of every row tile (rows [t RB, t RB + 128) of M samples), one block per tile: used when several tone groups
+// share each row tile, so that the scan is done once and not once per (row tile, tone group).
+__global__ void __launch_bounds__(256) direct_i8_amax_kernel(const Window w, int M, int RB, float* __restrict__ amax_rows) {
+    __shared__ unsigned int best;
+    if (threadIdx.x == 0) best = 0u;
+    __syncthreads();
+    const long long s0 = (long long)blockIdx.x * RB * M, s1 = s0 + (long long)I8_ROWS * M;
+    float m = 0.f;
+    for (long long s = s0 + threadIdx.x; s < s1; s += 256 * 8) {
+        float2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (s + u * 256 < s1) ? dev_win_at(w, s + u * 256) : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) m = fmaxf(m, fmaxf(fabsf(v[u].x), fabsf(v[u].y)));
+    }
+    const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));
+    if ((threadIdx.x & 31) == 0) atomicMax(&best, wm);
+    __syncthreads();
+    if (threadIdx.x == 0) amax_rows[blockIdx.x] = __uint_as_float(best);
 }
 
 typedef CUresult (*I8EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -525,7 +656,7 @@ bool i8_make_tensor_map_a(const Window& w, int M, CUtensorMap* map, long long* h
 }
 
 template <int F>
-int i8_launch(const DirectI8Bank& bank, const Window& w, const int* freq_dev, int T, int M, int rate, long long pos0, long long n_out,
+int i8_launch(DirectI8Bank& bank, const Window& w, const int* freq_dev, int T, int M, int rate, long long pos0, long long n_out,
               float2* out, int sm_count, cudaStream_t stream, int rotate, bool allow_tma) {
     constexpr int TG = 64 / F, RB = I8_ROWS - (F - 1);
     const int row_tiles = (int)((n_out + RB - 1) / RB), tone_groups = (T + TG - 1) / TG;
@@ -544,18 +675,55 @@ int i8_launch(const DirectI8Bank& bank, const Window& w, const int* freq_dev, in
     memcpy(&map_b, bank.tmap_b, sizeof(map_b));
     const long long tiles = (long long)row_tiles * tone_groups;
     const int grid = (int)(tiles < sm_count ? tiles : sm_count);
+    int launches = 1;
+    const float* amax_rows = nullptr;
+    if (tone_groups > 2) {   // the in-kernel scan would read every row tile once per tone group
+        if ((size_t)row_tiles > bank.row_amax_cap) {
+            if (bank.d_row_amax) cudaFree(bank.d_row_amax);
+            bank.d_row_amax = nullptr;
+            bank.row_amax_cap = 0;
+            GSDR_CUDA_OK(cudaMalloc(&bank.d_row_amax, sizeof(float) * (size_t)row_tiles));
+            bank.row_amax_cap = (size_t)row_tiles;
+        }
+        direct_i8_amax_kernel<<<row_tiles, 256, 0, stream>>>(w, M, RB, bank.d_row_amax);
+        GSDR_CUDA_OK(cudaGetLastError());
+        amax_rows = bank.d_row_amax;
+        launches = 2;
+    }
+    // GSDR_DIRECT_I8_DEBUG=1: per-role wait / run cycles of this launch on stderr (synchronises; schedule tuning only)
+    static const bool debug = [] {
+        const char* e = getenv("GSDR_DIRECT_I8_DEBUG");
+        return e && e[0] == '1';
+    }();
+    long long* dbg = nullptr;
+    if (debug) {
+        GSDR_CUDA_OK(cudaMalloc(&dbg, 16 * sizeof(long long)));
+        GSDR_CUDA_OK(cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), stream));
+    }
     static const unsigned int a_order = [] {
         const char* e = getenv("GSDR_I8_AORDER");
         return (e && e[0] == '1') ? 1u : 0u;
     }();
     if (rotate)
         direct_fir_i8_kernel<F, true><<<grid, I8_THREADS, I8_SMEM_BYTES, stream>>>(map_a, map_b, use_tma, hist_rows, w, bank.d_inv_sb, freq_dev, T, M,
-                                                                                   rate, pos0, n_out, row_tiles, tone_groups, bank.KQ, a_order, out);
+                                                                                   rate, pos0, n_out, row_tiles, tone_groups, bank.KQ, a_order, amax_rows, out, dbg);
     else
         direct_fir_i8_kernel<F, false><<<grid, I8_THREADS, I8_SMEM_BYTES, stream>>>(map_a, map_b, use_tma, hist_rows, w, bank.d_inv_sb, freq_dev, T, M,
-                                                                                    rate, pos0, n_out, row_tiles, tone_groups, bank.KQ, a_order, out);
+                                                                                    rate, pos0, n_out, row_tiles, tone_groups, bank.KQ, a_order, amax_rows, out, dbg);
     GSDR_CUDA_OK(cudaGetLastError());
-    return 1;
+    if (dbg) {
+        long long h[16];
+        GSDR_CUDA_OK(cudaStreamSynchronize(stream));
+        GSDR_CUDA_OK(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
+        cudaFree(dbg);
+        const double nt = h[15] > 0 ? (double)h[15] : 1.0;   // tiles
+        fprintf(stderr,
+                "[direct_i8] grid %d tiles %lld KB %d use_tma %d | cycles per tile: epilogue wait-acc %.0f scan %.0f of %.0f | mma wait-acc %.0f wait-B %.0f "
+                "wait-A %.0f of %.0f | producers wait-scale %.0f wait-stage %.0f wait-rows %.0f of %.0f | tma wait-B %.0f wait-slot %.0f of %.0f\n",
+                grid, tiles, (M + I8_KC - 1) / I8_KC, use_tma, h[0] / nt, h[1] / nt, h[2] / nt, h[3] / nt, h[4] / nt, h[5] / nt, h[6] / nt, h[7] / nt, h[8] / nt,
+                h[9] / nt, h[10] / nt, h[11] / nt, h[12] / nt, h[13] / nt);
+    }
+    return launches;
 }
 
 }  // namespace
@@ -656,12 +824,13 @@ int direct_i8_bank_create(const double* g, int T, int M, int ntaps, DirectI8Bank
 }
 
 void direct_i8_bank_destroy(DirectI8Bank* bank) {
+    if (bank->d_row_amax) cudaFree(bank->d_row_amax);
     if (bank->d_bank) cudaFree(bank->d_bank);
     if (bank->d_inv_sb) cudaFree(bank->d_inv_sb);
     memset(bank, 0, sizeof(*bank));
 }
 
-int direct_fir_i8_launch(const DirectI8Bank& bank, const Window& w, const int* freq_dev, int T, int M, int ntaps, int rate, long long pos0,
+int direct_fir_i8_launch(DirectI8Bank& bank, const Window& w, const int* freq_dev, int T, int M, int ntaps, int rate, long long pos0,
                          long long n_out, float2* out, int sm_count, cudaStream_t stream, int rotate, bool allow_tma) {
     if (n_out <= 0) return 0;
     if (!bank.d_bank || !direct_fir_i8_supported(T, M, ntaps, n_out)) {

@@ -41,6 +41,22 @@ __device__ __forceinline__ float2 win_at(const Window& w, long long s) {
     return make_float2(0.f, 0.f);
 }
 
+// sc16 ingest fused into the channelizer: the `in` segment then holds interleaved int16 I/Q pairs (the USRP wire format)
+// and every sample is converted on the fly exactly as UHD's fc32 conversion does, (float)v * (1 / 32767)
+// (cpp/USRP_hardware_manager.cpp:764-820 asks UHD for fc32); the carried-over history is always fc32.
+constexpr float kSc16ToFloat = 1.0f / 32767.0f;
+template <bool SC16>
+__device__ __forceinline__ float2 win_at_t(const Window& w, long long s) {
+    if (!SC16) return win_at(w, s);
+    if (s < w.n_hist) return w.hist[s];
+    s -= w.n_hist;
+    if (s < w.n_in) {
+        const short2 v = reinterpret_cast<const short2*>(w.in)[s];
+        return make_float2((float)v.x * kSc16ToFloat, (float)v.y * kSc16ToFloat);
+    }
+    return make_float2(0.f, 0.f);
+}
+
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
     return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
@@ -515,7 +531,7 @@ __device__ __forceinline__ void for_each_index(std::integer_sequence<int, I...>,
 
 // LA = input rows in flight per producer thread (register look-ahead, in frames); HOIST = keep all seven
 // stage-1 twiddles in registers instead of three plus per-frame products.
-template <int P, int LA, bool HOIST>
+template <int P, int LA, bool HOIST, bool SC16>
 __global__ void __launch_bounds__(WP_THREADS, 1)
 pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, const int* __restrict__ tile_begin, int n_jobs,
                           int frames_per_tile, int total_tiles, const float2* __restrict__ tw_global,
@@ -548,13 +564,13 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
                 const PfbJob jb = table[tt.job];
                 if (jb.tail_dst != nullptr) {
                     const long long first = jb.win.n_hist + jb.win.n_in - jb.tail_n;
-                    for (long long i = t; i < jb.tail_n; i += WS_THREADS) jb.tail_dst[i] = win_at(jb.win, first + i);
+                    for (long long i = t; i < jb.tail_n; i += WS_THREADS) jb.tail_dst[i] = win_at_t<SC16>(jb.win, first + i);
                 }
             }
         }
     } else if (n_jobs == 1 && single.tail_dst != nullptr && blockIdx.x == gridDim.x - 1) {
         const long long first = single.win.n_hist + single.win.n_in - single.tail_n;
-        for (long long i = t; i < single.tail_n; i += WS_THREADS) single.tail_dst[i] = win_at(single.win, first + i);
+        for (long long i = t; i < single.tail_n; i += WS_THREADS) single.tail_dst[i] = win_at_t<SC16>(single.win, first + i);
     }
     __syncthreads();
     // frame number n (per CTA) -> team n & 1, that team's frame c = n >> 1, tile c % WP_XB, use c / WP_XB of the tile
@@ -667,22 +683,39 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
                     if (kFast || (kMode == 2 && (row >= fast_lo || row < hist_full))) {
                         // volatile: the loads stay where the pipeline puts them (after the FIR that frees their
                         // landing registers) instead of being hoisted into extra registers by the scheduler
-                        const float2* base = (kFast || row >= fast_lo) ? win.in + (row * FN - win.n_hist) : win.hist + row * FN;
-                        const c2* p = reinterpret_cast<const c2*>(base + l);
+                        const bool from_in = kFast || row >= fast_lo;
+                        if (SC16 && from_in) {   // wire format: 4 bytes per sample, kept raw in the landing register until the FIR uses it
+                            const unsigned int* p = reinterpret_cast<const unsigned int*>(win.in) + (row * FN - win.n_hist) + l;
 #pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            asm volatile("ld.global.L1::no_allocate.b64 %0, [%1];" : "=l"(dst[j]) : "l"(p + 256 * j) : "memory");
+                            for (int j = 0; j < 8; ++j) {
+                                unsigned int raw;
+                                asm volatile("ld.global.L1::no_allocate.b32 %0, [%1];" : "=r"(raw) : "l"(p + 256 * j) : "memory");
+                                dst[j] = (c2)raw;   // converted where the FIR consumes it (step knows which rows are raw)
+                            }
+                        } else {
+                            const float2* base = from_in ? win.in + (row * FN - win.n_hist) : win.hist + row * FN;
+                            const c2* p = reinterpret_cast<const c2*>(base + l);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                asm volatile("ld.global.L1::no_allocate.b64 %0, [%1];" : "=l"(dst[j]) : "l"(p + 256 * j) : "memory");
+                        }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) dst[j] = c2_from(win_at(win, row * FN + l + 256 * j));
+                        for (int j = 0; j < 8; ++j) dst[j] = c2_from(win_at_t<SC16>(win, row * FN + l + 256 * j));
                     }
                 };
                 // warp 0 pulls a whole row (128 lines of 128 bytes) towards L2 several frames ahead
                 auto prefetch_row = [&](long long row) {
                     if ((kFast || (kMode == 2 && row >= fast_lo)) && l < 32 && row < last_row) {
-                        const float2* p = win.in + (row * FN - win.n_hist) + 16 * l;
+                        if (SC16) {   // 8 KB per row: 64 lines
+                            const short2* p = reinterpret_cast<const short2*>(win.in) + (row * FN - win.n_hist) + 32 * l;
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 512 * jj));
+                            for (int jj = 0; jj < 2; ++jj) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 1024 * jj));
+                        } else {
+                            const float2* p = win.in + (row * FN - win.n_hist) + 16 * l;
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 512 * jj));
+                        }
                     }
                 };
 #pragma unroll
@@ -695,6 +728,13 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
                 auto step = [&](const long long s, auto u_tag, const bool guarded, const bool emit) {
                     constexpr int u = decltype(u_tag)::value;
                     c2(&x)[8] = land[u % LA];
+                    if (SC16 && kMode != 0 && (kFast || fa + s >= fast_lo)) {   // this row came in as raw int16 pairs
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const unsigned int raw = (unsigned int)x[j];
+                            x[j] = c2_pack((float)(short)(raw & 0xffffu) * kSc16ToFloat, (float)(short)(raw >> 16) * kSc16ToFloat);
+                        }
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
 #if GSDR_PK_MODE & 8
@@ -1063,12 +1103,22 @@ static int launch_ws(const PfbJob* jobs, int n_jobs, void* scratch, const float2
     constexpr size_t smem_bytes = sizeof(WpSmem);
     // Windows in pinned host memory (zero-copy calls) are latency-bound on PCIe reads: two input rows in flight per producer
     // thread instead of one (LA = 2) doubles the bytes a CTA keeps outstanding.
-    bool host_window = false;
-    for (int j = 0; j < n_jobs; ++j) host_window = host_window || jobs[j].min_tile > 0;
-    auto kernel = host_window ? pfb_fused_wsp_2048_kernel<P, 2, WP_HOIST> : pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST>;
+    bool host_window = false, sc16 = false;
+    for (int j = 0; j < n_jobs; ++j) {
+        host_window = host_window || jobs[j].min_tile > 0;
+        sc16 = sc16 || jobs[j].in_sc16 != 0;
+        if ((jobs[j].in_sc16 != 0) != (jobs[0].in_sc16 != 0)) {
+            set_error("pfb_launch: fc32 and sc16 windows cannot share a launch");
+            return -1;
+        }
+    }
+    auto kernel = sc16 ? (host_window ? pfb_fused_wsp_2048_kernel<P, 2, WP_HOIST, true> : pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST, true>)
+                       : (host_window ? pfb_fused_wsp_2048_kernel<P, 2, WP_HOIST, false> : pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST, false>);
     if (const int dev = attr_once.pending(); dev >= 0) {
-        GSDR_CUDA_OK(cudaFuncSetAttribute(pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
-        GSDR_CUDA_OK(cudaFuncSetAttribute(pfb_fused_wsp_2048_kernel<P, 2, WP_HOIST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        GSDR_CUDA_OK(cudaFuncSetAttribute(pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        GSDR_CUDA_OK(cudaFuncSetAttribute(pfb_fused_wsp_2048_kernel<P, 2, WP_HOIST, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        GSDR_CUDA_OK(cudaFuncSetAttribute(pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+        GSDR_CUDA_OK(cudaFuncSetAttribute(pfb_fused_wsp_2048_kernel<P, 2, WP_HOIST, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
         attr_once.done(dev);
     }
     long long total_frames = 0;
@@ -1177,6 +1227,8 @@ static int pfb_variant() {
     return v;
 }
 
+bool pfb_fused_sc16_available() { return pfb_variant() == 1; }
+
 int pfb_fused_twiddle_count() { return FTW1 + FTW2 + WS_TW1 + WS_TW2; }
 
 int pfb_launch(const PfbJob* jobs, int n_jobs, void* scratch, void* workspace, const float2* tw, int sm_count,
@@ -1202,6 +1254,11 @@ int pfb_launch(const PfbJob* jobs, int n_jobs, void* scratch, void* workspace, c
         }
         return tail_after(nl, nl > 0);   // nl == 0: no frames, no launch
     }
+    for (int j = 0; j < n_jobs; ++j)
+        if (jobs[j].in_sc16) {
+            set_error("pfb_launch: sc16 windows are read by the warp-specialised fused kernel only");
+            return -1;
+        }
     if (fused) {
         int nl;
         switch (jobs[0].P) {

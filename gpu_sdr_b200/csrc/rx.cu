@@ -108,6 +108,7 @@ struct gsdr_rx {
     bool zc_enabled = true;    // GSDR_PROCESS_ZEROCOPY (read once, at create): blocking process() on pinned buffers is one launch
     bool host_window = false;  // this call's input window is pinned host memory read in place (zero-copy blocking call)
     bool tc_tma = true, tc_host_tma = false;  // GSDR_DIRECT_TC_TMA=0 / GSDR_DIRECT_TC_HOST_TMA=1, read at create
+    bool in_sc16 = false;      // this call's input window holds int16 I/Q pairs, converted inside the fused channelizer
     gsdr_buffer_helper bh{};
 
     // CHIRP
@@ -442,6 +443,7 @@ long long enqueue_compute_impl(gsdr_rx* rx, const float2* d_in, int n_buf, float
                 job.tail_dst = rx->hist[rx->hist_cur ^ 1];
                 job.tail_n = tail;
             }
+            job.in_sc16 = rx->in_sc16 ? 1 : 0;
             if (rx->host_window) {
                 // Tile length when the window is read over PCIe: the largest power of two that still leaves six CTAs, at most
                 // 128 frames.  Measured (tools/process_latency.py, B200, us per buffer): 488 frames (buffer_len 1e6): 4 (one
@@ -961,7 +963,9 @@ int gsdr_rx_submit_sc16(gsdr_rx* rx, const int16_t* in_iq, gsdr_float2* out, int
     GSDR_CUDA_OK(cudaMemcpyAsync(s.d_raw, in_iq, sizeof(short2) * rx->L, cudaMemcpyHostToDevice, rx->s_in));
     GSDR_CUDA_OK(cudaEventRecord(s.in_done, rx->s_in));
     GSDR_CUDA_OK(cudaStreamWaitEvent(rx->s_comp, s.in_done, 0));
-    {
+    // the fused channelizer reads the wire format itself; every other kernel gets an fc32 copy first
+    const bool fused_sc16 = (rx->mode == GSDR_TONES || rx->mode == GSDR_NOISE) && rx->fused && pfb_fused_sc16_available();
+    if (!fused_sc16) {
         long long blocks = ((rx->L >> 2) + 255) / 256;
         if (blocks < 1) blocks = 1;
         if (blocks > (long long)rx->sm_count * 8) blocks = (long long)rx->sm_count * 8;
@@ -970,7 +974,9 @@ int gsdr_rx_submit_sc16(gsdr_rx* rx, const int16_t* in_iq, gsdr_float2* out, int
         rx->launches++;
     }
     int len = 0;
-    const long long total = enqueue_compute(rx, s.d_in, 1, s.d_out, &len);
+    rx->in_sc16 = fused_sc16;
+    const long long total = enqueue_compute(rx, fused_sc16 ? reinterpret_cast<const float2*>(s.d_raw) : s.d_in, 1, s.d_out, &len);
+    rx->in_sc16 = false;
     if (total < 0) return -1;
     GSDR_CUDA_OK(cudaEventRecord(s.comp_done, rx->s_comp));
     GSDR_CUDA_OK(cudaStreamWaitEvent(rx->s_out, s.comp_done, 0));
@@ -983,6 +989,24 @@ int gsdr_rx_submit_sc16(gsdr_rx* rx, const int16_t* in_iq, gsdr_float2* out, int
 }
 
 int gsdr_rx_process_sc16(gsdr_rx* rx, const int16_t* in_iq, gsdr_float2* out) {
+    // pinned buffers + fused channelizer: one launch reads the wire-format buffer and writes the tones in place over PCIe
+    if (rx && in_iq && out && rx->zc_enabled && !rx->slots.empty() && (rx->mode == GSDR_TONES || rx->mode == GSDR_NOISE) && rx->fused &&
+        !rx->post_decim && rx->L >= 64LL * rx->N && pfb_fused_sc16_available()) {
+        if (set_dev(rx)) return -1;
+        void* ia = host_alias_of(in_iq, sizeof(short2) * (size_t)rx->L);
+        void* oa = ia ? host_alias_of(out, sizeof(float2) * (rx->max_out ? rx->max_out : 1)) : nullptr;
+        if (ia && oa) {
+            for (auto& sl : rx->slots)
+                if (sl.used) {
+                    GSDR_CUDA_OK(cudaEventSynchronize(sl.out_done));
+                    sl.used = false;
+                }
+            rx->in_sc16 = true;
+            const int n = process_zerocopy(rx, static_cast<const float2*>(ia), static_cast<float2*>(oa));
+            rx->in_sc16 = false;
+            return n;
+        }
+    }
     int len = 0;
     const int ticket = gsdr_rx_submit_sc16(rx, in_iq, out, &len);
     if (ticket < 0) return -1;
@@ -1181,7 +1205,8 @@ void group_free(gsdr_rx_group* g) {
 
 // One channelizer launch over n_buffers consecutive buffers of every member (in[i] / out[i]: device pointers or device
 // aliases of pinned host buffers).  Member state is advanced on copies and committed only after every launch succeeded.
-int64_t group_enqueue(gsdr_rx_group* g, const float2* const* in, int n_buffers, float2* const* out, int* valid_lens, bool host_window) {
+int64_t group_enqueue(gsdr_rx_group* g, const float2* const* in, int n_buffers, float2* const* out, int* valid_lens, bool host_window,
+                      bool in_sc16 = false) {
     const int n = (int)g->members.size();
     std::vector<PfbJob> jobs(n);
     std::vector<long long> tails(n);
@@ -1210,6 +1235,7 @@ int64_t group_enqueue(gsdr_rx_group* g, const float2* const* in, int n_buffers, 
         jobs[i].tail_dst = rx->hist[rx->hist_cur ^ 1];   // the launch carries every member's carry-over copy
         jobs[i].tail_n = tails[i];
         if (host_window) jobs[i].min_tile = 64;          // reads over PCIe: long tiles (see gsdr_rx_process, zero-copy form)
+        jobs[i].in_sc16 = in_sc16 ? 1 : 0;
     }
     int nl = pfb_launch(jobs.data(), n, g->d_table, nullptr, g->members[0]->d_tw, g->members[0]->sm_count, g->stream);
     if (nl < 0) return -1;
@@ -1306,7 +1332,7 @@ int64_t gsdr_rx_group_process_device(gsdr_rx_group* g, const gsdr_float2* const*
 }
 
 // kDepth pipeline slots, allocated on the first host-fed call (a device-resident-only group never pays for them)
-static int group_slots_ready(gsdr_rx_group* g, bool need_staging, bool need_raw) {
+static int group_slots_ready(gsdr_rx_group* g, bool need_staging, bool need_raw, bool need_fc32_of_raw) {
     if (g->slots.empty()) {
         g->slots.resize(kDepth);
         for (auto& s : g->slots) {
@@ -1317,7 +1343,7 @@ static int group_slots_ready(gsdr_rx_group* g, bool need_staging, bool need_raw)
     }
     const size_t S = g->members.size();
     for (auto& s : g->slots) {
-        if ((need_staging || need_raw) && !s.d_in) GSDR_CUDA_OK(cudaMalloc(&s.d_in, sizeof(float2) * S * (size_t)g->L));
+        if (((need_staging && !need_raw) || need_fc32_of_raw) && !s.d_in) GSDR_CUDA_OK(cudaMalloc(&s.d_in, sizeof(float2) * S * (size_t)g->L));
         if (need_staging && !s.d_out) GSDR_CUDA_OK(cudaMalloc(&s.d_out, sizeof(float2) * (g->out_total ? g->out_total : 1)));
         if (need_raw && !s.d_raw) GSDR_CUDA_OK(cudaMalloc(&s.d_raw, sizeof(short2) * S * (size_t)g->L));
     }
@@ -1345,12 +1371,14 @@ static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool s
         oa[i] = static_cast<float2*>(host_alias_of(out_host[i], sizeof(float2) * g->members[i]->max_out));
         zero_copy = ia[i] && oa[i];
     }
-    if (group_slots_ready(g, !zero_copy, sc16)) return -1;
+    if (group_slots_ready(g, !zero_copy, sc16 && !(zero_copy && pfb_fused_sc16_available()), sc16 && !pfb_fused_sc16_available())) return -1;
     const int ticket = (int)(g->tickets % 0x40000000u);
     GroupSlot& s = g->slots[(size_t)ticket % g->slots.size()];
     if (s.used) GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));   // the slot's previous period is fully done
     std::vector<const float2*> kin(S);
     std::vector<float2*> kout(S);
+    // sc16: the fused channelizer converts the wire format itself (no fc32 copy exists); the lock-step cross-check kernel needs one
+    const bool fused_sc16 = sc16 && pfb_fused_sc16_available();
     if (!zero_copy) {
         // ---- copied form: one cudaMemcpyAsync per stream buffer ----------------------------------------------------------
         for (int i = 0; i < S; ++i) {
@@ -1360,18 +1388,18 @@ static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool s
             }
             void* dst = sc16 ? static_cast<void*>(s.d_raw + (size_t)i * g->L) : static_cast<void*>(s.d_in + (size_t)i * g->L);
             GSDR_CUDA_OK(cudaMemcpyAsync(dst, in_host[i], in_bytes, cudaMemcpyHostToDevice, g->s_in));
-            kin[i] = s.d_in + (size_t)i * g->L;
+            kin[i] = fused_sc16 ? reinterpret_cast<const float2*>(s.d_raw + (size_t)i * g->L) : s.d_in + (size_t)i * g->L;
             kout[i] = s.d_out + g->out_off[i];
         }
     } else {
         for (int i = 0; i < S; ++i) {
-            kin[i] = sc16 ? s.d_in + (size_t)i * g->L : static_cast<const float2*>(ia[i]);
+            kin[i] = (sc16 && !fused_sc16) ? s.d_in + (size_t)i * g->L : static_cast<const float2*>(ia[i]);
             kout[i] = oa[i];
         }
     }
-    if (sc16) {
+    if (sc16 && !fused_sc16) {
         // wire format -> fc32 on the copy-in stream, one launch per 64 streams (reading the host buffers in place in the
-        // zero-copy form): the conversion of period k+1 overlaps the channelizer launch and the output traffic of period k
+        // zero-copy form)
         long long blocks = ((g->L >> 2) + 255) / 256;
         blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
         for (int i0 = 0; i0 < S; i0 += 64) {
@@ -1386,12 +1414,13 @@ static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool s
             g->launches++;
         }
     }
-    if (!zero_copy || sc16) {
+    const bool staged = !zero_copy || (sc16 && !fused_sc16);   // the inputs reach the device on the copy-in stream
+    if (staged) {
         GSDR_CUDA_OK(cudaEventRecord(s.in_done, g->s_in));   // the inputs are on the device: the host buffers are free
         GSDR_CUDA_OK(cudaStreamWaitEvent(g->stream, s.in_done, 0));
     }
     std::vector<int> lens(S);
-    const int64_t total = group_enqueue(g, kin.data(), 1, kout.data(), lens.data(), zero_copy && !sc16);
+    const int64_t total = group_enqueue(g, kin.data(), 1, kout.data(), lens.data(), zero_copy && !(sc16 && !fused_sc16), fused_sc16);
     if (total < 0) return -1;
     GSDR_CUDA_OK(cudaEventRecord(s.comp_done, g->stream));
     if (!zero_copy) {
@@ -1401,7 +1430,7 @@ static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool s
                 GSDR_CUDA_OK(cudaMemcpyAsync(out_host[i], kout[i], sizeof(float2) * (size_t)lens[i], cudaMemcpyDeviceToHost, g->s_out));
         GSDR_CUDA_OK(cudaEventRecord(s.out_done, g->s_out));
     } else {
-        if (!sc16) GSDR_CUDA_OK(cudaEventRecord(s.in_done, g->stream));   // the launch itself consumes the inputs
+        if (!staged) GSDR_CUDA_OK(cudaEventRecord(s.in_done, g->stream));   // the launch itself consumes the inputs
         GSDR_CUDA_OK(cudaEventRecord(s.out_done, g->stream));
     }
     s.used = true;

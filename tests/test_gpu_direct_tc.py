@@ -37,7 +37,9 @@ def run_case(p, nbuf, noise=1e-3, expect_tc=True):
         worst = max(worst, orc.rel_l2(a, want))
     assert worst <= TOL, worst
     if expect_tc and VARIANT["name"] == "i8":
-        assert worst <= 2e-7, worst   # exact accumulation: what is left is the 24-bit operand grid and two fp32 roundings
+        # exact accumulation: what is left is the 24-bit operand grid (relative to the tile's largest sample and the tone's
+        # largest tap, so it grows with the crest factor: 1e-7 at 16 tones, 3e-7 at 70 equal tones) and two fp32 roundings
+        assert worst <= 5e-7, worst
     return ours, worst
 
 
@@ -109,7 +111,7 @@ def test_device_batch_equals_sequential_tc():
     rx.sync()
     assert lens == [len(s) for s in seq]
     if VARIANT["name"] == "i8":   # the fixed-point scale is per tile and the tiles of a batch are cut elsewhere: equal to ~1e-7, not bit for bit
-        assert orc.rel_l2(dout.download(tot), np.concatenate(seq)) <= 2e-7
+        assert orc.rel_l2(dout.download(tot), np.concatenate(seq)) <= 5e-7
     else:
         assert np.array_equal(dout.download(tot), np.concatenate(seq))
     rx.close()
