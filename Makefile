@@ -8,7 +8,7 @@ OBJDIR := build/obj
 # hostlogic.cpp builds the taps: no fast-math, no FMA contraction (bit-exact with the reference's
 # nvcc-default host flags).  Device code keeps nvcc's default -fmad=true like the reference.
 NVFLAGS := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC,-O2,-ffp-contract=off,-fno-fast-math,-Wall
-CU_SRCS := pfb_kernels chirp_kernels direct_kernels direct_tc_kernels direct_i8_kernels tones_kernels rx tx host
+CU_SRCS := pfb_kernels chirp_kernels direct_kernels direct_tc_kernels direct_i8_kernels tones_kernels welch_kernels rx tx host
 OBJS    := $(addprefix $(OBJDIR)/,$(addsuffix .o,$(CU_SRCS))) $(OBJDIR)/hostlogic.o
 
 FEEDER := tests/cpp/bin/realtime_feeder

@@ -69,7 +69,6 @@ struct I8Shared {
     unsigned long long a_full[I8_AST], a_empty[I8_AST];       // producers <-> MMA: A digits in TMEM
     unsigned long long b_full[I8_BST], b_empty[I8_BST];       // TMA <-> MMA: digit planes of B
     unsigned long long tmem_full, tmem_empty;                 // MMA <-> epilogue: the accumulators
-    unsigned long long scale_full[4];                         // epilogue (scan) -> producers: largest |sample| of a tile
     unsigned int tmem_base;
     unsigned int amax_bits[4];
     double2 ph[64];          // per tone of the group: (LO phase of the tile's first row, phase step per row), integers < rate
@@ -221,7 +220,6 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         }
         mbar_init(smem_u32(&sh->tmem_full), 1);
         mbar_init(smem_u32(&sh->tmem_empty), 32 * I8_EPI_WARPS);
-        for (int s = 0; s < 4; ++s) mbar_init(smem_u32(&sh->scale_full[s]), I8_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == I8_EPI_WARPS) {
@@ -255,75 +253,6 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         int* xw = sh->xch[warp];
         const int* xn = sh->xch[(warp + 1) & 3];
         const unsigned int lane_base = tmem_base + ((unsigned int)(warp * 32) << 16);
-        // Largest |sample| of tile n -> amax_bits[n & 3], then scale_full[n & 3].  The tile's rows are one contiguous run of the
-        // window (the rows do not overlap and the pitch is M), so the scan is a coalesced sweep.
-        auto scan_tile = [&](int n) {
-            const int slot = n & 3;
-            const I8Tile tl = tile_of(n);
-            if (amax_rows != nullptr) {   // many tone groups share a row tile: a pre-pass has scanned every row tile once
-                if (et == 0) sh->amax_bits[slot] = __float_as_uint(amax_rows[tl.row0 / RB]);
-                __syncwarp();
-                epi_bar();
-                if (lane == 0) mbar_arrive(smem_u32(&sh->scale_full[slot]));
-                return;
-            }
-            if (et == 0) sh->amax_bits[slot] = 0u;
-            epi_bar();
-            const long long s0 = tl.row0 * (long long)M, s1 = s0 + (long long)I8_ROWS * M;
-            float m = 0.f;
-            if (s0 >= w.n_hist && s1 <= w.n_hist + w.n_in) {
-                // whole tile inside the new samples: batches of independent loads (one load per iteration would pay a
-                // memory latency per load: 100 of them per tile at M = 100)
-                const float2* p = w.in + (s0 - w.n_hist);
-                const int n_s = I8_ROWS * M;
-                if (((reinterpret_cast<uintptr_t>(p) & 15) == 0) && (n_s & 1) == 0) {
-                    const float4* p4 = reinterpret_cast<const float4*>(p);
-                    const int n4 = n_s >> 1;
-                    // the tile after this one: pull its lines towards L2 now, so that its own scan (one tile period from now)
-                    // and the TMA boxes that follow find them there
-                    {
-                        const long long step = (long long)gridDim.x / n_tone_groups * RB * M;   // samples between this CTA's consecutive row tiles (approx.)
-                        const char* q = reinterpret_cast<const char*>(p + step);
-                        const char* q_end = reinterpret_cast<const char*>(w.in + w.n_in);
-                        for (int i = et * 128; i < n_s * 8; i += 128 * 128)
-                            if (q + i + 128 <= q_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(q + i));
-                    }
-                    for (int i = et; i < n4; i += 128 * 16) {
-                        float4 v[16];
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) {
-                            const int idx = i + u * 128;
-                            v[u] = idx < n4 ? __ldg(p4 + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-#pragma unroll
-                        for (int u = 0; u < 16; ++u) m = fmaxf(fmaxf(m, fmaxf(fabsf(v[u].x), fabsf(v[u].y))), fmaxf(fabsf(v[u].z), fabsf(v[u].w)));
-                    }
-                } else {
-                    for (int i = et; i < n_s; i += 128 * 10) {
-                        float2 v[10];
-#pragma unroll
-                        for (int u = 0; u < 10; ++u) {
-                            const int idx = i + u * 128;
-                            v[u] = idx < n_s ? __ldg(p + idx) : make_float2(0.f, 0.f);
-                        }
-#pragma unroll
-                        for (int u = 0; u < 10; ++u) m = fmaxf(m, fmaxf(fabsf(v[u].x), fabsf(v[u].y)));
-                    }
-                }
-            } else {
-                for (long long s = s0 + et; s < s1; s += 32 * I8_EPI_WARPS) {
-                    const float2 v = dev_win_at(w, s);
-                    m = fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y)));
-                }
-            }
-            const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));   // non-negative floats order like integers
-            if (lane == 0) {
-                atomicMax(&sh->amax_bits[slot], wm);
-                mbar_arrive(smem_u32(&sh->scale_full[slot]));   // release: the atomic is visible to whoever acquires the phase
-            }
-        };
-        if (my_tiles > 0) scan_tile(0);
-        if (my_tiles > 1) scan_tile(1);
         for (int n = 0; n < my_tiles; ++n) {
             const I8Tile tl = tile_of(n);
             if (et < TG) {
@@ -344,12 +273,11 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 sh->ph[et] = make_double2(base, step);
                 sh->inv_sb[et] = isb;
             }
-            // all four scan arrivals of this tile happened long ago (two tiles back): plain acquire
-            mbar_wait(smem_u32(&sh->scale_full[n & 3]), (unsigned)(n >> 2) & 1u);
-            const float amax = __uint_as_float(sh->amax_bits[n & 3]);
-            const float inv_sa = amax * (1.0f / I8_FULL_SCALE);
             mbar_wait_t(smem_u32(&sh->tmem_full), (unsigned)n & 1u, wt0, timed);
             tc_fence_after();
+            // the tile's scale was fixed by the producers before they cut its first K block (they ran ahead of these MMAs)
+            const float amax = __uint_as_float(sh->amax_bits[n & 3]);
+            const float inv_sa = amax * (1.0f / I8_FULL_SCALE);
             const long long p = tl.row0 + row_in_tile;
 #pragma unroll 1
             for (int u = 0; u < NUNIT; ++u) {
@@ -357,6 +285,7 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 // overlap-add, cpp/fir.cu:55-69) per accumulator, in int32 -- |D| <= 3 * 2 M * 2^14, times F, stays below 2^31 --
                 // so the 64-bit combine D1 2^16 + D2 2^8 + D3 runs once per output and not once per block.
                 int S[3][16];
+                const long long te0 = timed ? clock64() : 0;
 #pragma unroll
                 for (int a = 0; a < 3; ++a) {   // one accumulator at a time: 16 sums + 16 fresh values live
 #pragma unroll
@@ -388,7 +317,9 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     tc_fence_before();
                     mbar_arrive(smem_u32(&sh->tmem_empty));
                 }
+                const long long te1 = timed ? clock64() : 0;
                 epi_bar();   // exchange buffers written; sh->ph / sh->inv_sb published
+                if (timed) wt1 += te1 - te0, wt2 += clock64() - te1;
                 if (F > 1) {
 #pragma unroll
                     for (int i = 1; i < F; ++i) {
@@ -432,15 +363,11 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 }
                 epi_bar();   // the exchange buffer (and sh->ph after the last unit) may be rewritten
             }
-            if (n + 2 < my_tiles) {
-                const long long ts = timed ? clock64() : 0;
-                scan_tile(n + 2);
-                if (timed) wt1 += clock64() - ts;
-            }
         }
         if (dbg && threadIdx.x == 0) {
             atomicAdd((unsigned long long*)&dbg[0], (unsigned long long)wt0);                     // epilogue: wait for accumulators
-            atomicAdd((unsigned long long*)&dbg[1], (unsigned long long)wt1);                     // epilogue: scan
+            atomicAdd((unsigned long long*)&dbg[1], (unsigned long long)wt1);                     // epilogue: TMEM loads + row shift-add
+            atomicAdd((unsigned long long*)&dbg[14], (unsigned long long)wt2);                    // epilogue: first barrier of each unit
             atomicAdd((unsigned long long*)&dbg[2], (unsigned long long)(clock64() - t_role0));   // epilogue: role time
             atomicAdd((unsigned long long*)&dbg[15], (unsigned long long)my_tiles);
         }
@@ -491,13 +418,82 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         const unsigned int sel_pair = a_order ? 0x0004u : 0x0040u;   // (x.b0, y.b0) -> low half-word
         const unsigned int sel_quad = a_order ? 0x1054u : 0x5410u;
         int it = 0;
+        const int pt = (int)threadIdx.x - 32 * (I8_EPI_WARPS + 1);   // 0..255
+        // The fixed-point scale of a tile comes from its largest |sample|.  The producers find it themselves, one tile ahead and
+        // spread over the K blocks of the tile they are cutting: the 256 threads sweep the NEXT tile's samples (one contiguous
+        // run of the window: 128 rows of M) with coalesced 8-byte loads, eight per thread issued when a K block starts and folded
+        // into a running maximum when the K block is done, so their latency hides behind the digit work (and the lines are in
+        // L2 when the TMA boxes of that tile ask for them).  8 loads x KB K blocks x 256 threads >= 128 M samples.
+        const int scan_n = I8_ROWS * M;                              // samples per tile
+        auto scan_src = [&](const I8Tile& t, bool& inside) -> long long {
+            const long long t0 = t.row0 * (long long)M, t1 = t0 + (long long)I8_ROWS * M;
+            inside = t0 >= w.n_hist && t1 <= w.n_hist + w.n_in;      // uniform over the CTA
+            return t0;
+        };
+        auto publish_scale = [&](int n_next, float m) {              // all 256 producers, between two tiles
+            const int slot = n_next & 3;
+            if (amax_rows != nullptr) {                              // many tone groups share a row tile: a pre-pass has scanned it
+                if (pt == 0) sh->amax_bits[slot] = __float_as_uint(amax_rows[tile_of(n_next).row0 / RB]);
+            } else {
+                const unsigned int wm = __reduce_max_sync(0xffffffffu, __float_as_uint(m));   // non-negative floats order like integers
+                if (lane == 0) atomicMax(&sh->amax_bits[slot], wm);
+            }
+            asm volatile("bar.sync 2, %0;" ::"n"(32 * I8_PROD_WARPS) : "memory");
+            if (pt == 0) sh->amax_bits[(n_next + 1) & 3] = 0u;       // the slot of the tile after: its last reader finished long ago
+        };
+        if (my_tiles > 0) {   // the first tile: scan it now
+            if (pt < 4) sh->amax_bits[pt] = 0u;
+            asm volatile("bar.sync 2, %0;" ::"n"(32 * I8_PROD_WARPS) : "memory");
+            float m = 0.f;
+            if (amax_rows == nullptr) {
+                bool inside;
+                const long long s0 = scan_src(tile_of(0), inside);
+                for (int i = pt; i < scan_n; i += 32 * I8_PROD_WARPS) {
+                    const float2 v = dev_win_at(w, s0 + i);
+                    m = fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y)));
+                }
+            }
+            publish_scale(0, m);
+        }
         for (int n = 0; n < my_tiles; ++n) {
             const I8Tile tl = tile_of(n);
-            mbar_wait_t(smem_u32(&sh->scale_full[n & 3]), (unsigned)(n >> 2) & 1u, wt0, timed);
             const float amax = __uint_as_float(sh->amax_bits[n & 3]);
             const float sa = amax > 0.f ? I8_FULL_SCALE / amax : 0.f;
+            const bool scan_next = amax_rows == nullptr && n + 1 < my_tiles;
+            bool nx_inside = false;
+            const long long nx_s0 = scan_next ? scan_src(tile_of(n + 1), nx_inside) : 0;
+            const float2* nx_p = w.in + (nx_s0 - w.n_hist);
+            // byte distance from tile n+1 to tile n+2 of this CTA (same tone group order: consecutive tiles of a CTA are gridDim.x apart)
+            const long long nx_stride_bytes = (n + 2 < my_tiles) ? (tile_of(n + 2).row0 - tile_of(n + 1).row0) * (long long)M * 8 : -1;
+            const char* nx_end = reinterpret_cast<const char*>(w.in + w.n_in);
+            float nx_m = 0.f;
             for (int kb = 0; kb < KB; ++kb, ++it) {
                 const int st = it & (I8_AST - 1), r = it & (I8_RAW - 1);
+                float2 sv[8];
+                if (scan_next) {   // eight loads of the next tile's samples, consumed when this K block is done
+                    if (nx_inside) {   // straight-line: indices clamped into the tile (a repeated sample does not change a maximum)
+                        // and the tile after that one: its lines are pulled towards L2 now (one 128-byte line per thread and K
+                        // block), so that the loads above find them there one tile period from now instead of in HBM
+                        {
+                            const long long line = (long long)pt + 32LL * I8_PROD_WARPS * kb;
+                            const char* q = reinterpret_cast<const char*>(nx_p) + nx_stride_bytes + line * 128;
+                            if (nx_stride_bytes > 0 && line * 128 < (long long)scan_n * 8 && q + 128 <= nx_end) asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+                        }
+#pragma unroll
+                        for (int u8 = 0; u8 < 8; ++u8) {
+                            const int idx = min(pt + 32 * I8_PROD_WARPS * (kb * 8 + u8), scan_n - 1);
+                            unsigned long long raw;
+                            asm volatile("ld.global.nc.L1::no_allocate.b64 %0, [%1];" : "=l"(raw) : "l"(nx_p + idx));
+                            sv[u8] = make_float2(__uint_as_float((unsigned int)raw), __uint_as_float((unsigned int)(raw >> 32)));
+                        }
+                    } else {
+#pragma unroll
+                        for (int u8 = 0; u8 < 8; ++u8) {
+                            const int idx = pt + 32 * I8_PROD_WARPS * (kb * 8 + u8);
+                            sv[u8] = idx < scan_n ? dev_win_at(w, nx_s0 + idx) : make_float2(0.f, 0.f);
+                        }
+                    }
+                }
                 mbar_wait_t(smem_u32(&sh->a_empty[st]), ((unsigned)(it >> 2) & 1u) ^ 1u, wt1, timed);   // the MMAs of this stage's previous use are done
                 mbar_wait_t(smem_u32(&sh->raw_full[r]), (unsigned)(it >> 2) & 1u, wt2, timed);
                 tc_fence_after();
@@ -544,10 +540,19 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&sh->a_full[st]));
+                if (scan_next) {
+#pragma unroll
+                    for (int u8 = 0; u8 < 8; ++u8) nx_m = fmaxf(nx_m, fmaxf(fabsf(sv[u8].x), fabsf(sv[u8].y)));
+                }
+            }
+            if (n + 1 < my_tiles) {
+                const long long tsc = timed ? clock64() : 0;
+                publish_scale(n + 1, nx_m);
+                if (timed) wt0 += clock64() - tsc;
             }
         }
         if (dbg && (int)threadIdx.x == 32 * (I8_EPI_WARPS + 1)) {
-            atomicAdd((unsigned long long*)&dbg[7], (unsigned long long)wt0);                     // producers: wait for the tile's scale
+            atomicAdd((unsigned long long*)&dbg[7], (unsigned long long)wt0);                     // producers: scale hand-over between tiles
             atomicAdd((unsigned long long*)&dbg[8], (unsigned long long)wt1);                     // producers: wait for a free A stage
             atomicAdd((unsigned long long*)&dbg[9], (unsigned long long)wt2);                     // producers: wait for the TMA rows
             atomicAdd((unsigned long long*)&dbg[10], (unsigned long long)(clock64() - t_role0));  // producers: role time
@@ -718,9 +723,9 @@ int i8_launch(DirectI8Bank& bank, const Window& w, const int* freq_dev, int T, i
         cudaFree(dbg);
         const double nt = h[15] > 0 ? (double)h[15] : 1.0;   // tiles
         fprintf(stderr,
-                "[direct_i8] grid %d tiles %lld KB %d use_tma %d | cycles per tile: epilogue wait-acc %.0f scan %.0f of %.0f | mma wait-acc %.0f wait-B %.0f "
-                "wait-A %.0f of %.0f | producers wait-scale %.0f wait-stage %.0f wait-rows %.0f of %.0f | tma wait-B %.0f wait-slot %.0f of %.0f\n",
-                grid, tiles, (M + I8_KC - 1) / I8_KC, use_tma, h[0] / nt, h[1] / nt, h[2] / nt, h[3] / nt, h[4] / nt, h[5] / nt, h[6] / nt, h[7] / nt, h[8] / nt,
+                "[direct_i8] grid %d tiles %lld KB %d use_tma %d | cycles per tile: epilogue wait-acc %.0f loads+shift %.0f bar %.0f of %.0f | mma wait-acc %.0f wait-B %.0f "
+                "wait-A %.0f of %.0f | producers scale-handover %.0f wait-stage %.0f wait-rows %.0f of %.0f | tma wait-B %.0f wait-slot %.0f of %.0f\n",
+                grid, tiles, (M + I8_KC - 1) / I8_KC, use_tma, h[0] / nt, h[1] / nt, h[14] / nt, h[2] / nt, h[3] / nt, h[4] / nt, h[5] / nt, h[6] / nt, h[7] / nt, h[8] / nt,
                 h[9] / nt, h[10] / nt, h[11] / nt, h[12] / nt, h[13] / nt);
     }
     return launches;

@@ -210,6 +210,17 @@ int init_pfb(gsdr_rx* rx, bool all_bins) {
     rx->fcut = (float)(1. / (2 * N));  // cpp/USRP_demodulator.cpp:131
     rx->taps_host.resize((size_t)N * P);
     make_sinc_window(N * P, rx->fcut, rx->taps_host.data());
+    if (rx->diagnostic) {
+        // init_diagnostic = true: the reference dumps the polyphase window as float2 (imaginary parts zero) into the working
+        // directory (make_sinc_window(..., diagnostic, ...), cpp/kernels.cu:290-296; call at cpp/USRP_demodulator.cpp:134)
+        fprintf(stderr, "gsdr_rx: warning: Demodulator diagnostic enabled.\n");
+        if (FILE* f = fopen("USRP_polyphase_filter_window.dat", "wb")) {
+            std::vector<float2> wz(rx->taps_host.size());
+            for (size_t i = 0; i < wz.size(); ++i) wz[i] = make_float2(rx->taps_host[i], 0.f);
+            fwrite(wz.data(), sizeof(float2), wz.size(), f);
+            fclose(f);
+        }
+    }
     rx->batching = pfb_batching((int)rx->L, N, P);
     if (all_bins) {
         rx->T_sel = N;  // full spectrum, bins in natural order (cpp/USRP_demodulator.cpp:301)

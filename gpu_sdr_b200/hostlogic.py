@@ -93,3 +93,23 @@ def probe_direct_phase(tone_freq, rate, index_counter, n0, n, device: int = 0) -
     check(_lib.load().gsdr_probe_direct_phase(int(device), int(tone_freq), int(rate), int(index_counter), int(n0), int(n),
                                               out.ctypes.data_as(C.c_void_p)), "gsdr_probe_direct_phase")
     return out
+
+
+def spec_from_samples(samples, sampling_rate=1.0, welch=None, dbc=False, rotate=True, clip_samples=False, device=0):
+    """pyUSRP/USRP_noise.py:655-703 on the GPU (gsdr_spec_from_samples): returns (freqs, 10 log10 PSD of the real part,
+    10 log10 PSD of the imaginary part), the order the reference returns."""
+    import ctypes as C
+    lib = _lib.load()
+    z = np.ascontiguousarray(samples, dtype=np.complex64)
+    clip = int(clip_samples) if clip_samples else 0
+    w = 0 if welch is None else int(welch)
+    nf = int(lib.gsdr_spec_n_freq(z.size, w, clip))
+    if nf <= 0:
+        raise _lib.GsdrError("spec_from_samples: empty record")
+    f = np.empty(nf, dtype=np.float64)
+    re = np.empty(nf, dtype=np.float32)
+    im = np.empty(nf, dtype=np.float32)
+    _lib.check(lib.gsdr_spec_from_samples(int(device), z.ctypes.data_as(C.c_void_p), z.size, float(sampling_rate), w, int(bool(dbc)),
+                                          int(bool(rotate)), clip, f.ctypes.data_as(C.c_void_p), re.ctypes.data_as(C.c_void_p),
+                                          im.ctypes.data_as(C.c_void_p)), "gsdr_spec_from_samples")
+    return f, re, im

@@ -228,6 +228,17 @@ int gsdr_probe_direct_phase(int device, int tone_freq, int rate, uint64_t index_
                             int64_t *phase_out_host);
 
 /* ------------------------------------------------------------------------------------------
+ * Client-side Welch spectra: pyUSRP/USRP_noise.py:655-703, spec_from_samples --
+ * rotate the IQ plane onto the real axis, optionally scale to and remove the carrier (dBc), clip `clip_samples` at both
+ * ends, then the one-sided Welch density of the real and of the imaginary part (nperseg = n / welch, periodic Hann, 50 %
+ * overlap, linear detrend), as 10 log10.  `samples`: n float2 in host memory.  Outputs: gsdr_spec_n_freq() values each;
+ * `freqs` may be NULL.  Returns the number of frequencies or <0.  welch <= 0: one segment of the whole record.
+ * ------------------------------------------------------------------------------------------ */
+long long gsdr_spec_n_freq(size_t n, int welch, size_t clip_samples);
+int gsdr_spec_from_samples(int device, const gsdr_float2 *samples, size_t n, double sampling_rate, int welch, int dbc, int rotate,
+                           size_t clip_samples, double *freqs, float *re_db, float *im_db);
+
+/* ------------------------------------------------------------------------------------------
  * Memory: pinned host pool with the preallocator<float2> contract, plus raw helpers
  * ------------------------------------------------------------------------------------------ */
 typedef struct gsdr_pool gsdr_pool;

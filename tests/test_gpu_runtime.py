@@ -274,3 +274,31 @@ def test_blocking_process_zero_copy_equals_copied(L, T, mode, monkeypatch):
     for a, b, c in zip(zc, copied, pageable):
         assert len(a) == len(b) == len(c) and len(a) > 0
         assert np.array_equal(a, b) and np.array_equal(a, c)
+
+
+def test_diagnostic_flag_dumps_the_polyphase_window(tmp_path, monkeypatch):
+    """init_diagnostic = true: the reference writes the polyphase window as float2 into USRP_polyphase_filter_window.dat
+    (make_sinc_window(..., diagnostic, ...), cpp/kernels.cu:290-296, called from cpp/USRP_demodulator.cpp:134)."""
+    monkeypatch.chdir(tmp_path)
+    p = pfb_param(N=2048, P=4, T=5, L=100_000)
+    rx = g.RX_buffer_demodulator(p, True)
+    taps = rx.taps()
+    rx.close()
+    dump = np.fromfile(tmp_path / "USRP_polyphase_filter_window.dat", dtype=np.complex64)
+    assert dump.size == 2048 * 4 and np.array_equal(dump.real, taps) and not dump.imag.any()
+
+
+def test_fallback_direct_kernel_on_a_second_device_after_the_first():
+    """direct_fir_kernel<staged> (pf_average > 8) raises its dynamic shared-memory limit per device: a demodulator on GPU 1
+    must work after one on GPU 0 has run (the limit used to be remembered process-wide)."""
+    lib = g.load()
+    if lib.gsdr_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from common import direct_param
+    p = direct_param(rate=1_000_000, T=3, decim=100, f=9, L=50_000)
+    x = tone_stream(p.rate, p.freq, p.ampl, 0, p.buffer_len)
+    o = orc.DirectDemodulator(p.rate, p.freq, p.decim, p.pf_average, p.buffer_len)
+    want = o.process(x)
+    for dev in (0, 1):
+        got = rx_run(p, [x], device=dev)[0]
+        assert orc.rel_l2(got, want) <= TOL
