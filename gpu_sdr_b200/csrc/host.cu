@@ -568,15 +568,34 @@ int gsdr_pcie_copy_ceiling(int device, size_t h2d_bytes, size_t d2h_bytes, int r
             if (ok) memset(h_in[i], 1, h2d_bytes ? h2d_bytes : 1), memset(h_out[i], 0, d2h_bytes ? d2h_bytes : 1);
         }
         if (!ok) break;
+        // One pass: `reps` buffers each way.  With both directions on, the two streams are kept in lockstep (copy i of one
+        // direction waits for copy i-2 of the other), so both rates are taken over the same interval with the workload's own
+        // byte ratio -- a direction that finished early would otherwise leave the other one running alone, at the
+        // single-direction rate, for the rest of its pass.
+        cudaEvent_t lock_up[kBufs] = {nullptr}, lock_dn[kBufs] = {nullptr};
+        for (int i = 0; i < kBufs; ++i)
+            if (cudaEventCreateWithFlags(&lock_up[i], cudaEventDisableTiming) != cudaSuccess ||
+                cudaEventCreateWithFlags(&lock_dn[i], cudaEventDisableTiming) != cudaSuccess)
+                ok = false;
+        if (!ok) break;
         auto pass = [&](bool up, bool dn, double* up_gbs, double* dn_gbs) -> bool {
+            const bool both = up && dn && h2d_bytes && d2h_bytes;
             for (int w = 0; w < 2; ++w) {   // w == 0: warm-up
                 const int n = w ? reps : 2;
                 if (cudaStreamSynchronize(s_up) != cudaSuccess || cudaStreamSynchronize(s_dn) != cudaSuccess) return false;
                 if (up) cudaEventRecord(e[0], s_up);
                 if (dn) cudaEventRecord(e[2], s_dn);
                 for (int i = 0; i < n; ++i) {
+                    if (both && i >= 2) {
+                        cudaStreamWaitEvent(s_up, lock_dn[(i - 2) % kBufs], 0);
+                        cudaStreamWaitEvent(s_dn, lock_up[(i - 2) % kBufs], 0);
+                    }
                     if (up && h2d_bytes) cudaMemcpyAsync(d_in, h_in[i % kBufs], h2d_bytes, cudaMemcpyHostToDevice, s_up);
                     if (dn && d2h_bytes) cudaMemcpyAsync(h_out[i % kBufs], d_out, d2h_bytes, cudaMemcpyDeviceToHost, s_dn);
+                    if (both) {
+                        cudaEventRecord(lock_up[i % kBufs], s_up);
+                        cudaEventRecord(lock_dn[i % kBufs], s_dn);
+                    }
                 }
                 if (up) cudaEventRecord(e[1], s_up);
                 if (dn) cudaEventRecord(e[3], s_dn);
@@ -588,7 +607,12 @@ int gsdr_pcie_copy_ceiling(int device, size_t h2d_bytes, size_t d2h_bytes, int r
             return true;
         };
         out_gbs[0] = out_gbs[1] = out_gbs[2] = out_gbs[3] = 0.0;
-        if (!pass(true, false, &out_gbs[0], nullptr) || !pass(false, true, nullptr, &out_gbs[1]) || !pass(true, true, &out_gbs[2], &out_gbs[3])) break;
+        const bool done = pass(true, false, &out_gbs[0], nullptr) && pass(false, true, nullptr, &out_gbs[1]) && pass(true, true, &out_gbs[2], &out_gbs[3]);
+        for (int i = 0; i < kBufs; ++i) {
+            cudaEventDestroy(lock_up[i]);
+            cudaEventDestroy(lock_dn[i]);
+        }
+        if (!done) break;
         rc = 0;
     } while (false);
     if (rc) set_error("gsdr_pcie_copy_ceiling: %s", cudaGetErrorString(cudaGetLastError()));
