@@ -8,7 +8,7 @@ OBJDIR := build/obj
 # hostlogic.cpp builds the taps: no fast-math, no FMA contraction (bit-exact with the reference's
 # nvcc-default host flags).  Device code keeps nvcc's default -fmad=true like the reference.
 NVFLAGS := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC,-O2,-ffp-contract=off,-fno-fast-math,-Wall
-CU_SRCS := pfb_kernels chirp_kernels direct_kernels direct_tc_kernels direct_i8_kernels tones_kernels welch_kernels rx tx host
+CU_SRCS := pfb_kernels pfb_wsp_p1 pfb_wsp_p2 pfb_wsp_p3 pfb_wsp_p4 chirp_kernels direct_kernels direct_tc_kernels direct_i8_kernels tones_kernels welch_kernels rx tx host
 OBJS    := $(addprefix $(OBJDIR)/,$(addsuffix .o,$(CU_SRCS))) $(OBJDIR)/hostlogic.o
 
 FEEDER := tests/cpp/bin/realtime_feeder
@@ -20,7 +20,7 @@ $(FEEDER): tests/cpp/realtime_feeder.cpp include/gsdr.h $(OUT)
 	@mkdir -p tests/cpp/bin
 	g++ -O2 -std=c++17 -Wall -I include $< -o $@ $(OUT) -pthread -Wl,-rpath,'$$ORIGIN/../../../gpu_sdr_b200'
 
-$(OBJDIR)/%.o: $(SRC)/%.cu $(SRC)/common.hpp $(SRC)/devmath.cuh $(SRC)/direct_common.cuh $(SRC)/packed_f32x2.cuh include/gsdr.h
+$(OBJDIR)/%.o: $(SRC)/%.cu $(SRC)/common.hpp $(SRC)/devmath.cuh $(SRC)/direct_common.cuh $(SRC)/packed_f32x2.cuh $(SRC)/pfb_fused.cuh include/gsdr.h
 	@mkdir -p $(OBJDIR)
 	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJDIR)/$*.ptxas.log || (cat $(OBJDIR)/$*.ptxas.log; false)
 

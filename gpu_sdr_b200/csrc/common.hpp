@@ -119,6 +119,10 @@ struct PfbJob {          // one stream's share of a launch
 struct PfbTile {
     int job, fa, fb, flags;
 };
+// The host side of that cut (hostlogic.cpp; gsdr_pfb_partition exposes it to the CPU tests): equal COST per CTA, where
+// every tile a CTA starts costs kPfbTileCost frames' worth of pipeline fill, drain and per-stream constants.
+constexpr long long kPfbTileCost = 24;
+void pfb_partition(const int* n_frames, int n_jobs, int grid, std::vector<PfbTile>& tiles, std::vector<int>& cta_begin);
 // Device scratch a multi-stream launch needs for its job table, tile list and per-CTA tile ranges.
 size_t pfb_table_bytes(int n_jobs, int sm_count);
 // Returns the number of kernel launches issued (>0) or -1.  `workspace` is device scratch of at

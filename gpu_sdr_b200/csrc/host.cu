@@ -445,6 +445,18 @@ int gsdr_tone_bins(int rate, int fft_tones, const int32_t* freq, int n, int32_t*
     tone_bins(rate, fft_tones, freq, n, bins);
     return n;
 }
+int gsdr_pfb_partition(const int32_t* n_frames, int n_jobs, int grid, int32_t* tiles_out, int cap_tiles, int32_t* cta_begin_out) {
+    if (!n_frames || n_jobs <= 0 || grid <= 0 || !tiles_out || !cta_begin_out) return -1;
+    std::vector<PfbTile> tiles;
+    std::vector<int> cb;
+    pfb_partition(n_frames, n_jobs, grid, tiles, cb);
+    if ((int)tiles.size() > cap_tiles) return -1;
+    for (size_t i = 0; i < tiles.size(); ++i) {
+        tiles_out[4 * i] = tiles[i].job, tiles_out[4 * i + 1] = tiles[i].fa, tiles_out[4 * i + 2] = tiles[i].fb, tiles_out[4 * i + 3] = tiles[i].flags;
+    }
+    for (int c = 0; c <= grid; ++c) cta_begin_out[c] = cb[c];
+    return (int)tiles.size();
+}
 int gsdr_pfb_gather_layout(const int32_t* bins, int n_tones, uint8_t* pos_out) {
     if (n_tones < 0 || n_tones > 2048 || !pos_out) return -1;
     pfb_gather_coloring(bins, n_tones, pos_out);

@@ -263,4 +263,53 @@ void pfb_gather_coloring(const int32_t* bins, int T, uint8_t* perm /* [2048] */)
     for (int bin = 0; bin < NB; ++bin) perm[bin] = (uint8_t)bin_color[bin];
 }
 
+// Multi-stream launch of the fused channelizer: cut the concatenated frame sequence of all streams into tiles (never
+// spanning two streams) and hand every CTA a contiguous run of tiles of equal COST.  A tile costs its frames plus
+// kPfbTileCost: the pipeline fill and drain and the reload of the stream's constants, measured at ~26 frames' worth
+// (64 streams x 1 buffer in one launch: 189 us against 168 us for one stream with the same frames per CTA).  Splitting by
+// frames alone put the stream boundaries' extra tiles on the critical path (8 streams x 8 buffers: 0.61 of the HBM roofline
+// against 0.68 for one stream).
+void pfb_partition(const int* n_frames, int n_jobs, int grid, std::vector<PfbTile>& tiles, std::vector<int>& cta_begin) {
+    tiles.clear();
+    cta_begin.assign((size_t)(grid > 0 ? grid : 0) + 1, 0);
+    long long total = 0;
+    int live_jobs = 0;
+    for (int k = 0; k < n_jobs; ++k)
+        if (n_frames[k] > 0) total += n_frames[k], ++live_jobs;
+    if (grid <= 0 || total == 0) return;
+    int j = 0;
+    while (n_frames[j] <= 0) ++j;
+    long long job_lo = 0, lo = 0;   // global index of job j's first frame, next unassigned frame
+    int boundaries_left = live_jobs - 1;
+    for (int c = 0; c < grid; ++c) {
+        cta_begin[c] = (int)tiles.size();
+        if (lo >= total) continue;
+        const int ctas_left = grid - c;
+        // what is left, shared equally: every remaining CTA starts one tile, every remaining stream boundary adds one
+        long long budget = (total - lo + kPfbTileCost * (ctas_left + boundaries_left) + ctas_left - 1) / ctas_left;
+        const bool last = c == grid - 1;
+        for (;;) {
+            const long long job_hi = job_lo + n_frames[j];
+            long long take = last ? job_hi - lo : budget - kPfbTileCost;
+            if (take > job_hi - lo) take = job_hi - lo;
+            if (take < 1) take = 1;
+            // no slivers: a remainder shorter than a tile's own cost rides along
+            if (!last && job_hi - lo - take > 0 && job_hi - lo - take < kPfbTileCost) take = job_hi - lo;
+            const long long e = lo + take;
+            tiles.push_back(PfbTile{j, (int)(lo - job_lo), (int)(e - job_lo), e == job_hi ? 1 : 0});
+            budget -= kPfbTileCost + take;
+            lo = e;
+            if (lo >= total) break;
+            if (e == job_hi) {
+                job_lo = job_hi;
+                ++j;
+                while (n_frames[j] <= 0) ++j;
+                --boundaries_left;
+            }
+            if (!last && budget < 2 * kPfbTileCost) break;   // not worth starting another tile here
+        }
+    }
+    cta_begin[grid] = (int)tiles.size();
+}
+
 }  // namespace gsdr

@@ -1,0 +1,6 @@
+// pfb_fused_wsp_2048_kernel<3, ...>: every instantiation for 3 polyphase tap(s) per channel (see pfb_fused.cuh)
+#include "pfb_fused.cuh"
+
+namespace gsdr {
+template int pfb_launch_ws<3>(const PfbJob*, int, void*, const float2*, int, cudaStream_t);
+}

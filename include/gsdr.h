@@ -207,6 +207,12 @@ int gsdr_tone_bins(int rate, int fft_tones, const int32_t *freq, int n, int32_t 
  * (bin & 7, bin >> 7).  bins == NULL means all 2048 bins in order (NOISE).  Diagnostic/test hook. */
 int gsdr_pfb_gather_layout(const int32_t *bins, int n_tones, uint8_t *pos_out /* [2048] */);
 
+/* How a multi-stream launch of the fused channelizer (gsdr_rx_group_*) is cut: tiles (job, first frame, end frame, flags:
+ * bit 0 = last tile of its stream) never span two streams, CTA c works through tiles [cta_begin[c], cta_begin[c+1]), and
+ * every CTA carries the same cost (frames + 24 per tile started).  tiles_out: 4 int32 per tile; cta_begin_out: grid + 1
+ * entries.  Returns the number of tiles or -1.  Diagnostic/test hook. */
+int gsdr_pfb_partition(const int32_t *n_frames, int n_jobs, int grid, int32_t *tiles_out, int cap_tiles, int32_t *cta_begin_out);
+
 typedef struct gsdr_buffer_helper {
     int n_tones, eff_length, buffer_len, average, n_eff_tones;
     int new_0, copy_size, current_batch, spare_samples, spare_begin;

@@ -200,3 +200,32 @@ def test_packet_header_matches_the_client_dtype():
     assert lib.gsdr_packet_header_read(raw.ctypes.data_as(C.c_void_p), C.byref(back)) == 21
     assert (back.usrp_number, back.front_end_code, back.packet_number, back.length, back.errors, back.channels) == \
         (3, b"B", 123456, 488000, -2, 1000)
+
+
+@pytest.mark.parametrize("frames,grid", [([488] * 64, 148), ([3904] * 8, 148), ([488], 148), ([5, 0, 700, 3, 0, 1200], 148),
+                                         ([488] * 3, 5), ([1] * 200, 148), ([97, 488, 2929], 148), ([3904] * 64, 148), ([488] * 2, 148)])
+def test_multi_stream_tile_partition(frames, grid):
+    """gsdr_pfb_partition (the cut of a gsdr_rx_group launch): every frame of every stream exactly once and in order, tiles never
+    span streams, each stream's last tile flagged (it carries the carry-over copy), CTA ranges contiguous, costs balanced."""
+    import ctypes as C
+    lib = g.load()
+    nf = np.array(frames, dtype=np.int32)
+    cap = 2 * grid + 2 * len(frames) + 8
+    tiles = np.zeros((cap, 4), dtype=np.int32)
+    cb = np.zeros(grid + 1, dtype=np.int32)
+    n = lib.gsdr_pfb_partition(nf.ctypes.data_as(C.c_void_p), len(frames), grid, tiles.ctypes.data_as(C.c_void_p), cap, cb.ctypes.data_as(C.c_void_p))
+    assert n > 0
+    tiles = tiles[:n]
+    assert cb[0] == 0 and cb[grid] == n and np.all(np.diff(cb) >= 0)
+    nxt = {j: 0 for j, f in enumerate(frames) if f > 0}
+    order = []
+    for job, fa, fb, flags in tiles:
+        assert fa == nxt[job] and fb > fa and fb <= frames[job]
+        nxt[job] = fb
+        assert (flags & 1) == (1 if fb == frames[job] else 0)
+        order.append(job)
+    assert all(nxt[j] == frames[j] for j in nxt) and order == sorted(order)
+    cost = [sum(24 + (tiles[t][2] - tiles[t][1]) for t in range(cb[c], cb[c + 1])) for c in range(grid)]
+    busy = [c for c in cost if c > 0]
+    if sum(frames) >= 40 * grid:   # enough work per CTA for the balance to mean something
+        assert len(busy) == grid and max(busy) <= 1.12 * (sum(busy) / len(busy)), (max(busy), sum(busy) / len(busy))
