@@ -7,8 +7,8 @@ GPU under torchrun for N>1, ONE JSON line on rank 0.
 Workload = BASELINE.json configs[4] built from configs[1]: 64 concurrent 200 MS/s IQ streams, each
 channelized by the 2048-channel, 4-tap PFB into 1000 selected tones (pf_average=4), transport buffers
 of 1e6 complex samples, sharded by stream over the N GPUs (64/N streams per GPU, stream s -> rank
-s mod N, no data-path collective).  One step = 8 transport buffers (8 packet periods) of every
-stream = 512e6 input samples for the whole job at every N ("strong": total work is fixed).
+s mod N, no data-path collective).  One step = 8 N transport buffers (packet periods) of every
+stream, i.e. 512e6 input samples per GPU at every N ("weak": per-GPU work is fixed).
 
   value    inputs already resident in HBM (two alternating 512 MB batches per GPU, i.e. larger than
            the 126 MB L2, so no step can be served from cache); ONE group launch per step; CUDA
@@ -84,14 +84,16 @@ def synth_buffers(p, n_distinct, seed):
     return out
 
 
-BUFFERS_PER_STEP = 8                          # transport buffers (packet periods) per stream per step
+SAMPLES_PER_GPU_STEP = 512_000_000            # per-GPU work of one step: streams per GPU x buffers per stream x 1e6
 
 
 def layout(world: int, streams_total: int = TOTAL_STREAMS):
-    """(streams per GPU, buffers per stream per step).  The whole job is streams_total x 8e6 samples per step at every N.
-    (One buffer per stream per launch -- the real-time shape at 64 streams on ONE GPU -- costs 0.62 instead of 0.69 of the
-    HBM roofline: 64 of the 148 CTAs then carry two tiles, each with its own pipeline fill and drain; see DESIGN.md.)"""
-    return max(1, streams_total // world), BUFFERS_PER_STEP
+    """(streams per GPU, buffers per stream per step): every GPU processes 512e6 samples per step at every N -- 64 streams x 8
+    buffers on one GPU, 8 streams x 64 buffers on each of eight.  (Short launches cost roofline: every stream boundary inside
+    a launch is an extra pipeline fill and drain on some CTA.  64 streams x 1 buffer per launch, the real-time shape on ONE
+    GPU, runs at 0.60 of the HBM roofline, 8 streams x 8 buffers at 0.68, this shape at 0.71)"""
+    s = max(1, streams_total // world)
+    return s, max(1, SAMPLES_PER_GPU_STEP // (s * BUFLEN))
 
 
 def shared_config(world, S, B):
@@ -499,7 +501,7 @@ def run_ours(args, dd: Dist):
         o.free()
 
     base = {"metric": METRIC, "value": value, "unit": "MS/s", "n_gpus": dd.world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": shared_config(dd.world, S, B), "kernel": kernel_name, "clock_ramp_steps": ramp_steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "frac_min_over_ranks": achieved_min / peak,
@@ -666,7 +668,7 @@ def run_reference(args, dd: Dist):
         cpu = cpu_baseline(params[0], budget_s=8.0)
         return {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "MS/s", "n_gpus": dd.world, "steps": args.steps,
                 "warmup": args.warmup, "higher_is_better": True, "ms_per_step": S * B * BUFLEN / (cpu["value"] * 1e6) * 1e3,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": shared_config(dd.world, S, B),
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": shared_config(dd.world, S, B),
                 "impl_detail": "oracle/_ref unavailable: CPU port of the chain (oracle/cpu_port.py)", "cpu_baseline": cpu,
                 "e2e": {"value": cpu["value"], "unit": "MS/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     refs = [RefRX(p) for p in params]
@@ -716,7 +718,7 @@ def run_reference(args, dd: Dist):
         return None
     cpu = cpu_baseline(params[0], budget_s=8.0) if (dd.world == 1 and not args.no_cpu) else None
     res = {"impl": "reference", "metric": METRIC, "value": val, "unit": "MS/s", "n_gpus": dd.world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": shared_config(dd.world, S, B),
            "impl_detail": {"reference": "unmodified cpp/kernels.cu + cpp/USRP_demodulator.cpp compiled for sm_100a (oracle/_ref/libgsdr_ref.so), one "
                                         "RX_buffer_demodulator per stream, one process per GPU; the reference has no CPU DSP path, so this arm runs "
@@ -741,7 +743,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams-total", type=int, default=TOTAL_STREAMS, help="IQ streams of the whole job (cfg5: 64)")
-    ap.add_argument("--buffers", type=int, default=0, help="transport buffers per stream per step (default 8)")
+    ap.add_argument("--buffers", type=int, default=0, help="transport buffers per stream per step (default: 512 / streams per GPU)")
     ap.add_argument("--e2e-form", default="zero_copy", choices=["zero_copy", "copied"], help="form of the host-fed call behind e2e.value")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-modes", action="store_true", help="skip the per-configuration `modes` legs (N=1)")

@@ -467,6 +467,12 @@ constexpr int WP_XB = GSDR_WP_XB;   // spectrum tiles per team (a team may finis
 #ifndef GSDR_WP_LA
 #define GSDR_WP_LA 1
 #endif
+// 1: the head frames of a stream's window (those that read carried-over history rows) take the "mixed" span body instead
+// of the general one.  Off: a third instantiation of the span body cost the single-stream kernel 4 - 6 % (register
+// allocation of the producers' loop), more than the four head frames per stream are worth.
+#ifndef GSDR_WP_MIXED_HEAD
+#define GSDR_WP_MIXED_HEAD 0
+#endif
 #ifndef GSDR_WP_HOIST
 #define GSDR_WP_HOIST 0
 #endif
@@ -536,6 +542,333 @@ __device__ __forceinline__ void for_each_index(std::integer_sequence<int, I...>,
 
 // LA = input rows in flight per producer thread (register look-ahead, in frames); HOIST = keep all seven
 // stage-1 twiddles in registers instead of three plus per-frame products.
+// The round-1 form of the kernel below, kept verbatim for the single-stream fc32 launch from device memory (the headline
+// path): the generalised kernel (tile table, sc16, mixed head rows) loses 4 - 6 % there to ptxas's register allocation of the
+// producers' loop (362 against 385 GS/s on the same B200, A/B'd through GSDR_LIB_PATH), so that launch keeps this one.
+// LA = input rows in flight per producer thread (register look-ahead, in frames); HOIST = keep all seven
+// stage-1 twiddles in registers instead of three plus per-frame products.
+template <int P, int LA, bool HOIST>
+__global__ void __launch_bounds__(WP_THREADS, 1)
+pfb_fused_wsp1_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, const int* __restrict__ tile_begin, int n_jobs,
+                          int frames_per_tile, int total_tiles, const float2* __restrict__ tw_global) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WpSmem& sm = *reinterpret_cast<WpSmem*>(smem_raw);
+    const int t = threadIdx.x;
+    unsigned int f = 0;  // frames this CTA has started, counted identically by every role
+    PfbJob job;
+    const unsigned int xfull0 = (unsigned int)__cvta_generic_to_shared(&sm.xfull[0][0]);
+    const unsigned int xempty0 = (unsigned int)__cvta_generic_to_shared(&sm.xempty[0][0]);
+    if (t == 0) {
+#pragma unroll
+        for (int i = 0; i < WS_TEAMS * WP_XB; ++i) {
+            mbar_init(xfull0 + 8 * i, WS_TEAM / 32);   // one arrival per warp (see mbar_arrive_warp)
+            mbar_init(xempty0 + 8 * i, WS_FRONT / 32);
+        }
+    }
+    // carry-over of a single-stream launch (what move_buffer does in the reference, cpp/kernels.cu:444-470): the CTA with
+    // the last, shorter tile copies the window's tail into the other history buffer -- input only, nothing here reads it
+    if (n_jobs == 1 && single.tail_dst != nullptr && blockIdx.x == gridDim.x - 1) {
+        const long long first = single.win.n_hist + single.win.n_in - single.tail_n;
+        for (long long i = t; i < single.tail_n; i += WS_THREADS) single.tail_dst[i] = win_at(single.win, first + i);
+    }
+    __syncthreads();
+    // frame number n (per CTA) -> team n & 1, that team's frame c = n >> 1, tile c % WP_XB, use c / WP_XB of the tile
+
+    if (t < WS_FRONT) {
+        // ======================================= FRONT ===========================================
+        // Transposed-form FIR: each arriving input row updates the P frames it contributes to, so a thread
+        // holds P accumulators (the finished one IS the FFT input) and only the rows still in flight.  The
+        // per-frame FMA chain is the reference's (i = 0..P-1, cpp/kernels.cu:495-506), bit for bit.
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(WP_FRONT_REGS));
+        const int l = t;
+        constexpr int NTW = HOIST ? 8 : 5;
+        float2 tw[NTW];  // W_2048^(l k1): k1 = 1..7, or k1 = 1, 2, 4 (slots 1, 2, 4)
+        if (HOIST) {
+#pragma unroll
+            for (int k1 = 1; k1 < 8; ++k1) tw[k1 % NTW] = __ldg(&tw_global[k1 * 256 + l]);
+        } else {
+            tw[1] = __ldg(&tw_global[1 * 256 + l]);
+            tw[2] = __ldg(&tw_global[2 * 256 + l]);
+            tw[4] = __ldg(&tw_global[4 * 256 + l]);
+        }
+        float w[P][8];
+        constexpr int U = (P % LA == 0) ? P : P * LA;  // unroll period: accumulator and landing roles repeat
+        c2 acc[P][8];
+        c2 land[LA][8];
+        // Tone selection (tone_select of the reference, cpp/kernels.cu:531-554) also lives here: the producers
+        // have issue slots to spare, the FFT teams do not.  Thread l stores out[frame*T + l + 256 j], j < 8.
+        constexpr int NU = FN / WS_FRONT;
+        unsigned int bp[NU / 2];  // byte offsets (inside a spectrum tile) of the bins this thread gathers, two per register
+        int nv = 0;               // how many of the NU output slots exist (u < T)
+        const unsigned int x_base = (unsigned int)__cvta_generic_to_shared(&sm.x[0][0][0]);
+        int loaded_job = -1;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const WsTile tl = ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
+            if (tl.job != loaded_job) {
+#pragma unroll
+                for (int i = 0; i < P; ++i)
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) w[i][j] = __ldg(job.taps + i * FN + l + 256 * j);
+#pragma unroll
+                for (int jj = 0; jj < NU / 2; ++jj) {
+                    unsigned int pk = 0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int u = l + WS_FRONT * (2 * jj + h);
+                        unsigned int bin = 0;
+                        if (u < job.T) bin = job.bins ? (unsigned int)__ldg(job.bins + u) : (unsigned int)u;
+                        bin &= (FN - 1);
+                        const unsigned int pos = job.xperm ? (unsigned int)__ldg(job.xperm + bin) : ((bin >> 3) & 15u);
+                        const unsigned int idx = (bin & 7u) * 256u + (bin >> 7) * 16u + (pos & 15u);
+                        pk |= (idx * 8u) << (16 * h);
+                    }
+                    bp[jj] = pk;
+                }
+                nv = (job.T - l + WS_FRONT - 1) / WS_FRONT;
+                nv = nv < 0 ? 0 : (nv > NU ? NU : nv);
+                loaded_job = tl.job;
+            }
+            const unsigned int f_tile0 = f;  // CTA frame counter of the tile's first frame
+            unsigned int g = f;              // next frame whose tones are still to be stored
+            // Gather the selected bins of frame n (CTA numbering) from its team's spectrum tile and store them
+            // sample-major (coalesced 8-byte stores).  `block` = wait for the tile; otherwise poll once and
+            // return false when the team has not finished the frame yet.
+            auto gather = [&](const unsigned int n, const bool block) -> bool {
+                const unsigned int qq = n & 1u, cc = n >> 1;
+                const unsigned int tile_i = qq * WP_XB + (cc % WP_XB), par = (cc / WP_XB) & 1u;
+                if (block) {
+                    mbar_wait(xfull0 + 8 * tile_i, par);
+                } else {
+                    // warp-uniform decision (lanes can observe the phase flip at different times)
+                    if (!__all_sync(0xffffffffu, mbar_test(xfull0 + 8 * tile_i, par))) return false;
+                }
+                const unsigned int xa = x_base + tile_i * (unsigned int)(WP_X * sizeof(float2));
+                c2* o = reinterpret_cast<c2*>(job.out) + ((tl.fa - job.first_frame) + (long long)(n - f_tile0)) * (long long)job.T + l;
+#pragma unroll
+                for (int h = 0; h < NU / 4; ++h) {
+                    if (h * 4 < nv) {
+                        c2 val[4];
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int j2 = h * 4 + jj;
+                            const unsigned int off = (j2 & 1) ? (bp[j2 >> 1] >> 16) : (bp[j2 >> 1] & 0xffffu);
+                            asm volatile("ld.shared.b64 %0, [%1];" : "=l"(val[jj]) : "r"(xa + off) : "memory");
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj)
+                            if (h * 4 + jj < nv) o[WS_FRONT * (h * 4 + jj)] = val[jj];
+                    }
+                }
+                mbar_arrive_warp(xempty0 + 8 * tile_i);  // after the stores: they have consumed the gathered values
+                return true;
+            };
+            const Window win = job.win;
+            const long long fast_lo = (win.n_hist + FN - 1) / FN;    // first row fully inside `in`
+            const long long fast_hi = (win.n_hist + win.n_in) / FN;  // first row not fully present
+            // The span body is instantiated twice: kFast when every row it touches lies fully inside the
+            // `in` segment (plain coalesced 8-byte loads, no per-row range logic), general otherwise.
+            auto run_tile = [&](auto fast_tag, const long long fa, const long long fb) {
+                constexpr bool kFast = decltype(fast_tag)::value;
+                const long long last_row = fb + P - 1;      // rows this span needs: [fa, last_row)
+                const long long n_steps = last_row - fa;    // one step per input row
+                auto load_row8 = [&](long long row, c2 (&dst)[8]) {
+                    if (kFast) {
+                        // volatile: the loads stay where the pipeline puts them (after the FIR that frees their
+                        // landing registers) instead of being hoisted into extra registers by the scheduler
+                        const c2* p = reinterpret_cast<const c2*>(win.in + (row * FN - win.n_hist) + l);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            asm volatile("ld.global.L1::no_allocate.b64 %0, [%1];" : "=l"(dst[j]) : "l"(p + 256 * j) : "memory");
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) dst[j] = c2_from(win_at(win, row * FN + l + 256 * j));
+                    }
+                };
+                // warp 0 pulls a whole row (128 lines of 128 bytes) towards L2 several frames ahead
+                auto prefetch_row = [&](long long row) {
+                    if (kFast && l < 32 && row < last_row) {
+                        const float2* p = win.in + (row * FN - win.n_hist) + 16 * l;
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) asm volatile("prefetch.global.L2 [%0];" ::"l"(p + 512 * jj));
+                    }
+                };
+#pragma unroll
+                for (int i = 0; i < LA; ++i)
+                    if (fa + i < last_row) load_row8(fa + i, land[i]);
+#pragma unroll
+                for (int i = LA; i < LA + 4; ++i) prefetch_row(fa + i);
+
+                // one step: row (fa + s) arrives, frame (fa + s - P + 1) completes
+                auto step = [&](const long long s, auto u_tag, const bool guarded, const bool emit) {
+                    constexpr int u = decltype(u_tag)::value;
+                    c2(&x)[8] = land[u % LA];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+#if GSDR_PK_MODE & 8
+                        float xr, xi;
+                        c2_unpack(x[j], xr, xi);
+#pragma unroll
+                        for (int i = P - 1; i >= 1; --i) {
+                            float ar, ai;
+                            c2_unpack(acc[(u + P * U - i) % P][j], ar, ai);
+                            acc[(u + P * U - i) % P][j] = c2_pack(fmaf(xr, w[i][j], ar), fmaf(xi, w[i][j], ai));
+                        }
+                        acc[u % P][j] = c2_pack(xr * w[0][j], xi * w[0][j]);
+#else
+#pragma unroll
+                        for (int i = P - 1; i >= 1; --i) acc[(u + P * U - i) % P][j] = c2_fma_s(x[j], w[i][j], acc[(u + P * U - i) % P][j]);
+                        acc[u % P][j] = c2_scale(x[j], w[0][j]);
+#endif
+                    }
+                    if (!guarded || s + LA < n_steps) load_row8(fa + s + LA, x);
+                    prefetch_row(fa + s + LA + 4);
+                    if (!emit) return;
+                    // ---- FFT stage 1: radix-8 over j, then twiddle; X[ka + 4 kb] sits in z[2 ka + kb]
+                    c2 z[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) z[j] = acc[(u + 1) % P][j];
+                    c2_fft8(z);
+                    const int slot = f % WP_D1;
+                    if (f >= WP_D1) bar_sync(WP_BAR_EMPTY + slot, WS_PC);
+                    float2* E = sm.e1[slot] + l;
+                    sts_c2(E + 0 * 258, z[0]);
+                    if (HOIST) {
+                        sts_c2(E + 1 * 258, c2_cmul(z[2], tw[1 % NTW].x, tw[1 % NTW].y));
+                        sts_c2(E + 2 * 258, c2_cmul(z[4], tw[2 % NTW].x, tw[2 % NTW].y));
+                        sts_c2(E + 3 * 258, c2_cmul(z[6], tw[3 % NTW].x, tw[3 % NTW].y));
+                        sts_c2(E + 4 * 258, c2_cmul(z[1], tw[4 % NTW].x, tw[4 % NTW].y));
+                        sts_c2(E + 5 * 258, c2_cmul(z[3], tw[5 % NTW].x, tw[5 % NTW].y));
+                        sts_c2(E + 6 * 258, c2_cmul(z[5], tw[6 % NTW].x, tw[6 % NTW].y));
+                        sts_c2(E + 7 * 258, c2_cmul(z[7], tw[7 % NTW].x, tw[7 % NTW].y));
+                    } else {
+                        const float2 t1 = tw[1], t2 = tw[2], t4 = tw[4];
+                        const float2 t3 = cmul(t1, t2), t5 = cmul(t1, t4), t6 = cmul(t2, t4);
+                        const float2 t7 = cmul(t3, t4);
+                        sts_c2(E + 1 * 258, c2_cmul(z[2], t1.x, t1.y));
+                        sts_c2(E + 2 * 258, c2_cmul(z[4], t2.x, t2.y));
+                        sts_c2(E + 3 * 258, c2_cmul(z[6], t3.x, t3.y));
+                        sts_c2(E + 4 * 258, c2_cmul(z[1], t4.x, t4.y));
+                        sts_c2(E + 5 * 258, c2_cmul(z[3], t5.x, t5.y));
+                        sts_c2(E + 6 * 258, c2_cmul(z[5], t6.x, t6.y));
+                        sts_c2(E + 7 * 258, c2_cmul(z[7], t7.x, t7.y));
+                    }
+                    bar_arrive(WP_BAR_FULL + slot, WS_PC);
+                    ++f;
+                    // One poll per produced frame keeps the stores a frame or two behind the teams.  (Polling once
+                    // per unrolled group instead -- smaller hot code -- measured 8 % slower: the stores then come in
+                    // bursts and the teams wait for their tiles.)
+                    if (g + 1 < f && gather(g, false)) ++g;
+                };
+                auto guarded_group = [&](const long long s0) {
+                    for_each_index(std::make_integer_sequence<int, U>{}, [&](auto u_tag) {
+                        const long long ss = s0 + decltype(u_tag)::value;
+                        if (ss < n_steps) step(ss, u_tag, true, ss >= P - 1);
+                    });
+                };
+                // head: the first P-1 rows only prime the accumulators
+                guarded_group(0);
+                long long s = U;
+                // steady state: whole groups whose frames all emit and whose look-ahead rows all exist
+                for (; s + U - 1 + LA < n_steps; s += U)
+                    for_each_index(std::make_integer_sequence<int, U>{}, [&](auto u_tag) {
+                        step(s + decltype(u_tag)::value, u_tag, false, true);
+                    });
+                // tail
+                for (; s < n_steps; s += U) guarded_group(s);
+            };
+            // frames whose P rows all lie inside `in` take the fast body; the few that touch the carried-over
+            // history (head of a window) or its ragged end take the general one
+            long long f0 = tl.fa > fast_lo ? tl.fa : fast_lo;
+            long long f1 = tl.fb < fast_hi - P + 1 ? tl.fb : fast_hi - P + 1;
+            if (f0 > tl.fb) f0 = tl.fb;
+            if (f1 < f0) f1 = f0;
+            if (tl.fa < f0) run_tile(std::false_type{}, tl.fa, f0);
+            if (f0 < f1) run_tile(std::true_type{}, f0, f1);
+            if (f1 < tl.fb) run_tile(std::false_type{}, f1, tl.fb);
+            // drain: what the polls have not stored yet
+            for (; g < f; ++g) gather(g, true);
+        }
+    } else {
+        // ======================================== BACK ============================================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(WP_BACK_REGS));
+        const int q = (t - WS_FRONT) / WS_TEAM;       // team: frames with (f & 1) == q
+        const int tid = (t - WS_FRONT) % WS_TEAM;
+        const int lane16 = tid & 15;                  // n3 in stage 2, k2 in stage 3
+        const int k1 = tid >> 4;                      // the 256-point sub-transform of this half-warp
+        float2 tw2[16];  // W_256^(n3 k2)
+#pragma unroll
+        for (int k2 = 1; k2 < 16; ++k2) tw2[k2] = __ldg(&tw_global[WS_TW1 + lane16 * 16 + k2]);
+        float2* H = sm.h[(t - WS_FRONT) >> 5][(tid >> 4) & 1];
+        unsigned int c = 0;  // frames this team has finished
+        const unsigned int xw0 = (unsigned int)__cvta_generic_to_shared(&sm.x[q][0][0]) + (unsigned int)(k1 * 256 * sizeof(float2));
+        unsigned int xo[4];  // byte offset inside row (k1, k3) of this thread's bin k1 + 8 k2 + 128 k3, one byte per k3
+        int loaded_job = -1;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const WsTile tl = ws_locate(tile, single, table, tile_begin, n_jobs, frames_per_tile, job);
+            if (tl.job != loaded_job) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    unsigned int pk = 0;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const int bin = k1 + 8 * lane16 + 128 * (4 * i + b);
+                        const unsigned int pos = job.xperm ? (unsigned int)__ldg(job.xperm + bin) : (unsigned int)lane16;
+                        pk |= ((pos & 15u) * 8u) << (8 * b);
+                    }
+                    xo[i] = pk;
+                }
+                loaded_job = tl.job;
+            }
+            const int nf = (int)(tl.fb - tl.fa);
+            for (int i = (int)((q - f) & 1u); i < nf; i += 2) {
+                const int slot = (f + i) % WP_D1;
+                c2 v[16];
+                // ---- stage 2: radix-16 over n2; lane = n3
+                bar_sync(WP_BAR_FULL + slot, WS_PC);
+                {
+                    const float2* E = sm.e1[slot] + k1 * 258 + lane16;
+#pragma unroll
+                    for (int n2 = 0; n2 < 16; ++n2) v[n2] = lds_c2(E + n2 * 16);
+                }
+                c2_fft16_first(v);  // consumes every loaded value: the slot can go back to the producers
+                bar_arrive(WP_BAR_EMPTY + slot, WS_PC);
+                c2_fft16_second(v);
+#pragma unroll
+                for (int ka = 0; ka < 4; ++ka)
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb) {
+                        const int k2 = ka + 4 * kb;
+                        c2 x = v[4 * ka + kb];
+                        if (k2 != 0) x = c2_cmul(x, tw2[k2].x, tw2[k2].y);
+                        sts_c2(H + k2 * 17 + lane16, x);
+                    }
+                __syncwarp();
+                // ---- stage 3: radix-16 over n3; lane = k2; bin = k1 + 8 k2 + 128 k3
+#pragma unroll
+                for (int m = 0; m < 16; ++m) v[m] = lds_c2(H + lane16 * 17 + m);
+                __syncwarp();
+                c2_fft16(v);
+                const unsigned int tile_i = q * WP_XB + (c % WP_XB), use = c / WP_XB;
+                if (use > 0) mbar_wait(xempty0 + 8 * tile_i, (use - 1) & 1u);  // the tile's previous frame has been gathered
+                const unsigned int xw = xw0 + (c % WP_XB) * (unsigned int)(WP_X * sizeof(float2));
+#pragma unroll
+                for (int ka = 0; ka < 4; ++ka)
+#pragma unroll
+                    for (int kb = 0; kb < 4; ++kb)
+                    {
+                        const int k3 = ka + 4 * kb;
+                        const unsigned int off = __byte_perm(xo[k3 >> 2], 0u, 0x4440u + (k3 & 3));
+                        asm volatile("st.shared.b64 [%0], %1;" ::"r"(xw + off + (unsigned int)(k3 * 16 * sizeof(float2))), "l"(v[4 * ka + kb])
+                                     : "memory");
+                    }
+                mbar_arrive_warp(xfull0 + 8 * tile_i);
+                ++c;
+            }
+            f += nf;
+        }
+    }
+}
+
 // TABLE: multi-stream launch driven by the host-built tile list (the single-stream arguments are unused and vice versa: two
 // instantiations, so that neither carries the other's live registers through the producers' loop)
 template <int P, int LA, bool HOIST, bool SC16, bool TABLE>
@@ -824,7 +1157,11 @@ pfb_fused_wsp_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table,
             if (f1 < tl.fa) f1 = tl.fa;
             long long f0 = tl.fa > fast_lo ? tl.fa : fast_lo;   // first frame whose rows all lie in `in`
             if (f0 > f1) f0 = f1;
+#if GSDR_WP_MIXED_HEAD
             if (tl.fa < f0) run_tile(std::integral_constant<int, 2>{}, tl.fa, f0);
+#else
+            if (tl.fa < f0) run_tile(std::integral_constant<int, 0>{}, tl.fa, f0);
+#endif
             if (f0 < f1) run_tile(std::integral_constant<int, 1>{}, f0, f1);
             if (f1 < tl.fb) run_tile(std::integral_constant<int, 0>{}, f1, tl.fb);
             // drain: what the polls have not stored yet
@@ -938,8 +1275,10 @@ int pfb_launch_ws(const PfbJob* jobs, int n_jobs, void* scratch, const float2* t
                     : (host_window ? pfb_fused_wsp_2048_kernel<P, 2, WP_HOIST, false, TB> : pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST, false, TB>);
     };
     auto kernel = table_mode ? pick(std::true_type{}) : pick(std::false_type{});
+    const bool classic = !table_mode && !sc16 && !host_window;   // the headline launch: the round-1 kernel (see its comment)
     if (const int dev = attr_once.pending(); dev >= 0) {
         auto raise = [&](auto k) { return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes); };
+        GSDR_CUDA_OK(raise(pfb_fused_wsp1_2048_kernel<P, WP_LA, WP_HOIST>));
         GSDR_CUDA_OK(raise(pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST, false, false>));
         GSDR_CUDA_OK(raise(pfb_fused_wsp_2048_kernel<P, 2, WP_HOIST, false, false>));
         GSDR_CUDA_OK(raise(pfb_fused_wsp_2048_kernel<P, WP_LA, WP_HOIST, true, false>));
@@ -1023,7 +1362,10 @@ int pfb_launch_ws(const PfbJob* jobs, int n_jobs, void* scratch, const float2* t
     const int total_tiles = (int)((total_frames + frames_per_tile - 1) / frames_per_tile);
     int grid = total_tiles < sm_count ? total_tiles : sm_count;
     if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
-    kernel<<<grid, WS_THREADS, smem_bytes, stream>>>(jobs[0], nullptr, nullptr, 1, frames_per_tile, total_tiles, tw, nullptr, nullptr);
+    if (classic)
+        pfb_fused_wsp1_2048_kernel<P, WP_LA, WP_HOIST><<<grid, WS_THREADS, smem_bytes, stream>>>(jobs[0], nullptr, nullptr, 1, frames_per_tile, total_tiles, tw);
+    else
+        kernel<<<grid, WS_THREADS, smem_bytes, stream>>>(jobs[0], nullptr, nullptr, 1, frames_per_tile, total_tiles, tw, nullptr, nullptr);
     GSDR_CUDA_OK(cudaGetLastError());
     return 1;
 }
