@@ -554,14 +554,16 @@ def run_ours(args, dd: Dist):
 
     forms = {}
     d2h_bytes = 0
-    for form, on in (("copied", 0), ("zero_copy", 1)):
-        lib.gsdr_rx_group_set_zero_copy(group._h, on)
+    form_modes = {"copied": 0, "zero_copy": 1, "copy_in_store_out": 2}
+    for form, mode in form_modes.items():
+        lib.gsdr_rx_group_set_zero_copy(group._h, mode)
         for r in rxs:
             r.reset()
         v, d2h_bytes, sec = timed_e2e(ptrs)
-        forms[form] = {"value": v, "unit": "MS/s", "s_per_step": sec, "took_zero_copy_form": bool(group.zero_copy())}
-    default_form = "zero_copy" if args.e2e_form == "zero_copy" else "copied"
-    lib.gsdr_rx_group_set_zero_copy(group._h, 1 if default_form == "zero_copy" else 0)
+        lf = int(lib.gsdr_rx_group_last_form(group._h))
+        forms[form] = {"value": v, "unit": "MS/s", "s_per_step": sec, "inputs_read_in_place": bool(lf & 1), "outputs_written_in_place": bool(lf & 2)}
+    default_form = args.e2e_form
+    lib.gsdr_rx_group_set_zero_copy(group._h, form_modes[default_form])
     e2e_val = forms[default_form]["value"]
     # sc16 ingest: the wire format crosses PCIe, conversion on the GPU.  Reported beside the
     # fc32 figure, never instead of it: the reference's interface is fc32.
@@ -744,7 +746,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams-total", type=int, default=TOTAL_STREAMS, help="IQ streams of the whole job (cfg5: 64)")
     ap.add_argument("--buffers", type=int, default=0, help="transport buffers per stream per step (default: 512 / streams per GPU)")
-    ap.add_argument("--e2e-form", default="zero_copy", choices=["zero_copy", "copied"], help="form of the host-fed call behind e2e.value")
+    ap.add_argument("--e2e-form", default="zero_copy", choices=["zero_copy", "copied", "copy_in_store_out"],
+                    help="form of the host-fed call behind e2e.value (the library's default is zero_copy)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-modes", action="store_true", help="skip the per-configuration `modes` legs (N=1)")
     ap.add_argument("--profile", action="store_true", help="device-resident leg only (for ncu launch lists / captures)")

@@ -1190,8 +1190,9 @@ struct gsdr_rx_group {
     size_t out_total = 0;
     long long L = 0;
     uint64_t tickets = 0;
-    bool zc_enabled = true;        // GSDR_GROUP_ZEROCOPY (read at create)
+    int zc_mode = 1;               // GSDR_GROUP_ZEROCOPY (read at create): 0 copied, 1 zero-copy both ways, 2 copy in / kernel stores out
     bool last_zero_copy = false;
+    int last_form = 0;             // bit 0: inputs read in place, bit 1: outputs written in place
 };
 
 namespace {
@@ -1297,7 +1298,7 @@ gsdr_rx_group* gsdr_rx_group_create(gsdr_rx** members, int n) {
     g->L = members[0]->L;
     {
         const char* zc = getenv("GSDR_GROUP_ZEROCOPY");
-        g->zc_enabled = !(zc && zc[0] == '0');
+        g->zc_mode = (zc && zc[0] >= '0' && zc[0] <= '2') ? zc[0] - '0' : 1;
     }
     g->out_off.resize(n);
     for (int i = 0; i < n; ++i) {
@@ -1343,7 +1344,7 @@ int64_t gsdr_rx_group_process_device(gsdr_rx_group* g, const gsdr_float2* const*
 }
 
 // kDepth pipeline slots, allocated on the first host-fed call (a device-resident-only group never pays for them)
-static int group_slots_ready(gsdr_rx_group* g, bool need_staging, bool need_raw, bool need_fc32_of_raw) {
+static int group_slots_ready(gsdr_rx_group* g, bool need_d_in, bool need_d_out, bool need_d_raw) {
     if (g->slots.empty()) {
         g->slots.resize(kDepth);
         for (auto& s : g->slots) {
@@ -1354,9 +1355,9 @@ static int group_slots_ready(gsdr_rx_group* g, bool need_staging, bool need_raw,
     }
     const size_t S = g->members.size();
     for (auto& s : g->slots) {
-        if (((need_staging && !need_raw) || need_fc32_of_raw) && !s.d_in) GSDR_CUDA_OK(cudaMalloc(&s.d_in, sizeof(float2) * S * (size_t)g->L));
-        if (need_staging && !s.d_out) GSDR_CUDA_OK(cudaMalloc(&s.d_out, sizeof(float2) * (g->out_total ? g->out_total : 1)));
-        if (need_raw && !s.d_raw) GSDR_CUDA_OK(cudaMalloc(&s.d_raw, sizeof(short2) * S * (size_t)g->L));
+        if (need_d_in && !s.d_in) GSDR_CUDA_OK(cudaMalloc(&s.d_in, sizeof(float2) * S * (size_t)g->L));
+        if (need_d_out && !s.d_out) GSDR_CUDA_OK(cudaMalloc(&s.d_out, sizeof(float2) * (g->out_total ? g->out_total : 1)));
+        if (need_d_raw && !s.d_raw) GSDR_CUDA_OK(cudaMalloc(&s.d_raw, sizeof(short2) * S * (size_t)g->L));
     }
     return 0;
 }
@@ -1369,55 +1370,48 @@ static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool s
     if (ensure_device(g->device)) return -1;
     const int S = (int)g->members.size();
     const size_t in_bytes = (sc16 ? sizeof(short2) : sizeof(float2)) * (size_t)g->L;
-    // zero-copy when every buffer of the period is pinned and mapped
-    std::vector<const void*> ia(S);
-    std::vector<float2*> oa(S);
-    bool zero_copy = g->zc_enabled;
-    for (int i = 0; i < S && zero_copy; ++i) {
+    for (int i = 0; i < S; ++i)
         if (!in_host[i] || !out_host[i]) {
             set_error("gsdr_rx_group_submit: null buffer for member %d", i);
             return -1;
         }
-        ia[i] = host_alias_of(in_host[i], in_bytes);
-        oa[i] = static_cast<float2*>(host_alias_of(out_host[i], sizeof(float2) * g->members[i]->max_out));
-        zero_copy = ia[i] && oa[i];
-    }
-    if (group_slots_ready(g, !zero_copy, sc16 && !(zero_copy && pfb_fused_sc16_available()), sc16 && !pfb_fused_sc16_available())) return -1;
+    // Each direction on its own: zin = the launch reads the host input buffers in place, zout = it writes the host output
+    // buffers in place; both need every buffer of the period pinned and mapped.  g->zc_mode: 0 copied both ways, 1 zero-copy
+    // both ways, 2 copy engine in / kernel stores out.
+    std::vector<const void*> ia(S, nullptr);
+    std::vector<float2*> oa(S, nullptr);
+    bool zin = g->zc_mode == 1, zout = g->zc_mode != 0;
+    for (int i = 0; i < S && zin; ++i) zin = (ia[i] = host_alias_of(in_host[i], in_bytes)) != nullptr;
+    for (int i = 0; i < S && zout; ++i)
+        zout = (oa[i] = static_cast<float2*>(host_alias_of(out_host[i], sizeof(float2) * g->members[i]->max_out))) != nullptr;
+    // sc16: the fused channelizer converts the wire format itself (no fc32 copy exists); the lock-step cross-check kernel needs one
+    const bool fused_sc16 = sc16 && pfb_fused_sc16_available();
+    const bool convert = sc16 && !fused_sc16;
+    if (group_slots_ready(g, (!zin && !sc16) || convert, !zout, sc16 && !zin)) return -1;
     const int ticket = (int)(g->tickets % 0x40000000u);
     GroupSlot& s = g->slots[(size_t)ticket % g->slots.size()];
     if (s.used) GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));   // the slot's previous period is fully done
     std::vector<const float2*> kin(S);
     std::vector<float2*> kout(S);
-    // sc16: the fused channelizer converts the wire format itself (no fc32 copy exists); the lock-step cross-check kernel needs one
-    const bool fused_sc16 = sc16 && pfb_fused_sc16_available();
-    if (!zero_copy) {
-        // ---- copied form: one cudaMemcpyAsync per stream buffer ----------------------------------------------------------
-        for (int i = 0; i < S; ++i) {
-            if (!in_host[i] || !out_host[i]) {
-                set_error("gsdr_rx_group_submit: null buffer for member %d", i);
-                return -1;
-            }
+    for (int i = 0; i < S; ++i) {
+        if (!zin) {   // one cudaMemcpyAsync per stream buffer
             void* dst = sc16 ? static_cast<void*>(s.d_raw + (size_t)i * g->L) : static_cast<void*>(s.d_in + (size_t)i * g->L);
             GSDR_CUDA_OK(cudaMemcpyAsync(dst, in_host[i], in_bytes, cudaMemcpyHostToDevice, g->s_in));
-            kin[i] = fused_sc16 ? reinterpret_cast<const float2*>(s.d_raw + (size_t)i * g->L) : s.d_in + (size_t)i * g->L;
-            kout[i] = s.d_out + g->out_off[i];
         }
-    } else {
-        for (int i = 0; i < S; ++i) {
-            kin[i] = (sc16 && !fused_sc16) ? s.d_in + (size_t)i * g->L : static_cast<const float2*>(ia[i]);
-            kout[i] = oa[i];
-        }
+        if (convert) kin[i] = s.d_in + (size_t)i * g->L;
+        else if (zin) kin[i] = static_cast<const float2*>(ia[i]);
+        else kin[i] = sc16 ? reinterpret_cast<const float2*>(s.d_raw + (size_t)i * g->L) : s.d_in + (size_t)i * g->L;
+        kout[i] = zout ? oa[i] : s.d_out + g->out_off[i];
     }
-    if (sc16 && !fused_sc16) {
-        // wire format -> fc32 on the copy-in stream, one launch per 64 streams (reading the host buffers in place in the
-        // zero-copy form)
+    if (convert) {
+        // wire format -> fc32 on the copy-in stream, one launch per 64 streams (reading the host buffers in place when zin)
         long long blocks = ((g->L >> 2) + 255) / 256;
         blocks = blocks < 1 ? 1 : (blocks > 64 ? 64 : blocks);
         for (int i0 = 0; i0 < S; i0 += 64) {
             Sc16Batch b{};
             const int nb = S - i0 < 64 ? S - i0 : 64;
             for (int k = 0; k < nb; ++k) {
-                b.src[k] = zero_copy ? static_cast<const short2*>(ia[i0 + k]) : s.d_raw + (size_t)(i0 + k) * g->L;
+                b.src[k] = zin ? static_cast<const short2*>(ia[i0 + k]) : s.d_raw + (size_t)(i0 + k) * g->L;
                 b.dst[k] = s.d_in + (size_t)(i0 + k) * g->L;
             }
             sc16_to_fc32_batch_kernel<<<dim3((unsigned)blocks, (unsigned)nb), 256, 0, g->s_in>>>(b, g->L);
@@ -1425,27 +1419,28 @@ static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool s
             g->launches++;
         }
     }
-    const bool staged = !zero_copy || (sc16 && !fused_sc16);   // the inputs reach the device on the copy-in stream
+    const bool staged = !zin || convert;   // the inputs reach the device on the copy-in stream
     if (staged) {
         GSDR_CUDA_OK(cudaEventRecord(s.in_done, g->s_in));   // the inputs are on the device: the host buffers are free
         GSDR_CUDA_OK(cudaStreamWaitEvent(g->stream, s.in_done, 0));
     }
     std::vector<int> lens(S);
-    const int64_t total = group_enqueue(g, kin.data(), 1, kout.data(), lens.data(), zero_copy && !(sc16 && !fused_sc16), fused_sc16);
+    const int64_t total = group_enqueue(g, kin.data(), 1, kout.data(), lens.data(), zin && !convert, fused_sc16);
     if (total < 0) return -1;
     GSDR_CUDA_OK(cudaEventRecord(s.comp_done, g->stream));
-    if (!zero_copy) {
+    if (!staged) GSDR_CUDA_OK(cudaEventRecord(s.in_done, g->stream));   // the launch itself consumes the inputs
+    if (!zout) {
         GSDR_CUDA_OK(cudaStreamWaitEvent(g->s_out, s.comp_done, 0));
         for (int i = 0; i < S; ++i)
             if (lens[i] > 0)
                 GSDR_CUDA_OK(cudaMemcpyAsync(out_host[i], kout[i], sizeof(float2) * (size_t)lens[i], cudaMemcpyDeviceToHost, g->s_out));
         GSDR_CUDA_OK(cudaEventRecord(s.out_done, g->s_out));
     } else {
-        if (!staged) GSDR_CUDA_OK(cudaEventRecord(s.in_done, g->stream));   // the launch itself consumes the inputs
         GSDR_CUDA_OK(cudaEventRecord(s.out_done, g->stream));
     }
     s.used = true;
-    g->last_zero_copy = zero_copy;
+    g->last_zero_copy = zin && zout;
+    g->last_form = (zin ? 1 : 0) | (zout ? 2 : 0);
     g->tickets++;
     if (valid_lens)
         for (int i = 0; i < S; ++i) valid_lens[i] = lens[i];
@@ -1482,11 +1477,12 @@ int gsdr_rx_group_process(gsdr_rx_group* g, const gsdr_float2* const* in_host, g
 int gsdr_rx_group_pipeline_depth(const gsdr_rx_group* g) { return g ? kDepth : 0; }
 int gsdr_rx_group_members(const gsdr_rx_group* g) { return g ? (int)g->members.size() : 0; }
 int gsdr_rx_group_zero_copy(const gsdr_rx_group* g) { return g && g->last_zero_copy ? 1 : 0; }
-int gsdr_rx_group_set_zero_copy(gsdr_rx_group* g, int on) {
-    if (!g) return -1;
-    g->zc_enabled = on != 0;
+int gsdr_rx_group_set_zero_copy(gsdr_rx_group* g, int mode) {
+    if (!g || mode < 0 || mode > 2) return -1;
+    g->zc_mode = mode;
     return 0;
 }
+int gsdr_rx_group_last_form(const gsdr_rx_group* g) { return g ? g->last_form : 0; }
 
 int gsdr_rx_group_sync(gsdr_rx_group* g) {
     if (!g) return -1;

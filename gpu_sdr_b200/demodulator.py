@@ -234,6 +234,13 @@ class RxGroup:
     def zero_copy(self) -> bool:
         return bool(self.lib.gsdr_rx_group_zero_copy(self._h))
 
+    def set_form(self, mode: int) -> None:
+        """0 copied both ways, 1 zero-copy both ways (default), 2 copy engine in / kernel stores out."""
+        check(self.lib.gsdr_rx_group_set_zero_copy(self._h, int(mode)), "gsdr_rx_group_set_zero_copy")
+
+    def last_form(self) -> int:
+        return int(self.lib.gsdr_rx_group_last_form(self._h))
+
     def sync(self):
         check(self.lib.gsdr_rx_group_sync(self._h), "gsdr_rx_group_sync")
 

@@ -158,7 +158,8 @@ int64_t gsdr_rx_group_process_device(gsdr_rx_group *g, const gsdr_float2 *const 
  * may be outstanding; wait blocks until every out_host[i] of that ticket is complete; input buffers may be recycled once
  * gsdr_rx_group_input_consumed(ticket) returns 1 (always true after wait).
  * Pinned, mapped buffers (gsdr_pool / gsdr_host_alloc / cudaMallocHost): ONE launch per period reads the S input
- * buffers and writes the S outputs in place over PCIe (GSDR_GROUP_ZEROCOPY=0 at create selects the copied form).
+ * buffers and writes the S outputs in place over PCIe (GSDR_GROUP_ZEROCOPY=0 at create selects the copied form, =2 the
+ * mixed one: copy engine in, kernel stores out).
  * Otherwise: one cudaMemcpyAsync per stream buffer up, one launch, one cudaMemcpyAsync per stream down, on three
  * streams so that consecutive periods overlap.  gsdr_rx_group_process = submit + wait. */
 int gsdr_rx_group_submit(gsdr_rx_group *g, const gsdr_float2 *const *in_host, gsdr_float2 *const *out_host, int *valid_lens);
@@ -169,7 +170,11 @@ int gsdr_rx_group_process(gsdr_rx_group *g, const gsdr_float2 *const *in_host, g
 int gsdr_rx_group_pipeline_depth(const gsdr_rx_group *g);
 int gsdr_rx_group_members(const gsdr_rx_group *g);
 int gsdr_rx_group_zero_copy(const gsdr_rx_group *g);   /* 1 when the last submit took the zero-copy form */
-int gsdr_rx_group_set_zero_copy(gsdr_rx_group *g, int on);   /* allow (default) / forbid the zero-copy form from the next submit on */
+/* Form of the host-fed call from the next submit on: 0 = copied both ways, 1 = zero-copy both ways (default), 2 = inputs by
+ * the copy engine (one cudaMemcpyAsync per buffer), outputs written in place by the kernel's stores.  Forms that need
+ * pinned buffers fall back per direction when a buffer of the period is pageable. */
+int gsdr_rx_group_set_zero_copy(gsdr_rx_group *g, int mode);
+int gsdr_rx_group_last_form(const gsdr_rx_group *g);   /* of the last submit: bit 0 inputs read in place, bit 1 outputs written in place */
 int gsdr_rx_group_sync(gsdr_rx_group *g);
 int gsdr_rx_group_timer_start(gsdr_rx_group *g);
 int gsdr_rx_group_timer_stop(gsdr_rx_group *g, float *elapsed_ms);
