@@ -558,86 +558,72 @@ int gsdr_packet_frame(const gsdr_rx_packet* pkt, const void** frame, size_t* fra
 // figure is measured against.  One cudaMemcpyAsync per buffer (h2d_bytes up / d2h_bytes down, `reps` buffers each way), three
 // passes: upload alone, download alone, both directions at once on two streams.  out_gbs = {h2d, d2h, duplex h2d, duplex d2h}
 // in 1e9 bytes/s.  Ranks of a multi-GPU job call it between barriers, so the numbers include what the host shares out.
+int gsdr_pcie_copy_ceiling_streams(int device, size_t h2d_bytes, size_t d2h_bytes, int reps, int n_streams, double* out_gbs);
 int gsdr_pcie_copy_ceiling(int device, size_t h2d_bytes, size_t d2h_bytes, int reps, double* out_gbs) {
-    if (!out_gbs || reps < 1 || (h2d_bytes == 0 && d2h_bytes == 0)) {
+    return gsdr_pcie_copy_ceiling_streams(device, h2d_bytes, d2h_bytes, reps, 1, out_gbs);
+}
+// n_streams copy queues per direction, buffers dealt round-robin (several copy-engine queues keep more PCIe reads in flight when
+// the host memory is contended); out_gbs as above, rates summed over the queues of a direction.
+int gsdr_pcie_copy_ceiling_streams(int device, size_t h2d_bytes, size_t d2h_bytes, int reps, int n_streams, double* out_gbs) {
+    if (!out_gbs || reps < 1 || n_streams < 1 || n_streams > 8 || (h2d_bytes == 0 && d2h_bytes == 0)) {
         set_error("gsdr_pcie_copy_ceiling: bad argument");
         return -1;
     }
     GSDR_CUDA_OK(cudaSetDevice(device));
-    constexpr int kBufs = 4;
-    void *h_in[kBufs] = {nullptr}, *h_out[kBufs] = {nullptr}, *d_in = nullptr, *d_out = nullptr;
-    cudaStream_t s_up = nullptr, s_dn = nullptr;
-    cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+    constexpr int kBufs = 8;
+    void *h_in[kBufs] = {nullptr}, *h_out[kBufs] = {nullptr}, *d_in[kBufs] = {nullptr}, *d_out[kBufs] = {nullptr};
+    cudaStream_t s_up[8] = {nullptr}, s_dn[8] = {nullptr};
     int rc = -1;
     do {
-        bool ok = cudaStreamCreateWithFlags(&s_up, cudaStreamNonBlocking) == cudaSuccess &&
-                  cudaStreamCreateWithFlags(&s_dn, cudaStreamNonBlocking) == cudaSuccess;
-        for (int i = 0; i < 4 && ok; ++i) ok = cudaEventCreate(&e[i]) == cudaSuccess;
-        ok = ok && cudaMalloc(&d_in, h2d_bytes ? h2d_bytes : 1) == cudaSuccess && cudaMalloc(&d_out, d2h_bytes ? d2h_bytes : 1) == cudaSuccess;
+        bool ok = true;
+        for (int k = 0; k < n_streams && ok; ++k)
+            ok = cudaStreamCreateWithFlags(&s_up[k], cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&s_dn[k], cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < kBufs && ok; ++i) {
-            ok = pinned_alloc_local(&h_in[i], h2d_bytes ? h2d_bytes : 1) == cudaSuccess &&
-                 pinned_alloc_local(&h_out[i], d2h_bytes ? d2h_bytes : 1) == cudaSuccess;
+            ok = pinned_alloc_local(&h_in[i], h2d_bytes ? h2d_bytes : 1) == cudaSuccess && pinned_alloc_local(&h_out[i], d2h_bytes ? d2h_bytes : 1) == cudaSuccess &&
+                 cudaMalloc(&d_in[i], h2d_bytes ? h2d_bytes : 1) == cudaSuccess && cudaMalloc(&d_out[i], d2h_bytes ? d2h_bytes : 1) == cudaSuccess;
             if (ok) memset(h_in[i], 1, h2d_bytes ? h2d_bytes : 1), memset(h_out[i], 0, d2h_bytes ? d2h_bytes : 1);
         }
         if (!ok) break;
-        // One pass: `reps` buffers each way.  With both directions on, the two streams are kept in lockstep (copy i of one
-        // direction waits for copy i-2 of the other), so both rates are taken over the same interval with the workload's own
-        // byte ratio -- a direction that finished early would otherwise leave the other one running alone, at the
-        // single-direction rate, for the rest of its pass.
-        cudaEvent_t lock_up[kBufs] = {nullptr}, lock_dn[kBufs] = {nullptr};
-        for (int i = 0; i < kBufs; ++i)
-            if (cudaEventCreateWithFlags(&lock_up[i], cudaEventDisableTiming) != cudaSuccess ||
-                cudaEventCreateWithFlags(&lock_dn[i], cudaEventDisableTiming) != cudaSuccess)
-                ok = false;
-        if (!ok) break;
+        auto sync_all = [&]() -> bool {
+            for (int k = 0; k < n_streams; ++k)
+                if (cudaStreamSynchronize(s_up[k]) != cudaSuccess || cudaStreamSynchronize(s_dn[k]) != cudaSuccess) return false;
+            return true;
+        };
+        // One pass: `reps` buffers each way, dealt round-robin over the queues; both rates are taken over the SAME interval
+        // (until the last copy of either direction has finished), so the duplex figures are the rate of (upload, download)
+        // PAIRS in the workload's own byte ratio.
         auto pass = [&](bool up, bool dn, double* up_gbs, double* dn_gbs) -> bool {
-            const bool both = up && dn && h2d_bytes && d2h_bytes;
+            double sec = 0.0;
             for (int w = 0; w < 2; ++w) {   // w == 0: warm-up
-                const int n = w ? reps : 2;
-                if (cudaStreamSynchronize(s_up) != cudaSuccess || cudaStreamSynchronize(s_dn) != cudaSuccess) return false;
-                if (up) cudaEventRecord(e[0], s_up);
-                if (dn) cudaEventRecord(e[2], s_dn);
+                const int n = w ? reps : 2 * n_streams;
+                if (!sync_all()) return false;
+                const auto t0 = std::chrono::steady_clock::now();
                 for (int i = 0; i < n; ++i) {
-                    if (both && i >= 2) {
-                        cudaStreamWaitEvent(s_up, lock_dn[(i - 2) % kBufs], 0);
-                        cudaStreamWaitEvent(s_dn, lock_up[(i - 2) % kBufs], 0);
-                    }
-                    if (up && h2d_bytes) cudaMemcpyAsync(d_in, h_in[i % kBufs], h2d_bytes, cudaMemcpyHostToDevice, s_up);
-                    if (dn && d2h_bytes) cudaMemcpyAsync(h_out[i % kBufs], d_out, d2h_bytes, cudaMemcpyDeviceToHost, s_dn);
-                    if (both) {
-                        cudaEventRecord(lock_up[i % kBufs], s_up);
-                        cudaEventRecord(lock_dn[i % kBufs], s_dn);
-                    }
+                    if (up && h2d_bytes) cudaMemcpyAsync(d_in[i % kBufs], h_in[i % kBufs], h2d_bytes, cudaMemcpyHostToDevice, s_up[i % n_streams]);
+                    if (dn && d2h_bytes) cudaMemcpyAsync(h_out[i % kBufs], d_out[i % kBufs], d2h_bytes, cudaMemcpyDeviceToHost, s_dn[i % n_streams]);
                 }
-                if (up) cudaEventRecord(e[1], s_up);
-                if (dn) cudaEventRecord(e[3], s_dn);
-                if (cudaStreamSynchronize(s_up) != cudaSuccess || cudaStreamSynchronize(s_dn) != cudaSuccess) return false;
+                if (!sync_all()) return false;
+                sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             }
-            float ms = 0.f;
-            if (up && up_gbs) *up_gbs = cudaEventElapsedTime(&ms, e[0], e[1]) == cudaSuccess && ms > 0 ? (double)h2d_bytes * reps / (ms * 1e6) : 0.0;
-            if (dn && dn_gbs) *dn_gbs = cudaEventElapsedTime(&ms, e[2], e[3]) == cudaSuccess && ms > 0 ? (double)d2h_bytes * reps / (ms * 1e6) : 0.0;
+            if (up && up_gbs) *up_gbs = sec > 0 ? (double)h2d_bytes * reps / (sec * 1e9) : 0.0;
+            if (dn && dn_gbs) *dn_gbs = sec > 0 ? (double)d2h_bytes * reps / (sec * 1e9) : 0.0;
             return true;
         };
         out_gbs[0] = out_gbs[1] = out_gbs[2] = out_gbs[3] = 0.0;
-        const bool done = pass(true, false, &out_gbs[0], nullptr) && pass(false, true, nullptr, &out_gbs[1]) && pass(true, true, &out_gbs[2], &out_gbs[3]);
-        for (int i = 0; i < kBufs; ++i) {
-            cudaEventDestroy(lock_up[i]);
-            cudaEventDestroy(lock_dn[i]);
-        }
-        if (!done) break;
+        if (!(pass(true, false, &out_gbs[0], nullptr) && pass(false, true, nullptr, &out_gbs[1]) && pass(true, true, &out_gbs[2], &out_gbs[3]))) break;
         rc = 0;
     } while (false);
     if (rc) set_error("gsdr_pcie_copy_ceiling: %s", cudaGetErrorString(cudaGetLastError()));
     for (int i = 0; i < kBufs; ++i) {
         if (h_in[i]) cudaFreeHost(h_in[i]);
         if (h_out[i]) cudaFreeHost(h_out[i]);
+        if (d_in[i]) cudaFree(d_in[i]);
+        if (d_out[i]) cudaFree(d_out[i]);
     }
-    if (d_in) cudaFree(d_in);
-    if (d_out) cudaFree(d_out);
-    for (auto ev : e)
-        if (ev) cudaEventDestroy(ev);
-    if (s_up) cudaStreamDestroy(s_up);
-    if (s_dn) cudaStreamDestroy(s_dn);
+    for (int k = 0; k < 8; ++k) {
+        if (s_up[k]) cudaStreamDestroy(s_up[k]);
+        if (s_dn[k]) cudaStreamDestroy(s_dn[k]);
+    }
     return rc;
 }
 

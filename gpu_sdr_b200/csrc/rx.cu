@@ -1190,6 +1190,12 @@ struct gsdr_rx_group {
     size_t out_total = 0;
     long long L = 0;
     uint64_t tickets = 0;
+    // Copied form: the per-stream copies of a period are spread round-robin over n_copy streams per direction (s_in / s_out
+    // are streams 0).  One copy engine queue is latency-bound when eight GPUs pull on the same host memory (20 GB/s per GPU
+    // measured at N = 8 against 52 alone); several queues keep more reads in flight.  GSDR_GROUP_COPY_STREAMS (default 4).
+    std::vector<cudaStream_t> x_in, x_out;          // extra streams 1 .. n_copy-1
+    std::vector<cudaEvent_t> j_in, j_out, f_out;    // join events (extra stream -> stream 0) and the fork event for the downloads
+    int n_copy = 1;
     int zc_mode = 1;               // GSDR_GROUP_ZEROCOPY (read at create): 0 copied, 1 zero-copy both ways, 2 copy in / kernel stores out
     bool last_zero_copy = false;
     int last_form = 0;             // bit 0: inputs read in place, bit 1: outputs written in place
@@ -1213,6 +1219,11 @@ void group_free(gsdr_rx_group* g) {
     if (g->stream) cudaStreamDestroy(g->stream);
     if (g->s_in) cudaStreamDestroy(g->s_in);
     if (g->s_out) cudaStreamDestroy(g->s_out);
+    for (auto st : g->x_in) cudaStreamDestroy(st);
+    for (auto st : g->x_out) cudaStreamDestroy(st);
+    for (auto e : g->j_in) cudaEventDestroy(e);
+    for (auto e : g->j_out) cudaEventDestroy(e);
+    for (auto e : g->f_out) cudaEventDestroy(e);
 }
 
 // One channelizer launch over n_buffers consecutive buffers of every member (in[i] / out[i]: device pointers or device
@@ -1299,6 +1310,9 @@ gsdr_rx_group* gsdr_rx_group_create(gsdr_rx** members, int n) {
     {
         const char* zc = getenv("GSDR_GROUP_ZEROCOPY");
         g->zc_mode = (zc && zc[0] >= '0' && zc[0] <= '2') ? zc[0] - '0' : 1;
+        const char* cs = getenv("GSDR_GROUP_COPY_STREAMS");
+        const int k = cs ? atoi(cs) : 4;
+        g->n_copy = k < 1 ? 1 : (k > 8 ? 8 : k);
     }
     g->out_off.resize(n);
     for (int i = 0; i < n; ++i) {
@@ -1313,6 +1327,16 @@ gsdr_rx_group* gsdr_rx_group_create(gsdr_rx** members, int n) {
               cudaEventCreate(&g->t0) == cudaSuccess && cudaEventCreate(&g->t1) == cudaSuccess &&
               cudaMalloc(&g->d_table, pfb_table_bytes(n, members[0]->sm_count)) == cudaSuccess &&
               cudaMalloc(&g->d_tail, window_tail_multi_scratch_bytes(n)) == cudaSuccess;
+    for (int k = 1; k < g->n_copy && ok; ++k) {
+        cudaStream_t a = nullptr, b = nullptr;
+        cudaEvent_t ea = nullptr, eb = nullptr;
+        ok = cudaStreamCreateWithPriority(&a, cudaStreamNonBlocking, lo) == cudaSuccess && cudaStreamCreateWithPriority(&b, cudaStreamNonBlocking, lo) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ea, cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&eb, cudaEventDisableTiming) == cudaSuccess;
+        if (a) g->x_in.push_back(a);
+        if (b) g->x_out.push_back(b);
+        if (ea) g->j_in.push_back(ea);
+        if (eb) g->j_out.push_back(eb);
+    }
     if (!ok) {
         set_error("gsdr_rx_group_create: CUDA resource allocation failed: %s", cudaGetErrorString(cudaGetLastError()));
         group_free(g);
@@ -1396,13 +1420,19 @@ static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool s
     for (int i = 0; i < S; ++i) {
         if (!zin) {   // one cudaMemcpyAsync per stream buffer
             void* dst = sc16 ? static_cast<void*>(s.d_raw + (size_t)i * g->L) : static_cast<void*>(s.d_in + (size_t)i * g->L);
-            GSDR_CUDA_OK(cudaMemcpyAsync(dst, in_host[i], in_bytes, cudaMemcpyHostToDevice, g->s_in));
+            const int k = i % g->n_copy;
+            GSDR_CUDA_OK(cudaMemcpyAsync(dst, in_host[i], in_bytes, cudaMemcpyHostToDevice, k == 0 ? g->s_in : g->x_in[k - 1]));
         }
         if (convert) kin[i] = s.d_in + (size_t)i * g->L;
         else if (zin) kin[i] = static_cast<const float2*>(ia[i]);
         else kin[i] = sc16 ? reinterpret_cast<const float2*>(s.d_raw + (size_t)i * g->L) : s.d_in + (size_t)i * g->L;
         kout[i] = zout ? oa[i] : s.d_out + g->out_off[i];
     }
+    if (!zin)   // the extra upload queues join stream 0 (before the conversion launch, when there is one)
+        for (size_t k = 0; k < g->x_in.size(); ++k) {
+            GSDR_CUDA_OK(cudaEventRecord(g->j_in[k], g->x_in[k]));
+            GSDR_CUDA_OK(cudaStreamWaitEvent(g->s_in, g->j_in[k], 0));
+        }
     if (convert) {
         // wire format -> fc32 on the copy-in stream, one launch per 64 streams (reading the host buffers in place when zin)
         long long blocks = ((g->L >> 2) + 255) / 256;
@@ -1431,9 +1461,17 @@ static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool s
     if (!staged) GSDR_CUDA_OK(cudaEventRecord(s.in_done, g->stream));   // the launch itself consumes the inputs
     if (!zout) {
         GSDR_CUDA_OK(cudaStreamWaitEvent(g->s_out, s.comp_done, 0));
+        for (auto st : g->x_out) GSDR_CUDA_OK(cudaStreamWaitEvent(st, s.comp_done, 0));
         for (int i = 0; i < S; ++i)
-            if (lens[i] > 0)
-                GSDR_CUDA_OK(cudaMemcpyAsync(out_host[i], kout[i], sizeof(float2) * (size_t)lens[i], cudaMemcpyDeviceToHost, g->s_out));
+            if (lens[i] > 0) {
+                const int k = i % g->n_copy;
+                GSDR_CUDA_OK(cudaMemcpyAsync(out_host[i], kout[i], sizeof(float2) * (size_t)lens[i], cudaMemcpyDeviceToHost,
+                                             k == 0 ? g->s_out : g->x_out[k - 1]));
+            }
+        for (size_t k = 0; k < g->x_out.size(); ++k) {
+            GSDR_CUDA_OK(cudaEventRecord(g->j_out[k], g->x_out[k]));
+            GSDR_CUDA_OK(cudaStreamWaitEvent(g->s_out, g->j_out[k], 0));
+        }
         GSDR_CUDA_OK(cudaEventRecord(s.out_done, g->s_out));
     } else {
         GSDR_CUDA_OK(cudaEventRecord(s.out_done, g->stream));

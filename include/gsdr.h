@@ -261,9 +261,12 @@ int gsdr_pool_available(const gsdr_pool *pool);
 int gsdr_pool_size(const gsdr_pool *pool);
 
 /* Plain cudaMemcpyAsync ceiling between pinned host memory and `device` (one call per buffer): out_gbs[4] =
- * {h2d alone, d2h alone, h2d while both run, d2h while both run} in 1e9 bytes/s.  bench.py reports end-to-end figures
+ * {h2d alone, d2h alone, h2d and d2h with both running, taken over the same interval} in 1e9 bytes/s.  bench.py reports end-to-end figures
  * against it. */
 int gsdr_pcie_copy_ceiling(int device, size_t h2d_bytes, size_t d2h_bytes, int reps, double *out_gbs);
+/* the same with n_streams (1..8) copy queues per direction, buffers dealt round-robin: when several GPUs pull on one host's
+ * memory a single copy-engine queue is latency-bound and more queues move more bytes */
+int gsdr_pcie_copy_ceiling_streams(int device, size_t h2d_bytes, size_t d2h_bytes, int reps, int n_streams, double *out_gbs);
 void *gsdr_host_alloc(size_t bytes);   /* cudaMallocHost, on the NUMA node of the current GPU when the kernel allows (GSDR_NUMA_LOCAL=0: off) */
 int gsdr_device_numa_node(int device); /* /sys/bus/pci/devices/<bus id>/numa_node of the GPU, -1 when unknown */
 void gsdr_host_free(void *p);
