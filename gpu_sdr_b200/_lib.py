@@ -141,6 +141,9 @@ SIGNATURES = {
     "gsdr_pool_size": (C.c_int, [C.c_void_p]),
     "gsdr_pcie_copy_ceiling": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
     "gsdr_pcie_copy_ceiling_streams": (C.c_int, [C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "gsdr_pcie_probe_create": (C.c_void_p, [C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_int]),
+    "gsdr_pcie_probe_run": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "gsdr_pcie_probe_destroy": (None, [C.c_void_p]),
     "gsdr_host_alloc": (C.c_void_p, [C.c_size_t]),
     "gsdr_device_numa_node": (C.c_int, [C.c_int]),
     "gsdr_host_free": (None, [C.c_void_p]),

@@ -22,17 +22,21 @@
 //
 //   sB  per tone, fixed when the demodulator is created (the bank is built on the host from the double-precision taps and
 //       lies in HBM as ready-made K-major tiles: the producers never touch the filters, TMA brings them);
-//   sA  per tile (128 window rows), from the largest |sample| of the tile: the epilogue warps scan the rows of tile n+2
-//       (plain coalesced loads, which also pull them into L2 for the TMA boxes that follow) while the MMAs of tile n+1 run.
+//   sA  per tile (128 window rows), from the largest |sample| of the tile, found one tile ahead: the scan-issue warp lands the
+//       NEXT tile's K-block boxes in two slots of their own (the same boxes the operand path asks for one tile later, by then
+//       from L2: the window crosses HBM once) and the producers fold them into a running maximum between two K blocks.
 //
-// Warp roles (one persistent CTA per SM, static scheduler over (row tile, tone group)):
-//   warps 0-3   epilogue: tcgen05.ld of the three accumulators, 64-bit combine, row shift-and-add, int -> float, LO rotation
-//               from the integer phase (cpp/kernels.cu:59-75), sample-major store; then the |x| scan of tile n+2
-//   warp  4     TMEM allocation + single-thread tcgen05.mma issue: per K block two N=256 and two N=128 MMAs
-//   warps 5-12  operand producers: thread = one window row (TMEM lane) and one half of its K block: 4 x LDS.128 from the TMA
-//               landing slot, scale, round, digits, tcgen05.st -- the A operand only ever exists in tensor memory
-//   warp  13    TMA issue: one box (128 rows x 32 floats, SWIZZLE_128B) per K block for A, three boxes (128 x 128 bytes)
-//               per four K blocks for the digit planes of B
+// Warp roles (one persistent CTA of 20 warps per SM, static scheduler over (row tile, tone group)):
+//   warps 0-3, 4-7    two epilogue teams, units of 8 tones dealt alternately: tcgen05.ld of the three accumulators, row
+//                     shift-and-add in int32, 64-bit combine, int -> float, LO rotation from the integer phase
+//                     (cpp/kernels.cu:59-75), sample-major store.  The accumulators are single-buffered (3 x 128 + 96 operand
+//                     columns of the 512): the teams read them side by side so that the MMA warp gets them back early.
+//   warps 8-15        operand producers: thread = one window row (TMEM lane) and one half of its K block: 4 x LDS.128 from the
+//                     TMA landing slot, scale, round, digits, tcgen05.st -- the A operand only ever exists in tensor memory
+//   warp  16          TMEM allocation + single-thread tcgen05.mma issue: per K block two N = 256 and two N = 128 MMAs
+//   warp  17          TMA issue: one box (128 rows x 32 floats, SWIZZLE_128B) per K block for A, three boxes (128 x 128 bytes)
+//                     per four K blocks for the digit planes of B
+//   warp  18          scan-box issue (above); warp 19 idles
 #include <cuda.h>
 
 #include <cmath>
@@ -50,33 +54,54 @@ constexpr int I8_KC = 16;                    // complex taps per K block: 32 rea
 constexpr int I8_RAW = 4;                    // TMA landing slots for A
 constexpr int I8_AST = 4;                    // A operand stages in TMEM
 constexpr int I8_BST = 2;                    // B operand stages in shared memory (each: 3 digit planes x 4 K blocks)
-constexpr int I8_EPI_WARPS = 4;
+// Twenty warps (96 registers each: ptxas keeps every role inside the launch allocation, with or without setmaxnreg):
+//   warps 0-3, 4-7    two epilogue teams (units of 8 tones dealt alternately)
+//   warps 8-11, 12-15 operand producers (first / second half of a K block)
+//   warp 16 MMA issue, 17 TMA issue, 18 scan-box issue, 19 idle
+constexpr int I8_EPI_TEAMS = 2;
+constexpr int I8_EPI_WARPS = 4 * I8_EPI_TEAMS;
 constexpr int I8_PROD_WARPS = 8;
-constexpr int I8_THREADS = 32 * (I8_EPI_WARPS + 1 + I8_PROD_WARPS + 1);
-constexpr int I8_TMA_WARP = I8_EPI_WARPS + 1 + I8_PROD_WARPS;
+constexpr int I8_PROD_WARP0 = I8_EPI_WARPS;
+constexpr int I8_MMA_WARP = I8_PROD_WARP0 + I8_PROD_WARPS;
+constexpr int I8_TMA_WARP = I8_MMA_WARP + 1;
+constexpr int I8_SCAN_WARP = I8_MMA_WARP + 2;   // issues the scan boxes (see the producers)
+constexpr int I8_THREADS = 32 * (I8_MMA_WARP + 4);
 constexpr int I8_RAW_BYTES = I8_ROWS * 128;  // one landing slot: 128 rows x 128 bytes
 constexpr int I8_B_PLANE = I8_N * 128;       // one digit plane: 128 columns (rows of the K-major tile) x 128 bytes (4 K blocks)
 constexpr int I8_B_STAGE = 3 * I8_B_PLANE;
 constexpr unsigned int I8_COL_A = 384;       // accumulators: weight 2^32 at column 0, 2^24 at 128, 2^16 at 256; A stage s at 384 + 24 s
 constexpr int I8_TMEM_COLS = 512;
-constexpr int I8_XCH = 7 * 7 * 3 * 16;       // per epilogue warp: (F-1) lanes x (F-1) blocks x 3 accumulators x 16 columns, F <= 8
+// exchange buffer per epilogue warp: (F-1) lanes x (F-1) blocks x 3 accumulators x 16 columns
+__host__ __device__ constexpr int i8_xch_ints(int F) { return F > 1 ? (F - 1) * (F - 1) * 3 * 16 : 16; }
+// landing slots (one A-sized box each) for the scan of the NEXT tile's largest sample; F = 8 has no room for them (its exchange
+// buffer is 37 KB) and keeps the scan on global loads
+// epilogue warps with work: with one unit per tile (F = 8) the second team idles
+__host__ __device__ constexpr int i8_xch_warps(int F) { return 64 / F / 8 >= 2 ? 8 : 4; }
+__host__ __device__ constexpr int i8_scan_slots(int F) { return F <= 4 ? 2 : 0; }
 constexpr int I8_HIST_MAX = 7 * 128;
 constexpr float I8_FULL_SCALE = 8355000.0f;  // |digits| <= 127 * (2^16 + 2^8 + 1) = 8355711
-static_assert((I8_EPI_WARPS + 1) % 4 == 1, "producer warp w owns TMEM lane quarter w % 4");
+static_assert(I8_PROD_WARP0 % 4 == 0, "warp w owns TMEM lane quarter w % 4");
 
-struct I8Shared {
+template <int XCH, int XW>
+struct I8SharedT {
     unsigned long long raw_full[I8_RAW], raw_empty[I8_RAW];   // TMA <-> producers: window rows of a K block
     unsigned long long a_full[I8_AST], a_empty[I8_AST];       // producers <-> MMA: A digits in TMEM
     unsigned long long b_full[I8_BST], b_empty[I8_BST];       // TMA <-> MMA: digit planes of B
     unsigned long long tmem_full, tmem_empty;                 // MMA <-> epilogue: the accumulators
+    unsigned long long scan_full[4], scan_empty[4];           // scan-issue warp <-> producers: boxes of the next tile
     unsigned int tmem_base;
     unsigned int amax_bits[4];
     double2 ph[64];          // per tone of the group: (LO phase of the tile's first row, phase step per row), integers < rate
     float inv_sb[64];        // per tone of the group: 1 / sB
-    alignas(16) int xch[I8_EPI_WARPS][I8_XCH];
+    alignas(16) int xch[XW][XCH];   // one per epilogue warp that has units to do
     alignas(16) float2 hist[I8_HIST_MAX];
 };
-constexpr size_t I8_SMEM_BYTES = 1024 + (size_t)I8_RAW * I8_RAW_BYTES + (size_t)I8_BST * I8_B_STAGE + sizeof(I8Shared);
+constexpr size_t i8_smem_bytes(int F) {
+    return 1024 + (size_t)(I8_RAW + i8_scan_slots(F)) * I8_RAW_BYTES + (size_t)I8_BST * I8_B_STAGE +
+           (F == 1 ? sizeof(I8SharedT<i8_xch_ints(1), i8_xch_warps(1)>) : F == 2 ? sizeof(I8SharedT<i8_xch_ints(2), i8_xch_warps(2)>) :
+            F == 4 ? sizeof(I8SharedT<i8_xch_ints(4), i8_xch_warps(4)>) : sizeof(I8SharedT<i8_xch_ints(8), i8_xch_warps(8)>));
+}
+static_assert(i8_smem_bytes(1) <= 232448 && i8_smem_bytes(2) <= 232448 && i8_smem_bytes(4) <= 232448 && i8_smem_bytes(8) <= 232448, "shared memory per CTA");
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
@@ -86,19 +111,24 @@ __device__ __forceinline__ void mbar_init(unsigned int addr, unsigned int count)
 __device__ __forceinline__ void mbar_arrive(unsigned int addr) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
+// (a suspend-time hint on try_wait was measured: the waiting warps free issue slots but wake late, 232 -> 215 GS/s on cfg1)
 // Bounded wait: a protocol error traps (the launch fails) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(unsigned int addr, unsigned int parity) {
+    // A tight poll loop (the waiting warps share issue slots with the working ones: the round-2 profile showed 17 instructions per
+    // poll, a fifth of everything issued); the clock is read once per 4096 polls only.
     long long t0 = 0;
-    for (unsigned int spins = 0;; ++spins) {
+    for (unsigned int rounds = 0;; ++rounds) {
         unsigned int done;
         asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            "{\n\t.reg .pred p, q;\n\t.reg .u32 n;\n\tmov.u32 n, 4096;\n"
+            "WAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t@p bra DONE_%=;\n\tsub.u32 n, n, 1;\n\tsetp.ne.u32 q, n, 0;\n\t@q bra WAIT_%=;\n"
+            "DONE_%=:\n\tselp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
             : "r"(addr), "r"(parity)
             : "memory");
         if (done) return;
-        if (spins == 64) t0 = clock64();
-        if (spins > 64 && (spins & 255u) == 0 && clock64() - t0 > 4000000000LL) __trap();
+        if (rounds == 0) t0 = clock64();
+        else if (clock64() - t0 > 4000000000LL) __trap();
     }
 }
 // schedule tuning (GSDR_DIRECT_I8_DEBUG=1): cycles spent in a wait, accumulated per role
@@ -161,7 +191,10 @@ __device__ __forceinline__ void tmem_st4(unsigned int taddr, unsigned int a, uns
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(32 * I8_EPI_WARPS) : "memory"); }
+__device__ __forceinline__ void epi_bar(int team) {   // one named barrier per epilogue team (2 belongs to the producers)
+    if (team == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+    else asm volatile("bar.sync 3, 128;" ::: "memory");
+}
 
 // round_to_nearest_float(s1 2^16 + s2 2^8 + s3): the exact 64-bit sum, cut into a high part (arithmetic shift by 21: an int32
 // here, |sum| < 2^52) and a 21-bit low part, both converted exactly; the one rounding is the FFMA's.
@@ -189,12 +222,15 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     constexpr int TG = 64 / F;
     constexpr int RB = I8_ROWS - (F - 1);
     constexpr int NUNIT = TG / 8;              // epilogue units of 8 tones (16 accumulator columns) per tile
-    static_assert(TG % 8 == 0 && (F - 1) * (F - 1) * 3 * 16 <= I8_XCH, "exchange buffer");
+    constexpr int NSCAN = i8_scan_slots(F);
+    using I8Shared = I8SharedT<i8_xch_ints(F), i8_xch_warps(F)>;
+    static_assert(TG % 8 == 0 && NSCAN <= 4, "tile shape");
 
     extern __shared__ unsigned char i8_smem_raw[];
     unsigned char* smem = i8_smem_raw + ((1024u - (smem_u32(i8_smem_raw) & 1023u)) & 1023u);
     unsigned char* smem_b = smem + (size_t)I8_RAW * I8_RAW_BYTES;
-    I8Shared* sh = reinterpret_cast<I8Shared*>(smem_b + (size_t)I8_BST * I8_B_STAGE);
+    unsigned char* smem_scan = smem_b + (size_t)I8_BST * I8_B_STAGE;
+    I8Shared* sh = reinterpret_cast<I8Shared*>(smem_scan + (size_t)NSCAN * I8_RAW_BYTES);
     const unsigned int smem_base = smem_u32(smem);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -218,11 +254,15 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             mbar_init(smem_u32(&sh->b_full[s]), 1);
             mbar_init(smem_u32(&sh->b_empty[s]), 1);
         }
+        for (int s = 0; s < 4; ++s) {
+            mbar_init(smem_u32(&sh->scan_full[s]), 1);
+            mbar_init(smem_u32(&sh->scan_empty[s]), 32 * I8_PROD_WARPS);
+        }
         mbar_init(smem_u32(&sh->tmem_full), 1);
         mbar_init(smem_u32(&sh->tmem_empty), 32 * I8_EPI_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == I8_EPI_WARPS) {
+    if (warp == I8_MMA_WARP) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
                      "r"(I8_TMEM_COLS)
                      : "memory");
@@ -244,18 +284,27 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         return t;
     };
 
+    // Tile n + 1 of this CTA is scanned out of TMA-landed boxes (instead of with global loads) when every one of its rows lies in
+    // the tensor map: the producers and the scan-issue warp take the same decision.
+    auto scan_by_tma = [&](int n_next) -> bool {
+        return NSCAN > 0 && use_tma && amax_rows == nullptr && n_next < my_tiles && tile_of(n_next).row0 >= hist_rows;
+    };
+
     if (warp < I8_EPI_WARPS) {
-        // ======================================= EPILOGUE (+ scan) =======================================
-        const int et = (int)threadIdx.x;                      // 0..127
-        const int row_in_tile = warp * 32 + lane;
+        // ======================================= EPILOGUE =======================================
+        const int team = warp >> 2, wq = warp & 3;            // team: units u = team, team + 2, ...; wq: TMEM lane quarter
+        const int u_last = NUNIT - 1 - ((NUNIT - 1 - team) & 1);   // this team's last unit (< team: it has none)
+        const bool u_has = u_last >= team;
+        const int et = (int)threadIdx.x & 127;                // 0..127 inside the team
+        const int row_in_tile = wq * 32 + lane;
         const double row_d = (double)row_in_tile;
         const double word_per_phase = 4294967296.0 / (double)rate;
-        int* xw = sh->xch[warp];
-        const int* xn = sh->xch[(warp + 1) & 3];
-        const unsigned int lane_base = tmem_base + ((unsigned int)(warp * 32) << 16);
+        int* xw = sh->xch[u_has ? warp : 0];   // a team without units never touches them
+        const int* xn = sh->xch[u_has ? 4 * team + ((wq + 1) & 3) : 0];
+        const unsigned int lane_base = tmem_base + ((unsigned int)(wq * 32) << 16);
         for (int n = 0; n < my_tiles; ++n) {
             const I8Tile tl = tile_of(n);
-            if (et < TG) {
+            if (et < TG && ((et >> 3) & 1) == team) {   // the tones of this team's units
                 const int ch = tl.ch0 + et;
                 double base = 0.0, step = 0.0;
                 float isb = 0.f;
@@ -279,8 +328,12 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const float amax = __uint_as_float(sh->amax_bits[n & 3]);
             const float inv_sa = amax * (1.0f / I8_FULL_SCALE);
             const long long p = tl.row0 + row_in_tile;
+            if (u_last < team) {   // nothing to read: the accumulators are free as far as this team is concerned
+                tc_fence_before();
+                mbar_arrive(smem_u32(&sh->tmem_empty));
+            }
 #pragma unroll 1
-            for (int u = 0; u < NUNIT; ++u) {
+            for (int u = team; u < NUNIT; u += I8_EPI_TEAMS) {
                 // One unit = 8 tones = 16 accumulator columns.  The F blocks are added with their row shift (the reference's
                 // overlap-add, cpp/fir.cu:55-69) per accumulator, in int32 -- |D| <= 3 * 2 M * 2^14, times F, stays below 2^31 --
                 // so the 64-bit combine D1 2^16 + D2 2^8 + D3 runs once per output and not once per block.
@@ -312,13 +365,13 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         }
                     }
                 }
-                // every accumulator column of the tile is in registers: the MMA warp may start the next tile
-                if (u == NUNIT - 1) {
+                // every accumulator column this team reads is in registers: the MMA warp may start the next tile
+                if (u == u_last) {
                     tc_fence_before();
                     mbar_arrive(smem_u32(&sh->tmem_empty));
                 }
                 const long long te1 = timed ? clock64() : 0;
-                epi_bar();   // exchange buffers written; sh->ph / sh->inv_sb published
+                epi_bar(team);   // exchange buffers written; sh->ph / sh->inv_sb published
                 if (timed) wt1 += te1 - te0, wt2 += clock64() - te1;
                 if (F > 1) {
 #pragma unroll
@@ -361,7 +414,7 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                             if (t < n_valid) dst[t] = o[t];
                     }
                 }
-                epi_bar();   // the exchange buffer (and sh->ph after the last unit) may be rewritten
+                epi_bar(team);   // the exchange buffer (and sh->ph after the last unit) may be rewritten
             }
         }
         if (dbg && threadIdx.x == 0) {
@@ -371,45 +424,9 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             atomicAdd((unsigned long long*)&dbg[2], (unsigned long long)(clock64() - t_role0));   // epilogue: role time
             atomicAdd((unsigned long long*)&dbg[15], (unsigned long long)my_tiles);
         }
-    } else if (warp == I8_EPI_WARPS) {
-        // ======================================= MMA ISSUE =======================================
-        int it = 0, bc = 0;   // K blocks issued (A stage = it & 3), B stages consumed (stage = bc & 1)
-        const unsigned int d1 = tmem_base, d2 = tmem_base + 128u, d3 = tmem_base + 256u;
-        for (int n = 0; n < my_tiles; ++n) {
-            mbar_wait_t(smem_u32(&sh->tmem_empty), ((unsigned)n & 1u) ^ 1u, wt0, timed);
-            tc_fence_after();
-            for (int kb = 0; kb < KB; ++kb, ++it) {
-                const int st = it & (I8_AST - 1), bs = bc & (I8_BST - 1);
-                if ((kb & 3) == 0) mbar_wait_t(smem_u32(&sh->b_full[bs]), (unsigned)(bc >> 1) & 1u, wt1, timed);
-                mbar_wait_t(smem_u32(&sh->a_full[st]), (unsigned)(it >> 2) & 1u, wt2, timed);
-                tc_fence_after();
-                if (lane == 0) {
-                    const unsigned int a1 = tmem_base + I8_COL_A + 24u * st, a2 = a1 + 8u, a3 = a1 + 16u;
-                    const unsigned int b0 = smem_u32(smem_b) + (unsigned)bs * I8_B_STAGE;
-                    const unsigned long long adv = (unsigned long long)(2 * (kb & 3));   // 32 bytes >> 4 per K block inside the 128-byte row
-                    const unsigned long long B1 = i8_smem_desc(b0) + adv, B3 = i8_smem_desc(b0 + 2 * I8_B_PLANE) + adv;
-                    const unsigned int acc = kb > 0 ? 1u : 0u;
-                    mma_i8_ts(d3, a1, B3, I8_IDESC, acc);          // 2^16: a1 b3
-                    mma_i8_ts(d1, a1, B1, I8_IDESC_WIDE, acc);     // 2^32: a1 b1 | 2^24: a1 b2      ([B1 | B2] -> [D1 | D2])
-                    mma_i8_ts(d2, a2, B1, I8_IDESC_WIDE, 1u);      // 2^24: a2 b1 | 2^16: a2 b2      ([B1 | B2] -> [D2 | D3])
-                    mma_i8_ts(d3, a3, B1, I8_IDESC, 1u);           // 2^16: a3 b1
-                    tc_commit(smem_u32(&sh->a_empty[st]));
-                    if ((kb & 3) == 3 || kb == KB - 1) tc_commit(smem_u32(&sh->b_empty[bs]));
-                    if (kb == KB - 1) tc_commit(smem_u32(&sh->tmem_full));
-                }
-                __syncwarp();
-                if ((kb & 3) == 3 || kb == KB - 1) ++bc;
-            }
-        }
-        if (dbg && lane == 0) {
-            atomicAdd((unsigned long long*)&dbg[3], (unsigned long long)wt0);                     // MMA: wait for free accumulators
-            atomicAdd((unsigned long long*)&dbg[4], (unsigned long long)wt1);                     // MMA: wait for B planes
-            atomicAdd((unsigned long long*)&dbg[5], (unsigned long long)wt2);                     // MMA: wait for A digits
-            atomicAdd((unsigned long long*)&dbg[6], (unsigned long long)(clock64() - t_role0));   // MMA: role time
-        }
-    } else if (warp < I8_TMA_WARP) {
+    } else if (warp >= I8_PROD_WARP0 && warp < I8_MMA_WARP) {
         // ======================================= OPERAND PRODUCERS =======================================
-        const int half = (warp - (I8_EPI_WARPS + 1)) / 4;    // which 16 reals of the 32-real K block
+        const int half = (warp - I8_PROD_WARP0) / 4;         // which 16 reals of the 32-real K block
         const int q = warp & 3;                              // TMEM lane quarter this warp may access
         const int row = 32 * q + lane;                       // window row of the tile == TMEM lane
         const unsigned int a_rowoff = (unsigned)(row >> 3) * 1024u + (unsigned)(row & 7) * 128u;
@@ -417,13 +434,16 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         // byte order of the four K elements inside a 32-bit TMEM column: a_order = 0 -> K ascending with byte significance
         const unsigned int sel_pair = a_order ? 0x0004u : 0x0040u;   // (x.b0, y.b0) -> low half-word
         const unsigned int sel_quad = a_order ? 0x1054u : 0x5410u;
-        int it = 0;
-        const int pt = (int)threadIdx.x - 32 * (I8_EPI_WARPS + 1);   // 0..255
+        int it = 0, sit = 0;   // K blocks cut, scan boxes consumed
+        long long wt3 = 0, wt4 = 0, wt5 = 0;
+        const int pt = (int)threadIdx.x - 32 * I8_PROD_WARP0;   // 0..255
         // The fixed-point scale of a tile comes from its largest |sample|.  The producers find it themselves, one tile ahead and
-        // spread over the K blocks of the tile they are cutting: the 256 threads sweep the NEXT tile's samples (one contiguous
-        // run of the window: 128 rows of M) with coalesced 8-byte loads, eight per thread issued when a K block starts and folded
-        // into a running maximum when the K block is done, so their latency hides behind the digit work (and the lines are in
-        // L2 when the TMA boxes of that tile ask for them).  8 loads x KB K blocks x 256 threads >= 128 M samples.
+        // spread over the K blocks of the tile they are cutting.  Normal case (scan_by_tma): the scan-issue warp lands the NEXT
+        // tile's K-block boxes in their own slots -- the same boxes the operand path will ask for one tile later, by then from
+        // L2 -- and after cutting a K block each producer folds 64 bytes of a landed box into its running maximum: four LDS.128,
+        // no load latency on the producers' critical path.  Otherwise (history rows, no tensor map, F = 8): the 256 threads
+        // sweep the next tile with coalesced 8-byte global loads, eight per thread issued when a K block starts and folded in
+        // when it is done.  8 loads x KB K blocks x 256 threads >= 128 M samples.
         const int scan_n = I8_ROWS * M;                              // samples per tile
         auto scan_src = [&](const I8Tile& t, bool& inside) -> long long {
             const long long t0 = t.row0 * (long long)M, t1 = t0 + (long long)I8_ROWS * M;
@@ -459,7 +479,8 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const I8Tile tl = tile_of(n);
             const float amax = __uint_as_float(sh->amax_bits[n & 3]);
             const float sa = amax > 0.f ? I8_FULL_SCALE / amax : 0.f;
-            const bool scan_next = amax_rows == nullptr && n + 1 < my_tiles;
+            const bool nx_tma = scan_by_tma(n + 1);
+            const bool scan_next = amax_rows == nullptr && n + 1 < my_tiles && !nx_tma;
             bool nx_inside = false;
             const long long nx_s0 = scan_next ? scan_src(tile_of(n + 1), nx_inside) : 0;
             const float2* nx_p = w.in + (nx_s0 - w.n_hist);
@@ -497,6 +518,7 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 mbar_wait_t(smem_u32(&sh->a_empty[st]), ((unsigned)(it >> 2) & 1u) ^ 1u, wt1, timed);   // the MMAs of this stage's previous use are done
                 mbar_wait_t(smem_u32(&sh->raw_full[r]), (unsigned)(it >> 2) & 1u, wt2, timed);
                 tc_fence_after();
+                const long long tp0 = timed ? clock64() : 0;
                 const unsigned char* raw = smem + (size_t)r * I8_RAW_BYTES;
                 const bool from_smem = use_tma && tl.row0 + row >= hist_rows;   // else: history row, or no TMA at all
                 const long long s_row = (tl.row0 + row) * (long long)M + kb * I8_KC + 8 * half;
@@ -517,22 +539,24 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     }
                 }
                 mbar_arrive(smem_u32(&sh->raw_empty[r]));   // this thread's reads of the landing slot are complete (values in registers)
-                // fixed point, three signed digits: q = d1 2^16 + d2 2^8 + d3 with d = low byte taken as signed and the carry moved up
+                // fixed point, three signed digits: q = d1 2^16 + d2 2^8 + d3, each the low byte taken as signed with the carry moved
+                // up: d3 = byte 0 of q, d2 = byte 1 of q + 128, d1 = byte 2 of q + 128 + 128 * 256 (the two carries folded into one add)
                 unsigned int w1[4], w2[4], w3[4];
 #pragma unroll
                 for (int g4 = 0; g4 < 4; ++g4) {
-                    int q0[4], q1[4], q2[4];
+                    int q0[4], t1[4], t2[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         q0[e] = __float2int_rn(v[4 * g4 + e] * sa);
-                        q1[e] = (q0[e] + 128) >> 8;
-                        q2[e] = (q1[e] + 128) >> 8;
+                        t1[e] = q0[e] + 128;
+                        t2[e] = q0[e] + 32896;
                     }
                     w3[g4] = __byte_perm(__byte_perm(q0[0], q0[1], sel_pair), __byte_perm(q0[2], q0[3], sel_pair), sel_quad);
-                    w2[g4] = __byte_perm(__byte_perm(q1[0], q1[1], sel_pair), __byte_perm(q1[2], q1[3], sel_pair), sel_quad);
-                    w1[g4] = __byte_perm(__byte_perm(q2[0], q2[1], sel_pair), __byte_perm(q2[2], q2[3], sel_pair), sel_quad);
+                    w2[g4] = __byte_perm(__byte_perm(t1[0], t1[1], sel_pair + 0x11u), __byte_perm(t1[2], t1[3], sel_pair + 0x11u), sel_quad);
+                    w1[g4] = __byte_perm(__byte_perm(t2[0], t2[1], sel_pair + 0x22u), __byte_perm(t2[2], t2[3], sel_pair + 0x22u), sel_quad);
                 }
                 __syncwarp();   // tcgen05.st is warp-collective: reconverge after the per-lane source selection
+                const long long tp1 = timed ? clock64() : 0;
                 const unsigned int ta = a_tmem0 + 24u * st;
                 tmem_st4(ta, w1[0], w1[1], w1[2], w1[3]);
                 tmem_st4(ta + 8u, w2[0], w2[1], w2[2], w2[3]);
@@ -540,9 +564,23 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 tmem_st_wait();
                 tc_fence_before();
                 mbar_arrive(smem_u32(&sh->a_full[st]));
+                if (timed) wt4 += tp1 - tp0, wt5 += clock64() - tp1;
                 if (scan_next) {
 #pragma unroll
                     for (int u8 = 0; u8 < 8; ++u8) nx_m = fmaxf(nx_m, fmaxf(fabsf(sv[u8].x), fabsf(sv[u8].y)));
+                }
+                if (NSCAN > 0 && nx_tma) {   // this thread's 64 bytes of the next tile's box kb (any order: it is a maximum)
+                    const int ss = sit % (NSCAN > 0 ? NSCAN : 1);
+                    mbar_wait_t(smem_u32(&sh->scan_full[ss]), (unsigned)(sit / (NSCAN > 0 ? NSCAN : 1)) & 1u, wt3, timed);
+                    const float4* bx = reinterpret_cast<const float4*>(smem_scan + (size_t)ss * I8_RAW_BYTES) + pt;
+                    float4 x[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) x[j] = bx[256 * j];
+                    mbar_arrive(smem_u32(&sh->scan_empty[ss]));
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        nx_m = fmaxf(fmaxf(nx_m, fmaxf(fabsf(x[j].x), fabsf(x[j].y))), fmaxf(fabsf(x[j].z), fabsf(x[j].w)));
+                    ++sit;
                 }
             }
             if (n + 1 < my_tiles) {
@@ -551,13 +589,58 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 if (timed) wt0 += clock64() - tsc;
             }
         }
-        if (dbg && (int)threadIdx.x == 32 * (I8_EPI_WARPS + 1)) {
+        if (dbg && (int)threadIdx.x == 32 * I8_PROD_WARP0) {
             atomicAdd((unsigned long long*)&dbg[7], (unsigned long long)wt0);                     // producers: scale hand-over between tiles
             atomicAdd((unsigned long long*)&dbg[8], (unsigned long long)wt1);                     // producers: wait for a free A stage
             atomicAdd((unsigned long long*)&dbg[9], (unsigned long long)wt2);                     // producers: wait for the TMA rows
             atomicAdd((unsigned long long*)&dbg[10], (unsigned long long)(clock64() - t_role0));  // producers: role time
+            atomicAdd((unsigned long long*)&dbg[16], (unsigned long long)wt3);                    // producers: wait for a scan box
+            atomicAdd((unsigned long long*)&dbg[18], (unsigned long long)wt4);                    // producers: rows out of shared memory + digits
+            atomicAdd((unsigned long long*)&dbg[19], (unsigned long long)wt5);                    // producers: tcgen05.st + wait + hand-over
         }
-    } else if (warp == I8_TMA_WARP) {
+    } else {
+        // three single-thread issue roles and an idle warp
+        if (warp == I8_MMA_WARP) {
+        // ======================================= MMA ISSUE =======================================
+        int it = 0, bc = 0;   // K blocks issued (A stage = it & 3), B stages consumed (stage = bc & 1)
+        long long wt3 = 0;
+        const unsigned int d1 = tmem_base, d2 = tmem_base + 128u, d3 = tmem_base + 256u;
+        for (int n = 0; n < my_tiles; ++n) {
+            mbar_wait_t(smem_u32(&sh->tmem_empty), ((unsigned)n & 1u) ^ 1u, wt0, timed);
+            tc_fence_after();
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int st = it & (I8_AST - 1), bs = bc & (I8_BST - 1);
+                if ((kb & 3) == 0) mbar_wait_t(smem_u32(&sh->b_full[bs]), (unsigned)(bc >> 1) & 1u, wt1, timed);
+                mbar_wait_t(smem_u32(&sh->a_full[st]), (unsigned)(it >> 2) & 1u, wt2, timed);
+                tc_fence_after();
+                const long long tm0 = timed ? clock64() : 0;
+                if (lane == 0) {
+                    const unsigned int a1 = tmem_base + I8_COL_A + 24u * st, a2 = a1 + 8u, a3 = a1 + 16u;
+                    const unsigned int b0 = smem_u32(smem_b) + (unsigned)bs * I8_B_STAGE;
+                    const unsigned long long adv = (unsigned long long)(2 * (kb & 3));   // 32 bytes >> 4 per K block inside the 128-byte row
+                    const unsigned long long B1 = i8_smem_desc(b0) + adv, B3 = i8_smem_desc(b0 + 2 * I8_B_PLANE) + adv;
+                    const unsigned int acc = kb > 0 ? 1u : 0u;
+                    mma_i8_ts(d3, a1, B3, I8_IDESC, acc);          // 2^16: a1 b3
+                    mma_i8_ts(d1, a1, B1, I8_IDESC_WIDE, acc);     // 2^32: a1 b1 | 2^24: a1 b2      ([B1 | B2] -> [D1 | D2])
+                    mma_i8_ts(d2, a2, B1, I8_IDESC_WIDE, 1u);      // 2^24: a2 b1 | 2^16: a2 b2      ([B1 | B2] -> [D2 | D3])
+                    mma_i8_ts(d3, a3, B1, I8_IDESC, 1u);           // 2^16: a3 b1
+                    tc_commit(smem_u32(&sh->a_empty[st]));
+                    if ((kb & 3) == 3 || kb == KB - 1) tc_commit(smem_u32(&sh->b_empty[bs]));
+                    if (kb == KB - 1) tc_commit(smem_u32(&sh->tmem_full));
+                }
+                __syncwarp();
+                if (timed) wt3 += clock64() - tm0;
+                if ((kb & 3) == 3 || kb == KB - 1) ++bc;
+            }
+        }
+        if (dbg && lane == 0) {
+            atomicAdd((unsigned long long*)&dbg[3], (unsigned long long)wt0);                     // MMA: wait for free accumulators
+            atomicAdd((unsigned long long*)&dbg[4], (unsigned long long)wt1);                     // MMA: wait for B planes
+            atomicAdd((unsigned long long*)&dbg[5], (unsigned long long)wt2);                     // MMA: wait for A digits
+            atomicAdd((unsigned long long*)&dbg[6], (unsigned long long)(clock64() - t_role0));   // MMA: role time
+            atomicAdd((unsigned long long*)&dbg[17], (unsigned long long)wt3);                    // MMA: the issue block (4 MMAs + commits)
+        }
+        } else if (warp == I8_TMA_WARP) {
         // ======================================= TMA ISSUE =======================================
         if (lane == 0) {
             int it = 0, bc = 0;
@@ -591,13 +674,30 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 atomicAdd((unsigned long long*)&dbg[13], (unsigned long long)(clock64() - t_role0));   // TMA: role time
             }
         }
+        } else if (warp == I8_SCAN_WARP) {
+        // ======================================= SCAN BOX ISSUE =======================================
+        if (NSCAN > 0 && lane == 0) {
+            int sit = 0;
+            for (int n = 0; n + 1 < my_tiles; ++n) {
+                if (!scan_by_tma(n + 1)) continue;
+                const I8Tile nx = tile_of(n + 1);
+                for (int kb = 0; kb < KB; ++kb, ++sit) {
+                    const int ss = sit % (NSCAN > 0 ? NSCAN : 1);
+                    mbar_wait(smem_u32(&sh->scan_empty[ss]), ((unsigned)(sit / (NSCAN > 0 ? NSCAN : 1)) & 1u) ^ 1u);
+                    const unsigned int bar = smem_u32(&sh->scan_full[ss]);
+                    mbar_arrive_expect_tx(bar, I8_RAW_BYTES);
+                    tma_load_2d(smem_u32(smem_scan) + (unsigned)ss * I8_RAW_BYTES, &tmap_a, kb * 2 * I8_KC, (int)(nx.row0 - hist_rows), bar);
+                }
+            }
+        }
+        }
     }
 
     // teardown: every MMA has completed before the last tmem_full arrival, every tcgen05.ld before this barrier
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    if (warp == I8_EPI_WARPS) {
+    if (warp == I8_MMA_WARP) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(I8_TMEM_COLS) : "memory");
     }
 }
@@ -667,8 +767,8 @@ int i8_launch(DirectI8Bank& bank, const Window& w, const int* freq_dev, int T, i
     const int row_tiles = (int)((n_out + RB - 1) / RB), tone_groups = (T + TG - 1) / TG;
     static DeviceOnce attr_once;
     if (const int dev = attr_once.pending(); dev >= 0) {
-        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_i8_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM_BYTES));
-        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_i8_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)I8_SMEM_BYTES));
+        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_i8_kernel<F, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)i8_smem_bytes(F)));
+        GSDR_CUDA_OK(cudaFuncSetAttribute(direct_fir_i8_kernel<F, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)i8_smem_bytes(F)));
         attr_once.done(dev);
     }
     CUtensorMap map_a;
@@ -702,31 +802,31 @@ int i8_launch(DirectI8Bank& bank, const Window& w, const int* freq_dev, int T, i
     }();
     long long* dbg = nullptr;
     if (debug) {
-        GSDR_CUDA_OK(cudaMalloc(&dbg, 16 * sizeof(long long)));
-        GSDR_CUDA_OK(cudaMemsetAsync(dbg, 0, 16 * sizeof(long long), stream));
+        GSDR_CUDA_OK(cudaMalloc(&dbg, 20 * sizeof(long long)));
+        GSDR_CUDA_OK(cudaMemsetAsync(dbg, 0, 20 * sizeof(long long), stream));
     }
     static const unsigned int a_order = [] {
         const char* e = getenv("GSDR_I8_AORDER");
         return (e && e[0] == '1') ? 1u : 0u;
     }();
     if (rotate)
-        direct_fir_i8_kernel<F, true><<<grid, I8_THREADS, I8_SMEM_BYTES, stream>>>(map_a, map_b, use_tma, hist_rows, w, bank.d_inv_sb, freq_dev, T, M,
+        direct_fir_i8_kernel<F, true><<<grid, I8_THREADS, i8_smem_bytes(F), stream>>>(map_a, map_b, use_tma, hist_rows, w, bank.d_inv_sb, freq_dev, T, M,
                                                                                    rate, pos0, n_out, row_tiles, tone_groups, bank.KQ, a_order, amax_rows, out, dbg);
     else
-        direct_fir_i8_kernel<F, false><<<grid, I8_THREADS, I8_SMEM_BYTES, stream>>>(map_a, map_b, use_tma, hist_rows, w, bank.d_inv_sb, freq_dev, T, M,
+        direct_fir_i8_kernel<F, false><<<grid, I8_THREADS, i8_smem_bytes(F), stream>>>(map_a, map_b, use_tma, hist_rows, w, bank.d_inv_sb, freq_dev, T, M,
                                                                                     rate, pos0, n_out, row_tiles, tone_groups, bank.KQ, a_order, amax_rows, out, dbg);
     GSDR_CUDA_OK(cudaGetLastError());
     if (dbg) {
-        long long h[16];
+        long long h[20];
         GSDR_CUDA_OK(cudaStreamSynchronize(stream));
         GSDR_CUDA_OK(cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost));
         cudaFree(dbg);
         const double nt = h[15] > 0 ? (double)h[15] : 1.0;   // tiles
         fprintf(stderr,
                 "[direct_i8] grid %d tiles %lld KB %d use_tma %d | cycles per tile: epilogue wait-acc %.0f loads+shift %.0f bar %.0f of %.0f | mma wait-acc %.0f wait-B %.0f "
-                "wait-A %.0f of %.0f | producers scale-handover %.0f wait-stage %.0f wait-rows %.0f of %.0f | tma wait-B %.0f wait-slot %.0f of %.0f\n",
-                grid, tiles, (M + I8_KC - 1) / I8_KC, use_tma, h[0] / nt, h[1] / nt, h[14] / nt, h[2] / nt, h[3] / nt, h[4] / nt, h[5] / nt, h[6] / nt, h[7] / nt, h[8] / nt,
-                h[9] / nt, h[10] / nt, h[11] / nt, h[12] / nt, h[13] / nt);
+                "wait-A %.0f issue %.0f of %.0f | producers scale-handover %.0f wait-stage %.0f wait-rows %.0f wait-scan %.0f digits %.0f store %.0f of %.0f | tma wait-B %.0f wait-slot %.0f of %.0f\n",
+                grid, tiles, (M + I8_KC - 1) / I8_KC, use_tma, h[0] / nt, h[1] / nt, h[14] / nt, h[2] / nt, h[3] / nt, h[4] / nt, h[5] / nt, h[17] / nt, h[6] / nt, h[7] / nt, h[8] / nt,
+                h[9] / nt, h[16] / nt, h[18] / nt, h[19] / nt, h[10] / nt, h[11] / nt, h[12] / nt, h[13] / nt);
     }
     return launches;
 }

@@ -558,73 +558,114 @@ int gsdr_packet_frame(const gsdr_rx_packet* pkt, const void** frame, size_t* fra
 // figure is measured against.  One cudaMemcpyAsync per buffer (h2d_bytes up / d2h_bytes down, `reps` buffers each way), three
 // passes: upload alone, download alone, both directions at once on two streams.  out_gbs = {h2d, d2h, duplex h2d, duplex d2h}
 // in 1e9 bytes/s.  Ranks of a multi-GPU job call it between barriers, so the numbers include what the host shares out.
-int gsdr_pcie_copy_ceiling_streams(int device, size_t h2d_bytes, size_t d2h_bytes, int reps, int n_streams, double* out_gbs);
-int gsdr_pcie_copy_ceiling(int device, size_t h2d_bytes, size_t d2h_bytes, int reps, double* out_gbs) {
-    return gsdr_pcie_copy_ceiling_streams(device, h2d_bytes, d2h_bytes, reps, 1, out_gbs);
+// The probe is an object so that several processes (one per GPU) can do their allocations first, meet at a barrier, and then run
+// each timed pass at the same moment: pinning memory takes longer than a short pass, and ranks that drift apart measure an
+// uncontended link.
+struct gsdr_pcie_probe {
+    int device = 0, n_streams = 1, n_bufs = 0;
+    size_t h2d_bytes = 0, d2h_bytes = 0;
+    std::vector<void*> h_in, h_out, d_in, d_out;
+    cudaStream_t s_up[8] = {nullptr}, s_dn[8] = {nullptr};
+};
+void gsdr_pcie_probe_destroy(gsdr_pcie_probe* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    for (void* q : p->h_in) cudaFreeHost(q);
+    for (void* q : p->h_out) cudaFreeHost(q);
+    for (void* q : p->d_in) cudaFree(q);
+    for (void* q : p->d_out) cudaFree(q);
+    for (int k = 0; k < 8; ++k) {
+        if (p->s_up[k]) cudaStreamDestroy(p->s_up[k]);
+        if (p->s_dn[k]) cudaStreamDestroy(p->s_dn[k]);
+    }
+    delete p;
 }
-// n_streams copy queues per direction, buffers dealt round-robin (several copy-engine queues keep more PCIe reads in flight when
-// the host memory is contended); out_gbs as above, rates summed over the queues of a direction.
+gsdr_pcie_probe* gsdr_pcie_probe_create(int device, size_t h2d_bytes, size_t d2h_bytes, int n_streams, int n_bufs) {
+    if (n_streams < 1 || n_streams > 8 || n_bufs < 1 || n_bufs > 4096 || (h2d_bytes == 0 && d2h_bytes == 0)) {
+        set_error("gsdr_pcie_probe_create: bad argument");
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        set_error("gsdr_pcie_probe_create: cudaSetDevice(%d): %s", device, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    auto* p = new gsdr_pcie_probe;
+    p->device = device, p->n_streams = n_streams, p->n_bufs = n_bufs, p->h2d_bytes = h2d_bytes, p->d2h_bytes = d2h_bytes;
+    bool ok = true;
+    for (int k = 0; k < n_streams && ok; ++k)
+        ok = cudaStreamCreateWithFlags(&p->s_up[k], cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&p->s_dn[k], cudaStreamNonBlocking) == cudaSuccess;
+    // device side: a few buffers are enough (HBM is never the limit here); host side: n_bufs distinct pinned buffers each way
+    const int n_dev = n_bufs < 8 ? n_bufs : 8;
+    for (int i = 0; i < n_bufs && ok; ++i) {
+        void *hi = nullptr, *ho = nullptr;
+        ok = pinned_alloc_local(&hi, h2d_bytes ? h2d_bytes : 1) == cudaSuccess;
+        if (ok) p->h_in.push_back(hi), memset(hi, 1, h2d_bytes ? h2d_bytes : 1);
+        ok = ok && pinned_alloc_local(&ho, d2h_bytes ? d2h_bytes : 1) == cudaSuccess;
+        if (ok) p->h_out.push_back(ho), memset(ho, 0, d2h_bytes ? d2h_bytes : 1);
+    }
+    for (int i = 0; i < n_dev && ok; ++i) {
+        void *di = nullptr, *dout = nullptr;
+        ok = cudaMalloc(&di, h2d_bytes ? h2d_bytes : 1) == cudaSuccess;
+        if (ok) p->d_in.push_back(di);
+        ok = ok && cudaMalloc(&dout, d2h_bytes ? d2h_bytes : 1) == cudaSuccess;
+        if (ok) p->d_out.push_back(dout);
+    }
+    if (!ok) {
+        set_error("gsdr_pcie_probe_create: %s", cudaGetErrorString(cudaGetLastError()));
+        gsdr_pcie_probe_destroy(p);
+        return nullptr;
+    }
+    return p;
+}
+// One timed pass: `reps` buffers in each enabled direction, one cudaMemcpyAsync per buffer, dealt round-robin over the queues and
+// over the host buffers.  Both rates are taken over the SAME interval (until the last copy of either direction has finished), so
+// with both directions on they are the rate of (upload, download) PAIRS in the workload's own byte ratio.  out_gbs[2] = {h2d, d2h}
+// in 1e9 bytes/s (0 for a direction that was off).
+int gsdr_pcie_probe_run(gsdr_pcie_probe* p, int up, int dn, int reps, double* out_gbs) {
+    if (!p || !out_gbs || reps < 1 || (!up && !dn)) {
+        set_error("gsdr_pcie_probe_run: bad argument");
+        return -1;
+    }
+    GSDR_CUDA_OK(cudaSetDevice(p->device));
+    up = up && p->h2d_bytes, dn = dn && p->d2h_bytes;
+    const int n_dev = (int)p->d_in.size();
+    for (int k = 0; k < p->n_streams; ++k) {
+        GSDR_CUDA_OK(cudaStreamSynchronize(p->s_up[k]));
+        GSDR_CUDA_OK(cudaStreamSynchronize(p->s_dn[k]));
+    }
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < reps; ++i) {
+        if (up) GSDR_CUDA_OK(cudaMemcpyAsync(p->d_in[i % n_dev], p->h_in[i % p->n_bufs], p->h2d_bytes, cudaMemcpyHostToDevice, p->s_up[i % p->n_streams]));
+        if (dn) GSDR_CUDA_OK(cudaMemcpyAsync(p->h_out[i % p->n_bufs], p->d_out[i % n_dev], p->d2h_bytes, cudaMemcpyDeviceToHost, p->s_dn[i % p->n_streams]));
+    }
+    for (int k = 0; k < p->n_streams; ++k) {
+        GSDR_CUDA_OK(cudaStreamSynchronize(p->s_up[k]));
+        GSDR_CUDA_OK(cudaStreamSynchronize(p->s_dn[k]));
+    }
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    out_gbs[0] = up && sec > 0 ? (double)p->h2d_bytes * reps / (sec * 1e9) : 0.0;
+    out_gbs[1] = dn && sec > 0 ? (double)p->d2h_bytes * reps / (sec * 1e9) : 0.0;
+    return 0;
+}
+// Single-process convenience forms: out_gbs[4] = {h2d alone, d2h alone, h2d and d2h with both running}.
 int gsdr_pcie_copy_ceiling_streams(int device, size_t h2d_bytes, size_t d2h_bytes, int reps, int n_streams, double* out_gbs) {
-    if (!out_gbs || reps < 1 || n_streams < 1 || n_streams > 8 || (h2d_bytes == 0 && d2h_bytes == 0)) {
+    if (!out_gbs || reps < 1) {
         set_error("gsdr_pcie_copy_ceiling: bad argument");
         return -1;
     }
-    GSDR_CUDA_OK(cudaSetDevice(device));
-    constexpr int kBufs = 8;
-    void *h_in[kBufs] = {nullptr}, *h_out[kBufs] = {nullptr}, *d_in[kBufs] = {nullptr}, *d_out[kBufs] = {nullptr};
-    cudaStream_t s_up[8] = {nullptr}, s_dn[8] = {nullptr};
-    int rc = -1;
-    do {
-        bool ok = true;
-        for (int k = 0; k < n_streams && ok; ++k)
-            ok = cudaStreamCreateWithFlags(&s_up[k], cudaStreamNonBlocking) == cudaSuccess && cudaStreamCreateWithFlags(&s_dn[k], cudaStreamNonBlocking) == cudaSuccess;
-        for (int i = 0; i < kBufs && ok; ++i) {
-            ok = pinned_alloc_local(&h_in[i], h2d_bytes ? h2d_bytes : 1) == cudaSuccess && pinned_alloc_local(&h_out[i], d2h_bytes ? d2h_bytes : 1) == cudaSuccess &&
-                 cudaMalloc(&d_in[i], h2d_bytes ? h2d_bytes : 1) == cudaSuccess && cudaMalloc(&d_out[i], d2h_bytes ? d2h_bytes : 1) == cudaSuccess;
-            if (ok) memset(h_in[i], 1, h2d_bytes ? h2d_bytes : 1), memset(h_out[i], 0, d2h_bytes ? d2h_bytes : 1);
-        }
-        if (!ok) break;
-        auto sync_all = [&]() -> bool {
-            for (int k = 0; k < n_streams; ++k)
-                if (cudaStreamSynchronize(s_up[k]) != cudaSuccess || cudaStreamSynchronize(s_dn[k]) != cudaSuccess) return false;
-            return true;
-        };
-        // One pass: `reps` buffers each way, dealt round-robin over the queues; both rates are taken over the SAME interval
-        // (until the last copy of either direction has finished), so the duplex figures are the rate of (upload, download)
-        // PAIRS in the workload's own byte ratio.
-        auto pass = [&](bool up, bool dn, double* up_gbs, double* dn_gbs) -> bool {
-            double sec = 0.0;
-            for (int w = 0; w < 2; ++w) {   // w == 0: warm-up
-                const int n = w ? reps : 2 * n_streams;
-                if (!sync_all()) return false;
-                const auto t0 = std::chrono::steady_clock::now();
-                for (int i = 0; i < n; ++i) {
-                    if (up && h2d_bytes) cudaMemcpyAsync(d_in[i % kBufs], h_in[i % kBufs], h2d_bytes, cudaMemcpyHostToDevice, s_up[i % n_streams]);
-                    if (dn && d2h_bytes) cudaMemcpyAsync(h_out[i % kBufs], d_out[i % kBufs], d2h_bytes, cudaMemcpyDeviceToHost, s_dn[i % n_streams]);
-                }
-                if (!sync_all()) return false;
-                sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-            }
-            if (up && up_gbs) *up_gbs = sec > 0 ? (double)h2d_bytes * reps / (sec * 1e9) : 0.0;
-            if (dn && dn_gbs) *dn_gbs = sec > 0 ? (double)d2h_bytes * reps / (sec * 1e9) : 0.0;
-            return true;
-        };
-        out_gbs[0] = out_gbs[1] = out_gbs[2] = out_gbs[3] = 0.0;
-        if (!(pass(true, false, &out_gbs[0], nullptr) && pass(false, true, nullptr, &out_gbs[1]) && pass(true, true, &out_gbs[2], &out_gbs[3]))) break;
-        rc = 0;
-    } while (false);
-    if (rc) set_error("gsdr_pcie_copy_ceiling: %s", cudaGetErrorString(cudaGetLastError()));
-    for (int i = 0; i < kBufs; ++i) {
-        if (h_in[i]) cudaFreeHost(h_in[i]);
-        if (h_out[i]) cudaFreeHost(h_out[i]);
-        if (d_in[i]) cudaFree(d_in[i]);
-        if (d_out[i]) cudaFree(d_out[i]);
-    }
-    for (int k = 0; k < 8; ++k) {
-        if (s_up[k]) cudaStreamDestroy(s_up[k]);
-        if (s_dn[k]) cudaStreamDestroy(s_dn[k]);
-    }
+    gsdr_pcie_probe* p = gsdr_pcie_probe_create(device, h2d_bytes, d2h_bytes, n_streams, 8);
+    if (!p) return -1;
+    double w[2], a[2] = {0, 0}, b[2] = {0, 0}, c[2] = {0, 0};
+    int rc = gsdr_pcie_probe_run(p, 1, 1, 2 * n_streams, w);   // warm-up
+    if (!rc && h2d_bytes) rc = gsdr_pcie_probe_run(p, 1, 0, reps, a);
+    if (!rc && d2h_bytes) rc = gsdr_pcie_probe_run(p, 0, 1, reps, b);
+    if (!rc) rc = gsdr_pcie_probe_run(p, 1, 1, reps, c);
+    gsdr_pcie_probe_destroy(p);
+    out_gbs[0] = a[0], out_gbs[1] = b[1], out_gbs[2] = c[0], out_gbs[3] = c[1];
     return rc;
+}
+int gsdr_pcie_copy_ceiling(int device, size_t h2d_bytes, size_t d2h_bytes, int reps, double* out_gbs) {
+    return gsdr_pcie_copy_ceiling_streams(device, h2d_bytes, d2h_bytes, reps, 1, out_gbs);
 }
 
 void* gsdr_host_alloc(size_t bytes) {

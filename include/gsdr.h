@@ -260,12 +260,17 @@ void gsdr_pool_close(gsdr_pool *pool);
 int gsdr_pool_available(const gsdr_pool *pool);
 int gsdr_pool_size(const gsdr_pool *pool);
 
-/* Plain cudaMemcpyAsync ceiling between pinned host memory and `device` (one call per buffer): out_gbs[4] =
- * {h2d alone, d2h alone, h2d and d2h with both running, taken over the same interval} in 1e9 bytes/s.  bench.py reports end-to-end figures
- * against it. */
+/* Plain cudaMemcpyAsync ceiling between pinned host memory and `device` (one call per buffer): what every host-fed figure is
+ * measured against.  The probe is an object so that the ranks of a multi-GPU job can allocate first, meet at a barrier, and start
+ * every timed pass at the same moment (the host's memory and PCIe root are shared).  n_streams (1..8) copy queues per direction,
+ * n_bufs distinct pinned host buffers per direction, buffers dealt round-robin.  gsdr_pcie_probe_run: `reps` buffers in each
+ * enabled direction; out_gbs[2] = {h2d, d2h} in 1e9 bytes/s, both over the same interval. */
+typedef struct gsdr_pcie_probe gsdr_pcie_probe;
+gsdr_pcie_probe *gsdr_pcie_probe_create(int device, size_t h2d_bytes, size_t d2h_bytes, int n_streams, int n_bufs);
+int gsdr_pcie_probe_run(gsdr_pcie_probe *probe, int up, int dn, int reps, double *out_gbs);
+void gsdr_pcie_probe_destroy(gsdr_pcie_probe *probe);
+/* single-process convenience forms: out_gbs[4] = {h2d alone, d2h alone, h2d and d2h with both running} */
 int gsdr_pcie_copy_ceiling(int device, size_t h2d_bytes, size_t d2h_bytes, int reps, double *out_gbs);
-/* the same with n_streams (1..8) copy queues per direction, buffers dealt round-robin: when several GPUs pull on one host's
- * memory a single copy-engine queue is latency-bound and more queues move more bytes */
 int gsdr_pcie_copy_ceiling_streams(int device, size_t h2d_bytes, size_t d2h_bytes, int reps, int n_streams, double *out_gbs);
 void *gsdr_host_alloc(size_t bytes);   /* cudaMallocHost, on the NUMA node of the current GPU when the kernel allows (GSDR_NUMA_LOCAL=0: off) */
 int gsdr_device_numa_node(int device); /* /sys/bus/pci/devices/<bus id>/numa_node of the GPU, -1 when unknown */
