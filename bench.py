@@ -576,7 +576,9 @@ def run_ours(args, dd: Dist):
             v = hin[k][s].view(np.float32) * np.float32(32767.0)
             hraw[k][s][:] = np.clip(np.round(v), -32768, 32767).astype(np.int16)
     ptrs16 = [group.pointer_arrays(hraw[k], hout[k]) for k in range(ring)]
+    lib.gsdr_rx_group_set_zero_copy(group._h, form_modes["zero_copy"])   # the library's default form: int16 read in place by the channelizer
     sc16_val, _, _ = timed_e2e(ptrs16, sc16=True)
+    lib.gsdr_rx_group_set_zero_copy(group._h, form_modes[default_form])
     # the unchanged blocking drop-in call, RX_buffer_demodulator::process: (a) one stream alone, (b) every stream of this GPU
     # from its own worker thread at once (the reference's threading model, cpp/USRP_server_link_threads.cpp:605-702)
     for r in rxs:
@@ -656,7 +658,7 @@ def run_ours(args, dd: Dist):
                                                            "api": "gsdr_rx_process (RX_buffer_demodulator::process), one worker thread per stream"},
                   "pinned_numa_node_rank0": numa_node,
                   "sc16_ingest": {"value": sc16_val, "unit": "MS/s", "h2d_bytes_per_step": S * B * BUFLEN * 4,
-                                  "api": "gsdr_rx_group_submit_sc16 (int16 I/Q in, conversion on the GPU)"}}
+                                  "api": "gsdr_rx_group_submit_sc16 (int16 I/Q in, converted inside the channelizer), zero_copy form"}}
     group.close()
     for r in rxs:
         r.close()
@@ -769,8 +771,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams-total", type=int, default=TOTAL_STREAMS, help="IQ streams of the whole job (cfg5: 64)")
     ap.add_argument("--buffers", type=int, default=0, help="transport buffers per stream per step (default: 512 / streams per GPU)")
-    ap.add_argument("--e2e-form", default="zero_copy", choices=["zero_copy", "copied", "copy_in_store_out"],
-                    help="form of the host-fed call behind e2e.value (the library's default is zero_copy)")
+    ap.add_argument("--e2e-form", default="copied", choices=["zero_copy", "copied", "copy_in_store_out"],
+                    help="form of the host-fed call behind e2e.value: copied = one cudaMemcpyAsync per buffer each way over "
+                         "GSDR_GROUP_COPY_STREAMS queues (equal to zero_copy at N=1, 2-3 %% ahead at N=8 where eight GPUs pull on one "
+                         "host); the library's own default is zero_copy (lower latency per packet period); every form is reported "
+                         "under e2e.forms")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-modes", action="store_true", help="skip the per-configuration `modes` legs (N=1)")
     ap.add_argument("--profile", action="store_true", help="device-resident leg only (for ncu launch lists / captures)")

@@ -130,6 +130,7 @@ SIGNATURES = {
     "gsdr_chirp_params": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.POINTER(ChirpParam)]),
     "gsdr_probe_chirp_index": (C.c_int, [C.c_int, C.POINTER(ChirpParam), C.c_uint64, C.c_uint32, C.c_void_p]),
     "gsdr_probe_direct_phase": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32, C.c_void_p]),
+    "gsdr_probe_direct_tile_phase": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "gsdr_spec_n_freq": (C.c_longlong, [C.c_size_t, C.c_int, C.c_size_t]),
     "gsdr_spec_from_samples": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_double, C.c_int, C.c_int, C.c_int, C.c_size_t, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),

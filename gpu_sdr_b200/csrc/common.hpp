@@ -190,6 +190,8 @@ int direct_fir_i8_launch(DirectI8Bank& bank, const Window& w, const int* freq_de
                          long long n_out, float2* out, int sm_count, cudaStream_t stream, int rotate = 1, bool allow_tma = true);
 int direct_mix_launch(const float2* in, long long n, const int* freq_dev, int T, int rate, long long pos0, float2* out,
                       cudaStream_t stream);
+int direct_tile_phase_probe_launch(long long* phase, unsigned int* word, int n_rows, int tone_freq, int rate, long long pos0,
+                                   long long row0, int M, cudaStream_t stream);
 int direct_phase_probe_launch(long long* out, unsigned int n, int tone_freq, int rate, unsigned long long index_counter,
                               unsigned long long n0, cudaStream_t stream);
 

@@ -306,20 +306,13 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
             const I8Tile tl = tile_of(n);
             if (et < TG && ((et >> 3) & 1) == team) {   // the tones of this team's units
                 const int ch = tl.ch0 + et;
-                double base = 0.0, step = 0.0;
+                double2 bs = make_double2(0.0, 0.0);
                 float isb = 0.f;
                 if (ch < T) {
                     isb = inv_sb[ch];
-                    if (rotate) {
-                        long long tf = (long long)freq[ch] % rate;
-                        if (tf < 0) tf += rate;   // same residue class as the reference's signed remainder
-                        long long n0 = (pos0 + tl.row0 * (long long)M) % rate;
-                        if (n0 < 0) n0 += rate;
-                        base = (double)(((unsigned long long)tf * (unsigned long long)n0) % (unsigned long long)rate);
-                        step = (double)(((unsigned long long)tf * (unsigned long long)(M % rate)) % (unsigned long long)rate);
-                    }
+                    if (rotate) bs = lo_phase_tile(freq[ch], rate, pos0, tl.row0, M);
                 }
-                sh->ph[et] = make_double2(base, step);
+                sh->ph[et] = bs;
                 sh->inv_sb[et] = isb;
             }
             mbar_wait_t(smem_u32(&sh->tmem_full), (unsigned)n & 1u, wt0, timed);
@@ -395,9 +388,7 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         const float sc = inv_sa * sh->inv_sb[u * 8 + t] * 65536.0f;   // the sum is in units of 2^-16 of a digit-1 product
                         o[t] = make_float2(i8_combine(S[0][2 * t], S[1][2 * t], S[2][2 * t]) * sc, i8_combine(S[0][2 * t + 1], S[1][2 * t + 1], S[2][2 * t + 1]) * sc);
                         if (rotate) {   // the channelizer form (pfb as GEMM) has no LO: whole turns per row
-                            const double2 bs = sh->ph[u * 8 + t];
-                            const double r = fma(row_d, bs.y, bs.x);
-                            const unsigned int word = (unsigned int)__double2loint(fma(r, word_per_phase, 6755399441055744.0));
+                            const unsigned int word = lo_phase_word(sh->ph[u * 8 + t], row_d, word_per_phase);
                             float sn, cs;
                             sincos_phase32(word, sn, cs);
                             o[t] = dev_cmul(o[t], make_float2(cs, -sn));

@@ -287,7 +287,27 @@ __global__ void direct_phase_probe_kernel(long long* __restrict__ out, unsigned 
         out[i] = direct_phase_signed(tf, n0 + i + index_counter, rate);
 }
 
+// The tile form of the LO phase (direct_common.cuh: lo_phase_tile / lo_phase_row / lo_phase_word), as the epilogues of
+// direct_fir_tc_kernel and direct_fir_i8_kernel evaluate it: row r of a tile -> (unreduced integer phase, 32-bit phase word).
+__global__ void direct_tile_phase_probe_kernel(long long* __restrict__ phase, unsigned int* __restrict__ word, int n_rows, int tf,
+                                               int rate, long long pos0, long long row0, int M) {
+    const double2 bs = lo_phase_tile(tf, rate, pos0, row0, M);
+    const double word_per_phase = 4294967296.0 / (double)rate;
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
+        phase[r] = (long long)lo_phase_row(bs, (double)r);
+        word[r] = lo_phase_word(bs, (double)r, word_per_phase);
+    }
+}
+
 }  // namespace
+
+int direct_tile_phase_probe_launch(long long* phase, unsigned int* word, int n_rows, int tone_freq, int rate, long long pos0,
+                                   long long row0, int M, cudaStream_t stream) {
+    if (n_rows <= 0) return 0;
+    direct_tile_phase_probe_kernel<<<1, 128, 0, stream>>>(phase, word, n_rows, tone_freq, rate, pos0, row0, M);
+    GSDR_CUDA_OK(cudaGetLastError());
+    return 1;
+}
 
 int direct_fir_launch(const Window& w, const float2* g, const int* freq_dev, int T, int M, int ntaps, int rate,
                       long long pos0, long long n_out, float2* out, cudaStream_t stream) {

@@ -345,16 +345,8 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
             // exactly by one DFMA.
             if (rotate && threadIdx.x < TG) {
                 const int ch = tl.ch0 + (int)threadIdx.x;
-                double base = 0.0, step = 0.0;
-                if (ch < T) {
-                    long long tf = (long long)freq[ch] % rate;
-                    if (tf < 0) tf += rate;   // same residue class as the reference's signed remainder
-                    long long n0 = (pos0 + tl.row0 * (long long)M) % rate;
-                    if (n0 < 0) n0 += rate;
-                    base = (double)(((unsigned long long)tf * (unsigned long long)n0) % (unsigned long long)rate);
-                    step = (double)(((unsigned long long)tf * (unsigned long long)(M % rate)) % (unsigned long long)rate);
-                }
-                sh->ph[threadIdx.x] = make_double2(base, step);
+                const double2 bs = ch < T ? lo_phase_tile(freq[ch], rate, pos0, tl.row0, M) : make_double2(0.0, 0.0);
+                sh->ph[threadIdx.x] = bs;
             }
             // The tensor core's accumulate truncates, so a chain is cut after TC_SEG K blocks (at most 32 k-steps): every segment
             // is a separate accumulation, handed over like a tile (as = segment counter & 1), and the segments of a tile
@@ -451,9 +443,7 @@ direct_fir_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int use_tma
                     for (int t = 0; t < TCW; ++t) {
                         o[t] = make_float2(y[2 * t], y[2 * t + 1]);
                         if (rotate) {   // the channelizer form (pfb as GEMM) has no LO: whole turns per row
-                            const double2 bs = sh->ph[c * TCW + t];
-                            const double r = fma(row_d, bs.y, bs.x);
-                            const unsigned int word = (unsigned int)__double2loint(fma(r, word_per_phase, 6755399441055744.0));
+                            const unsigned int word = lo_phase_word(sh->ph[c * TCW + t], row_d, word_per_phase);
                             float sn, cs;
                             sincos_phase32(word, sn, cs);
                             o[t] = dev_cmul(o[t], make_float2(cs, -sn));

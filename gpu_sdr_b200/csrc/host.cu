@@ -516,6 +516,32 @@ int gsdr_probe_direct_phase(int device, int tone_freq, int rate, uint64_t index_
     return rc < 0 ? -1 : 0;
 }
 
+int gsdr_probe_direct_tile_phase(int device, int tone_freq, int rate, int64_t pos0, int64_t row0, int M, int n_rows,
+                                 int64_t* phase_out_host, uint32_t* word_out_host) {
+    if (!phase_out_host || !word_out_host || rate <= 0 || M <= 0 || n_rows <= 0 || n_rows > 128) {
+        set_error("gsdr_probe_direct_tile_phase: bad argument");
+        return -1;
+    }
+    GSDR_CUDA_OK(cudaSetDevice(device));
+    long long* d_ph = nullptr;
+    unsigned int* d_w = nullptr;
+    GSDR_CUDA_OK(cudaMalloc(&d_ph, sizeof(long long) * n_rows));
+    if (cudaMalloc(&d_w, sizeof(unsigned int) * n_rows) != cudaSuccess) {
+        cudaFree(d_ph);
+        set_error("gsdr_probe_direct_tile_phase: %s", cudaGetErrorString(cudaGetLastError()));
+        return -1;
+    }
+    int rc = direct_tile_phase_probe_launch(d_ph, d_w, n_rows, tone_freq, rate, pos0, row0, M, 0);
+    if (rc >= 0 && (cudaMemcpy(phase_out_host, d_ph, sizeof(long long) * n_rows, cudaMemcpyDeviceToHost) != cudaSuccess ||
+                    cudaMemcpy(word_out_host, d_w, sizeof(unsigned int) * n_rows, cudaMemcpyDeviceToHost) != cudaSuccess)) {
+        set_error("gsdr_probe_direct_tile_phase: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = -1;
+    }
+    cudaFree(d_ph);
+    cudaFree(d_w);
+    return rc < 0 ? -1 : 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Data-socket framing.  Reference: Sync_server::format_net_buffer (cpp/USRP_server_network.cpp:164-191) packs
 // usrp_number | front_end_code | packet_number | length | errors | channels (4+1+4+4+4+4 = 21 bytes, host byte order,

@@ -28,10 +28,6 @@
 #include "common.hpp"
 #include "packed_f32x2.cuh"
 
-#ifndef GSDR_EXP
-#define GSDR_EXP 0  // bit mask of timing experiments (never set in the product build)
-#endif
-
 namespace gsdr {
 
 namespace {
@@ -178,10 +174,6 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
         else sm.tw2[i - FTW1] = tw_global[i];
     }
 
-    if (GSDR_EXP & 64) {  // experiment: de-phase the SMs so memory and compute phases interleave chip-wide
-        const unsigned int ns = (blockIdx.x & 3u) * 1150u;
-        if (ns) __nanosleep(ns);
-    }
     int loaded_job = -1;
     float w[P][2][2];       // taps of this thread's 4 columns
     unsigned int bp[8];     // the (up to 16) selected bins this thread gathers, two per register
@@ -236,7 +228,7 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
         };
         // pull rows [row_lo, row_lo+FTEAMS) towards L2 (one request per 128-byte line)
         auto prefetch_rows = [&](long long row_lo) {
-            if ((t & 7) != 0 || (GSDR_EXP & 128)) return;
+            if ((t & 7) != 0) return;
             const long long s = (row_lo * FN - win.n_hist) + 2 * (long long)t;
             if (s < 0) return;
 #pragma unroll
@@ -283,17 +275,9 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
                 r[i][1] = r[i + FTEAMS][1];
             }
             __syncthreads();
-            if ((GSDR_EXP & 256) && it + 1 < n_it) {
-                load_new_rows(fbase + FTEAMS + P - 1);
-                if (it + 2 < n_it) prefetch_rows(fbase + 2 * FTEAMS + P - 1);
-            }
-
-            if (GSDR_EXP & 512) { if (team >= 2) __nanosleep(250); }
-            if (GSDR_EXP & 1024) { if (team) __nanosleep(team * 100); }
-            if (GSDR_EXP & 2048) { if (team & 1) __nanosleep(200); }
             // ---- one 2048-point FFT per team ------------------------------------------------------
             const long long frame = fbase + team;
-            if (frame < last_frame && !(GSDR_EXP & 16)) {
+            if (frame < last_frame) {
                 float2* A = sm.a[team];
                 float2* B = sm.b[team];
                 float2 v[16];
@@ -308,7 +292,7 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
                         for (int kb = 0; kb < 4; ++kb) {
                             const int k1 = ka + 4 * kb;
                             float2 x = v[4 * ka + kb];
-                            if (k1 != 0) x = cmul(x, (GSDR_EXP & 1) ? make_float2(0.6f, 0.8f) : sm.tw1[k1 * 128 + l]);
+                            if (k1 != 0) x = cmul(x, sm.tw1[k1 * 128 + l]);
                             B[k1 * 129 + l] = x;
                         }
                 }
@@ -324,7 +308,7 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
                         for (int kb = 0; kb < 4; ++kb) {
                             const int k2 = ka + 4 * kb;
                             float2 x = v[4 * ka + kb];
-                            if (k2 != 0) x = cmul(x, (GSDR_EXP & 2) ? make_float2(0.6f, 0.8f) : sm.tw2[n3 * 16 + k2]);
+                            if (k2 != 0) x = cmul(x, sm.tw2[n3 * 16 + k2]);
                             A[n3 * 256 + k2 * 16 + k1] = x;
                         }
                 }
@@ -345,11 +329,11 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
             }
             // The FFT registers are dead from here on: issue the next iteration's row loads now so
             // their latency hides under the barrier, the gather and the next FIR's first FMAs.
-            if (!(GSDR_EXP & 256) && it + 1 < n_it) {
+            if (it + 1 < n_it) {
                 load_new_rows(fbase + FTEAMS + P - 1);
                 if (it + 2 < n_it) prefetch_rows(fbase + 2 * FTEAMS + P - 1);
             }
-            if (frame < last_frame && !(GSDR_EXP & 8)) {
+            if (frame < last_frame) {
                 float2* A = sm.a[team];
                 team_barrier(team, FTEAM_THREADS);
                 // tone selection: coalesced sample-major store, 8 independent gathers in flight
@@ -361,8 +345,7 @@ pfb_fused_2048_kernel(const PfbJob single, const PfbJob* __restrict__ table, con
 #pragma unroll
                         for (int jj = 0; jj < 8; ++jj) {
                             const int j2 = h * 8 + jj;
-                            const unsigned int bin = (GSDR_EXP & 4) ? (unsigned)(tid + FTEAM_THREADS * j2)
-                                                                    : ((bp[j2 >> 1] >> (16 * (j2 & 1))) & 0xffffu);
+                            const unsigned int bin = (bp[j2 >> 1] >> (16 * (j2 & 1))) & 0xffffu;
                             val[jj] = A[bin];
                         }
 #pragma unroll

@@ -95,6 +95,17 @@ def probe_direct_phase(tone_freq, rate, index_counter, n0, n, device: int = 0) -
     return out
 
 
+def probe_direct_tile_phase(tone_freq, rate, pos0, row0, M, n_rows=128, device: int = 0):
+    """(unreduced integer phase, 32-bit phase word) of the rows of one tile, from the device functions the tensor-core DIRECT
+    kernels' epilogues call (gsdr_probe_direct_tile_phase)."""
+    ph = np.empty(int(n_rows), dtype=np.int64)
+    wd = np.empty(int(n_rows), dtype=np.uint32)
+    check(_lib.load().gsdr_probe_direct_tile_phase(int(device), int(tone_freq), int(rate), int(pos0), int(row0), int(M), int(n_rows),
+                                                   ph.ctypes.data_as(C.c_void_p), wd.ctypes.data_as(C.c_void_p)),
+          "gsdr_probe_direct_tile_phase")
+    return ph, wd
+
+
 def spec_from_samples(samples, sampling_rate=1.0, welch=None, dbc=False, rotate=True, clip_samples=False, device=0):
     """pyUSRP/USRP_noise.py:655-703 on the GPU (gsdr_spec_from_samples): returns (freqs, 10 log10 PSD of the real part,
     10 log10 PSD of the imaginary part), the order the reference returns."""

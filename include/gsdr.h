@@ -237,6 +237,11 @@ int gsdr_chirp_params(int rate, int freq0, int chirp_f0, int swipe_s0, float chi
 int gsdr_probe_chirp_index(int device, const gsdr_chirp_param *p, uint64_t last_index, uint32_t n, int32_t *index_out_host);
 int gsdr_probe_direct_phase(int device, int tone_freq, int rate, uint64_t index_counter, uint64_t n0, uint32_t n,
                             int64_t *phase_out_host);
+/* The tile form the tensor-core DIRECT kernels use: for rows r < n_rows (<= 128) of the tile whose first window row is row0
+ * (window rows of M samples, stream position pos0 at row 0): phase_out[r] = the unreduced integer phase base + r * step
+ * (congruent to f * (pos0 + (row0 + r) * M) modulo rate), word_out[r] = the 32-bit phase word handed to the sin/cos. */
+int gsdr_probe_direct_tile_phase(int device, int tone_freq, int rate, int64_t pos0, int64_t row0, int M, int n_rows,
+                                 int64_t *phase_out_host, uint32_t *word_out_host);
 
 /* ------------------------------------------------------------------------------------------
  * Client-side Welch spectra: pyUSRP/USRP_noise.py:655-703, spec_from_samples --

@@ -83,6 +83,31 @@ def test_direct_lo_phase_is_bit_exact(tf, counter):
     assert np.array_equal(got, orc.direct_phase(tf, 0, rate, counter, 7, 300_000))
 
 
+@pytest.mark.parametrize("tf", [12_345_677, -49_999_999, 1, -1, 0, 50_000_000, 99_999_999])
+@pytest.mark.parametrize("pos0,row0,M", [(0, 0, 100), (99_999_900, 125, 100), (3_000_000_000_123, 7_812_375, 100), (12_345, 640, 2048),
+                                         (199_999_999, 1, 16_384)])
+def test_direct_tile_lo_phase_is_bit_exact(tf, pos0, row0, M):
+    """The tensor-core DIRECT kernels (tc and i8 epilogues) form the LO phase per tile as base + row * step: the integer must be
+    congruent to the reference's (f * n) % rate (cpp/kernels.cu:59-75) and the phase word must be that integer times 2^32 / rate,
+    rounded: checked here against Python integers (the word within one unit of the exactly rounded value: the product with the
+    rounded double 2^32 / rate carries 2^-13 of a unit of error, and exact on all but a few rows)."""
+    rate = 200_000_000
+    ph, wd = g.hostlogic.probe_direct_tile_phase(tf, rate, pos0, row0, M)
+    exact_ph = [((tf % rate) * ((pos0 + (row0 + r) * M) % rate)) % rate for r in range(128)]
+    assert [int(p) % rate for p in ph] == exact_ph
+    assert all(0 <= int(p) < 129 * rate for p in ph)
+    n_exact = 0
+    for r in range(128):
+        num = int(ph[r]) * (1 << 32)
+        q, rem = divmod(num, rate)
+        lo, hi = q % (1 << 32), (q + 1) % (1 << 32)
+        w = int(wd[r])
+        assert w in (lo, hi) or (rem == 0 and w == lo)
+        nearest = lo if 2 * rem < rate else hi if 2 * rem > rate else (lo if q % 2 == 0 else hi)
+        n_exact += w == nearest
+    assert n_exact >= 126
+
+
 def test_device_batch_equals_sequential():
     p = chirp_param(steps=1000, t=0.01, decim=3, L=50_000)
     bufs = chirp_inputs(p, 5)
