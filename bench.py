@@ -771,11 +771,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams-total", type=int, default=TOTAL_STREAMS, help="IQ streams of the whole job (cfg5: 64)")
     ap.add_argument("--buffers", type=int, default=0, help="transport buffers per stream per step (default: 512 / streams per GPU)")
-    ap.add_argument("--e2e-form", default="copied", choices=["zero_copy", "copied", "copy_in_store_out"],
-                    help="form of the host-fed call behind e2e.value: copied = one cudaMemcpyAsync per buffer each way over "
-                         "GSDR_GROUP_COPY_STREAMS queues (equal to zero_copy at N=1, 2-3 %% ahead at N=8 where eight GPUs pull on one "
-                         "host); the library's own default is zero_copy (lower latency per packet period); every form is reported "
-                         "under e2e.forms")
+    ap.add_argument("--e2e-form", default="zero_copy", choices=["zero_copy", "copied", "copy_in_store_out"],
+                    help="form of the host-fed call behind e2e.value (the library's default is zero_copy: equal to copied at N=1, "
+                         "+16 %% at N=2, -2.5 %% at N=8; every form is reported under e2e.forms)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-modes", action="store_true", help="skip the per-configuration `modes` legs (N=1)")
     ap.add_argument("--profile", action="store_true", help="device-resident leg only (for ncu launch lists / captures)")
