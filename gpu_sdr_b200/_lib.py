@@ -101,6 +101,7 @@ SIGNATURES = {
     "gsdr_rx_group_members": (C.c_int, [C.c_void_p]),
     "gsdr_rx_group_zero_copy": (C.c_int, [C.c_void_p]),
     "gsdr_rx_group_set_zero_copy": (C.c_int, [C.c_void_p, C.c_int]),
+    "gsdr_rx_group_auto_choice": (C.c_int, [C.c_void_p, C.c_int]),
     "gsdr_rx_group_last_form": (C.c_int, [C.c_void_p]),
     "gsdr_rx_group_sync": (C.c_int, [C.c_void_p]),
     "gsdr_rx_group_timer_start": (C.c_int, [C.c_void_p]),

@@ -11,6 +11,7 @@
 //     is no move_buffer and no upload-at-offset;
 //   - valid lengths come from the same integer helpers as the reference, evaluated on the host
 //     before the GPU runs, and only the valid part is copied back.
+#include <chrono>
 #include <cmath>
 #include <memory>
 #include <mutex>
@@ -1196,7 +1197,31 @@ struct gsdr_rx_group {
     std::vector<cudaStream_t> x_in, x_out;          // extra streams 1 .. n_copy-1
     std::vector<cudaEvent_t> j_in, j_out, f_out;    // join events (extra stream -> stream 0) and the fork event for the downloads
     int n_copy = 1;
-    int zc_mode = 1;               // GSDR_GROUP_ZEROCOPY (read at create): 0 copied, 1 zero-copy both ways, 2 copy in / kernel stores out
+    int zc_mode = 3;               // GSDR_GROUP_ZEROCOPY (read at create): 0 copied, 1 zero-copy both ways, 2 copy in / kernel stores out,
+                                   // 3 (default) = measured: see GroupAutoForm
+    // Which form moves a packet period faster depends on the platform (who else pulls on the host's memory, PCIe topology):
+    // measured on B200 boxes with the pipeline kept full, the zero-copy form is level at 1 GPU, 16 % ahead at 2, 6 % behind at 4
+    // and 2.5 % behind at 8.  It is always the lower-latency form (no separate copy phases), so a caller that feeds packets at
+    // their own pace -- the previous period done before the next is submitted -- simply gets it.  Only when the caller keeps
+    // the pipeline full (kAutoBusy submits in a row that found the previous period still in flight: throughput is what counts)
+    // the default form is MEASURED: kAutoBlock periods zero-copy, kAutoBlock copied, the time from submit to the return of the
+    // wait averaged over each block (its first kAutoSkip periods, which queue behind the other form, left out), the faster
+    // form kept from then on.  A submit that finds the pipeline drained abandons the measurement.  Both forms give
+    // bit-identical results, so the switches are invisible in the data.  Separate decisions for fc32 and sc16 input.
+    static constexpr int kAutoBlock = 8, kAutoSkip = 3, kAutoBusy = 4;
+    struct GroupAutoForm {
+        int choice = -1;            // -1 undecided, else 0 (copied) or 1 (zero-copy)
+        bool measuring = false;
+        int busy_run = 0;           // consecutive submits that found the previous period in flight
+        int cal_submits = 0;        // submits since the measurement began
+        double sum[2] = {0.0, 0.0};
+        int cnt[2] = {0, 0};
+    } auto_form[2];                 // [0] fc32 input, [1] sc16 input
+    struct AutoStamp {
+        std::chrono::steady_clock::time_point t;
+        int kind = -1, block = -1;  // block -1: not a measured period
+        uint64_t ticket = ~0ull;
+    } auto_stamp[8];
     bool last_zero_copy = false;
     int last_form = 0;             // bit 0: inputs read in place, bit 1: outputs written in place
 };
@@ -1309,7 +1334,7 @@ gsdr_rx_group* gsdr_rx_group_create(gsdr_rx** members, int n) {
     g->L = members[0]->L;
     {
         const char* zc = getenv("GSDR_GROUP_ZEROCOPY");
-        g->zc_mode = (zc && zc[0] >= '0' && zc[0] <= '2') ? zc[0] - '0' : 1;
+        g->zc_mode = (zc && zc[0] >= '0' && zc[0] <= '3') ? zc[0] - '0' : 3;
         const char* cs = getenv("GSDR_GROUP_COPY_STREAMS");
         const int k = cs ? atoi(cs) : 4;
         g->n_copy = k < 1 ? 1 : (k > 8 ? 8 : k);
@@ -1404,14 +1429,49 @@ static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool s
     // both ways, 2 copy engine in / kernel stores out.
     std::vector<const void*> ia(S, nullptr);
     std::vector<float2*> oa(S, nullptr);
-    bool zin = g->zc_mode == 1, zout = g->zc_mode != 0;
+    int mode = g->zc_mode, auto_block = -1;
+    if (mode == 3) {   // measured default (GroupAutoForm)
+        auto& af = g->auto_form[sc16 ? 1 : 0];
+        mode = af.choice >= 0 ? af.choice : 1;
+        if (af.choice < 0) {
+            bool busy = false;   // is the previous period still in flight?
+            if (g->tickets > 0 && !g->slots.empty()) {
+                GroupSlot& prev = g->slots[(size_t)((g->tickets - 1) % 0x40000000u) % g->slots.size()];
+                if (prev.used && cudaEventQuery(prev.out_done) == cudaErrorNotReady) busy = true;
+                cudaGetLastError();   // "not ready" is an answer, not an error to be found by the next launch check
+            }
+            if (!busy) {
+                af = gsdr_rx_group::GroupAutoForm();   // paced caller (or pipeline drained): zero-copy, nothing to measure
+            } else if (!af.measuring) {
+                if (++af.busy_run >= gsdr_rx_group::kAutoBusy) af.measuring = true, af.cal_submits = 0;
+            }
+            if (af.measuring) {
+                if (af.cal_submits >= 2 * gsdr_rx_group::kAutoBlock) {
+                    // every measured period has been submitted: decide with what the waits have reported
+                    const double m0 = af.cnt[0] ? af.sum[0] / af.cnt[0] : 0.0, m1 = af.cnt[1] ? af.sum[1] / af.cnt[1] : 0.0;
+                    af.choice = (af.cnt[0] && af.cnt[1] && m1 < m0) ? 0 : 1;   // block 0 ran zero-copy, block 1 copied
+                    af.measuring = false;
+                    mode = af.choice;
+                } else {
+                    auto_block = af.cal_submits / gsdr_rx_group::kAutoBlock;
+                    mode = auto_block == 0 ? 1 : 0;
+                    if (af.cal_submits % gsdr_rx_group::kAutoBlock < gsdr_rx_group::kAutoSkip) auto_block = -1;
+                    af.cal_submits++;
+                }
+            }
+        }
+    }
+    bool zin = mode == 1, zout = mode != 0;
     for (int i = 0; i < S && zin; ++i) zin = (ia[i] = host_alias_of(in_host[i], in_bytes)) != nullptr;
     for (int i = 0; i < S && zout; ++i)
         zout = (oa[i] = static_cast<float2*>(host_alias_of(out_host[i], sizeof(float2) * g->members[i]->max_out))) != nullptr;
     // sc16: the fused channelizer converts the wire format itself (no fc32 copy exists); the lock-step cross-check kernel needs one
     const bool fused_sc16 = sc16 && pfb_fused_sc16_available();
     const bool convert = sc16 && !fused_sc16;
-    if (group_slots_ready(g, (!zin && !sc16) || convert, !zout, sc16 && !zin)) return -1;
+    // a measurement of the forms needs the staging of the copied form a few periods from now: allocate it as the measurement
+    // begins (inside the periods it leaves out), not in the middle of a measured block
+    const bool all_staging = g->zc_mode == 3 && g->auto_form[sc16 ? 1 : 0].measuring;
+    if (group_slots_ready(g, (!zin && !sc16) || convert || (all_staging && !sc16), !zout || all_staging, sc16 && (!zin || all_staging))) return -1;
     const int ticket = (int)(g->tickets % 0x40000000u);
     GroupSlot& s = g->slots[(size_t)ticket % g->slots.size()];
     if (s.used) GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));   // the slot's previous period is fully done
@@ -1479,6 +1539,13 @@ static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool s
     s.used = true;
     g->last_zero_copy = zin && zout;
     g->last_form = (zin ? 1 : 0) | (zout ? 2 : 0);
+    if (g->zc_mode == 3) {
+        auto& st = g->auto_stamp[g->tickets % 8];
+        st.t = std::chrono::steady_clock::now();
+        st.kind = sc16 ? 1 : 0;
+        st.block = auto_block;
+        st.ticket = g->tickets;
+    }
     g->tickets++;
     if (valid_lens)
         for (int i = 0; i < S; ++i) valid_lens[i] = lens[i];
@@ -1498,6 +1565,15 @@ int gsdr_rx_group_wait(gsdr_rx_group* g, int ticket) {
     GroupSlot& s = g->slots[(uint64_t)ticket % g->slots.size()];
     if (!s.used) return 0;
     GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));
+    if (g->zc_mode == 3) {   // a measured period: time from its submit to now
+        auto& st = g->auto_stamp[(uint64_t)ticket % 8];
+        if (st.block >= 0 && st.kind >= 0 && (st.ticket % 0x40000000u) == (uint64_t)ticket && g->auto_form[st.kind].measuring) {
+            auto& af = g->auto_form[st.kind];
+            af.sum[st.block] += std::chrono::duration<double>(std::chrono::steady_clock::now() - st.t).count();
+            af.cnt[st.block]++;
+            st.block = -1;
+        }
+    }
     return 0;
 }
 int gsdr_rx_group_input_consumed(gsdr_rx_group* g, int ticket) {
@@ -1516,10 +1592,16 @@ int gsdr_rx_group_pipeline_depth(const gsdr_rx_group* g) { return g ? kDepth : 0
 int gsdr_rx_group_members(const gsdr_rx_group* g) { return g ? (int)g->members.size() : 0; }
 int gsdr_rx_group_zero_copy(const gsdr_rx_group* g) { return g && g->last_zero_copy ? 1 : 0; }
 int gsdr_rx_group_set_zero_copy(gsdr_rx_group* g, int mode) {
-    if (!g || mode < 0 || mode > 2) return -1;
+    if (!g || mode < 0 || mode > 3) return -1;
     g->zc_mode = mode;
+    if (mode == 3) {   // measure again
+        g->auto_form[0] = gsdr_rx_group::GroupAutoForm();
+        g->auto_form[1] = gsdr_rx_group::GroupAutoForm();
+        for (auto& st : g->auto_stamp) st.block = -1;
+    }
     return 0;
 }
+int gsdr_rx_group_auto_choice(const gsdr_rx_group* g, int sc16) { return g ? g->auto_form[sc16 ? 1 : 0].choice : -1; }
 int gsdr_rx_group_last_form(const gsdr_rx_group* g) { return g ? g->last_form : 0; }
 
 int gsdr_rx_group_sync(gsdr_rx_group* g) {

@@ -173,3 +173,55 @@ def test_group_forms_are_bit_identical(mode, form):
     grp.close()
     for rx in rxs:
         rx.close()
+
+
+@pytest.mark.parametrize("sc16", [False, True])
+def test_measured_default_form_switches_without_a_trace(sc16):
+    """Mode 3 (the default): a caller that keeps the pipeline full gets 8 periods zero-copy and 8 copied timed against each other
+    and then the faster form -- the outputs over the switches must equal the per-stream calls bit for bit.  Whether this loop
+    keeps the pipeline full depends on the box, so the form sequence is checked for consistency, not prescribed."""
+    L, n_periods = 400_000, 30
+    ps, bufs = _streams(L, n_periods, SPECS[:3])
+    if sc16:
+        bufs = [[np.clip(np.round(x.view(np.float32) * 32767.0), -32768, 32767).astype(np.int16) for x in bs] for bs in bufs]
+    want = _per_stream(ps, bufs, sc16=sc16)
+    rxs = [g.RX_buffer_demodulator(p) for p in ps]
+    grp = g.RxGroup(rxs)
+    assert grp.auto_choice(sc16) == -1
+    depth = 3
+    hin = [[(g.pinned_empty(L // 2).view(np.int16) if sc16 else g.pinned_empty(L)) for _ in ps] for _ in range(n_periods)]
+    for b in range(n_periods):
+        for i in range(len(ps)):
+            hin[b][i][:] = bufs[i][b]
+    hout = [[g.pinned_empty(rx.max_output()) for rx in rxs] for _ in range(n_periods)]
+    arrays = [grp.pointer_arrays(hin[b], hout[b]) for b in range(n_periods)]
+    pending, lens_all, forms = [], [], []
+    for b in range(n_periods):   # a tight loop on prebuilt pointer arrays: the previous period is normally still in flight
+        if len(pending) >= depth - 1:
+            grp.wait(pending.pop(0))
+        t, lens = grp.submit(*arrays[b], sc16=sc16)
+        forms.append(grp.last_form())
+        pending.append(t)
+        lens_all.append(lens)
+    for t in pending:
+        grp.wait(t)
+    assert set(forms) <= {0, 3}
+    kept = grp.auto_choice(sc16)
+    assert kept in (-1, 0, 1) and grp.auto_choice(not sc16) == -1
+    if 0 in forms:                                   # a measurement ran: its copied block is one run of at most 8 periods
+        first = forms.index(0)
+        assert forms[:first] == [3] * first and first >= 4 + 8
+    if kept == -1:
+        assert forms[-1] == 3 or forms.count(0) <= 8  # never decided: zero-copy outside an unfinished measurement
+    else:
+        assert forms[-1] == (3 if kept else 0)
+    for i in range(len(ps)):
+        for b in range(n_periods):
+            n = lens_all[b][i]
+            assert n == len(want[i][b]) and n > 0
+            assert np.array_equal(hout[b][i][:n].view(np.uint32), want[i][b].view(np.uint32)), (i, b)
+    grp.set_form(3)                                  # start over
+    assert grp.auto_choice(sc16) == -1
+    grp.close()
+    for rx in rxs:
+        rx.close()

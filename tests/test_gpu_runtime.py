@@ -302,3 +302,22 @@ def test_fallback_direct_kernel_on_a_second_device_after_the_first():
     for dev in (0, 1):
         got = rx_run(p, [x], device=dev)[0]
         assert orc.rel_l2(got, want) <= TOL
+
+
+def test_pcie_probe_reports_both_directions():
+    """gsdr_pcie_probe_*: the cudaMemcpyAsync ceiling bench.py reports its host-fed figures against."""
+    import ctypes as C
+    lib = g.load()
+    probe = lib.gsdr_pcie_probe_create(0, 8 << 20, 4 << 20, 2, 6)
+    assert probe
+    try:
+        w = (C.c_double * 2)()
+        assert lib.gsdr_pcie_probe_run(probe, 1, 0, 8, w) == 0 and w[0] > 1.0 and w[1] == 0.0
+        assert lib.gsdr_pcie_probe_run(probe, 0, 1, 8, w) == 0 and w[0] == 0.0 and w[1] > 1.0
+        assert lib.gsdr_pcie_probe_run(probe, 1, 1, 8, w) == 0 and w[0] > 1.0 and w[1] > 0.5
+        assert lib.gsdr_pcie_probe_run(probe, 0, 0, 8, w) != 0   # nothing to time
+    finally:
+        lib.gsdr_pcie_probe_destroy(probe)
+    assert not lib.gsdr_pcie_probe_create(0, 0, 0, 1, 1)          # no bytes either way
+    four = (C.c_double * 4)()
+    assert lib.gsdr_pcie_copy_ceiling_streams(0, 1 << 20, 1 << 20, 4, 2, four) == 0 and min(four) > 0.5

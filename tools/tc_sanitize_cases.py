@@ -7,7 +7,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
-os.environ["GSDR_DIRECT_VARIANT"] = "tc"
+os.environ.setdefault("GSDR_DIRECT_VARIANT", "tc")   # GSDR_DIRECT_VARIANT=i8 / GSDR_PFB_VARIANT=i8: the integer kernel
 from common import direct_param, orc, pfb_param, rx_run, tone_stream  # noqa: E402
 
 
