@@ -52,7 +52,10 @@ constexpr int I8_ROWS = 128;                 // window rows per tile = UMMA M
 constexpr int I8_N = 128;                    // accumulator columns = F * TG * 2
 constexpr int I8_KC = 16;                    // complex taps per K block: 32 reals = one kind::i8 MMA (K = 32)
 constexpr int I8_RAW = 4;                    // TMA landing slots for A
-constexpr int I8_AST = 5;                    // A operand stages in TMEM (24 columns each: 384 + 120 of the 512 columns)
+#ifndef GSDR_I8_AST
+#define GSDR_I8_AST 4
+#endif
+constexpr int I8_AST = GSDR_I8_AST;          // A operand stages in TMEM (24 columns each; a fifth fits and changes nothing)
 constexpr int I8_BST = 2;                    // B operand stages in shared memory (each: 3 digit planes x 4 K blocks)
 // Twenty warps (96 registers each: ptxas keeps every role inside the launch allocation, with or without setmaxnreg):
 //   warps 0-3, 4-7    two epilogue teams (units of 8 tones dealt alternately)
@@ -186,20 +189,6 @@ __device__ __forceinline__ void tmem_ld16(unsigned int taddr, int* r) {
           "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
         : "r"(taddr)
         : "memory");
-}
-__device__ __forceinline__ void tmem_ld8(unsigned int taddr, int* r) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-}
-// wait for the outstanding tcgen05.ld's; the eight registers pass THROUGH the statement so that no use of them can be scheduled
-// ahead of it (a second load may already be in flight into other registers)
-__device__ __forceinline__ void tmem_ld_wait8(int* r) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
-                 :
-                 : "memory");
 }
 __device__ __forceinline__ void tmem_st4(unsigned int taddr, unsigned int a, unsigned int b, unsigned int c, unsigned int d) {
     asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -347,36 +336,30 @@ direct_fir_i8_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 // so the 64-bit combine D1 2^16 + D2 2^8 + D3 runs once per output and not once per block.
                 int S[3][16];
                 const long long te0 = timed ? clock64() : 0;
-                // 3 accumulators x F blocks x 2 halves of 8 columns, software-pipelined: the tcgen05.ld of the next step is in
-                // flight while this step's rows are shifted and added
-                {
-                    constexpr int NSTEP = 3 * F * 2;
-                    int dbuf[2][8];
-                    auto col_of = [&](int st) {
-                        const int a = st / (2 * F), i = (st >> 1) % F, h = st & 1;
-                        return 128u * (unsigned)a + (unsigned)((i * TG + u * 8) * 2 + 8 * h);
-                    };
-                    tmem_ld8(lane_base + col_of(0), dbuf[0]);
+                // (measured and dropped: x8 loads software-pipelined against the shift-add of the previous one, 223 -> 216 GS/s; a
+                // fifth operand stage: no change)
 #pragma unroll
-                    for (int st = 0; st < NSTEP; ++st) {
-                        int* d = dbuf[st & 1];
-                        tmem_ld_wait8(d);
-                        if (st + 1 < NSTEP) tmem_ld8(lane_base + col_of(st + 1), dbuf[(st + 1) & 1]);
-                        const int a = st / (2 * F), i = (st >> 1) % F, h = st & 1;
+                for (int a = 0; a < 3; ++a) {   // one accumulator at a time: 16 sums + 16 fresh values live
+#pragma unroll
+                    for (int i = 0; i < F; ++i) {
+                        const unsigned int col = 128u * a + (unsigned)((i * TG + u * 8) * 2);
+                        int d[16];
+                        tmem_ld16(lane_base + col, d);
+                        tmem_ld_wait();
                         if (i == 0) {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) S[a][8 * h + j] = d[j];
+                            for (int j = 0; j < 16; ++j) S[a][j] = d[j];
                         } else {
                             if (lane < F - 1) {   // rows the previous warp needs: its lanes 32 - i .. 31 read them after the barrier
-                                int4* dst = reinterpret_cast<int4*>(xw + (((lane * (F - 1) + (i - 1)) * 3) + a) * 16 + 8 * h);
-                                dst[0] = make_int4(d[0], d[1], d[2], d[3]);
-                                dst[1] = make_int4(d[4], d[5], d[6], d[7]);
+                                int4* dst = reinterpret_cast<int4*>(xw + (((lane * (F - 1) + (i - 1)) * 3) + a) * 16);
+#pragma unroll
+                                for (int j4 = 0; j4 < 4; ++j4) dst[j4] = make_int4(d[4 * j4], d[4 * j4 + 1], d[4 * j4 + 2], d[4 * j4 + 3]);
                             }
                             const bool here = lane + i < 32;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
+                            for (int j = 0; j < 16; ++j) {
                                 const int o = __shfl_down_sync(0xffffffffu, d[j], i);
-                                if (here) S[a][8 * h + j] += o;
+                                if (here) S[a][j] += o;
                             }
                         }
                     }
