@@ -124,6 +124,7 @@ SIGNATURES = {
     "gsdr_tone_bins": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "gsdr_pfb_gather_layout": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "gsdr_pfb_partition": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    "gsdr_group_form_simulate": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_void_p]),
     "gsdr_buffer_helper_init": (None, [C.POINTER(BufferHelper), C.c_int, C.c_int, C.c_int, C.c_int]),
     "gsdr_buffer_helper_update": (None, [C.POINTER(BufferHelper)]),
     "gsdr_vna_helper_init": (None, [C.POINTER(VnaHelper), C.c_int, C.c_int]),

@@ -123,6 +123,32 @@ struct PfbTile {
 // every tile a CTA starts costs kPfbTileCost frames' worth of pipeline fill, drain and per-stream constants.
 constexpr long long kPfbTileCost = 24;
 void pfb_partition(const int* n_frames, int n_jobs, int grid, std::vector<PfbTile>& tiles, std::vector<int>& cta_begin);
+
+// Default form of the host-fed group call (rx.cu, gsdr_rx_group_submit), decided by measurement (hostlogic.cpp;
+// gsdr_group_form_simulate exposes it to the CPU tests).  Which form moves a packet period faster depends on the platform (who
+// else pulls on the host's memory, PCIe topology): measured on B200 boxes with the pipeline kept full, the zero-copy form is
+// level at 1 GPU, 16 % ahead at 2, 6 % behind at 4 and 2.5 % behind at 8.  It is always the lower-latency form (no separate copy
+// phases), so a caller that feeds packets at their own pace -- the previous period done before the next is submitted --
+// simply gets it.  Only when the caller keeps the pipeline full (kBusy submits in a row that found the previous period still in
+// flight: throughput is what counts) the form is MEASURED: kBlock periods zero-copy, kBlock copied, the time from submit to
+// the return of the wait averaged over each block (its first kSkip periods, which queue behind the other form, left out),
+// the copied form kept from then on if it is at least 3 % faster, else zero-copy.  A submit that finds the pipeline drained
+// abandons the measurement.  Both forms give
+// bit-identical results, so the switches are invisible in the data.
+struct GroupAutoForm {
+    static constexpr int kBlock = 8, kSkip = 3, kBusy = 4;
+    static constexpr double kMargin = 0.97;   // the copied form must take less than this fraction of the zero-copy time
+    int choice = -1;            // -1 undecided, else 0 (copied) or 1 (zero-copy)
+    bool measuring = false;
+    int busy_run = 0;           // consecutive submits that found the previous period in flight
+    int cal_submits = 0;        // submits since the measurement began
+    double sum[2] = {0.0, 0.0};
+    int cnt[2] = {0, 0};
+    // One submit: `busy` = the previous period is still in flight.  Returns the form for this period (0 copied, 1 zero-copy);
+    // *block = 0 / 1 when the period is a measured one (report its submit-to-wait time with on_wait), else -1.
+    int on_submit(bool busy, int* block);
+    void on_wait(int block, double seconds);
+};
 // Device scratch a multi-stream launch needs for its job table, tile list and per-CTA tile ranges.
 size_t pfb_table_bytes(int n_jobs, int sm_count);
 // Returns the number of kernel launches issued (>0) or -1.  `workspace` is device scratch of at

@@ -457,6 +457,20 @@ int gsdr_pfb_partition(const int32_t* n_frames, int n_jobs, int grid, int32_t* t
     for (int c = 0; c <= grid; ++c) cta_begin_out[c] = cb[c];
     return (int)tiles.size();
 }
+int gsdr_group_form_simulate(const uint8_t* busy, int n_submits, double seconds_copied, double seconds_zero_copy, int wait_lag,
+                             int8_t* form_out) {
+    if (!busy || !form_out || n_submits < 0 || wait_lag < 0) return -2;
+    GroupAutoForm af;
+    std::vector<int> blocks((size_t)n_submits, -1);
+    std::vector<int> forms((size_t)n_submits, 1);
+    for (int i = 0; i < n_submits; ++i) {
+        if (i - wait_lag >= 0 && blocks[i - wait_lag] >= 0)   // the wait on an earlier ticket returns before this submit
+            af.on_wait(blocks[i - wait_lag], forms[i - wait_lag] ? seconds_zero_copy : seconds_copied);
+        forms[i] = af.on_submit(busy[i] != 0, &blocks[i]);
+        form_out[i] = (int8_t)forms[i];
+    }
+    return af.choice;
+}
 int gsdr_pfb_gather_layout(const int32_t* bins, int n_tones, uint8_t* pos_out) {
     if (n_tones < 0 || n_tones > 2048 || !pos_out) return -1;
     pfb_gather_coloring(bins, n_tones, pos_out);

@@ -269,6 +269,35 @@ void pfb_gather_coloring(const int32_t* bins, int T, uint8_t* perm /* [2048] */)
 // (64 streams x 1 buffer in one launch: 189 us against 168 us for one stream with the same frames per CTA).  Splitting by
 // frames alone put the stream boundaries' extra tiles on the critical path (8 streams x 8 buffers: 0.61 of the HBM roofline
 // against 0.68 for one stream).
+int GroupAutoForm::on_submit(bool busy, int* block) {
+    *block = -1;
+    if (choice >= 0) return choice;
+    if (!busy) {
+        *this = GroupAutoForm();   // paced caller (or pipeline drained): zero-copy, nothing to measure
+        return 1;
+    }
+    if (!measuring && ++busy_run >= kBusy) measuring = true, cal_submits = 0;
+    if (!measuring) return 1;
+    if (cal_submits >= 2 * kBlock) {
+        // every measured period has been submitted: decide with what the waits have reported (block 0 ran zero-copy, block 1
+        // copied).  Zero-copy is given up only for a clear win of the copied form (kMargin: five periods per block do not
+        // resolve a per cent or two, and zero-copy is the lower-latency form); without a report from both blocks it stays.
+        const double m0 = cnt[0] ? sum[0] / cnt[0] : 0.0, m1 = cnt[1] ? sum[1] / cnt[1] : 0.0;
+        choice = (cnt[0] && cnt[1] && m1 < kMargin * m0) ? 0 : 1;
+        measuring = false;
+        return choice;
+    }
+    const int b = cal_submits / kBlock;
+    if (cal_submits % kBlock >= kSkip) *block = b;
+    cal_submits++;
+    return b == 0 ? 1 : 0;
+}
+void GroupAutoForm::on_wait(int block, double seconds) {
+    if (!measuring || block < 0 || block > 1) return;
+    sum[block] += seconds;
+    cnt[block]++;
+}
+
 void pfb_partition(const int* n_frames, int n_jobs, int grid, std::vector<PfbTile>& tiles, std::vector<int>& cta_begin) {
     tiles.clear();
     cta_begin.assign((size_t)(grid > 0 ? grid : 0) + 1, 0);

@@ -1199,24 +1199,7 @@ struct gsdr_rx_group {
     int n_copy = 1;
     int zc_mode = 3;               // GSDR_GROUP_ZEROCOPY (read at create): 0 copied, 1 zero-copy both ways, 2 copy in / kernel stores out,
                                    // 3 (default) = measured: see GroupAutoForm
-    // Which form moves a packet period faster depends on the platform (who else pulls on the host's memory, PCIe topology):
-    // measured on B200 boxes with the pipeline kept full, the zero-copy form is level at 1 GPU, 16 % ahead at 2, 6 % behind at 4
-    // and 2.5 % behind at 8.  It is always the lower-latency form (no separate copy phases), so a caller that feeds packets at
-    // their own pace -- the previous period done before the next is submitted -- simply gets it.  Only when the caller keeps
-    // the pipeline full (kAutoBusy submits in a row that found the previous period still in flight: throughput is what counts)
-    // the default form is MEASURED: kAutoBlock periods zero-copy, kAutoBlock copied, the time from submit to the return of the
-    // wait averaged over each block (its first kAutoSkip periods, which queue behind the other form, left out), the faster
-    // form kept from then on.  A submit that finds the pipeline drained abandons the measurement.  Both forms give
-    // bit-identical results, so the switches are invisible in the data.  Separate decisions for fc32 and sc16 input.
-    static constexpr int kAutoBlock = 8, kAutoSkip = 3, kAutoBusy = 4;
-    struct GroupAutoForm {
-        int choice = -1;            // -1 undecided, else 0 (copied) or 1 (zero-copy)
-        bool measuring = false;
-        int busy_run = 0;           // consecutive submits that found the previous period in flight
-        int cal_submits = 0;        // submits since the measurement began
-        double sum[2] = {0.0, 0.0};
-        int cnt[2] = {0, 0};
-    } auto_form[2];                 // [0] fc32 input, [1] sc16 input
+    GroupAutoForm auto_form[2];    // [0] fc32 input, [1] sc16 input (common.hpp)
     struct AutoStamp {
         std::chrono::steady_clock::time_point t;
         int kind = -1, block = -1;  // block -1: not a measured period
@@ -1430,36 +1413,14 @@ static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool s
     std::vector<const void*> ia(S, nullptr);
     std::vector<float2*> oa(S, nullptr);
     int mode = g->zc_mode, auto_block = -1;
-    if (mode == 3) {   // measured default (GroupAutoForm)
-        auto& af = g->auto_form[sc16 ? 1 : 0];
-        mode = af.choice >= 0 ? af.choice : 1;
-        if (af.choice < 0) {
-            bool busy = false;   // is the previous period still in flight?
-            if (g->tickets > 0 && !g->slots.empty()) {
-                GroupSlot& prev = g->slots[(size_t)((g->tickets - 1) % 0x40000000u) % g->slots.size()];
-                if (prev.used && cudaEventQuery(prev.out_done) == cudaErrorNotReady) busy = true;
-                cudaGetLastError();   // "not ready" is an answer, not an error to be found by the next launch check
-            }
-            if (!busy) {
-                af = gsdr_rx_group::GroupAutoForm();   // paced caller (or pipeline drained): zero-copy, nothing to measure
-            } else if (!af.measuring) {
-                if (++af.busy_run >= gsdr_rx_group::kAutoBusy) af.measuring = true, af.cal_submits = 0;
-            }
-            if (af.measuring) {
-                if (af.cal_submits >= 2 * gsdr_rx_group::kAutoBlock) {
-                    // every measured period has been submitted: decide with what the waits have reported
-                    const double m0 = af.cnt[0] ? af.sum[0] / af.cnt[0] : 0.0, m1 = af.cnt[1] ? af.sum[1] / af.cnt[1] : 0.0;
-                    af.choice = (af.cnt[0] && af.cnt[1] && m1 < m0) ? 0 : 1;   // block 0 ran zero-copy, block 1 copied
-                    af.measuring = false;
-                    mode = af.choice;
-                } else {
-                    auto_block = af.cal_submits / gsdr_rx_group::kAutoBlock;
-                    mode = auto_block == 0 ? 1 : 0;
-                    if (af.cal_submits % gsdr_rx_group::kAutoBlock < gsdr_rx_group::kAutoSkip) auto_block = -1;
-                    af.cal_submits++;
-                }
-            }
+    if (mode == 3) {   // measured default (GroupAutoForm, common.hpp)
+        bool busy = false;   // is the previous period still in flight?
+        if (g->auto_form[sc16 ? 1 : 0].choice < 0 && g->tickets > 0 && !g->slots.empty()) {
+            GroupSlot& prev = g->slots[(size_t)((g->tickets - 1) % 0x40000000u) % g->slots.size()];
+            if (prev.used && cudaEventQuery(prev.out_done) == cudaErrorNotReady) busy = true;
+            cudaGetLastError();   // "not ready" is an answer, not an error to be found by the next launch check
         }
+        mode = g->auto_form[sc16 ? 1 : 0].on_submit(busy, &auto_block);
     }
     bool zin = mode == 1, zout = mode != 0;
     for (int i = 0; i < S && zin; ++i) zin = (ia[i] = host_alias_of(in_host[i], in_bytes)) != nullptr;
@@ -1567,10 +1528,8 @@ int gsdr_rx_group_wait(gsdr_rx_group* g, int ticket) {
     GSDR_CUDA_OK(cudaEventSynchronize(s.out_done));
     if (g->zc_mode == 3) {   // a measured period: time from its submit to now
         auto& st = g->auto_stamp[(uint64_t)ticket % 8];
-        if (st.block >= 0 && st.kind >= 0 && (st.ticket % 0x40000000u) == (uint64_t)ticket && g->auto_form[st.kind].measuring) {
-            auto& af = g->auto_form[st.kind];
-            af.sum[st.block] += std::chrono::duration<double>(std::chrono::steady_clock::now() - st.t).count();
-            af.cnt[st.block]++;
+        if (st.block >= 0 && st.kind >= 0 && (st.ticket % 0x40000000u) == (uint64_t)ticket) {
+            g->auto_form[st.kind].on_wait(st.block, std::chrono::duration<double>(std::chrono::steady_clock::now() - st.t).count());
             st.block = -1;
         }
     }
@@ -1595,8 +1554,8 @@ int gsdr_rx_group_set_zero_copy(gsdr_rx_group* g, int mode) {
     if (!g || mode < 0 || mode > 3) return -1;
     g->zc_mode = mode;
     if (mode == 3) {   // measure again
-        g->auto_form[0] = gsdr_rx_group::GroupAutoForm();
-        g->auto_form[1] = gsdr_rx_group::GroupAutoForm();
+        g->auto_form[0] = GroupAutoForm();
+        g->auto_form[1] = GroupAutoForm();
         for (auto& st : g->auto_stamp) st.block = -1;
     }
     return 0;

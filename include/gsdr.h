@@ -174,8 +174,8 @@ int gsdr_rx_group_zero_copy(const gsdr_rx_group *g);   /* 1 when the last submit
  * ways (the launch reads and writes the pinned host buffers in place), 2 = inputs by the copy engine, outputs written in place
  * by the kernel's stores, 3 = measured (default): zero-copy (the lower-latency form) as long as the caller feeds packets at their
  * own pace; a caller that keeps the pipeline full (four submits in a row that found the previous period still in flight) gets
- * 8 periods zero-copy and 8 copied timed against each other and the faster form from then on (which one wins depends on how
- * many GPUs share the host; the results are bit-identical).  Forms that need pinned buffers fall back per direction when a
+ * 8 periods zero-copy and 8 copied timed against each other, and the copied form from then on if it is at least 3 % faster
+ * (which one wins depends on how many GPUs share the host; the results are bit-identical).  Forms that need pinned buffers fall back per direction when a
  * buffer of the period is pageable.
  * gsdr_rx_group_auto_choice: -1 while mode 3 has not decided (or another mode is set), else the form it kept (0 or 1),
  * separately for fc32 (sc16 = 0) and sc16 input. */
@@ -224,6 +224,14 @@ int gsdr_pfb_gather_layout(const int32_t *bins, int n_tones, uint8_t *pos_out /*
  * every CTA carries the same cost (frames + 24 per tile started).  tiles_out: 4 int32 per tile; cta_begin_out: grid + 1
  * entries.  Returns the number of tiles or -1.  Diagnostic/test hook. */
 int gsdr_pfb_partition(const int32_t *n_frames, int n_jobs, int grid, int32_t *tiles_out, int cap_tiles, int32_t *cta_begin_out);
+
+/* The decision logic behind the default form of gsdr_rx_group_submit (mode 3 of gsdr_rx_group_set_zero_copy), run on a
+ * scripted sequence: busy[i] = submit i finds the previous period still in flight; a period takes seconds_copied /
+ * seconds_zero_copy from submit to the return of its wait, and that wait returns before submit i + wait_lag.  form_out[i] =
+ * the form submit i would use (0 copied, 1 zero-copy).  Returns the form kept (0 / 1), -1 while undecided, -2 on a bad
+ * argument.  Diagnostic/test hook, no GPU involved. */
+int gsdr_group_form_simulate(const uint8_t *busy, int n_submits, double seconds_copied, double seconds_zero_copy, int wait_lag,
+                             int8_t *form_out);
 
 typedef struct gsdr_buffer_helper {
     int n_tones, eff_length, buffer_len, average, n_eff_tones;

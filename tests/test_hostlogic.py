@@ -229,3 +229,41 @@ def test_multi_stream_tile_partition(frames, grid):
     busy = [c for c in cost if c > 0]
     if sum(frames) >= 40 * grid:   # enough work per CTA for the balance to mean something
         assert len(busy) == grid and max(busy) <= 1.12 * (sum(busy) / len(busy)), (max(busy), sum(busy) / len(busy))
+
+
+def _simulate_form(busy, copied, zero_copy, lag=2):
+    lib = g.load()
+    b = np.asarray(busy, dtype=np.uint8)
+    out = np.zeros(len(b), dtype=np.int8)
+    kept = lib.gsdr_group_form_simulate(b.ctypes.data_as(C.c_void_p), len(b), float(copied), float(zero_copy), int(lag),
+                                        out.ctypes.data_as(C.c_void_p))
+    return kept, out.tolist()
+
+
+def test_group_form_paced_caller_stays_zero_copy():
+    """gsdr_rx_group_submit's default form (GroupAutoForm): a caller whose previous period is always done never measures."""
+    kept, forms = _simulate_form([0] * 100, copied=1e-3, zero_copy=2e-3)
+    assert kept == -1 and forms == [1] * 100
+
+
+@pytest.mark.parametrize("copied,zero_copy,want", [(1.0e-3, 1.3e-3, 0), (1.3e-3, 1.0e-3, 1), (1.0e-3, 1.0e-3, 1), (0.98e-3, 1.0e-3, 1),
+                                                   (0.96e-3, 1.0e-3, 0)])
+def test_group_form_saturated_caller_measures_and_keeps_the_faster(copied, zero_copy, want):
+    busy = [0] + [1] * 60                      # the first submit has no predecessor
+    kept, forms = _simulate_form(busy, copied, zero_copy)
+    assert kept == want
+    # submit 0 plus three busy ones, then (from the fourth busy submit) 8 zero-copy and 8 copied periods, then the form kept
+    assert forms[:12] == [1] * 12 and forms[12:20] == [0] * 8 and forms[20:] == [want] * (len(busy) - 20)
+
+
+def test_group_form_drained_pipeline_abandons_the_measurement():
+    busy = [0] + [1] * 14 + [0] + [1] * 40     # the pipeline drains in the middle of the copied block
+    kept, forms = _simulate_form(busy, copied=1.0e-3, zero_copy=2.0e-3)
+    assert forms[12:15] == [0] * 3 and forms[15:19] == [1] * 4          # back to zero-copy, counting busy submits again
+    assert forms[19:27] == [1] * 8 and forms[27:35] == [0] * 8          # a fresh measurement
+    assert kept == 0 and forms[35:] == [0] * (len(busy) - 35)
+
+
+def test_group_form_without_wait_reports_keeps_zero_copy():
+    kept, forms = _simulate_form([0] + [1] * 40, copied=1e-3, zero_copy=2e-3, lag=1000)   # the caller never waits in time
+    assert kept == 1 and forms[20:] == [1] * (len(forms) - 20)
