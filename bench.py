@@ -626,14 +626,19 @@ def run_ours(args, dd: Dist):
             ok = lib.gsdr_pcie_probe_run(probe, 1, 1, 64, w) == 0 and w[0] > 0
             reps = int(dd.min(float(max(32, min(4096, int(0.3 * w[0] * 1e9 / h2d_need)))) if ok else 0.0))
             for up, dn, iu, idn in ((1, 0, 0, None), (0, 1, None, 1), (1, 1, 2, 3)):
-                dd.barrier()
-                if reps and lib.gsdr_pcie_probe_run(probe, up, dn, reps, w) == 0:
+                best = None   # two passes of each kind, the better kept (a ceiling: transients only ever read low)
+                for _ in range(2):
+                    dd.barrier()
+                    if reps and lib.gsdr_pcie_probe_run(probe, up, dn, reps, w) == 0:
+                        if best is None or w[0] + w[1] > best[0] + best[1]:
+                            best = (w[0], w[1])
+                    else:
+                        ok = False
+                if best is not None:
                     if iu is not None:
-                        gbs[iu] = w[0]
+                        gbs[iu] = best[0]
                     if idn is not None:
-                        gbs[idn] = w[1]
-                else:
-                    ok = False
+                        gbs[idn] = best[1]
             dd.barrier()
         if probe:
             lib.gsdr_pcie_probe_destroy(probe)
@@ -648,7 +653,8 @@ def run_ours(args, dd: Dist):
         pcie = dict(best)
         pcie.update({"rank": 0, "all": list(ceilings.values()),
                      "how": "gsdr_pcie_probe: one cudaMemcpyAsync per 8 MB buffer up and per 3.9 MB buffer down, the e2e loop's own pinned-buffer footprint, "
-                            "1 and 4 copy queues per direction, both rates over the same interval, ~0.3 s per pass, every rank started at a barrier; "
+                            "1 and 4 copy queues per direction, both rates over the same interval, two passes of ~0.3 s each (the better kept), every rank "
+                            "started at a barrier; "
                             "the better of the two",
                      "e2e_frac_of_ceiling": e2e_val / best["e2e_ceiling_MSps"]})
 
