@@ -124,7 +124,7 @@ struct PfbTile {
 constexpr long long kPfbTileCost = 24;
 void pfb_partition(const int* n_frames, int n_jobs, int grid, std::vector<PfbTile>& tiles, std::vector<int>& cta_begin);
 
-// Default form of the host-fed group call (rx.cu, gsdr_rx_group_submit), decided by measurement (hostlogic.cpp;
+// Form of the host-fed group call (rx.cu, gsdr_rx_group_submit) decided by measurement -- mode 3, opt-in -- (hostlogic.cpp;
 // gsdr_group_form_simulate exposes it to the CPU tests).  Which form moves a packet period faster depends on the platform (who
 // else pulls on the host's memory, PCIe topology): measured on B200 boxes with the pipeline kept full, the zero-copy form is
 // level at 1 GPU, 16 % ahead at 2, 6 % behind at 4 and 2.5 % behind at 8.  It is always the lower-latency form (no separate copy

@@ -235,8 +235,8 @@ class RxGroup:
         return bool(self.lib.gsdr_rx_group_zero_copy(self._h))
 
     def set_form(self, mode: int) -> None:
-        """0 copied both ways, 1 zero-copy both ways, 2 copy engine in / kernel stores out, 3 measured (default): the first
-        16 periods try zero-copy and copied, the faster one is kept."""
+        """0 copied both ways, 1 zero-copy both ways (default), 2 copy engine in / kernel stores out, 3 measured: a caller that
+        keeps the pipeline full gets zero-copy and copied timed against each other once, the clearly faster one is kept."""
         check(self.lib.gsdr_rx_group_set_zero_copy(self._h, int(mode)), "gsdr_rx_group_set_zero_copy")
 
     def auto_choice(self, sc16: bool = False) -> int:

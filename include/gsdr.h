@@ -171,12 +171,14 @@ int gsdr_rx_group_pipeline_depth(const gsdr_rx_group *g);
 int gsdr_rx_group_members(const gsdr_rx_group *g);
 int gsdr_rx_group_zero_copy(const gsdr_rx_group *g);   /* 1 when the last submit took the zero-copy form */
 /* Form of the host-fed call from the next submit on: 0 = copied both ways (one cudaMemcpyAsync per buffer), 1 = zero-copy both
- * ways (the launch reads and writes the pinned host buffers in place), 2 = inputs by the copy engine, outputs written in place
- * by the kernel's stores, 3 = measured (default): zero-copy (the lower-latency form) as long as the caller feeds packets at their
- * own pace; a caller that keeps the pipeline full (four submits in a row that found the previous period still in flight) gets
- * 8 periods zero-copy and 8 copied timed against each other, and the copied form from then on if it is at least 3 % faster
- * (which one wins depends on how many GPUs share the host; the results are bit-identical).  Forms that need pinned buffers fall back per direction when a
- * buffer of the period is pageable.
+ * ways (default: the launch reads and writes the pinned host buffers in place; the lower-latency form), 2 = inputs by the copy
+ * engine, outputs written in place by the kernel's stores, 3 = measured (opt-in): zero-copy as long as the caller feeds packets
+ * at their own pace; a caller that keeps the pipeline full (four submits in a row that found the previous period still in
+ * flight) gets 8 periods zero-copy and 8 copied timed against each other, and the copied form from then on if it came out at
+ * least 3 % faster.  Which form wins depends on how many GPUs share the host (measured: level at 1, zero-copy +16 % at 2,
+ * copied +6 % at 4 and +2.5 % at 8); the results are bit-identical.  The short blocks overrate the copied form by a few per
+ * cent, which is why mode 3 is not the default.  Forms that need pinned buffers fall back per direction
+ * when a buffer of the period is pageable.
  * gsdr_rx_group_auto_choice: -1 while mode 3 has not decided (or another mode is set), else the form it kept (0 or 1),
  * separately for fc32 (sc16 = 0) and sc16 input. */
 int gsdr_rx_group_set_zero_copy(gsdr_rx_group *g, int mode);

@@ -177,7 +177,7 @@ def test_group_forms_are_bit_identical(mode, form):
 
 @pytest.mark.parametrize("sc16", [False, True])
 def test_measured_default_form_switches_without_a_trace(sc16):
-    """Mode 3 (the default): a caller that keeps the pipeline full gets 8 periods zero-copy and 8 copied timed against each other
+    """Mode 3 (opt-in): a caller that keeps the pipeline full gets 8 periods zero-copy and 8 copied timed against each other
     and then the faster form -- the outputs over the switches must equal the per-stream calls bit for bit.  Whether this loop
     keeps the pipeline full depends on the box, so the form sequence is checked for consistency, not prescribed."""
     L, n_periods = 400_000, 30
@@ -187,6 +187,7 @@ def test_measured_default_form_switches_without_a_trace(sc16):
     want = _per_stream(ps, bufs, sc16=sc16)
     rxs = [g.RX_buffer_demodulator(p) for p in ps]
     grp = g.RxGroup(rxs)
+    grp.set_form(3)                                  # opt in (the default form is zero-copy)
     assert grp.auto_choice(sc16) == -1
     depth = 3
     hin = [[(g.pinned_empty(L // 2).view(np.int16) if sc16 else g.pinned_empty(L)) for _ in ps] for _ in range(n_periods)]
