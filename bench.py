@@ -546,7 +546,7 @@ def run_ours(args, dd: Dist):
         return d2h
 
     def timed_e2e(arrays, sc16=False):
-        e2e_run(max(B, ring, 32), arrays, sc16)  # warm-up (the measured default form decides within 4 + 16 periods, a few more if it restarts)
+        e2e_run(max(B, ring, 32), arrays, sc16)  # warm-up (the measured form decides within 4 + 16 periods, a few more if it restarts)
         dd.barrier()
         t0 = time.perf_counter()
         d2h = e2e_run(e2e_steps * B, arrays, sc16)   # e2e_steps steps of B periods each, pipelined across step boundaries

@@ -1417,7 +1417,7 @@ static int group_submit_any(gsdr_rx_group* g, const void* const* in_host, bool s
     std::vector<const void*> ia(S, nullptr);
     std::vector<float2*> oa(S, nullptr);
     int mode = g->zc_mode, auto_block = -1;
-    if (mode == 3) {   // measured default (GroupAutoForm, common.hpp)
+    if (mode == 3) {   // measured form (GroupAutoForm, common.hpp)
         bool busy = false;   // is the previous period still in flight?
         if (g->auto_form[sc16 ? 1 : 0].choice < 0 && g->tickets > 0 && !g->slots.empty()) {
             GroupSlot& prev = g->slots[(size_t)((g->tickets - 1) % 0x40000000u) % g->slots.size()];

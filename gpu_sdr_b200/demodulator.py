@@ -240,7 +240,7 @@ class RxGroup:
         check(self.lib.gsdr_rx_group_set_zero_copy(self._h, int(mode)), "gsdr_rx_group_set_zero_copy")
 
     def auto_choice(self, sc16: bool = False) -> int:
-        """-1 while the measured default is still measuring, else the form it kept (0 copied, 1 zero-copy)."""
+        """-1 while the measured form (mode 3) has not decided, else the form it kept (0 copied, 1 zero-copy)."""
         return int(self.lib.gsdr_rx_group_auto_choice(self._h, 1 if sc16 else 0))
 
     def last_form(self) -> int:
